@@ -1,0 +1,64 @@
+// ilf_pack.h -- host-side packer: VTM 2.1 data model -> plain side-information arrays of include/ilf_b200.h.
+//
+// Product host code (C++11, compiled against the reference's headers, which stay untouched).  It is the
+// only place that touches CodingStructure / CodingUnit / TransformUnit / MotionInfo / Slice; everything
+// after it (C ABI, kernels, the oracle restatement) sees flat arrays only.
+//
+// What is replayed here, by POSITION (not by CU list order, SURVEY.md section 7 "hard parts"):
+//   * LoopFilter::xDeblockCU edge marking      LoopFilter.cpp:243-284, 313-354  (edge / TU-edge / walked bits)
+//   * LoopFilter::xSetLoopfilterParam          LoopFilter.cpp:394-417           (slice boundary, disable flag)
+//   * inputs of xGetBoundaryStrengthSingle     LoopFilter.cpp:419-541           (intra, cbf, ref picture ids, MVs)
+//   * SampleAdaptiveOffset::xReconstructBlkSAOParams / getMergeList / invertQuantOffsets
+//                                              SampleAdaptiveOffset.cpp:147-289
+//   * deriveLoopFilterBoundaryAvailibility     SampleAdaptiveOffset.cpp:685-760
+//   * AdaptiveLoopFilter::reconstructCoeff     AdaptiveLoopFilter.cpp:141-194
+#ifndef ILF_PACK_H
+#define ILF_PACK_H
+
+#include <cstdint>
+#include <vector>
+
+#include "ilf_b200.h"
+
+class CodingStructure;
+struct SAOBlkParam;
+struct AlfSliceParam;
+
+struct IlfPackedDeblock
+{
+  int                   unitsW = 0, unitsH = 0, ctusW = 0, ctusH = 0;
+  ilf_deblock_params    params;
+  std::vector<uint32_t> info;        // luma-tree layer
+  std::vector<uint32_t> infoChroma;  // chroma-tree layer, empty when the picture has no dual-tree slice
+  std::vector<int32_t>  mv32;        // 4 per unit
+  std::vector<int16_t>  mv16;        // same values, filled when mvFits16
+  bool                  mvFits16 = true;
+  bool                  anyInter = false;
+  std::vector<uint8_t>  ctuSlice;
+};
+
+struct IlfPackedSao
+{
+  std::vector<ilf_sao_ctu> ctus;
+  bool                     anyEnabled = false;  // false -> SAOProcess returns early (SampleAdaptiveOffset.cpp:572-583)
+};
+
+struct IlfPackedAlf
+{
+  ilf_alf_params       params;
+  std::vector<uint8_t> ctuEnable;  // [3][numCtus]
+  bool                 enabled = false;  // false -> ALFProcess returns early (AdaptiveLoopFilter.cpp:70-73)
+};
+
+// Deblocking grid of the whole picture.
+void ilfPackDeblock( CodingStructure& cs, IlfPackedDeblock& out );
+
+// SAO: resolves merge candidates and scales the offsets IN `saoBlkParams` exactly as the reference does
+// (the array is left in the same "reconstructed" state SAOProcess leaves it in), then flattens it.
+void ilfPackSao( CodingStructure& cs, SAOBlkParam* saoBlkParams, const uint32_t offsetStepLog2[3], IlfPackedSao& out );
+
+// ALF: reconstructs the coefficients (mutating alfSliceParam like the reference) and flattens.
+void ilfReconstructAlfCoeff( AlfSliceParam& alfSliceParam, bool isLuma, short* coeffFinal /* [25*13], luma only */, bool redo );
+void ilfPackAlf( CodingStructure& cs, AlfSliceParam& alfSliceParam, IlfPackedAlf& out );
+
+#endif
