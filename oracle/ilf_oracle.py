@@ -1,0 +1,105 @@
+"""ctypes door onto oracle/liboracle.so (the CPU restatement, oracle/ilf_oracle.c).
+
+TEST INFRASTRUCTURE: imported only by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg.
+All functions take/return numpy arrays; pictures are dicts {"y","cb","cr"} of int16 2-D arrays.
+"""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def build():
+    subprocess.check_call(["make", "-s", "-C", _HERE, "oracle"])
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        path = os.path.join(_HERE, "liboracle.so")
+        if not os.path.exists(path):
+            build()
+        _LIB = C.CDLL(path)
+    return _LIB
+
+
+def _p(a, t=C.c_void_p):
+    return None if a is None else a.ctypes.data_as(t)
+
+
+def _c(a, dt):
+    return None if a is None else np.ascontiguousarray(a, dtype=dt)
+
+
+def deblock(pic, bd_luma, bd_chroma, ctu_log2, params_bytes, info, info_chroma=None, mv16=None, mv32=None, ctu_slice=None):
+    """LoopFilter::loopFilterPic on a copy of `pic`; returns the filtered picture."""
+    y, cb, cr = (np.array(pic[k], dtype=np.int16, order="C") for k in ("y", "cb", "cr"))
+    h, w = y.shape
+    pb = _c(np.frombuffer(bytes(params_bytes), dtype=np.uint8), np.uint8)
+    info = _c(info, np.uint32); info_chroma = _c(info_chroma, np.uint32)
+    mv16 = _c(mv16, np.int16); mv32 = _c(mv32, np.int32); ctu_slice = _c(ctu_slice, np.uint8)
+    f = lib().ilf_oracle_deblock
+    f.restype = C.c_int
+    f.argtypes = [C.c_void_p, C.c_ssize_t, C.c_void_p, C.c_void_p, C.c_ssize_t] + [C.c_int] * 5 + [C.c_void_p] * 6
+    rc = f(_p(y), y.shape[1], _p(cb), _p(cr), cb.shape[1], w, h, bd_luma, bd_chroma, ctu_log2, _p(pb), _p(info),
+           _p(info_chroma), _p(mv16), _p(mv32), _p(ctu_slice))
+    assert rc == 0
+    return {"y": y, "cb": cb, "cr": cr}
+
+
+def bs_map(width, height, params_bytes, info, mv16=None, mv32=None):
+    pb = _c(np.frombuffer(bytes(params_bytes), dtype=np.uint8), np.uint8)
+    info = _c(info, np.uint32); mv16 = _c(mv16, np.int16); mv32 = _c(mv32, np.int32)
+    out = np.zeros((2, height // 4, width // 4), dtype=np.uint8)
+    f = lib().ilf_oracle_bs_map
+    f.restype = C.c_int
+    f.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 4
+    assert f(_p(out), width, height, _p(pb), _p(info), _p(mv16), _p(mv32)) == 0
+    return out
+
+
+def _planes3(pic):
+    arrs = [np.array(pic[k], dtype=np.int16, order="C") for k in ("y", "cb", "cr")]
+    ptrs = (C.c_void_p * 3)(*[a.ctypes.data for a in arrs])
+    strides = (C.c_ssize_t * 3)(*[a.shape[1] for a in arrs])
+    return arrs, ptrs, strides
+
+
+def sao(pic, bd_luma, bd_chroma, ctu_log2, sao_ctus):
+    """SAOProcess with resolved per-CTU parameters (uint8 array [num_ctus, 32] of ilf_sao_ctu)."""
+    src, sp, ss = _planes3(pic)
+    dst, dp, ds = _planes3(pic)
+    ctus = _c(sao_ctus, np.uint8)
+    h, w = src[0].shape
+    f = lib().ilf_oracle_sao
+    f.restype = C.c_int
+    f.argtypes = [C.c_void_p] * 4 + [C.c_int] * 5 + [C.c_void_p]
+    assert f(sp, ss, dp, ds, w, h, bd_luma, bd_chroma, ctu_log2, _p(ctus)) == 0
+    return {"y": dst[0], "cb": dst[1], "cr": dst[2]}
+
+
+def alf(pic, bd_luma, bd_chroma, ctu_log2, alf_params_bytes, ctu_enable):
+    src, sp, ss = _planes3(pic)
+    dst, dp, ds = _planes3(pic)
+    pb = _c(np.frombuffer(bytes(alf_params_bytes), dtype=np.uint8), np.uint8)
+    en = _c(ctu_enable, np.uint8)
+    h, w = src[0].shape
+    f = lib().ilf_oracle_alf
+    f.restype = C.c_int
+    f.argtypes = [C.c_void_p] * 4 + [C.c_int] * 5 + [C.c_void_p] * 2
+    assert f(sp, ss, dp, ds, w, h, bd_luma, bd_chroma, ctu_log2, _p(pb), _p(en)) == 0
+    return {"y": dst[0], "cb": dst[1], "cr": dst[2]}
+
+
+def alf_classify(y, bd_luma):
+    y = np.ascontiguousarray(y, dtype=np.int16)
+    h, w = y.shape
+    out = np.zeros((h // 4, w // 4), dtype=np.uint8)
+    f = lib().ilf_oracle_alf_classify
+    f.restype = C.c_int
+    f.argtypes = [C.c_void_p, C.c_ssize_t, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    assert f(_p(y), w, w, h, bd_luma, _p(out)) == 0
+    return out
