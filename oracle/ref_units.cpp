@@ -1,0 +1,91 @@
+// oracle/ref_units.cpp -- TEST INFRASTRUCTURE: extern "C" doors onto the REFERENCE's own block functions so that
+// tests/test_oracle_units.py can drive them with random blocks, offsets and availability flags that real
+// bitstreams rarely produce (multi-slice availability patterns, extreme sample values):
+//   SampleAdaptiveOffset::offsetBlock                 SampleAdaptiveOffset.cpp:292-508
+//   AdaptiveLoopFilter::deriveClassificationBlk       AdaptiveLoopFilter.cpp:292-463 (scalar) / x86 SIMD
+//   AdaptiveLoopFilter::filterBlk<5|7>                AdaptiveLoopFilter.cpp:465-650 (scalar) / x86 SIMD
+// Linked against oracle/_ref/libvtm.a (unmodified reference objects).  Nothing here is product code.
+#include <cstring>
+#include <vector>
+
+#include "CommonLib/AdaptiveLoopFilter.h"
+#include "CommonLib/SampleAdaptiveOffset.h"
+
+namespace
+{
+struct SaoDoor : public SampleAdaptiveOffset
+{
+  void run( int bd, int type, int* offset, const Pel* src, Pel* dst, int ss, int ds, int w, int h, unsigned av )
+  {
+    if( m_signLineBuf1.size() < size_t( w + 2 ) ) { m_signLineBuf1.resize( w + 2 ); m_signLineBuf2.resize( w + 2 ); }
+    ClpRng clp; clp.min = 0; clp.max = ( 1 << bd ) - 1; clp.bd = bd; clp.n = 0;
+    offsetBlock( bd, clp, type, offset, src, dst, ss, ds, w, h, av & 1, av & 2, av & 4, av & 8, av & 16, av & 32, av & 64, av & 128 );
+  }
+};
+}  // namespace
+
+extern "C" {
+
+// offset32: the 32-entry offset array of SAOOffset (EO: entries 0..4, BO: per band).  avail: ILF_AVAIL_* bits
+// (L=1, R=2, A=4, B=8, AL=16, AR=32, BL=64, BR=128).  src/dst point at the block's first sample inside a larger
+// picture (the function reads one sample beyond the block on every side).
+int ref_sao_offset_block( int bit_depth, int type, const int* offset32, const int16_t* src, int16_t* dst, int src_stride, int dst_stride, int w, int h, unsigned avail )
+{
+  static SaoDoor door;
+  int off[MAX_NUM_SAO_CLASSES];
+  memcpy( off, offset32, sizeof( off ) );
+  door.run( bit_depth, type, off, src, dst, src_stride, dst_stride, w, h, avail );
+  return 0;
+}
+
+// luma points at sample (0,0) of a plane that is readable 3 samples beyond [0,w)x[0,h) (caller pads).  out[h/4][w/4]
+// = classIdx | transposeIdx << 5.  simd != 0 uses the x86 function the reference installs at start-up.
+int ref_alf_classify( int simd, const int16_t* luma, int stride, int w, int h, int bit_depth, uint8_t* out )
+{
+  static AdaptiveLoopFilter simdAlf;  // constructor installs the SIMD pointers (AdaptiveLoopFilter.cpp:57-65)
+  std::vector<AlfClassifier>  store( size_t( w ) * h );
+  std::vector<AlfClassifier*> rows( h );
+  for( int y = 0; y < h; y++ ) rows[y] = &store[size_t( y ) * w];
+  int  lapStore[NUM_DIRECTIONS][37][37];
+  int* lapRows[NUM_DIRECTIONS][37];
+  int** lap[NUM_DIRECTIONS];
+  for( int d = 0; d < NUM_DIRECTIONS; d++ ) { for( int y = 0; y < 37; y++ ) lapRows[d][y] = lapStore[d][y]; lap[d] = lapRows[d]; }
+  CPelBuf src( luma, stride, w, h );
+  for( int y = 0; y < h; y += 32 )
+    for( int x = 0; x < w; x += 32 )
+    {
+      const Area blk( x, y, std::min( 32, w - x ), std::min( 32, h - y ) );
+      if( simd ) simdAlf.m_deriveClassificationBlk( rows.data(), lap, src, blk, bit_depth + 4 );
+      else AdaptiveLoopFilter::deriveClassificationBlk( rows.data(), lap, src, blk, bit_depth + 4 );
+    }
+  for( int y = 0; y < h; y += 4 )
+    for( int x = 0; x < w; x += 4 ) out[size_t( y / 4 ) * ( w / 4 ) + x / 4] = uint8_t( rows[y][x].classIdx | ( rows[y][x].transposeIdx << 5 ) );
+  return 0;
+}
+
+// One plane through filterBlk.  cls (luma only) = output of ref_alf_classify; coeff = 25x13 (luma) or 7 (chroma) shorts.
+int ref_alf_filter( int simd, int is7, int chroma, const int16_t* src, int src_stride, int16_t* dst, int dst_stride, int w, int h, int bit_depth, const uint8_t* cls, const short* coeff )
+{
+  static AdaptiveLoopFilter simdAlf;
+  std::vector<AlfClassifier>  store( chroma ? 1 : size_t( w ) * h );
+  std::vector<AlfClassifier*> rows( chroma ? 1 : h );
+  if( !chroma )
+    for( int y = 0; y < h; y++ )
+    {
+      rows[y] = &store[size_t( y ) * w];
+      for( int x = 0; x < w; x++ ) { const uint8_t c = cls[size_t( y / 4 ) * ( w / 4 ) + x / 4]; rows[y][x] = AlfClassifier( c & 31, c >> 5 ); }
+    }
+  std::vector<short> cf( coeff, coeff + ( chroma ? 7 : 25 * 13 ) );
+  ClpRng clp; clp.min = 0; clp.max = ( 1 << bit_depth ) - 1; clp.bd = bit_depth; clp.n = 0;
+  // the function indexes recDst/recSrc by compId; give it the same plane in every slot
+  PelBuf  d( dst, dst_stride, w, h );
+  CPelBuf s( src, src_stride, w, h );
+  PelUnitBuf  dstU( CHROMA_420, d, d, d );
+  CPelUnitBuf srcU( CHROMA_420, s, s, s );
+  const Area blk( 0, 0, w, h );
+  const ComponentID comp = chroma ? COMPONENT_Cb : COMPONENT_Y;
+  if( simd ) { if( is7 ) simdAlf.m_filter7x7Blk( rows.data(), dstU, srcU, blk, comp, cf.data(), clp ); else simdAlf.m_filter5x5Blk( rows.data(), dstU, srcU, blk, comp, cf.data(), clp ); }
+  else { if( is7 ) AdaptiveLoopFilter::filterBlk<ALF_FILTER_7>( rows.data(), dstU, srcU, blk, comp, cf.data(), clp ); else AdaptiveLoopFilter::filterBlk<ALF_FILTER_5>( rows.data(), dstU, srcU, blk, comp, cf.data(), clp ); }
+  return 0;
+}
+}

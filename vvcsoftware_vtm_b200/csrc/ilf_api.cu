@@ -1,0 +1,444 @@
+// ilf_api.cu -- the extern "C" boundary of libilf_b200.so (see include/ilf_b200.h): contexts, device-resident
+// planes, pinned async transfers, side-information upload and stage launches.  No CPU fallback anywhere.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "ilf_common.cuh"
+
+using namespace ilf;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct Slot {
+  int16_t* planes = nullptr;   // one allocation: 3 buffers x (Y, Cb, Cr)
+  uint32_t* info = nullptr;
+  uint32_t* info_c = nullptr;
+  void* mv = nullptr;          // int16x4 or int32x4 per unit
+  uint8_t* ctu_slice = nullptr;
+  ilf_deblock_params* db_params = nullptr;
+  ilf_sao_ctu* sao = nullptr;
+  ilf_alf_params* alf = nullptr;
+  uint8_t* alf_ctu_enable = nullptr;
+  uint8_t* alf_class = nullptr;
+  int16_t* pinned = nullptr;   // host staging, one picture
+  uint8_t* pinned_side = nullptr;  // host staging for side information
+  size_t pinned_side_bytes = 0;
+  SlotDev dev;                 // host copy of the device descriptor
+  bool uploaded = false, has_db = false, has_sao = false, has_alf = false, has_ctree = false;
+  int mv_mode = 0;             // 0 none, 1 int16, 2 int32
+  int result_buf = 0;          // buffer holding the current picture
+  cudaEvent_t staged = nullptr;  // pinned staging buffer free again
+};
+
+}  // namespace
+
+struct ilf_ctx {
+  ilf_config cfg;
+  Geom g;
+  bool is_band = false;
+  ilf_band band;
+  cudaStream_t stream = nullptr;
+  std::vector<Slot> slots;
+  SlotDev* slots_dev = nullptr;
+  size_t plane_y = 0, plane_c = 0, buf_elems = 0;  // elements per plane / per 3-plane buffer
+  std::string err;
+  long long launches = 0;
+  bool timing = false;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  float stage_ms[3] = {0, 0, 0};
+  int num_ctus = 0;
+};
+
+namespace {
+
+int fail(ilf_ctx* ctx, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (ctx) ctx->err = buf; else g_create_error = buf;
+  return code;
+}
+
+#define CU(ctx, call)                                                                                     \
+  do {                                                                                                    \
+    cudaError_t e_ = (call);                                                                              \
+    if (e_ != cudaSuccess) return fail(ctx, ILF_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); \
+  } while (0)
+
+int check_slot(ilf_ctx* ctx, int slot) {
+  if (!ctx) return ILF_ERR_ARG;
+  if (slot < 0 || slot >= (int)ctx->slots.size()) return fail(ctx, ILF_ERR_ARG, "slot %d out of range [0,%d)", slot, (int)ctx->slots.size());
+  return ILF_OK;
+}
+
+int16_t* plane_ptr(const ilf_ctx* ctx, const Slot& s, int buf, int plane) {
+  int16_t* p = s.planes + (size_t)buf * ctx->buf_elems;
+  if (plane >= 1) p += ctx->plane_y;
+  if (plane == 2) p += ctx->plane_c;
+  return p;
+}
+
+int push_desc(ilf_ctx* ctx, int slot) {
+  CU(ctx, cudaMemcpyAsync(ctx->slots_dev + slot, &ctx->slots[slot].dev, sizeof(SlotDev), cudaMemcpyHostToDevice, ctx->stream));
+  return ILF_OK;
+}
+
+// Side information goes host -> pinned staging -> device, asynchronously on the context's stream.
+int stage_side(ilf_ctx* ctx, Slot& s, void* dst, const void* src, size_t bytes, size_t& cursor) {
+  if (cursor + bytes > s.pinned_side_bytes) return fail(ctx, ILF_ERR_STATE, "side-information staging overflow");
+  memcpy(s.pinned_side + cursor, src, bytes);
+  CU(ctx, cudaMemcpyAsync(dst, s.pinned_side + cursor, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  cursor += (bytes + 255) & ~size_t(255);
+  return ILF_OK;
+}
+
+int create_impl(ilf_ctx** out, const ilf_config* cfg, const ilf_band* band) {
+  if (!out || !cfg) return fail(nullptr, ILF_ERR_ARG, "null argument");
+  *out = nullptr;
+  if (cfg->width <= 0 || cfg->height <= 0 || (cfg->width & 7) || (cfg->height & 7))
+    return fail(nullptr, ILF_ERR_ARG, "picture size %dx%d must be positive multiples of 8", cfg->width, cfg->height);
+  if (cfg->bit_depth_luma < 8 || cfg->bit_depth_luma > 12 || cfg->bit_depth_chroma < 8 || cfg->bit_depth_chroma > 12)
+    return fail(nullptr, ILF_ERR_ARG, "bit depth must be in 8..12");
+  if (cfg->ctu_log2 < 5 || cfg->ctu_log2 > 7) return fail(nullptr, ILF_ERR_ARG, "ctu_log2 must be 5, 6 or 7");
+  if (cfg->chroma_format != 1) return fail(nullptr, ILF_ERR_UNSUPPORTED, "only 4:2:0 (chroma_format 1) is supported");
+  if (cfg->num_slots < 1) return fail(nullptr, ILF_ERR_ARG, "num_slots must be >= 1");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(nullptr, ILF_ERR_CUDA, "no CUDA device (%s); libilf_b200 has no CPU fallback", e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, ILF_ERR_ARG, "device %d out of range [0,%d)", cfg->device, ndev);
+
+  ilf_ctx* ctx = new (std::nothrow) ilf_ctx();
+  if (!ctx) return fail(nullptr, ILF_ERR_NOMEM, "out of host memory");
+  ctx->cfg = *cfg;
+  Geom& g = ctx->g;
+  g.width = cfg->width; g.height = cfg->height;
+  g.ctu_log2 = cfg->ctu_log2;
+  const int ctu = 1 << cfg->ctu_log2;
+  g.ctus_w = (cfg->width + ctu - 1) >> cfg->ctu_log2;
+  g.ctus_h = (cfg->height + ctu - 1) >> cfg->ctu_log2;
+  g.bd_luma = cfg->bit_depth_luma; g.bd_chroma = cfg->bit_depth_chroma;
+  g.units_w = cfg->width / 4;
+  g.row0 = 0; g.rows = cfg->height; g.out_row0 = 0; g.out_rows = cfg->height;
+  if (band) {
+    if (band->first_ctu_row < 0 || band->num_ctu_rows < 1 || band->first_ctu_row + band->num_ctu_rows > g.ctus_h) {
+      delete ctx;
+      return fail(nullptr, ILF_ERR_ARG, "band CTU rows [%d,+%d) outside the picture (%d CTU rows)", band->first_ctu_row, band->num_ctu_rows, g.ctus_h);
+    }
+    ctx->is_band = true;
+    ctx->band = *band;
+    const int halo = 8;  // luma rows held beyond the band on each side (4 luma / 3 chroma rows are needed)
+    g.out_row0 = band->first_ctu_row << cfg->ctu_log2;
+    const int out_end = std::min(cfg->height, (band->first_ctu_row + band->num_ctu_rows) << cfg->ctu_log2);
+    g.out_rows = out_end - g.out_row0;
+    g.row0 = std::max(0, g.out_row0 - halo);
+    g.rows = std::min(cfg->height, out_end + halo) - g.row0;
+  }
+  g.units_h = g.rows / 4;
+  g.pitch_y = (cfg->width + 63) & ~63;
+  g.pitch_c = (cfg->width / 2 + 63) & ~63;
+  ctx->plane_y = (size_t)g.pitch_y * g.rows;
+  ctx->plane_c = (size_t)g.pitch_c * (g.rows / 2);
+  ctx->buf_elems = ctx->plane_y + 2 * ctx->plane_c;
+  ctx->num_ctus = g.ctus_w * g.ctus_h;
+  *out = ctx;  // from here on errors are reported through ctx->err and the caller destroys
+
+  CU(ctx, cudaSetDevice(cfg->device));
+  CU(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 4; i++) CU(ctx, cudaEventCreate(&ctx->ev[i]));
+  ctx->slots.resize(cfg->num_slots);
+  CU(ctx, cudaMalloc(&ctx->slots_dev, sizeof(SlotDev) * cfg->num_slots));
+  const size_t units = (size_t)g.units_w * g.units_h;
+  for (int i = 0; i < cfg->num_slots; i++) {
+    Slot& s = ctx->slots[i];
+    CU(ctx, cudaMalloc(&s.planes, 3 * ctx->buf_elems * sizeof(int16_t)));
+    CU(ctx, cudaMemsetAsync(s.planes, 0, 3 * ctx->buf_elems * sizeof(int16_t), ctx->stream));
+    CU(ctx, cudaMalloc(&s.info, units * 4));
+    CU(ctx, cudaMalloc(&s.info_c, units * 4));
+    CU(ctx, cudaMalloc(&s.mv, units * 16));
+    CU(ctx, cudaMalloc(&s.ctu_slice, ctx->num_ctus));
+    CU(ctx, cudaMalloc(&s.db_params, sizeof(ilf_deblock_params)));
+    CU(ctx, cudaMalloc(&s.sao, sizeof(ilf_sao_ctu) * ctx->num_ctus));
+    CU(ctx, cudaMalloc(&s.alf, sizeof(ilf_alf_params)));
+    CU(ctx, cudaMalloc(&s.alf_ctu_enable, 3 * (size_t)ctx->num_ctus));
+    CU(ctx, cudaMalloc(&s.alf_class, units));
+    CU(ctx, cudaMallocHost(&s.pinned, ctx->buf_elems * sizeof(int16_t)));
+    s.pinned_side_bytes = units * (4 + 4 + 16) + 4096 + (size_t)ctx->num_ctus * (1 + sizeof(ilf_sao_ctu) + 3) + sizeof(ilf_deblock_params) + sizeof(ilf_alf_params) + 16 * 256;
+    CU(ctx, cudaMallocHost(&s.pinned_side, s.pinned_side_bytes));
+    CU(ctx, cudaEventCreateWithFlags(&s.staged, cudaEventDisableTiming));
+    memset(&s.dev, 0, sizeof(s.dev));
+    for (int b = 0; b < 3; b++)
+      for (int p = 0; p < 3; p++) s.dev.buf[b][p] = plane_ptr(ctx, s, b, p);
+    s.dev.alf_class = s.alf_class;
+  }
+  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  return ILF_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ilf_abi_version(void) { return ILF_ABI_VERSION; }
+
+int ilf_create(ilf_ctx** out, const ilf_config* cfg) {
+  int rc = create_impl(out, cfg, nullptr);
+  if (rc != ILF_OK && out && *out) { g_create_error = (*out)->err; ilf_destroy(*out); *out = nullptr; }
+  return rc;
+}
+
+int ilf_create_band(ilf_ctx** out, const ilf_config* cfg, const ilf_band* band) {
+  if (!band) return fail(nullptr, ILF_ERR_ARG, "null band");
+  int rc = create_impl(out, cfg, band);
+  if (rc != ILF_OK && out && *out) { g_create_error = (*out)->err; ilf_destroy(*out); *out = nullptr; }
+  return rc;
+}
+
+int ilf_destroy(ilf_ctx* ctx) {
+  if (!ctx) return ILF_OK;
+  cudaSetDevice(ctx->cfg.device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  for (Slot& s : ctx->slots) {
+    cudaFree(s.planes); cudaFree(s.info); cudaFree(s.info_c); cudaFree(s.mv); cudaFree(s.ctu_slice); cudaFree(s.db_params);
+    cudaFree(s.sao); cudaFree(s.alf); cudaFree(s.alf_ctu_enable); cudaFree(s.alf_class);
+    if (s.pinned) cudaFreeHost(s.pinned);
+    if (s.pinned_side) cudaFreeHost(s.pinned_side);
+    if (s.staged) cudaEventDestroy(s.staged);
+  }
+  cudaFree(ctx->slots_dev);
+  for (int i = 0; i < 4; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return ILF_OK;
+}
+
+const char* ilf_last_error(const ilf_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int ilf_get_config(const ilf_ctx* ctx, ilf_config* out) {
+  if (!ctx || !out) return ILF_ERR_ARG;
+  *out = ctx->cfg;
+  return ILF_OK;
+}
+
+int ilf_get_band(const ilf_ctx* ctx, ilf_band* out, int32_t* first_row, int32_t* num_rows) {
+  if (!ctx) return ILF_ERR_ARG;
+  if (out) { if (ctx->is_band) *out = ctx->band; else { out->first_ctu_row = 0; out->num_ctu_rows = ctx->g.ctus_h; } }
+  if (first_row) *first_row = ctx->g.row0;
+  if (num_rows) *num_rows = ctx->g.rows;
+  return ILF_OK;
+}
+
+// Host planes cover the rows the context HOLDS: the whole picture, or for a band context picture rows
+// [row0, row0 + rows) as reported by ilf_get_band (pointer = first held row).
+int ilf_upload(ilf_ctx* ctx, int slot, const int16_t* y, ptrdiff_t sy, const int16_t* cb, ptrdiff_t scb, const int16_t* cr, ptrdiff_t scr) {
+  if (int rc = check_slot(ctx, slot)) return rc;
+  if (!y || !cb || !cr) return fail(ctx, ILF_ERR_ARG, "null plane pointer");
+  Slot& s = ctx->slots[slot];
+  const Geom& g = ctx->g;
+  CU(ctx, cudaSetDevice(ctx->cfg.device));
+  CU(ctx, cudaEventSynchronize(s.staged));  // previous use of the staging buffer finished
+  const int16_t* srcs[3] = {y, cb, cr};
+  const ptrdiff_t strides[3] = {sy, scb, scr};
+  int16_t* stage = s.pinned;
+  for (int p = 0; p < 3; p++) {
+    const int w = p ? g.width / 2 : g.width, h = p ? g.rows / 2 : g.rows, pitch = p ? g.pitch_c : g.pitch_y;
+    for (int r = 0; r < h; r++) memcpy(stage + (size_t)r * w, srcs[p] + (ptrdiff_t)r * strides[p], (size_t)w * 2);
+    CU(ctx, cudaMemcpy2DAsync(plane_ptr(ctx, s, 0, p), (size_t)pitch * 2, stage, (size_t)w * 2, (size_t)w * 2, h, cudaMemcpyHostToDevice, ctx->stream));
+    stage += (size_t)w * h;
+  }
+  CU(ctx, cudaEventRecord(s.staged, ctx->stream));
+  s.uploaded = true;
+  s.has_db = s.has_sao = s.has_alf = false;
+  s.result_buf = 0;
+  return ILF_OK;
+}
+
+int ilf_download(ilf_ctx* ctx, int slot, int16_t* y, ptrdiff_t sy, int16_t* cb, ptrdiff_t scb, int16_t* cr, ptrdiff_t scr) {
+  if (int rc = check_slot(ctx, slot)) return rc;
+  if (!y || !cb || !cr) return fail(ctx, ILF_ERR_ARG, "null plane pointer");
+  Slot& s = ctx->slots[slot];
+  if (!s.uploaded) return fail(ctx, ILF_ERR_STATE, "slot %d: download before upload", slot);
+  const Geom& g = ctx->g;
+  CU(ctx, cudaSetDevice(ctx->cfg.device));
+  CU(ctx, cudaEventSynchronize(s.staged));
+  int16_t* dsts[3] = {y, cb, cr};
+  const ptrdiff_t strides[3] = {sy, scb, scr};
+  int16_t* stage = s.pinned;
+  for (int p = 0; p < 3; p++) {
+    const int w = p ? g.width / 2 : g.width, h = p ? g.rows / 2 : g.rows, pitch = p ? g.pitch_c : g.pitch_y;
+    CU(ctx, cudaMemcpy2DAsync(stage, (size_t)w * 2, plane_ptr(ctx, s, s.result_buf, p), (size_t)pitch * 2, (size_t)w * 2, h, cudaMemcpyDeviceToHost, ctx->stream));
+    stage += (size_t)w * h;
+  }
+  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  stage = s.pinned;
+  for (int p = 0; p < 3; p++) {
+    const int w = p ? g.width / 2 : g.width, h = p ? g.rows / 2 : g.rows;
+    for (int r = 0; r < h; r++) memcpy(dsts[p] + (ptrdiff_t)r * strides[p], stage + (size_t)r * w, (size_t)w * 2);
+    stage += (size_t)w * h;
+  }
+  return ILF_OK;
+}
+
+int ilf_sync(ilf_ctx* ctx) {
+  if (!ctx) return ILF_ERR_ARG;
+  CU(ctx, cudaSetDevice(ctx->cfg.device));
+  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  return ILF_OK;
+}
+
+// Grids cover the rows the context holds (units_h = held rows / 4); ctu_slice covers the full picture.
+int ilf_set_deblock_info(ilf_ctx* ctx, int slot, const ilf_deblock_params* params, const uint32_t* info, const uint32_t* info_chroma,
+                         const int16_t* mv16, const int32_t* mv32, const uint8_t* ctu_slice) {
+  if (int rc = check_slot(ctx, slot)) return rc;
+  if (!params || !info) return fail(ctx, ILF_ERR_ARG, "null params/info");
+  if (mv16 && mv32) return fail(ctx, ILF_ERR_ARG, "give mv16 or mv32, not both");
+  if (params->num_slices < 1 || params->num_slices > ILF_MAX_SLICES) return fail(ctx, ILF_ERR_ARG, "num_slices %d out of range", params->num_slices);
+  Slot& s = ctx->slots[slot];
+  CU(ctx, cudaSetDevice(ctx->cfg.device));
+  CU(ctx, cudaStreamSynchronize(ctx->stream));  // staging buffer reuse; side info is small next to the picture
+  const size_t units = (size_t)ctx->g.units_w * ctx->g.units_h;
+  size_t cur = 0;
+  if (int rc = stage_side(ctx, s, s.db_params, params, sizeof(*params), cur)) return rc;
+  if (int rc = stage_side(ctx, s, s.info, info, units * 4, cur)) return rc;
+  s.has_ctree = info_chroma != nullptr;
+  if (info_chroma) if (int rc = stage_side(ctx, s, s.info_c, info_chroma, units * 4, cur)) return rc;
+  s.mv_mode = mv16 ? 1 : (mv32 ? 2 : 0);
+  if (mv16) if (int rc = stage_side(ctx, s, s.mv, mv16, units * 8, cur)) return rc;
+  if (mv32) if (int rc = stage_side(ctx, s, s.mv, mv32, units * 16, cur)) return rc;
+  if (ctu_slice) if (int rc = stage_side(ctx, s, s.ctu_slice, ctu_slice, ctx->num_ctus, cur)) return rc;
+  s.dev.info = s.info;
+  s.dev.info_c = info_chroma ? s.info_c : nullptr;
+  s.dev.mv16 = mv16 ? (const int16_t*)s.mv : nullptr;
+  s.dev.mv32 = mv32 ? (const int32_t*)s.mv : nullptr;
+  s.dev.ctu_slice = ctu_slice ? s.ctu_slice : nullptr;
+  s.dev.db_params = s.db_params;
+  s.has_db = true;
+  return push_desc(ctx, slot);
+}
+
+int ilf_set_sao_params(ilf_ctx* ctx, int slot, const ilf_sao_ctu* ctus) {
+  if (int rc = check_slot(ctx, slot)) return rc;
+  if (!ctus) return fail(ctx, ILF_ERR_ARG, "null SAO parameters");
+  for (int i = 0; i < ctx->num_ctus; i++)
+    for (int c = 0; c < 3; c++)
+      if (ctus[i].type[c] < ILF_SAO_OFF || ctus[i].type[c] > ILF_SAO_BO) return fail(ctx, ILF_ERR_ARG, "CTU %d comp %d: bad SAO type %d", i, c, ctus[i].type[c]);
+  Slot& s = ctx->slots[slot];
+  CU(ctx, cudaSetDevice(ctx->cfg.device));
+  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  size_t cur = 0;
+  if (int rc = stage_side(ctx, s, s.sao, ctus, sizeof(ilf_sao_ctu) * ctx->num_ctus, cur)) return rc;
+  s.dev.sao = s.sao;
+  s.has_sao = true;
+  return push_desc(ctx, slot);
+}
+
+int ilf_set_alf_params(ilf_ctx* ctx, int slot, const ilf_alf_params* params, const uint8_t* ctu_enable) {
+  if (int rc = check_slot(ctx, slot)) return rc;
+  if (!params || !ctu_enable) return fail(ctx, ILF_ERR_ARG, "null ALF parameters");
+  Slot& s = ctx->slots[slot];
+  CU(ctx, cudaSetDevice(ctx->cfg.device));
+  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  size_t cur = 0;
+  if (int rc = stage_side(ctx, s, s.alf, params, sizeof(*params), cur)) return rc;
+  if (int rc = stage_side(ctx, s, s.alf_ctu_enable, ctu_enable, 3 * (size_t)ctx->num_ctus, cur)) return rc;
+  s.dev.alf = s.alf;
+  s.dev.alf_ctu_enable = s.alf_ctu_enable;
+  s.has_alf = true;
+  return push_desc(ctx, slot);
+}
+
+// One stage over a batch of slots.  Buffer rotation: the stage reads the slot's current buffer and writes the
+// next work buffer (1 or 2), never buffer 0, so the uploaded input survives and ilf_run can be repeated.
+static int run_stage(ilf_ctx* ctx, int first, int n, int stage) {
+  int mv_mode = 0;
+  for (int i = first; i < first + n; i++) {
+    Slot& s = ctx->slots[i];
+    if (!s.uploaded) return fail(ctx, ILF_ERR_STATE, "slot %d: run before upload", i);
+    const bool have = stage == 0 ? s.has_db : (stage == 1 ? s.has_sao : s.has_alf);
+    if (!have) return fail(ctx, ILF_ERR_STATE, "slot %d: side information of stage %d not set since the last upload", i, stage);
+    if (stage == 0) mv_mode = std::max(mv_mode, s.mv_mode);
+  }
+  if (stage == 0)
+    for (int i = first; i < first + n; i++)
+      if (ctx->slots[i].mv_mode != mv_mode) return fail(ctx, ILF_ERR_ARG, "slots of one batch must use the same MV representation (none / mv16 / mv32)");
+  const int src = ctx->slots[first].result_buf, dst = src == 1 ? 2 : 1;
+  for (int i = first; i < first + n; i++) {
+    if (ctx->slots[i].result_buf != src) return fail(ctx, ILF_ERR_STATE, "slots of one batch must be at the same stage");
+    ctx->slots[i].result_buf = dst;
+  }
+  if (stage == 0) launch_deblock(ctx->g, ctx->slots_dev, first, n, src, dst, mv_mode, ctx->stream);
+  else if (stage == 1) launch_sao(ctx->g, ctx->slots_dev, first, n, src, dst, ctx->stream);
+  else launch_alf(ctx->g, ctx->slots_dev, first, n, src, dst, false, ctx->stream);
+  ctx->launches += stage == 2 ? 2 : 1;
+  CU(ctx, cudaGetLastError());
+  return ILF_OK;
+}
+
+int ilf_run(ilf_ctx* ctx, int first_slot, int num_slots, unsigned stages) {
+  if (!ctx) return ILF_ERR_ARG;
+  if (first_slot < 0 || num_slots < 1 || first_slot + num_slots > (int)ctx->slots.size()) return fail(ctx, ILF_ERR_ARG, "slot range [%d,+%d) out of range", first_slot, num_slots);
+  if (!(stages & ILF_STAGE_ALL)) return fail(ctx, ILF_ERR_ARG, "empty stage mask");
+  CU(ctx, cudaSetDevice(ctx->cfg.device));
+  // A full run always restarts from the uploaded input.
+  if (stages & ILF_STAGE_DEBLOCK) for (int i = first_slot; i < first_slot + num_slots; i++) ctx->slots[i].result_buf = 0;
+  if (ctx->timing) CU(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
+  for (int st = 0; st < 3; st++) {
+    if (stages & (1u << st)) if (int rc = run_stage(ctx, first_slot, num_slots, st)) return rc;
+    if (ctx->timing) CU(ctx, cudaEventRecord(ctx->ev[st + 1], ctx->stream));
+  }
+  if (ctx->timing) {
+    CU(ctx, cudaEventSynchronize(ctx->ev[3]));
+    for (int st = 0; st < 3; st++) CU(ctx, cudaEventElapsedTime(&ctx->stage_ms[st], ctx->ev[st], ctx->ev[st + 1]));
+  }
+  return ILF_OK;
+}
+
+int ilf_deblock(ilf_ctx* ctx, int slot) { if (int rc = check_slot(ctx, slot)) return rc; return ilf_run(ctx, slot, 1, ILF_STAGE_DEBLOCK); }
+int ilf_sao(ilf_ctx* ctx, int slot) { if (int rc = check_slot(ctx, slot)) return rc; return ilf_run(ctx, slot, 1, ILF_STAGE_SAO); }
+int ilf_alf(ilf_ctx* ctx, int slot) { if (int rc = check_slot(ctx, slot)) return rc; return ilf_run(ctx, slot, 1, ILF_STAGE_ALF); }
+
+int ilf_alf_classify(ilf_ctx* ctx, int slot, uint8_t* out) {
+  if (int rc = check_slot(ctx, slot)) return rc;
+  if (!out) return fail(ctx, ILF_ERR_ARG, "null output");
+  Slot& s = ctx->slots[slot];
+  if (!s.uploaded) return fail(ctx, ILF_ERR_STATE, "slot %d: classify before upload", slot);
+  CU(ctx, cudaSetDevice(ctx->cfg.device));
+  launch_alf(ctx->g, ctx->slots_dev, slot, 1, s.result_buf, s.result_buf, true, ctx->stream);
+  ctx->launches += 1;
+  CU(ctx, cudaGetLastError());
+  CU(ctx, cudaMemcpyAsync(out, s.alf_class, (size_t)ctx->g.units_w * ctx->g.units_h, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  return ILF_OK;
+}
+
+int ilf_set_timing(ilf_ctx* ctx, int enable) { if (!ctx) return ILF_ERR_ARG; ctx->timing = enable != 0; return ILF_OK; }
+int ilf_last_stage_ms(ilf_ctx* ctx, float ms[3]) { if (!ctx || !ms) return ILF_ERR_ARG; for (int i = 0; i < 3; i++) ms[i] = ctx->stage_ms[i]; return ILF_OK; }
+long long ilf_launch_count(const ilf_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int ilf_slot_input_planes(ilf_ctx* ctx, int slot, void* planes[3], int32_t pitch[3]) {
+  if (int rc = check_slot(ctx, slot)) return rc;
+  Slot& s = ctx->slots[slot];
+  for (int p = 0; p < 3; p++) { planes[p] = plane_ptr(ctx, s, 0, p); pitch[p] = p ? ctx->g.pitch_c : ctx->g.pitch_y; }
+  s.uploaded = true;  // the caller fills the planes on the device
+  s.result_buf = 0;
+  return ILF_OK;
+}
+
+int ilf_slot_output_planes(ilf_ctx* ctx, int slot, void* planes[3], int32_t pitch[3]) {
+  if (int rc = check_slot(ctx, slot)) return rc;
+  Slot& s = ctx->slots[slot];
+  for (int p = 0; p < 3; p++) { planes[p] = plane_ptr(ctx, s, s.result_buf, p); pitch[p] = p ? ctx->g.pitch_c : ctx->g.pitch_y; }
+  return ILF_OK;
+}
+
+void* ilf_stream(ilf_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+}  // extern "C"

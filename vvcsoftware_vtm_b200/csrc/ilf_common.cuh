@@ -1,0 +1,51 @@
+// ilf_common.cuh -- shared device-side definitions of libilf_b200 (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "ilf_b200.h"
+
+namespace ilf {
+
+// Geometry shared by every slot of a context; passed to kernels by value.
+struct Geom {
+  int width, height;        // luma samples
+  int pitch_y, pitch_c;     // plane pitches in samples (multiples of 64 -> 128-byte rows)
+  int units_w, units_h;     // 4x4 luma units
+  int ctu_log2, ctus_w, ctus_h;
+  int bd_luma, bd_chroma;
+  // Band mode (one picture split into CTU-row bands across GPUs): the slot's planes hold picture rows
+  // [row0, row0 + rows) of the full picture; filtering decisions use full-picture coordinates.
+  int row0, rows;           // luma rows held (row0 multiple of 8); whole picture: 0, height
+  int out_row0, out_rows;   // luma rows this context must produce (its own CTU rows)
+};
+
+// Per-slot device pointers; an array of these lives in device memory (one entry per slot) and kernels index
+// it with first_slot + blockIdx.z, so one launch covers a batch of pictures.
+struct SlotDev {
+  int16_t* buf[3][3];       // [buffer: 0 = input, 1, 2 = work][plane]
+  const uint32_t* info;     // deblock grid, luma tree
+  const uint32_t* info_c;   // chroma tree layer or nullptr
+  const int16_t* mv16;
+  const int32_t* mv32;
+  const uint8_t* ctu_slice;
+  const ilf_deblock_params* db_params;
+  const ilf_sao_ctu* sao;
+  const ilf_alf_params* alf;
+  const uint8_t* alf_ctu_enable;  // [3][num_ctus]
+  uint8_t* alf_class;             // [units_h][units_w] scratch / output of ilf_alf_classify
+};
+
+__device__ __forceinline__ int clip3i(int lo, int hi, int v) { return min(max(v, lo), hi); }
+
+// 128-bit / 64-bit global accesses.  Pictures are streamed once per stage: bypass L1 allocation on loads
+// that have no intra-CTA reuse.
+__device__ __forceinline__ uint2 ldg_u2(const void* p) { return __ldg(reinterpret_cast<const uint2*>(p)); }
+__device__ __forceinline__ uint4 ldg_u4(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+
+// src_b / dst_b: which of the slot's three buffers the stage reads and writes (the same for every slot of a batch).
+void launch_deblock(const Geom& g, const SlotDev* slots, int first_slot, int num_slots, int src_b, int dst_b, int mv_mode, cudaStream_t st);
+void launch_sao(const Geom& g, const SlotDev* slots, int first_slot, int num_slots, int src_b, int dst_b, cudaStream_t st);
+void launch_alf(const Geom& g, const SlotDev* slots, int first_slot, int num_slots, int src_b, int dst_b, bool classify_only, cudaStream_t st);
+
+}  // namespace ilf

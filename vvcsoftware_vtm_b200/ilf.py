@@ -1,0 +1,204 @@
+"""ctypes binding of libilf_b200.so (include/ilf_b200.h).
+
+No fallback of any kind: if the CUDA library is missing or no GPU is present the calls raise.  numpy arrays
+in, numpy arrays out; device memory stays inside the library.  Method names follow the reference entry points:
+``loop_filter_pic`` = LoopFilter::loopFilterPic, ``sao_process`` = SampleAdaptiveOffset::SAOProcess,
+``alf_process`` = AdaptiveLoopFilter::ALFProcess (DecLib.cpp:516-530).
+"""
+import ctypes as C
+import os
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+STAGE_DEBLOCK, STAGE_SAO, STAGE_ALF, STAGE_ALL = 1, 2, 4, 7
+SAO_CTU_BYTES = 32
+MAX_SLICES = 64
+
+
+class IlfError(RuntimeError):
+    pass
+
+
+class IlfConfig(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("width", "height", "bit_depth_luma", "bit_depth_chroma", "ctu_log2",
+                                         "chroma_format", "device", "num_slots")]
+
+
+class IlfBand(C.Structure):
+    _fields_ = [("first_ctu_row", C.c_int32), ("num_ctu_rows", C.c_int32)]
+
+
+def lib_path():
+    return os.path.join(_HERE, "libilf_b200.so")
+
+
+_LIB = None
+
+
+def load_library():
+    """Load libilf_b200.so; raises IlfError if it was not built (run ``python -c 'import __graft_entry__ as g; g.build()'``)."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = lib_path()
+    if not os.path.exists(path):
+        raise IlfError(f"{path} is missing: the CUDA library was not built; there is no CPU fallback")
+    lib = C.CDLL(path)
+    vp, i, pd = C.c_void_p, C.c_int, C.c_ssize_t
+    lib.ilf_abi_version.restype = i
+    lib.ilf_create.argtypes = [C.POINTER(vp), C.POINTER(IlfConfig)]
+    lib.ilf_create_band.argtypes = [C.POINTER(vp), C.POINTER(IlfConfig), C.POINTER(IlfBand)]
+    lib.ilf_destroy.argtypes = [vp]
+    lib.ilf_last_error.argtypes = [vp]
+    lib.ilf_last_error.restype = C.c_char_p
+    lib.ilf_get_config.argtypes = [vp, C.POINTER(IlfConfig)]
+    lib.ilf_get_band.argtypes = [vp, C.POINTER(IlfBand), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+    lib.ilf_upload.argtypes = [vp, i, vp, pd, vp, pd, vp, pd]
+    lib.ilf_download.argtypes = [vp, i, vp, pd, vp, pd, vp, pd]
+    lib.ilf_sync.argtypes = [vp]
+    lib.ilf_set_deblock_info.argtypes = [vp, i, vp, vp, vp, vp, vp, vp]
+    lib.ilf_set_sao_params.argtypes = [vp, i, vp]
+    lib.ilf_set_alf_params.argtypes = [vp, i, vp, vp]
+    lib.ilf_run.argtypes = [vp, i, i, C.c_uint]
+    for n in ("ilf_deblock", "ilf_sao", "ilf_alf"):
+        getattr(lib, n).argtypes = [vp, i]
+    lib.ilf_alf_classify.argtypes = [vp, i, vp]
+    lib.ilf_last_stage_ms.argtypes = [vp, C.POINTER(C.c_float * 3)]
+    lib.ilf_set_timing.argtypes = [vp, i]
+    lib.ilf_launch_count.argtypes = [vp]
+    lib.ilf_launch_count.restype = C.c_longlong
+    lib.ilf_slot_input_planes.argtypes = [vp, i, C.POINTER(vp * 3), C.POINTER(C.c_int32 * 3)]
+    lib.ilf_slot_output_planes.argtypes = [vp, i, C.POINTER(vp * 3), C.POINTER(C.c_int32 * 3)]
+    lib.ilf_stream.argtypes = [vp]
+    lib.ilf_stream.restype = vp
+    if lib.ilf_abi_version() != 1:
+        raise IlfError("libilf_b200.so ABI version mismatch")
+    _LIB = lib
+    return lib
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _arr(a, dt):
+    return None if a is None else np.ascontiguousarray(a, dtype=dt)
+
+
+class InLoopFilter:
+    """One context: a CUDA device plus ``num_slots`` resident pictures of one geometry."""
+
+    def __init__(self, width, height, bit_depth_luma=10, bit_depth_chroma=10, ctu_log2=7, device=0, num_slots=1, band=None):
+        self._lib = load_library()
+        self.cfg = IlfConfig(width, height, bit_depth_luma, bit_depth_chroma, ctu_log2, 1, device, num_slots)
+        self._h = C.c_void_p()
+        if band is None:
+            rc = self._lib.ilf_create(C.byref(self._h), C.byref(self.cfg))
+        else:
+            b = IlfBand(*band)
+            rc = self._lib.ilf_create_band(C.byref(self._h), C.byref(self.cfg), C.byref(b))
+        if rc != 0:
+            msg = self._lib.ilf_last_error(None).decode()
+            self._h = C.c_void_p()
+            raise IlfError(f"ilf_create failed ({rc}): {msg}")
+        r0, nr = C.c_int32(), C.c_int32()
+        self._lib.ilf_get_band(self._h, None, C.byref(r0), C.byref(nr))
+        self.row0, self.rows = r0.value, nr.value   # picture rows held by this context
+        self.width, self.height = width, height
+        ctu = 1 << ctu_log2
+        self.ctus_w, self.ctus_h = (width + ctu - 1) // ctu, (height + ctu - 1) // ctu
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._lib.ilf_destroy(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise IlfError(f"libilf_b200 error {rc}: {self._lib.ilf_last_error(self._h).decode()}")
+
+    # ---- transfers -------------------------------------------------------------------------------
+    def upload(self, slot, y, cb, cr):
+        y, cb, cr = (_arr(a, np.int16) for a in (y, cb, cr))
+        assert y.shape == (self.rows, self.width) and cb.shape == cr.shape == (self.rows // 2, self.width // 2)
+        self._ck(self._lib.ilf_upload(self._h, slot, _ptr(y), y.shape[1], _ptr(cb), cb.shape[1], _ptr(cr), cr.shape[1]))
+
+    def download(self, slot):
+        y = np.empty((self.rows, self.width), np.int16)
+        cb = np.empty((self.rows // 2, self.width // 2), np.int16)
+        cr = np.empty_like(cb)
+        self._ck(self._lib.ilf_download(self._h, slot, _ptr(y), y.shape[1], _ptr(cb), cb.shape[1], _ptr(cr), cr.shape[1]))
+        return {"y": y, "cb": cb, "cr": cr}
+
+    def sync(self):
+        self._ck(self._lib.ilf_sync(self._h))
+
+    # ---- side information ------------------------------------------------------------------------
+    def set_deblock_info(self, slot, params_bytes, info, info_chroma=None, mv16=None, mv32=None, ctu_slice=None):
+        pb = np.frombuffer(bytes(params_bytes), dtype=np.uint8).copy()
+        info = _arr(info, np.uint32); info_chroma = _arr(info_chroma, np.uint32)
+        mv16 = _arr(mv16, np.int16); mv32 = _arr(mv32, np.int32); ctu_slice = _arr(ctu_slice, np.uint8)
+        assert info.size == (self.rows // 4) * (self.width // 4)
+        self._ck(self._lib.ilf_set_deblock_info(self._h, slot, _ptr(pb), _ptr(info), _ptr(info_chroma), _ptr(mv16), _ptr(mv32), _ptr(ctu_slice)))
+
+    def set_sao_params(self, slot, sao_ctus):
+        a = _arr(sao_ctus, np.uint8)
+        assert a.size == self.ctus_w * self.ctus_h * SAO_CTU_BYTES
+        self._ck(self._lib.ilf_set_sao_params(self._h, slot, _ptr(a)))
+
+    def set_alf_params(self, slot, alf_params_bytes, ctu_enable):
+        pb = np.frombuffer(bytes(alf_params_bytes), dtype=np.uint8).copy()
+        en = _arr(ctu_enable, np.uint8)
+        assert en.size == 3 * self.ctus_w * self.ctus_h
+        self._ck(self._lib.ilf_set_alf_params(self._h, slot, _ptr(pb), _ptr(en)))
+
+    # ---- execution -------------------------------------------------------------------------------
+    def run(self, first_slot=0, num_slots=1, stages=STAGE_ALL):
+        self._ck(self._lib.ilf_run(self._h, first_slot, num_slots, stages))
+
+    def loop_filter_pic(self, slot=0):
+        self._ck(self._lib.ilf_deblock(self._h, slot))
+
+    def sao_process(self, slot=0):
+        self._ck(self._lib.ilf_sao(self._h, slot))
+
+    def alf_process(self, slot=0):
+        self._ck(self._lib.ilf_alf(self._h, slot))
+
+    def alf_classify(self, slot=0):
+        out = np.empty((self.rows // 4, self.width // 4), np.uint8)
+        self._ck(self._lib.ilf_alf_classify(self._h, slot, _ptr(out)))
+        return out
+
+    # ---- measurement -----------------------------------------------------------------------------
+    def set_timing(self, on):
+        self._ck(self._lib.ilf_set_timing(self._h, int(on)))
+
+    def last_stage_ms(self):
+        ms = (C.c_float * 3)()
+        self._ck(self._lib.ilf_last_stage_ms(self._h, C.byref(ms)))
+        return list(ms)
+
+    def launch_count(self):
+        return int(self._lib.ilf_launch_count(self._h))
+
+    def input_planes(self, slot):
+        p = (C.c_void_p * 3)(); pitch = (C.c_int32 * 3)()
+        self._ck(self._lib.ilf_slot_input_planes(self._h, slot, C.byref(p), C.byref(pitch)))
+        return [int(v) for v in p], list(pitch)
+
+    def output_planes(self, slot):
+        p = (C.c_void_p * 3)(); pitch = (C.c_int32 * 3)()
+        self._ck(self._lib.ilf_slot_output_planes(self._h, slot, C.byref(p), C.byref(pitch)))
+        return [int(v) for v in p], list(pitch)
+
+    def stream(self):
+        return int(self._lib.ilf_stream(self._h) or 0)
