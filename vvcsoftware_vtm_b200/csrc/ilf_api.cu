@@ -178,6 +178,7 @@ int create_impl(ilf_ctx** out, const ilf_config* cfg, const ilf_band* band) {
     for (int b = 0; b < 3; b++)
       for (int p = 0; p < 3; p++) s.dev.buf[b][p] = plane_ptr(ctx, s, b, p);
     s.dev.alf_class = s.alf_class;
+    if (int rc = push_desc(ctx, i)) return rc;
   }
   CU(ctx, cudaStreamSynchronize(ctx->stream));
   return ILF_OK;
