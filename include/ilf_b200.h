@@ -211,13 +211,19 @@ int ilf_alf(ilf_ctx* ctx, int slot);
 int ilf_alf_classify(ilf_ctx* ctx, int slot, uint8_t* out);
 
 /* ---------------------------------------------------------------------------------------------
- * Measurement helpers (bench.py).  Kernel time of the last ilf_run per stage in milliseconds
- * (CUDA events on the context's stream), number of kernel launches issued since ilf_create, and
+ * Measurement helpers (bench.py).  Accumulated device time per kernel in milliseconds since
+ * ilf_set_timing(ctx, 1) (CUDA event pairs around every launch on the context's stream, collected
+ * without synchronising inside ilf_run), number of kernel launches issued since ilf_create, and
  * raw device pointers of a slot's input planes so that synthetic pictures can be generated on the
  * device. planes[0..2] = Y, Cb, Cr; pitch in samples.
  * ------------------------------------------------------------------------------------------- */
-int ilf_last_stage_ms(ilf_ctx* ctx, float ms[3]);
-int ilf_set_timing(ilf_ctx* ctx, int enable);
+#define ILF_KERNEL_DEBLOCK 0
+#define ILF_KERNEL_SAO 1
+#define ILF_KERNEL_ALF_LUMA 2
+#define ILF_KERNEL_ALF_CHROMA 3
+#define ILF_NUM_KERNELS 4
+int ilf_set_timing(ilf_ctx* ctx, int enable); /* enable != 0: clear the accumulators and time every launch */
+int ilf_kernel_times(ilf_ctx* ctx, double ms_sum[ILF_NUM_KERNELS], long long launches[ILF_NUM_KERNELS]); /* syncs */
 long long ilf_launch_count(const ilf_ctx* ctx);
 int ilf_slot_input_planes(ilf_ctx* ctx, int slot, void* planes[3], int32_t pitch[3]);
 int ilf_slot_output_planes(ilf_ctx* ctx, int slot, void* planes[3], int32_t pitch[3]);

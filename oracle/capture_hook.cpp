@@ -14,6 +14,7 @@
 //   ILF_CAPTURE_MAX=<n>     stop dumping after n pictures (default: all)
 //   ILF_CAPTURE_PLANES=0    side information only (no sample planes)
 //   ILF_TIMING=1            print "[ILFTIME] ..." per picture on stderr
+//   ILF_EXIT_AFTER=<n>      exit(0) after the filters of the n-th picture (bounded CPU-baseline samples)
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -188,4 +189,6 @@ void DecLib::executeLoopFilters()
   if( timing )
     fprintf( stderr, "[ILFTIME] pic=%d poc=%d w=%u h=%u deblock_us=%lld sao_us=%lld alf_us=%lld\n", picCount, cs.slice->getPOC(), pcv.lumaWidth, pcv.lumaHeight, dbUs, saoUs, alfUs );
   picCount++;
+  static const int exitAfter = getenv( "ILF_EXIT_AFTER" ) ? atoi( getenv( "ILF_EXIT_AFTER" ) ) : 0;
+  if( exitAfter > 0 && picCount >= exitAfter ) { fflush( stderr ); _Exit( 0 ); }
 }

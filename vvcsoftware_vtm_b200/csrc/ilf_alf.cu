@@ -321,7 +321,7 @@ __global__ void __launch_bounds__(NT) alf_chroma_kernel(Geom g, const SlotDev* _
 
 }  // namespace
 
-void launch_alf(const Geom& g, const SlotDev* slots, int first_slot, int num_slots, int src_b, int dst_b, bool classify_only, cudaStream_t st) {
+void launch_alf_luma(const Geom& g, const SlotDev* slots, int first_slot, int num_slots, int src_b, int dst_b, bool classify_only, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(alf_luma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LumaSmem));
@@ -334,6 +334,9 @@ void launch_alf(const Geom& g, const SlotDev* slots, int first_slot, int num_slo
     return;
   }
   alf_luma_kernel<false><<<gl, NT, sizeof(LumaSmem), st>>>(g, slots, first_slot, src_b, dst_b);
+}
+
+void launch_alf_chroma(const Geom& g, const SlotDev* slots, int first_slot, int num_slots, int src_b, int dst_b, cudaStream_t st) {
   dim3 gc((g.width / 2 + CT_W - 1) / CT_W, (g.rows / 2 + CT_H - 1) / CT_H, 2 * num_slots);
   alf_chroma_kernel<<<gc, NT, 0, st>>>(g, slots, first_slot, src_b, dst_b);
 }

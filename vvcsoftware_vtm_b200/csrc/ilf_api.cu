@@ -50,8 +50,12 @@ struct ilf_ctx {
   std::string err;
   long long launches = 0;
   bool timing = false;
-  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-  float stage_ms[3] = {0, 0, 0};
+  // per-kernel timing (bench.py): event pairs recorded around every launch while timing is on
+  struct TimedLaunch { int kernel; cudaEvent_t a, b; };
+  std::vector<TimedLaunch> timed;
+  std::vector<cudaEvent_t> free_events;
+  double kernel_ms[ILF_NUM_KERNELS] = {0, 0, 0, 0};
+  long long kernel_launches[ILF_NUM_KERNELS] = {0, 0, 0, 0};
   int num_ctus = 0;
 };
 
@@ -153,7 +157,6 @@ int create_impl(ilf_ctx** out, const ilf_config* cfg, const ilf_band* band) {
 
   CU(ctx, cudaSetDevice(cfg->device));
   CU(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-  for (int i = 0; i < 4; i++) CU(ctx, cudaEventCreate(&ctx->ev[i]));
   ctx->slots.resize(cfg->num_slots);
   CU(ctx, cudaMalloc(&ctx->slots_dev, sizeof(SlotDev) * cfg->num_slots));
   const size_t units = (size_t)g.units_w * g.units_h;
@@ -215,7 +218,8 @@ int ilf_destroy(ilf_ctx* ctx) {
     if (s.staged) cudaEventDestroy(s.staged);
   }
   cudaFree(ctx->slots_dev);
-  for (int i = 0; i < 4; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+  for (auto& t : ctx->timed) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
+  for (cudaEvent_t e : ctx->free_events) cudaEventDestroy(e);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return ILF_OK;
@@ -356,6 +360,38 @@ int ilf_set_alf_params(ilf_ctx* ctx, int slot, const ilf_alf_params* params, con
   return push_desc(ctx, slot);
 }
 
+// Event pair around one kernel launch while timing is on (ilf_set_timing / ilf_kernel_times).
+static int timed_begin(ilf_ctx* ctx, int kernel) {
+  if (!ctx->timing) return ILF_OK;
+  cudaEvent_t ev[2];
+  for (int i = 0; i < 2; i++) {
+    if (!ctx->free_events.empty()) { ev[i] = ctx->free_events.back(); ctx->free_events.pop_back(); }
+    else CU(ctx, cudaEventCreate(&ev[i]));
+  }
+  ctx->timed.push_back({kernel, ev[0], ev[1]});
+  CU(ctx, cudaEventRecord(ev[0], ctx->stream));
+  return ILF_OK;
+}
+static int timed_end(ilf_ctx* ctx) {
+  if (!ctx->timing) return ILF_OK;
+  CU(ctx, cudaEventRecord(ctx->timed.back().b, ctx->stream));
+  return ILF_OK;
+}
+static int timed_collect(ilf_ctx* ctx) {
+  if (ctx->timed.empty()) return ILF_OK;
+  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  for (auto& t : ctx->timed) {
+    float ms = 0;
+    CU(ctx, cudaEventElapsedTime(&ms, t.a, t.b));
+    ctx->kernel_ms[t.kernel] += ms;
+    ctx->kernel_launches[t.kernel]++;
+    ctx->free_events.push_back(t.a);
+    ctx->free_events.push_back(t.b);
+  }
+  ctx->timed.clear();
+  return ILF_OK;
+}
+
 // One stage over a batch of slots.  Buffer rotation: the stage reads the slot's current buffer and writes the
 // next work buffer (1 or 2), never buffer 0, so the uploaded input survives and ilf_run can be repeated.
 static int run_stage(ilf_ctx* ctx, int first, int n, int stage) {
@@ -375,9 +411,17 @@ static int run_stage(ilf_ctx* ctx, int first, int n, int stage) {
     if (ctx->slots[i].result_buf != src) return fail(ctx, ILF_ERR_STATE, "slots of one batch must be at the same stage");
     ctx->slots[i].result_buf = dst;
   }
+  if (ctx->timed.size() >= 4096) if (int rc = timed_collect(ctx)) return rc;
+  if (int rc = timed_begin(ctx, stage == 2 ? ILF_KERNEL_ALF_LUMA : stage)) return rc;
   if (stage == 0) launch_deblock(ctx->g, ctx->slots_dev, first, n, src, dst, mv_mode, ctx->stream);
   else if (stage == 1) launch_sao(ctx->g, ctx->slots_dev, first, n, src, dst, ctx->stream);
-  else launch_alf(ctx->g, ctx->slots_dev, first, n, src, dst, false, ctx->stream);
+  else launch_alf_luma(ctx->g, ctx->slots_dev, first, n, src, dst, false, ctx->stream);
+  if (int rc = timed_end(ctx)) return rc;
+  if (stage == 2) {
+    if (int rc = timed_begin(ctx, ILF_KERNEL_ALF_CHROMA)) return rc;
+    launch_alf_chroma(ctx->g, ctx->slots_dev, first, n, src, dst, ctx->stream);
+    if (int rc = timed_end(ctx)) return rc;
+  }
   ctx->launches += stage == 2 ? 2 : 1;
   CU(ctx, cudaGetLastError());
   return ILF_OK;
@@ -390,15 +434,8 @@ int ilf_run(ilf_ctx* ctx, int first_slot, int num_slots, unsigned stages) {
   CU(ctx, cudaSetDevice(ctx->cfg.device));
   // A full run always restarts from the uploaded input.
   if (stages & ILF_STAGE_DEBLOCK) for (int i = first_slot; i < first_slot + num_slots; i++) ctx->slots[i].result_buf = 0;
-  if (ctx->timing) CU(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
-  for (int st = 0; st < 3; st++) {
+  for (int st = 0; st < 3; st++)
     if (stages & (1u << st)) if (int rc = run_stage(ctx, first_slot, num_slots, st)) return rc;
-    if (ctx->timing) CU(ctx, cudaEventRecord(ctx->ev[st + 1], ctx->stream));
-  }
-  if (ctx->timing) {
-    CU(ctx, cudaEventSynchronize(ctx->ev[3]));
-    for (int st = 0; st < 3; st++) CU(ctx, cudaEventElapsedTime(&ctx->stage_ms[st], ctx->ev[st], ctx->ev[st + 1]));
-  }
   return ILF_OK;
 }
 
@@ -412,7 +449,7 @@ int ilf_alf_classify(ilf_ctx* ctx, int slot, uint8_t* out) {
   Slot& s = ctx->slots[slot];
   if (!s.uploaded) return fail(ctx, ILF_ERR_STATE, "slot %d: classify before upload", slot);
   CU(ctx, cudaSetDevice(ctx->cfg.device));
-  launch_alf(ctx->g, ctx->slots_dev, slot, 1, s.result_buf, s.result_buf, true, ctx->stream);
+  launch_alf_luma(ctx->g, ctx->slots_dev, slot, 1, s.result_buf, s.result_buf, true, ctx->stream);
   ctx->launches += 1;
   CU(ctx, cudaGetLastError());
   CU(ctx, cudaMemcpyAsync(out, s.alf_class, (size_t)ctx->g.units_w * ctx->g.units_h, cudaMemcpyDeviceToHost, ctx->stream));
@@ -420,8 +457,21 @@ int ilf_alf_classify(ilf_ctx* ctx, int slot, uint8_t* out) {
   return ILF_OK;
 }
 
-int ilf_set_timing(ilf_ctx* ctx, int enable) { if (!ctx) return ILF_ERR_ARG; ctx->timing = enable != 0; return ILF_OK; }
-int ilf_last_stage_ms(ilf_ctx* ctx, float ms[3]) { if (!ctx || !ms) return ILF_ERR_ARG; for (int i = 0; i < 3; i++) ms[i] = ctx->stage_ms[i]; return ILF_OK; }
+int ilf_set_timing(ilf_ctx* ctx, int enable) {
+  if (!ctx) return ILF_ERR_ARG;
+  CU(ctx, cudaSetDevice(ctx->cfg.device));
+  if (int rc = timed_collect(ctx)) return rc;
+  if (enable) for (int i = 0; i < ILF_NUM_KERNELS; i++) { ctx->kernel_ms[i] = 0; ctx->kernel_launches[i] = 0; }
+  ctx->timing = enable != 0;
+  return ILF_OK;
+}
+int ilf_kernel_times(ilf_ctx* ctx, double ms_sum[ILF_NUM_KERNELS], long long launches[ILF_NUM_KERNELS]) {
+  if (!ctx || !ms_sum || !launches) return ILF_ERR_ARG;
+  CU(ctx, cudaSetDevice(ctx->cfg.device));
+  if (int rc = timed_collect(ctx)) return rc;
+  for (int i = 0; i < ILF_NUM_KERNELS; i++) { ms_sum[i] = ctx->kernel_ms[i]; launches[i] = ctx->kernel_launches[i]; }
+  return ILF_OK;
+}
 long long ilf_launch_count(const ilf_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 int ilf_slot_input_planes(ilf_ctx* ctx, int slot, void* planes[3], int32_t pitch[3]) {

@@ -46,6 +46,7 @@ __device__ __forceinline__ uint4 ldg_u4(const void* p) { return __ldg(reinterpre
 // src_b / dst_b: which of the slot's three buffers the stage reads and writes (the same for every slot of a batch).
 void launch_deblock(const Geom& g, const SlotDev* slots, int first_slot, int num_slots, int src_b, int dst_b, int mv_mode, cudaStream_t st);
 void launch_sao(const Geom& g, const SlotDev* slots, int first_slot, int num_slots, int src_b, int dst_b, cudaStream_t st);
-void launch_alf(const Geom& g, const SlotDev* slots, int first_slot, int num_slots, int src_b, int dst_b, bool classify_only, cudaStream_t st);
+void launch_alf_luma(const Geom& g, const SlotDev* slots, int first_slot, int num_slots, int src_b, int dst_b, bool classify_only, cudaStream_t st);
+void launch_alf_chroma(const Geom& g, const SlotDev* slots, int first_slot, int num_slots, int src_b, int dst_b, cudaStream_t st);
 
 }  // namespace ilf

@@ -63,7 +63,7 @@ def load_library():
     for n in ("ilf_deblock", "ilf_sao", "ilf_alf"):
         getattr(lib, n).argtypes = [vp, i]
     lib.ilf_alf_classify.argtypes = [vp, i, vp]
-    lib.ilf_last_stage_ms.argtypes = [vp, C.POINTER(C.c_float * 3)]
+    lib.ilf_kernel_times.argtypes = [vp, C.POINTER(C.c_double * 4), C.POINTER(C.c_longlong * 4)]
     lib.ilf_set_timing.argtypes = [vp, i]
     lib.ilf_launch_count.argtypes = [vp]
     lib.ilf_launch_count.restype = C.c_longlong
@@ -131,10 +131,16 @@ class InLoopFilter:
         assert y.shape == (self.rows, self.width) and cb.shape == cr.shape == (self.rows // 2, self.width // 2)
         self._ck(self._lib.ilf_upload(self._h, slot, _ptr(y), y.shape[1], _ptr(cb), cb.shape[1], _ptr(cr), cr.shape[1]))
 
-    def download(self, slot):
-        y = np.empty((self.rows, self.width), np.int16)
-        cb = np.empty((self.rows // 2, self.width // 2), np.int16)
-        cr = np.empty_like(cb)
+    def download(self, slot, out=None):
+        """Filtered picture of `slot` as {"y","cb","cr"}; `out` = dict of preallocated int16 arrays to fill (e.g. pinned)."""
+        if out is not None:
+            y, cb, cr = out["y"], out["cb"], out["cr"]
+            assert y.shape == (self.rows, self.width) and cb.shape == cr.shape == (self.rows // 2, self.width // 2)
+            assert all(a.dtype == np.int16 and a.flags.c_contiguous for a in (y, cb, cr))
+        else:
+            y = np.empty((self.rows, self.width), np.int16)
+            cb = np.empty((self.rows // 2, self.width // 2), np.int16)
+            cr = np.empty_like(cb)
         self._ck(self._lib.ilf_download(self._h, slot, _ptr(y), y.shape[1], _ptr(cb), cb.shape[1], _ptr(cr), cr.shape[1]))
         return {"y": y, "cb": cb, "cr": cr}
 
@@ -182,10 +188,13 @@ class InLoopFilter:
     def set_timing(self, on):
         self._ck(self._lib.ilf_set_timing(self._h, int(on)))
 
-    def last_stage_ms(self):
-        ms = (C.c_float * 3)()
-        self._ck(self._lib.ilf_last_stage_ms(self._h, C.byref(ms)))
-        return list(ms)
+    KERNELS = ("deblock", "sao", "alf_luma", "alf_chroma")
+
+    def kernel_times(self):
+        """{kernel: (total ms, launches)} since set_timing(True); synchronises the context's stream."""
+        ms = (C.c_double * 4)(); n = (C.c_longlong * 4)()
+        self._ck(self._lib.ilf_kernel_times(self._h, C.byref(ms), C.byref(n)))
+        return {k: (ms[i], n[i]) for i, k in enumerate(self.KERNELS)}
 
     def launch_count(self):
         return int(self._lib.ilf_launch_count(self._h))
