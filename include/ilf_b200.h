@@ -223,7 +223,10 @@ int ilf_alf_classify(ilf_ctx* ctx, int slot, uint8_t* out);
 #define ILF_KERNEL_ALF_CHROMA 3
 #define ILF_NUM_KERNELS 4
 int ilf_set_timing(ilf_ctx* ctx, int enable); /* enable != 0: clear the accumulators and time every launch */
-int ilf_kernel_times(ilf_ctx* ctx, double ms_sum[ILF_NUM_KERNELS], long long launches[ILF_NUM_KERNELS]); /* syncs */
+/* algo_bytes: bytes the launches had to move = 2 bytes x (read + write) x samples of the planes they processed
+ * (planes whose stage is off for the whole picture are skipped and not counted).  Synchronises the stream. */
+int ilf_kernel_times(ilf_ctx* ctx, double ms_sum[ILF_NUM_KERNELS], long long launches[ILF_NUM_KERNELS],
+                     double algo_bytes[ILF_NUM_KERNELS]);
 long long ilf_launch_count(const ilf_ctx* ctx);
 int ilf_slot_input_planes(ilf_ctx* ctx, int slot, void* planes[3], int32_t pitch[3]);
 int ilf_slot_output_planes(ilf_ctx* ctx, int slot, void* planes[3], int32_t pitch[3]);

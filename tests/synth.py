@@ -1,0 +1,66 @@
+"""Synthetic side information and pictures for parity tests (seeded numpy; shapes follow include/ilf_b200.h)."""
+import numpy as np
+
+SAO_DT = np.dtype([("offset", "<i2", (3, 4)), ("type", "i1", (3,)), ("band_pos", "u1", (3,)), ("avail", "u1"), ("reserved", "u1")])
+assert SAO_DT.itemsize == 32
+ALF_DT = np.dtype([("luma_coeff", "<i2", (25, 13)), ("chroma_coeff", "<i2", (7,)), ("luma_filter_7x7", "<i2")])
+DB_DT = np.dtype([("cb_qp_offset", "<i4"), ("cr_qp_offset", "<i4"), ("mv_threshold", "<i4"), ("num_slices", "<i4"), ("slices", "i1", (64, 4))])
+
+
+def picture(rng, w, h, bd=10, kind="mix"):
+    """int16 planes with smooth areas, edges, noise and saturated patches (so clipping paths are hit)."""
+    mx = (1 << bd) - 1
+
+    def plane(ww, hh):
+        y, x = np.mgrid[0:hh, 0:ww]
+        base = mx / 2 + mx / 3 * np.sin(x / 9.0) * np.cos(y / 7.0)
+        blk = np.kron(rng.integers(-mx // 16, mx // 16 + 1, ((hh + 7) // 8, (ww + 7) // 8)), np.ones((8, 8), np.int64))[:hh, :ww]
+        p = base + blk + rng.normal(0, mx / 100, (hh, ww))
+        if kind == "noise":
+            p = rng.integers(0, mx + 1, (hh, ww)).astype(np.float64)
+        p = np.clip(np.rint(p), 0, mx)
+        # saturated and flat patches
+        for _ in range(4):
+            yy, xx = rng.integers(0, hh), rng.integers(0, ww)
+            p[yy:yy + 9, xx:xx + 13] = rng.choice([0, mx, mx // 2])
+        return p.astype(np.int16)
+
+    return {"y": plane(w, h), "cb": plane(w // 2, h // 2), "cr": plane(w // 2, h // 2)}
+
+
+def sao_params(rng, ctus_w, ctus_h, bd=10, p_off=0.25, all_avail=False):
+    n = ctus_w * ctus_h
+    a = np.zeros(n, SAO_DT)
+    maxo = min(127, 31 << max(0, bd - 10))
+    for i in range(n):
+        for c in range(3):
+            t = -1 if rng.random() < p_off else int(rng.integers(0, 5))
+            a["type"][i, c] = t
+            a["band_pos"][i, c] = rng.integers(0, 32)
+            a["offset"][i, c] = rng.integers(-maxo, maxo + 1, 4)
+        cx, cy = i % ctus_w, i // ctus_w
+        av = 0xFF if all_avail else int(rng.integers(0, 256)) | (0xFF if rng.random() < 0.3 else 0)
+        # picture borders are never available (deriveLoopFilterBoundaryAvailibility, SampleAdaptiveOffset.cpp:685-760)
+        if cx == 0: av &= ~(0x01 | 0x10 | 0x40)
+        if cx == ctus_w - 1: av &= ~(0x02 | 0x20 | 0x80)
+        if cy == 0: av &= ~(0x04 | 0x10 | 0x20)
+        if cy == ctus_h - 1: av &= ~(0x08 | 0x40 | 0x80)
+        a["avail"][i] = av
+    return a.view(np.uint8).reshape(n, 32)
+
+
+def alf_params(rng, ctus_w, ctus_h, is7=True, p_on=0.8, big=False):
+    a = np.zeros(1, ALF_DT)
+    lim = 511 if big else 40
+    lc = rng.integers(-lim, lim + 1, (25, 13))
+    lc[:, 12] = 512 - 2 * lc[:, :12].sum(axis=1) if is7 else 0
+    if not is7:
+        lc[:, 7:] = 0
+        lc[:, 6] = 512 - 2 * lc[:, :6].sum(axis=1)
+    a["luma_coeff"][0] = np.clip(lc, -32768, 32767)
+    cc = rng.integers(-lim, lim + 1, 7)
+    cc[6] = 512 - 2 * cc[:6].sum()
+    a["chroma_coeff"][0] = cc
+    a["luma_filter_7x7"][0] = 1 if is7 else 0
+    en = (rng.random((3, ctus_w * ctus_h)) < p_on).astype(np.uint8)
+    return a.tobytes(), en

@@ -1,0 +1,67 @@
+"""CUDA path vs the oracle on seeded synthetic pictures and side information that real streams rarely produce:
+every SAO type with random availability patterns, odd picture sizes, 8/10/12-bit, extreme ALF coefficients."""
+import numpy as np
+import pytest
+
+import synth
+
+pytestmark = pytest.mark.gpu
+K = ("y", "cb", "cr")
+
+
+def _diff(a, b):
+    return {k: int((a[k] != b[k]).sum()) for k in K}
+
+
+@pytest.mark.parametrize("w,h,bd,ctu_log2,seed", [(416, 240, 10, 7, 1), (200, 136, 10, 7, 2), (264, 72, 8, 6, 3), (136, 264, 12, 5, 4),
+                                                  (1920, 1080, 10, 7, 5), (8, 8, 10, 7, 6), (520, 392, 10, 7, 7)])
+def test_sao_all_types_random_availability(w, h, bd, ctu_log2, seed, ilf_lib, oracle):
+    rng = np.random.default_rng(seed)
+    ctu = 1 << ctu_log2
+    cw, ch = (w + ctu - 1) // ctu, (h + ctu - 1) // ctu
+    for kind in ("mix", "noise"):
+        pic = synth.picture(rng, w, h, bd, kind)
+        prm = synth.sao_params(rng, cw, ch, bd, p_off=0.2)
+        want = oracle.sao(pic, bd, bd, ctu_log2, prm)
+        with ilf_lib.InLoopFilter(w, h, bd, bd, ctu_log2) as f:
+            f.upload(0, *(pic[k] for k in K))
+            f.set_sao_params(0, prm)
+            f.sao_process(0)
+            got = f.download(0)
+        d = _diff(got, want)
+        assert not any(d.values()), f"{kind}: mismatching samples {d}"
+
+
+def test_sao_component_off_for_whole_picture_is_skipped(ilf_lib, oracle):
+    rng = np.random.default_rng(11)
+    w, h = 416, 240
+    pic = synth.picture(rng, w, h)
+    prm = synth.sao_params(rng, 4, 2, p_off=0.0).view(synth.SAO_DT).reshape(-1).copy()
+    prm["type"][:, 1] = -1          # Cb off everywhere
+    prm = prm.view(np.uint8).reshape(-1, 32)
+    want = oracle.sao(pic, 10, 10, 7, prm)
+    with ilf_lib.InLoopFilter(w, h) as f:
+        f.upload(0, *(pic[k] for k in K))
+        f.set_sao_params(0, prm)
+        f.sao_process(0)
+        got = f.download(0)
+    assert not any(_diff(got, want).values())
+    assert np.array_equal(got["cb"], pic["cb"])
+
+
+@pytest.mark.parametrize("w,h,bd,is7,seed", [(416, 240, 10, True, 1), (200, 136, 10, False, 2), (264, 72, 8, True, 3), (136, 264, 12, True, 4), (1920, 1080, 10, True, 5)])
+def test_alf_random_coefficients(w, h, bd, is7, seed, ilf_lib, oracle):
+    rng = np.random.default_rng(seed)
+    cw, ch = (w + 127) // 128, (h + 127) // 128
+    for kind, big in (("mix", False), ("noise", True)):
+        pic = synth.picture(rng, w, h, bd, kind)
+        pb, en = synth.alf_params(rng, cw, ch, is7, big=big)
+        want = oracle.alf(pic, bd, bd, 7, pb, en)
+        with ilf_lib.InLoopFilter(w, h, bd, bd, 7) as f:
+            f.upload(0, *(pic[k] for k in K))
+            f.set_alf_params(0, pb, en)
+            f.alf_process(0)
+            got = f.download(0)
+            cls = f.alf_classify(0)
+        d = _diff(got, want)
+        assert not any(d.values()), f"{kind}: mismatching samples {d}"

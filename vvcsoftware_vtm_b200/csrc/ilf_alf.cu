@@ -60,14 +60,16 @@ __device__ __forceinline__ int classify(int sum_v, int sum_h, int sum_d0, int su
 }
 
 template <bool CLASSIFY_ONLY>
-__global__ void __launch_bounds__(NT) alf_luma_kernel(Geom g, const SlotDev* __restrict__ slots, int first_slot, int src_b, int dst_b) {
+__global__ void __launch_bounds__(NT) alf_luma_kernel(Geom g, const SlotDev* __restrict__ slots, int first_slot, BatchCtl bc) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   LumaSmem& s = *reinterpret_cast<LumaSmem*>(smem_raw);
   const SlotDev& sd = slots[first_slot + blockIdx.z];
+  const unsigned ctl = bc.v[blockIdx.z];
+  if (ctl_skip(ctl, 0)) return;
   const int tid = threadIdx.x;
   const int x0 = blockIdx.x * LT_W, y0 = blockIdx.y * LT_H;  // local rows
-  const int16_t* __restrict__ src = sd.buf[src_b][0];
-  int16_t* __restrict__ dst = sd.buf[dst_b][0];
+  const int16_t* __restrict__ src = sd.buf[ctl_src(ctl, 0)][0];
+  int16_t* __restrict__ dst = sd.buf[ctl_dst(ctl, 0)][0];
   const int rows = g.rows;
 
   // filter phase mapping: thread = (4x4 block, upper/lower half)
@@ -246,15 +248,17 @@ __global__ void __launch_bounds__(NT) alf_luma_kernel(Geom g, const SlotDev* __r
 // ---------------------------------------------------------------------------------------------------------
 constexpr int CT_W = 64, CT_H = 16, CS_W = CT_W + 8, CS_H = CT_H + 4;
 
-__global__ void __launch_bounds__(NT) alf_chroma_kernel(Geom g, const SlotDev* __restrict__ slots, int first_slot, int src_b, int dst_b) {
+__global__ void __launch_bounds__(NT) alf_chroma_kernel(Geom g, const SlotDev* __restrict__ slots, int first_slot, BatchCtl bc) {
   __shared__ __align__(16) int t[CS_H][CS_W];
   const SlotDev& sd = slots[first_slot + (blockIdx.z >> 1)];
   const int plane = 1 + (blockIdx.z & 1);
+  const unsigned ctl = bc.v[blockIdx.z >> 1];
+  if (ctl_skip(ctl, plane)) return;
   const int tid = threadIdx.x;
   const int x0 = blockIdx.x * CT_W, y0 = blockIdx.y * CT_H;
   const int cw = g.width >> 1, crows = g.rows >> 1;
-  const int16_t* __restrict__ src = sd.buf[src_b][plane];
-  int16_t* __restrict__ dst = sd.buf[dst_b][plane];
+  const int16_t* __restrict__ src = sd.buf[ctl_src(ctl, plane)][plane];
+  int16_t* __restrict__ dst = sd.buf[ctl_dst(ctl, plane)][plane];
   const int r = tid >> 4, k = tid & 15;  // output: row r, columns 4k..4k+3 of the tile
   const int x = x0 + 4 * k, y = y0 + r;
   const bool in = x < cw && y < crows;
@@ -321,7 +325,7 @@ __global__ void __launch_bounds__(NT) alf_chroma_kernel(Geom g, const SlotDev* _
 
 }  // namespace
 
-void launch_alf_luma(const Geom& g, const SlotDev* slots, int first_slot, int num_slots, int src_b, int dst_b, bool classify_only, cudaStream_t st) {
+void launch_alf_luma(const Geom& g, const SlotDev* slots, int first_slot, int num_slots, const BatchCtl& ctl, bool classify_only, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(alf_luma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LumaSmem));
@@ -330,15 +334,15 @@ void launch_alf_luma(const Geom& g, const SlotDev* slots, int first_slot, int nu
   }
   dim3 gl((g.width + LT_W - 1) / LT_W, (g.rows + LT_H - 1) / LT_H, num_slots);
   if (classify_only) {
-    alf_luma_kernel<true><<<gl, NT, sizeof(LumaSmem), st>>>(g, slots, first_slot, src_b, dst_b);
+    alf_luma_kernel<true><<<gl, NT, sizeof(LumaSmem), st>>>(g, slots, first_slot, ctl);
     return;
   }
-  alf_luma_kernel<false><<<gl, NT, sizeof(LumaSmem), st>>>(g, slots, first_slot, src_b, dst_b);
+  alf_luma_kernel<false><<<gl, NT, sizeof(LumaSmem), st>>>(g, slots, first_slot, ctl);
 }
 
-void launch_alf_chroma(const Geom& g, const SlotDev* slots, int first_slot, int num_slots, int src_b, int dst_b, cudaStream_t st) {
+void launch_alf_chroma(const Geom& g, const SlotDev* slots, int first_slot, int num_slots, const BatchCtl& ctl, cudaStream_t st) {
   dim3 gc((g.width / 2 + CT_W - 1) / CT_W, (g.rows / 2 + CT_H - 1) / CT_H, 2 * num_slots);
-  alf_chroma_kernel<<<gc, NT, 0, st>>>(g, slots, first_slot, src_b, dst_b);
+  alf_chroma_kernel<<<gc, NT, 0, st>>>(g, slots, first_slot, ctl);
 }
 
 }  // namespace ilf

@@ -32,7 +32,9 @@ struct Slot {
   SlotDev dev;                 // host copy of the device descriptor
   bool uploaded = false, has_db = false, has_sao = false, has_alf = false, has_ctree = false;
   int mv_mode = 0;             // 0 none, 1 int16, 2 int32
-  int result_buf = 0;          // buffer holding the current picture
+  int result_buf[3] = {0, 0, 0};  // buffer holding the current picture, per plane
+  bool sao_on[3] = {false, false, false};  // any CTU with SAO enabled, per component
+  bool alf_on[3] = {false, false, false};
   cudaEvent_t staged = nullptr;  // pinned staging buffer free again
 };
 
@@ -55,6 +57,7 @@ struct ilf_ctx {
   std::vector<TimedLaunch> timed;
   std::vector<cudaEvent_t> free_events;
   double kernel_ms[ILF_NUM_KERNELS] = {0, 0, 0, 0};
+  double kernel_bytes[ILF_NUM_KERNELS] = {0, 0, 0, 0};
   long long kernel_launches[ILF_NUM_KERNELS] = {0, 0, 0, 0};
   int num_ctus = 0;
 };
@@ -262,7 +265,7 @@ int ilf_upload(ilf_ctx* ctx, int slot, const int16_t* y, ptrdiff_t sy, const int
   CU(ctx, cudaEventRecord(s.staged, ctx->stream));
   s.uploaded = true;
   s.has_db = s.has_sao = s.has_alf = false;
-  s.result_buf = 0;
+  s.result_buf[0] = s.result_buf[1] = s.result_buf[2] = 0;
   return ILF_OK;
 }
 
@@ -279,7 +282,7 @@ int ilf_download(ilf_ctx* ctx, int slot, int16_t* y, ptrdiff_t sy, int16_t* cb, 
   int16_t* stage = s.pinned;
   for (int p = 0; p < 3; p++) {
     const int w = p ? g.width / 2 : g.width, h = p ? g.rows / 2 : g.rows, pitch = p ? g.pitch_c : g.pitch_y;
-    CU(ctx, cudaMemcpy2DAsync(stage, (size_t)w * 2, plane_ptr(ctx, s, s.result_buf, p), (size_t)pitch * 2, (size_t)w * 2, h, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaMemcpy2DAsync(stage, (size_t)w * 2, plane_ptr(ctx, s, s.result_buf[p], p), (size_t)pitch * 2, (size_t)w * 2, h, cudaMemcpyDeviceToHost, ctx->stream));
     stage += (size_t)w * h;
   }
   CU(ctx, cudaStreamSynchronize(ctx->stream));
@@ -336,6 +339,16 @@ int ilf_set_sao_params(ilf_ctx* ctx, int slot, const ilf_sao_ctu* ctus) {
     for (int c = 0; c < 3; c++)
       if (ctus[i].type[c] < ILF_SAO_OFF || ctus[i].type[c] > ILF_SAO_BO) return fail(ctx, ILF_ERR_ARG, "CTU %d comp %d: bad SAO type %d", i, c, ctus[i].type[c]);
   Slot& s = ctx->slots[slot];
+  for (int c = 0; c < 3; c++) s.sao_on[c] = false;
+  for (int i = 0; i < ctx->num_ctus; i++)
+    for (int c = 0; c < 3; c++) {
+      if (ctus[i].type[c] == ILF_SAO_OFF) continue;
+      s.sao_on[c] = true;
+      // offsets are at most 31 << log2OffsetScale with log2OffsetScale <= bitDepth - 10 (SampleAdaptiveOffset.h getMaxOffsetQVal): int8 for <= 12 bit
+      for (int k = 0; k < 4; k++)
+        if (ctus[i].offset[c][k] < -128 || ctus[i].offset[c][k] > 127)
+          return fail(ctx, ILF_ERR_UNSUPPORTED, "CTU %d comp %d: SAO offset %d outside [-128,127]", i, c, ctus[i].offset[c][k]);
+    }
   CU(ctx, cudaSetDevice(ctx->cfg.device));
   CU(ctx, cudaStreamSynchronize(ctx->stream));
   size_t cur = 0;
@@ -349,6 +362,10 @@ int ilf_set_alf_params(ilf_ctx* ctx, int slot, const ilf_alf_params* params, con
   if (int rc = check_slot(ctx, slot)) return rc;
   if (!params || !ctu_enable) return fail(ctx, ILF_ERR_ARG, "null ALF parameters");
   Slot& s = ctx->slots[slot];
+  for (int c = 0; c < 3; c++) {
+    s.alf_on[c] = false;
+    for (int i = 0; i < ctx->num_ctus; i++) s.alf_on[c] |= ctu_enable[(size_t)c * ctx->num_ctus + i] != 0;
+  }
   CU(ctx, cudaSetDevice(ctx->cfg.device));
   CU(ctx, cudaStreamSynchronize(ctx->stream));
   size_t cur = 0;
@@ -361,8 +378,9 @@ int ilf_set_alf_params(ilf_ctx* ctx, int slot, const ilf_alf_params* params, con
 }
 
 // Event pair around one kernel launch while timing is on (ilf_set_timing / ilf_kernel_times).
-static int timed_begin(ilf_ctx* ctx, int kernel) {
+static int timed_begin(ilf_ctx* ctx, int kernel, double algo_bytes) {
   if (!ctx->timing) return ILF_OK;
+  ctx->kernel_bytes[kernel] += algo_bytes;
   cudaEvent_t ev[2];
   for (int i = 0; i < 2; i++) {
     if (!ctx->free_events.empty()) { ev[i] = ctx->free_events.back(); ctx->free_events.pop_back(); }
@@ -392,8 +410,9 @@ static int timed_collect(ilf_ctx* ctx) {
   return ILF_OK;
 }
 
-// One stage over a batch of slots.  Buffer rotation: the stage reads the slot's current buffer and writes the
-// next work buffer (1 or 2), never buffer 0, so the uploaded input survives and ilf_run can be repeated.
+// One stage over a batch of slots.  Buffer rotation per plane: the stage reads the plane's current buffer and writes
+// the other work buffer (1 or 2), never buffer 0, so the uploaded input survives and ilf_run can be repeated.  Planes
+// for which the stage is off in the whole picture are skipped and keep their buffer.
 static int run_stage(ilf_ctx* ctx, int first, int n, int stage) {
   int mv_mode = 0;
   for (int i = first; i < first + n; i++) {
@@ -406,24 +425,50 @@ static int run_stage(ilf_ctx* ctx, int first, int n, int stage) {
   if (stage == 0)
     for (int i = first; i < first + n; i++)
       if (ctx->slots[i].mv_mode != mv_mode) return fail(ctx, ILF_ERR_ARG, "slots of one batch must use the same MV representation (none / mv16 / mv32)");
-  const int src = ctx->slots[first].result_buf, dst = src == 1 ? 2 : 1;
-  for (int i = first; i < first + n; i++) {
-    if (ctx->slots[i].result_buf != src) return fail(ctx, ILF_ERR_STATE, "slots of one batch must be at the same stage");
-    ctx->slots[i].result_buf = dst;
+  const Geom& g = ctx->g;
+  const double plane_bytes[3] = {2.0 * g.width * g.rows * 2, 2.0 * (g.width / 2) * (g.rows / 2) * 2, 2.0 * (g.width / 2) * (g.rows / 2) * 2};  // read + write
+  for (int c0 = first; c0 < first + n; c0 += MAX_BATCH) {
+    const int cn = std::min(MAX_BATCH, first + n - c0);
+    BatchCtl ctl;
+    bool any[3] = {false, false, false};
+    double bytes[3] = {0, 0, 0};
+    for (int i = 0; i < cn; i++) {
+      Slot& s = ctx->slots[c0 + i];
+      unsigned v = 0;
+      for (int p = 0; p < 3; p++) {
+        const bool on = stage == 0 ? true : (stage == 1 ? s.sao_on[p] : s.alf_on[p]);
+        v |= (unsigned)s.result_buf[p] << (2 * p);
+        if (!on) { v |= 1u << (6 + p); continue; }
+        s.result_buf[p] = s.result_buf[p] == 1 ? 2 : 1;
+        any[p] = true;
+        bytes[p] += plane_bytes[p];
+      }
+      ctl.v[i] = (uint16_t)v;
+    }
+    if (ctx->timed.size() >= 4096) if (int rc = timed_collect(ctx)) return rc;
+    if (stage == 0 || stage == 1) {
+      if (!(any[0] || any[1] || any[2])) continue;
+      if (int rc = timed_begin(ctx, stage, bytes[0] + bytes[1] + bytes[2])) return rc;
+      if (stage == 0) launch_deblock(g, ctx->slots_dev, c0, cn, ctl, mv_mode, ctx->stream);
+      else launch_sao(g, ctx->slots_dev, c0, cn, ctl, ctx->stream);
+      if (int rc = timed_end(ctx)) return rc;
+      ctx->launches++;
+    } else {
+      if (any[0]) {
+        if (int rc = timed_begin(ctx, ILF_KERNEL_ALF_LUMA, bytes[0])) return rc;
+        launch_alf_luma(g, ctx->slots_dev, c0, cn, ctl, false, ctx->stream);
+        if (int rc = timed_end(ctx)) return rc;
+        ctx->launches++;
+      }
+      if (any[1] || any[2]) {
+        if (int rc = timed_begin(ctx, ILF_KERNEL_ALF_CHROMA, bytes[1] + bytes[2])) return rc;
+        launch_alf_chroma(g, ctx->slots_dev, c0, cn, ctl, ctx->stream);
+        if (int rc = timed_end(ctx)) return rc;
+        ctx->launches++;
+      }
+    }
+    CU(ctx, cudaGetLastError());
   }
-  if (ctx->timed.size() >= 4096) if (int rc = timed_collect(ctx)) return rc;
-  if (int rc = timed_begin(ctx, stage == 2 ? ILF_KERNEL_ALF_LUMA : stage)) return rc;
-  if (stage == 0) launch_deblock(ctx->g, ctx->slots_dev, first, n, src, dst, mv_mode, ctx->stream);
-  else if (stage == 1) launch_sao(ctx->g, ctx->slots_dev, first, n, src, dst, ctx->stream);
-  else launch_alf_luma(ctx->g, ctx->slots_dev, first, n, src, dst, false, ctx->stream);
-  if (int rc = timed_end(ctx)) return rc;
-  if (stage == 2) {
-    if (int rc = timed_begin(ctx, ILF_KERNEL_ALF_CHROMA)) return rc;
-    launch_alf_chroma(ctx->g, ctx->slots_dev, first, n, src, dst, ctx->stream);
-    if (int rc = timed_end(ctx)) return rc;
-  }
-  ctx->launches += stage == 2 ? 2 : 1;
-  CU(ctx, cudaGetLastError());
   return ILF_OK;
 }
 
@@ -433,7 +478,8 @@ int ilf_run(ilf_ctx* ctx, int first_slot, int num_slots, unsigned stages) {
   if (!(stages & ILF_STAGE_ALL)) return fail(ctx, ILF_ERR_ARG, "empty stage mask");
   CU(ctx, cudaSetDevice(ctx->cfg.device));
   // A full run always restarts from the uploaded input.
-  if (stages & ILF_STAGE_DEBLOCK) for (int i = first_slot; i < first_slot + num_slots; i++) ctx->slots[i].result_buf = 0;
+  if (stages & ILF_STAGE_DEBLOCK)
+    for (int i = first_slot; i < first_slot + num_slots; i++) ctx->slots[i].result_buf[0] = ctx->slots[i].result_buf[1] = ctx->slots[i].result_buf[2] = 0;
   for (int st = 0; st < 3; st++)
     if (stages & (1u << st)) if (int rc = run_stage(ctx, first_slot, num_slots, st)) return rc;
   return ILF_OK;
@@ -449,7 +495,9 @@ int ilf_alf_classify(ilf_ctx* ctx, int slot, uint8_t* out) {
   Slot& s = ctx->slots[slot];
   if (!s.uploaded) return fail(ctx, ILF_ERR_STATE, "slot %d: classify before upload", slot);
   CU(ctx, cudaSetDevice(ctx->cfg.device));
-  launch_alf_luma(ctx->g, ctx->slots_dev, slot, 1, s.result_buf, s.result_buf, true, ctx->stream);
+  BatchCtl ctl;
+  ctl.v[0] = (uint16_t)s.result_buf[0];
+  launch_alf_luma(ctx->g, ctx->slots_dev, slot, 1, ctl, true, ctx->stream);
   ctx->launches += 1;
   CU(ctx, cudaGetLastError());
   CU(ctx, cudaMemcpyAsync(out, s.alf_class, (size_t)ctx->g.units_w * ctx->g.units_h, cudaMemcpyDeviceToHost, ctx->stream));
@@ -461,15 +509,15 @@ int ilf_set_timing(ilf_ctx* ctx, int enable) {
   if (!ctx) return ILF_ERR_ARG;
   CU(ctx, cudaSetDevice(ctx->cfg.device));
   if (int rc = timed_collect(ctx)) return rc;
-  if (enable) for (int i = 0; i < ILF_NUM_KERNELS; i++) { ctx->kernel_ms[i] = 0; ctx->kernel_launches[i] = 0; }
+  if (enable) for (int i = 0; i < ILF_NUM_KERNELS; i++) { ctx->kernel_ms[i] = 0; ctx->kernel_launches[i] = 0; ctx->kernel_bytes[i] = 0; }
   ctx->timing = enable != 0;
   return ILF_OK;
 }
-int ilf_kernel_times(ilf_ctx* ctx, double ms_sum[ILF_NUM_KERNELS], long long launches[ILF_NUM_KERNELS]) {
-  if (!ctx || !ms_sum || !launches) return ILF_ERR_ARG;
+int ilf_kernel_times(ilf_ctx* ctx, double ms_sum[ILF_NUM_KERNELS], long long launches[ILF_NUM_KERNELS], double algo_bytes[ILF_NUM_KERNELS]) {
+  if (!ctx || !ms_sum || !launches || !algo_bytes) return ILF_ERR_ARG;
   CU(ctx, cudaSetDevice(ctx->cfg.device));
   if (int rc = timed_collect(ctx)) return rc;
-  for (int i = 0; i < ILF_NUM_KERNELS; i++) { ms_sum[i] = ctx->kernel_ms[i]; launches[i] = ctx->kernel_launches[i]; }
+  for (int i = 0; i < ILF_NUM_KERNELS; i++) { ms_sum[i] = ctx->kernel_ms[i]; launches[i] = ctx->kernel_launches[i]; algo_bytes[i] = ctx->kernel_bytes[i]; }
   return ILF_OK;
 }
 long long ilf_launch_count(const ilf_ctx* ctx) { return ctx ? ctx->launches : 0; }
@@ -479,14 +527,14 @@ int ilf_slot_input_planes(ilf_ctx* ctx, int slot, void* planes[3], int32_t pitch
   Slot& s = ctx->slots[slot];
   for (int p = 0; p < 3; p++) { planes[p] = plane_ptr(ctx, s, 0, p); pitch[p] = p ? ctx->g.pitch_c : ctx->g.pitch_y; }
   s.uploaded = true;  // the caller fills the planes on the device
-  s.result_buf = 0;
+  s.result_buf[0] = s.result_buf[1] = s.result_buf[2] = 0;
   return ILF_OK;
 }
 
 int ilf_slot_output_planes(ilf_ctx* ctx, int slot, void* planes[3], int32_t pitch[3]) {
   if (int rc = check_slot(ctx, slot)) return rc;
   Slot& s = ctx->slots[slot];
-  for (int p = 0; p < 3; p++) { planes[p] = plane_ptr(ctx, s, s.result_buf, p); pitch[p] = p ? ctx->g.pitch_c : ctx->g.pitch_y; }
+  for (int p = 0; p < 3; p++) { planes[p] = plane_ptr(ctx, s, s.result_buf[p], p); pitch[p] = p ? ctx->g.pitch_c : ctx->g.pitch_y; }
   return ILF_OK;
 }
 

@@ -36,6 +36,19 @@ struct SlotDev {
   uint8_t* alf_class;             // [units_h][units_w] scratch / output of ilf_alf_classify
 };
 
+// Per-launch control word of every slot of a batch (kernel parameter, indexed with blockIdx.z).  Each plane of a
+// slot lives in one of the slot's three buffers; a stage reads plane p from buffer src_p and writes the other work
+// buffer (dst = src == 1 ? 2 : 1, never buffer 0 = the uploaded input).  A plane whose stage is off for the whole
+// picture (the reference returns early: SampleAdaptiveOffset.cpp:572-583, AdaptiveLoopFilter.cpp:70-73) is skipped:
+// no CTA touches it and its result stays where it was.
+constexpr int MAX_BATCH = 128;
+struct BatchCtl {
+  uint16_t v[MAX_BATCH];  // bits 2p..2p+1: source buffer of plane p; bit 6+p: skip plane p
+};
+__host__ __device__ __forceinline__ int ctl_src(unsigned c, int plane) { return (c >> (2 * plane)) & 3; }
+__host__ __device__ __forceinline__ int ctl_dst(unsigned c, int plane) { return ctl_src(c, plane) == 1 ? 2 : 1; }
+__host__ __device__ __forceinline__ bool ctl_skip(unsigned c, int plane) { return (c >> (6 + plane)) & 1; }
+
 __device__ __forceinline__ int clip3i(int lo, int hi, int v) { return min(max(v, lo), hi); }
 
 // 128-bit / 64-bit global accesses.  Pictures are streamed once per stage: bypass L1 allocation on loads
@@ -43,10 +56,10 @@ __device__ __forceinline__ int clip3i(int lo, int hi, int v) { return min(max(v,
 __device__ __forceinline__ uint2 ldg_u2(const void* p) { return __ldg(reinterpret_cast<const uint2*>(p)); }
 __device__ __forceinline__ uint4 ldg_u4(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
 
-// src_b / dst_b: which of the slot's three buffers the stage reads and writes (the same for every slot of a batch).
-void launch_deblock(const Geom& g, const SlotDev* slots, int first_slot, int num_slots, int src_b, int dst_b, int mv_mode, cudaStream_t st);
-void launch_sao(const Geom& g, const SlotDev* slots, int first_slot, int num_slots, int src_b, int dst_b, cudaStream_t st);
-void launch_alf_luma(const Geom& g, const SlotDev* slots, int first_slot, int num_slots, int src_b, int dst_b, bool classify_only, cudaStream_t st);
-void launch_alf_chroma(const Geom& g, const SlotDev* slots, int first_slot, int num_slots, int src_b, int dst_b, cudaStream_t st);
+// One launch covers slots [first_slot, first_slot + num_slots), num_slots <= MAX_BATCH; ctl.v[i] controls slot first_slot + i.
+void launch_deblock(const Geom& g, const SlotDev* slots, int first_slot, int num_slots, const BatchCtl& ctl, int mv_mode, cudaStream_t st);
+void launch_sao(const Geom& g, const SlotDev* slots, int first_slot, int num_slots, const BatchCtl& ctl, cudaStream_t st);
+void launch_alf_luma(const Geom& g, const SlotDev* slots, int first_slot, int num_slots, const BatchCtl& ctl, bool classify_only, cudaStream_t st);
+void launch_alf_chroma(const Geom& g, const SlotDev* slots, int first_slot, int num_slots, const BatchCtl& ctl, cudaStream_t st);
 
 }  // namespace ilf

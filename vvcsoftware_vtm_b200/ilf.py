@@ -63,7 +63,7 @@ def load_library():
     for n in ("ilf_deblock", "ilf_sao", "ilf_alf"):
         getattr(lib, n).argtypes = [vp, i]
     lib.ilf_alf_classify.argtypes = [vp, i, vp]
-    lib.ilf_kernel_times.argtypes = [vp, C.POINTER(C.c_double * 4), C.POINTER(C.c_longlong * 4)]
+    lib.ilf_kernel_times.argtypes = [vp, C.POINTER(C.c_double * 4), C.POINTER(C.c_longlong * 4), C.POINTER(C.c_double * 4)]
     lib.ilf_set_timing.argtypes = [vp, i]
     lib.ilf_launch_count.argtypes = [vp]
     lib.ilf_launch_count.restype = C.c_longlong
@@ -191,10 +191,10 @@ class InLoopFilter:
     KERNELS = ("deblock", "sao", "alf_luma", "alf_chroma")
 
     def kernel_times(self):
-        """{kernel: (total ms, launches)} since set_timing(True); synchronises the context's stream."""
-        ms = (C.c_double * 4)(); n = (C.c_longlong * 4)()
-        self._ck(self._lib.ilf_kernel_times(self._h, C.byref(ms), C.byref(n)))
-        return {k: (ms[i], n[i]) for i, k in enumerate(self.KERNELS)}
+        """{kernel: (total ms, launches, algorithmic bytes)} since set_timing(True); synchronises the context's stream."""
+        ms = (C.c_double * 4)(); n = (C.c_longlong * 4)(); nb = (C.c_double * 4)()
+        self._ck(self._lib.ilf_kernel_times(self._h, C.byref(ms), C.byref(n), C.byref(nb)))
+        return {k: (ms[i], n[i], nb[i]) for i, k in enumerate(self.KERNELS)}
 
     def launch_count(self):
         return int(self._lib.ilf_launch_count(self._h))
