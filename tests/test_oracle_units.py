@@ -1,0 +1,109 @@
+"""Pins the oracle's SAO and ALF block functions against the REFERENCE's own functions, driven directly with random
+blocks, offsets, availability flags and coefficients (oracle/_ref/libvtm_units.so = extern "C" doors onto
+SampleAdaptiveOffset::offsetBlock, AdaptiveLoopFilter::deriveClassificationBlk and filterBlk of the unmodified
+reference objects, scalar and x86-SIMD flavours).  Skipped where oracle/_ref was not built."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+UNITS = os.path.join(ROOT, "oracle", "_ref", "libvtm_units.so")
+pytestmark = pytest.mark.skipif(not os.path.exists(UNITS), reason="oracle/_ref/libvtm_units.so not built (needs /root/reference)")
+K = ("y", "cb", "cr")
+
+
+@pytest.fixture(scope="module")
+def units():
+    lib = C.CDLL(UNITS)
+    lib.ref_sao_offset_block.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint]
+    lib.ref_alf_classify.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    lib.ref_alf_filter.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    return lib
+
+
+def ref_sao(units, pic, bd, ctu_log2, prm):
+    """SAOProcess restated with the reference's offsetBlock per CTU and component (offsetCTU, SampleAdaptiveOffset.cpp:510-562)."""
+    P = prm.view(synth.SAO_DT).reshape(-1)
+    h, w = pic["y"].shape
+    ctu = 1 << ctu_log2
+    cw = (w + ctu - 1) // ctu
+    out = {}
+    for ci, k in enumerate(K):
+        sh = 1 if ci else 0
+        pad = np.pad(pic[k], 1, mode="constant")          # offsetBlock may read one sample beyond the block
+        dst = pad.copy()
+        ph, pw = pic[k].shape
+        sz = ctu >> sh
+        for i in range(len(P)):
+            t = int(P["type"][i, ci])
+            if t < 0:
+                continue
+            cx, cy = i % cw, i // cw
+            x0, y0 = cx * sz, cy * sz
+            bw, bh = min(sz, pw - x0), min(sz, ph - y0)
+            off = np.zeros(32, np.int32)
+            o4 = P["offset"][i, ci].astype(np.int32)
+            if t == 4:
+                for j in range(4):
+                    off[(int(P["band_pos"][i, ci]) + j) % 32] = o4[j]
+            else:
+                off[[0, 1, 3, 4]] = o4
+            s = pad[1 + y0:, 1 + x0:]
+            d = dst[1 + y0:, 1 + x0:]
+            units.ref_sao_offset_block(bd, t, off.ctypes.data, s.ctypes.data, d.ctypes.data, pad.shape[1], pad.shape[1], bw, bh, int(P["avail"][i]))
+        out[k] = dst[1:-1, 1:-1].copy()
+    return out
+
+
+@pytest.mark.parametrize("w,h,bd,ctu_log2,seed", [(416, 240, 10, 7, 1), (200, 136, 10, 7, 2), (264, 72, 8, 6, 3), (136, 264, 12, 5, 4), (520, 392, 10, 7, 7)])
+def test_sao_oracle_equals_reference_offset_block(w, h, bd, ctu_log2, seed, units, oracle):
+    rng = np.random.default_rng(seed)
+    ctu = 1 << ctu_log2
+    cw, ch = (w + ctu - 1) // ctu, (h + ctu - 1) // ctu
+    for kind in ("mix", "noise"):
+        pic = synth.picture(rng, w, h, bd, kind)
+        prm = synth.sao_params(rng, cw, ch, bd, p_off=0.2)
+        want = ref_sao(units, pic, bd, ctu_log2, prm)
+        got = oracle.sao(pic, bd, bd, ctu_log2, prm)
+        for k in K:
+            bad = np.argwhere(got[k] != want[k])
+            assert not len(bad), f"{kind} {k}: {len(bad)} samples differ from the reference, first at {bad[:5].tolist()}"
+
+
+@pytest.mark.parametrize("simd", [0, 1])
+@pytest.mark.parametrize("w,h,bd,seed", [(64, 48, 10, 1), (136, 72, 8, 2), (96, 96, 10, 3)])
+def test_alf_classification_oracle_equals_reference(simd, w, h, bd, seed, units, oracle):
+    rng = np.random.default_rng(seed)
+    for kind in ("mix", "noise"):
+        y = synth.picture(rng, w, h, bd, kind)["y"]
+        pad = np.pad(y, 4, mode="edge")
+        out = np.zeros((h // 4, w // 4), np.uint8)
+        units.ref_alf_classify(simd, pad[4:, 4:].ctypes.data, pad.shape[1], w, h, bd, out.ctypes.data)
+        got = oracle.alf_classify(y, bd)
+        assert np.array_equal(got, out), f"{kind}: {(got != out).sum()} blocks differ"
+
+
+@pytest.mark.parametrize("simd", [0, 1])
+@pytest.mark.parametrize("is7", [True, False])
+def test_alf_filter_oracle_equals_reference(simd, is7, units, oracle):
+    rng = np.random.default_rng(5 + simd + 2 * is7)
+    w, h, bd = 128, 64, 10            # one CTU-sized picture, ALF on
+    for kind, big in (("mix", False), ("noise", False)):
+        pic = synth.picture(rng, w, h, bd, kind)
+        pb, en = synth.alf_params(rng, 1, 1, is7, p_on=1.1, big=big)
+        got = oracle.alf(pic, bd, bd, 7, pb, en)
+        A = np.frombuffer(pb, synth.ALF_DT)[0]
+        cls = oracle.alf_classify(pic["y"], bd)
+        for ci, k in enumerate(K):
+            ph, pw = pic[k].shape
+            pad = np.pad(pic[k], 4, mode="edge")
+            dst = pad.copy()
+            coeff = np.ascontiguousarray(A["luma_coeff"] if ci == 0 else A["chroma_coeff"], dtype=np.int16)
+            units.ref_alf_filter(simd, int(is7) if ci == 0 else 0, int(ci > 0), pad[4:, 4:].ctypes.data, pad.shape[1], dst[4:, 4:].ctypes.data, pad.shape[1],
+                                 pw, ph, bd, cls.ctypes.data, coeff.ctypes.data)
+            want = dst[4:-4, 4:-4]
+            assert np.array_equal(got[k], want), f"{kind} {k}: {(got[k] != want).sum()} samples differ"

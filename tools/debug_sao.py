@@ -4,8 +4,8 @@ sys.path[:0] = [ROOT, ROOT + "/tests", ROOT + "/oracle", ROOT + "/tools"]
 import numpy as np, synth, ilf_oracle as O
 import vvcsoftware_vtm_b200 as v
 K = ("y", "cb", "cr")
-w, h, bd, cl = 416, 240, 10, 7
-rng = np.random.default_rng(1)
+w, h, bd, cl = (int(a) for a in sys.argv[1:5])
+rng = np.random.default_rng(int(sys.argv[5]))
 ctu = 1 << cl
 cw, ch = (w + ctu - 1) // ctu, (h + ctu - 1) // ctu
 pic = synth.picture(rng, w, h, bd, "mix")

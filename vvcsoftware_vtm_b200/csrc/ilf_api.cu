@@ -24,6 +24,7 @@ struct Slot {
   ilf_deblock_params* db_params = nullptr;
   ilf_sao_ctu* sao = nullptr;
   ilf_alf_params* alf = nullptr;
+  int* alf_coef = nullptr;     // [25][4][16] transposed luma coefficient table
   uint8_t* alf_ctu_enable = nullptr;
   uint8_t* alf_class = nullptr;
   int16_t* pinned = nullptr;   // host staging, one picture
@@ -174,10 +175,11 @@ int create_impl(ilf_ctx** out, const ilf_config* cfg, const ilf_band* band) {
     CU(ctx, cudaMalloc(&s.db_params, sizeof(ilf_deblock_params)));
     CU(ctx, cudaMalloc(&s.sao, sizeof(ilf_sao_ctu) * ctx->num_ctus));
     CU(ctx, cudaMalloc(&s.alf, sizeof(ilf_alf_params)));
+    CU(ctx, cudaMalloc(&s.alf_coef, 25 * 4 * 16 * sizeof(int)));
     CU(ctx, cudaMalloc(&s.alf_ctu_enable, 3 * (size_t)ctx->num_ctus));
     CU(ctx, cudaMalloc(&s.alf_class, units));
     CU(ctx, cudaMallocHost(&s.pinned, ctx->buf_elems * sizeof(int16_t)));
-    s.pinned_side_bytes = units * (4 + 4 + 16) + 4096 + (size_t)ctx->num_ctus * (1 + sizeof(ilf_sao_ctu) + 3) + sizeof(ilf_deblock_params) + sizeof(ilf_alf_params) + 16 * 256;
+    s.pinned_side_bytes = units * (4 + 4 + 16) + 4096 + (size_t)ctx->num_ctus * (1 + sizeof(ilf_sao_ctu) + 3) + sizeof(ilf_deblock_params) + sizeof(ilf_alf_params) + 25 * 4 * 16 * sizeof(int) + 16 * 256;
     CU(ctx, cudaMallocHost(&s.pinned_side, s.pinned_side_bytes));
     CU(ctx, cudaEventCreateWithFlags(&s.staged, cudaEventDisableTiming));
     memset(&s.dev, 0, sizeof(s.dev));
@@ -215,7 +217,7 @@ int ilf_destroy(ilf_ctx* ctx) {
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   for (Slot& s : ctx->slots) {
     cudaFree(s.planes); cudaFree(s.info); cudaFree(s.info_c); cudaFree(s.mv); cudaFree(s.ctu_slice); cudaFree(s.db_params);
-    cudaFree(s.sao); cudaFree(s.alf); cudaFree(s.alf_ctu_enable); cudaFree(s.alf_class);
+    cudaFree(s.sao); cudaFree(s.alf); cudaFree(s.alf_coef); cudaFree(s.alf_ctu_enable); cudaFree(s.alf_class);
     if (s.pinned) cudaFreeHost(s.pinned);
     if (s.pinned_side) cudaFreeHost(s.pinned_side);
     if (s.staged) cudaEventDestroy(s.staged);
@@ -371,6 +373,21 @@ int ilf_set_alf_params(ilf_ctx* ctx, int slot, const ilf_alf_params* params, con
   size_t cur = 0;
   if (int rc = stage_side(ctx, s, s.alf, params, sizeof(*params), cur)) return rc;
   if (int rc = stage_side(ctx, s, s.alf_ctu_enable, ctu_enable, 3 * (size_t)ctx->num_ctus, cur)) return rc;
+  {
+    // Coefficient order after transposition (filterBlk, AdaptiveLoopFilter.cpp:541-575), expanded once per picture so
+    // that a 4x4 block fetches its 13 (7) coefficients with four 16-byte loads.
+    static const uint8_t perm7[4][13] = {{0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12}, {9, 4, 10, 8, 1, 5, 11, 7, 3, 0, 2, 6, 12},
+                                         {0, 3, 2, 1, 8, 7, 6, 5, 4, 9, 10, 11, 12}, {9, 8, 10, 4, 3, 7, 11, 5, 1, 0, 2, 6, 12}};
+    static const uint8_t perm5[4][7] = {{0, 1, 2, 3, 4, 5, 6}, {4, 1, 5, 3, 0, 2, 6}, {0, 3, 2, 1, 4, 5, 6}, {4, 3, 5, 1, 0, 2, 6}};
+    int tab[25][4][16];
+    const bool is7 = params->luma_filter_7x7 != 0;
+    for (int cl = 0; cl < 25; cl++)
+      for (int tr = 0; tr < 4; tr++)
+        for (int k = 0; k < 16; k++)
+          tab[cl][tr][k] = is7 ? (k < 13 ? params->luma_coeff[cl][perm7[tr][k]] : 0) : (k < 7 ? params->luma_coeff[cl][perm5[tr][k]] : 0);
+    if (int rc = stage_side(ctx, s, s.alf_coef, tab, sizeof(tab), cur)) return rc;
+  }
+  s.dev.alf_coef = s.alf_coef;
   s.dev.alf = s.alf;
   s.dev.alf_ctu_enable = s.alf_ctu_enable;
   s.has_alf = true;

@@ -32,6 +32,7 @@ struct SlotDev {
   const ilf_deblock_params* db_params;
   const ilf_sao_ctu* sao;
   const ilf_alf_params* alf;
+  const int* alf_coef;            // [25 classes][4 transposes][16] luma coefficients, transposition applied (set by ilf_set_alf_params)
   const uint8_t* alf_ctu_enable;  // [3][num_ctus]
   uint8_t* alf_class;             // [units_h][units_w] scratch / output of ilf_alf_classify
 };
