@@ -1,0 +1,188 @@
+// ilf_shim.cpp -- host shim: the three picture-level entry points of VTM 2.1's in-loop filter classes, re-implemented
+// on top of the C ABI of libilf_b200.so (include/ilf_b200.h).
+//
+//   LoopFilter::loopFilterPic            replaces source/Lib/CommonLib/LoopFilter.cpp:149-230
+//   SampleAdaptiveOffset::SAOProcess     replaces source/Lib/CommonLib/SampleAdaptiveOffset.cpp:564-612
+//   AdaptiveLoopFilter::ALFProcess       replaces source/Lib/CommonLib/AdaptiveLoopFilter.cpp:68-139
+//
+// Product host code, compiled against the reference's UNMODIFIED headers.  The class declarations, create()/destroy(),
+// the static tables and every protected helper the encoder subclasses use (offsetCTU, getMergeList, m_filter7x7Blk ...)
+// stay the reference's own code; only these three function bodies are swapped (INTEGRATION.md shows the CMake option
+// and the three #if blocks a maintainer adds; the demonstration build in oracle/Makefile obtains the same effect
+// without touching the reference sources by compiling its three .cpp files with the entry points renamed).
+//
+// Data flow per picture (DecLib::executeLoopFilters, DecLib.cpp:506-533): loopFilterPic packs the CU/TU/motion grid,
+// uploads the reconstructed picture once and runs the deblocking kernel; SAOProcess and ALFProcess continue on the
+// device-resident picture; the last stage that the SPS enables downloads the result into cs.getRecoBuf().  On the
+// encoder (cs.pcv->isEncoder) every stage downloads, because the RDO code reads the intermediate pictures on the host.
+// There is no CPU fallback: a CUDA/library error is THROWn like any other reference error (TypeDef.h:1187-1209).
+//
+// Environment: ILF_B200_DEVICE=<ordinal> (default 0), ILF_TIMING=1 prints "[ILFTIME] ..." per picture on stderr.
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+
+#include "CommonLib/AdaptiveLoopFilter.h"
+#include "CommonLib/CodingStructure.h"
+#include "CommonLib/LoopFilter.h"
+#include "CommonLib/Picture.h"
+#include "CommonLib/SampleAdaptiveOffset.h"
+#include "CommonLib/UnitTools.h"
+#include "ilf_b200.h"
+#include "ilf_pack.h"
+
+namespace
+{
+using clk = std::chrono::steady_clock;
+
+struct ShimState
+{
+  ilf_ctx*       ctx = nullptr;
+  ilf_config     cfg;
+  const Picture* resident = nullptr;  // picture whose current state lives on the device and not (yet) in the host reco buffer
+  bool           timing   = false;
+  long long      usDeblock = 0, usSao = 0, usAlf = 0;
+  int            picCount = 0;
+  ~ShimState()
+  {
+    if( ctx ) ilf_destroy( ctx );
+  }
+};
+
+ShimState& state()
+{
+  static ShimState s;
+  static bool      init = false;
+  if( !init )
+  {
+    init     = true;
+    s.timing = getenv( "ILF_TIMING" ) && atoi( getenv( "ILF_TIMING" ) ) != 0;
+  }
+  return s;
+}
+
+void ck( ShimState& s, int rc, const char* what )
+{
+  if( rc != ILF_OK ) THROW( "libilf_b200: " << what << " failed (" << rc << "): " << ilf_last_error( s.ctx ) );
+}
+
+// One context per geometry; the decoder re-creates the filter objects for every picture (DecLib.cpp:747-748,789), the
+// context survives that.
+ShimState& contextFor( const CodingStructure& cs )
+{
+  ShimState&           s   = state();
+  const PreCalcValues& pcv = *cs.pcv;
+  CHECK( pcv.chrFormat != CHROMA_420, "libilf_b200 supports 4:2:0 only" );
+  ilf_config c;
+  c.width            = int( pcv.lumaWidth );
+  c.height           = int( pcv.lumaHeight );
+  c.bit_depth_luma   = cs.sps->getBitDepth( CHANNEL_TYPE_LUMA );
+  c.bit_depth_chroma = cs.sps->getBitDepth( CHANNEL_TYPE_CHROMA );
+  c.ctu_log2         = int( pcv.maxCUWidthLog2 );
+  c.chroma_format    = 1;
+  c.device           = getenv( "ILF_B200_DEVICE" ) ? atoi( getenv( "ILF_B200_DEVICE" ) ) : 0;
+  c.num_slots        = 1;
+  CHECK( pcv.maxCUWidth != pcv.maxCUHeight, "square CTUs expected" );
+  if( s.ctx && ( c.width != s.cfg.width || c.height != s.cfg.height || c.bit_depth_luma != s.cfg.bit_depth_luma || c.bit_depth_chroma != s.cfg.bit_depth_chroma ||
+                 c.ctu_log2 != s.cfg.ctu_log2 ) )
+  {
+    ilf_destroy( s.ctx );
+    s.ctx      = nullptr;
+    s.resident = nullptr;
+  }
+  if( !s.ctx )
+  {
+    const int rc = ilf_create( &s.ctx, &c );
+    if( rc != ILF_OK ) THROW( "libilf_b200: ilf_create failed (" << rc << "): " << ilf_last_error( nullptr ) );
+    s.cfg = c;
+  }
+  return s;
+}
+
+void upload( ShimState& s, CodingStructure& cs )
+{
+  const CPelUnitBuf reco = cs.getRecoBuf();
+  const CPelBuf     y = reco.get( COMPONENT_Y ), cb = reco.get( COMPONENT_Cb ), cr = reco.get( COMPONENT_Cr );
+  ck( s, ilf_upload( s.ctx, 0, y.buf, y.stride, cb.buf, cb.stride, cr.buf, cr.stride ), "ilf_upload" );
+  s.resident = cs.picture;
+}
+
+void download( ShimState& s, CodingStructure& cs )
+{
+  PelUnitBuf reco = cs.getRecoBuf();
+  PelBuf     y = reco.get( COMPONENT_Y ), cb = reco.get( COMPONENT_Cb ), cr = reco.get( COMPONENT_Cr );
+  ck( s, ilf_download( s.ctx, 0, y.buf, y.stride, cb.buf, cb.stride, cr.buf, cr.stride ), "ilf_download" );
+  s.resident = nullptr;
+}
+
+long long usSince( clk::time_point t0 ) { return std::chrono::duration_cast<std::chrono::microseconds>( clk::now() - t0 ).count(); }
+
+void report( ShimState& s, const CodingStructure& cs )
+{
+  if( s.timing )
+    fprintf( stderr, "[ILFTIME] pic=%d poc=%d w=%u h=%u deblock_us=%lld sao_us=%lld alf_us=%lld impl=b200\n", s.picCount, cs.slice->getPOC(), cs.pcv->lumaWidth,
+             cs.pcv->lumaHeight, s.usDeblock, s.usSao, s.usAlf );
+  s.picCount++;
+  s.usDeblock = s.usSao = s.usAlf = 0;
+}
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------------------
+void LoopFilter::loopFilterPic( CodingStructure& cs )
+{
+  const auto t0 = clk::now();
+  ShimState& s  = contextFor( cs );
+  IlfPackedDeblock db;
+  ilfPackDeblock( cs, db );  // the walk over CUs/TUs/motion of LoopFilter.cpp:167-222, 243-541, flattened
+  upload( s, cs );
+  ck( s, ilf_set_deblock_info( s.ctx, 0, &db.params, db.info.data(), db.infoChroma.empty() ? nullptr : db.infoChroma.data(),
+                               ( db.anyInter && db.mvFits16 ) ? db.mv16.data() : nullptr, ( db.anyInter && !db.mvFits16 ) ? db.mv32.data() : nullptr, db.ctuSlice.data() ),
+      "ilf_set_deblock_info" );
+  ck( s, ilf_deblock( s.ctx, 0 ), "ilf_deblock" );
+  const bool laterStage = !cs.pcv->isEncoder && ( cs.sps->getUseSAO() || cs.sps->getUseALF() );
+  if( !laterStage ) download( s, cs );
+  s.usDeblock = usSince( t0 );
+  if( !laterStage ) report( s, cs );
+}
+
+// ------------------------------------------------------------------------------------------------------------
+void SampleAdaptiveOffset::SAOProcess( CodingStructure& cs, SAOBlkParam* saoBlkParams )
+{
+  CHECK( !saoBlkParams, "No parameters present" );
+  const auto t0 = clk::now();
+  ShimState& s  = contextFor( cs );
+  CHECK( cs.sps->getPCMFilterDisableFlag() || cs.pps->getTransquantBypassEnabledFlag(),
+         "libilf_b200: PCM loop-filter-disable / transquant-bypass sample restoration (SampleAdaptiveOffset.cpp:614-683) is not supported" );
+  IlfPackedSao ps;
+  ilfPackSao( cs, saoBlkParams, m_offsetStepLog2, ps );  // xReconstructBlkSAOParams: merge resolution + offset scaling, in place like the reference
+  const bool laterStage = !cs.pcv->isEncoder && cs.sps->getUseALF();
+  if( ps.anyEnabled )
+  {
+    if( s.resident != cs.picture ) upload( s, cs );
+    ck( s, ilf_set_sao_params( s.ctx, 0, ps.ctus.data() ), "ilf_set_sao_params" );
+    ck( s, ilf_sao( s.ctx, 0 ), "ilf_sao" );
+  }
+  if( !laterStage && s.resident == cs.picture ) download( s, cs );
+  s.usSao = usSince( t0 );
+  if( !laterStage ) report( s, cs );
+}
+
+// ------------------------------------------------------------------------------------------------------------
+void AdaptiveLoopFilter::ALFProcess( CodingStructure& cs, AlfSliceParam& alfSliceParam )
+{
+  const auto t0 = clk::now();
+  ShimState& s  = contextFor( cs );
+  if( alfSliceParam.enabledFlag[COMPONENT_Y] || alfSliceParam.enabledFlag[COMPONENT_Cb] || alfSliceParam.enabledFlag[COMPONENT_Cr] )
+  {
+    alfSliceParam.filterShapes = m_filterShapes;
+    m_clpRngs                  = cs.slice->getClpRngs();
+    IlfPackedAlf pa;
+    ilfPackAlf( cs, alfSliceParam, pa );  // reconstructCoeff luma + chroma (mutates alfSliceParam like the reference) + CTU flags
+    if( s.resident != cs.picture ) upload( s, cs );
+    ck( s, ilf_set_alf_params( s.ctx, 0, &pa.params, pa.ctuEnable.data() ), "ilf_set_alf_params" );
+    ck( s, ilf_alf( s.ctx, 0 ), "ilf_alf" );
+  }
+  if( s.resident == cs.picture ) download( s, cs );
+  s.usAlf = usSince( t0 );
+  report( s, cs );
+}
