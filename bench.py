@@ -293,34 +293,58 @@ def run_b200(args, wl):
     value = world * B * args.steps * mpx / (ms_total * 1e-3)
 
     # ---- end to end through the public API: host planes + side information in, filtered host planes out ----
-    pin = [tuple(torch.from_numpy(p).pin_memory() for p in planes[s % len(planes)]) for s in range(min(B, 4))]
-    pin_np = [tuple(t_.numpy() for t_ in trip) for trip in pin]
-    outs_t = [tuple(torch.empty(p.shape, dtype=torch.int16).pin_memory() for p in planes[0]) for _ in range(2)]
-    outs = [dict(zip(("y", "cb", "cr"), (t_.numpy() for t_ in trip))) for trip in outs_t]
+    # Host buffers are page-locked (what a host integration does with its picture buffers: ilf_host_alloc /
+    # ilf_host_register), every picture crosses PCIe in both directions inside the timed region, and the slots are
+    # cycled so that upload, kernels and download of neighbouring pictures overlap (include/ilf_b200.h "transfer pipeline").
+    def pin(a):
+        t_ = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        return t_, t_.numpy()
+
+    keep = []
+    pin_in = []
+    for trip in planes:
+        tn = [pin(p) for p in trip]
+        keep += [t_ for t_, _ in tn]
+        pin_in.append(tuple(n for _, n in tn))
+    pin_side = []
+    for si in side:
+        d = {}
+        for k, v_ in si.items():
+            if isinstance(v_, np.ndarray) and v_.nbytes >= 4096:
+                t_, n_ = pin(v_)
+                keep.append(t_)
+                d[k] = n_
+            else:
+                d[k] = v_
+        pin_side.append(d)
+    outs = [v.pinned_planes(w, h) for _ in range(B)]
     h2d = sum(p.nbytes for p in planes[0])
     d2h = h2d
 
     def side_bytes(si):
-        return sum(si[k].nbytes for k in ("db_params", "db_info", "db_mv16", "ctu_slice", "sao_ctus", "alf_params", "alf_ctu_enable") if k in si) + (si["db_info_c"].nbytes if "db_info_c" in si else 0)
+        return sum(si[k].nbytes for k in ("db_params", "db_info", "db_info_c", "db_mv16", "ctu_slice", "sao_ctus", "alf_params", "alf_ctu_enable") if k in si)
 
     def e2e_step():
         nb = 0
         for s in range(B):
-            f.upload(s, *pin_np[s % len(pin_np)])
-            si = side[s % len(side)]
+            f.wait(s)                       # the slot's previous result has reached the host
+            f.upload(s, *pin_in[s % len(pin_in)])
+            si = pin_side[s % len(pin_side)]
             set_side(s, si)
             nb += side_bytes(si)
             f.run(s, 1, 7)
-            f.download(s, out=outs[s & 1])
+            f.download_async(s, outs[s])
         return nb
 
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
     for _ in range(2):
         side_b = e2e_step()
+    f.sync()
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         e2e_step()
+    f.sync()
     barrier()
     dt = time.perf_counter() - t0
     t = torch.tensor([dt], dtype=torch.float64, device="cuda")
@@ -356,7 +380,7 @@ def run_b200(args, wl):
                              "peak_source": peak_src, "chain_algo_gbs_per_gpu": round(chain_gbs, 1), "chain_frac": round(chain_gbs / peak, 4), "per_kernel": per_kernel},
                 "cpu_baseline": cpu,
                 "e2e": {"value": round(e2e_value, 1), "unit": "Mpixel/s", "h2d_bytes_per_step": B * h2d + side_b, "d2h_bytes_per_step": B * d2h,
-                        "steps": e2e_steps, "path": "InLoopFilter.upload + set_*_info + run + download per picture (C ABI ilf_upload/ilf_set_*/ilf_run/ilf_download), pinned host planes"},
+                        "steps": e2e_steps, "path": "per picture InLoopFilter.upload + set_deblock_info/set_sao_params/set_alf_params + run + download_async (C ABI ilf_upload / ilf_set_* / ilf_run / ilf_download_async / ilf_wait), page-locked host buffers, slots cycled"},
                 "gpu_launches": launches, "clocks": clk}
         print(json.dumps(line), flush=True)
     f.close()
@@ -372,7 +396,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=None, choices=list(WORKLOADS))
     ap.add_argument("--batch", type=int, default=16, help="pictures resident per GPU and filtered per step")
-    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.workload = args.workload or default_workload()

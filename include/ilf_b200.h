@@ -86,6 +86,21 @@ int ilf_upload(ilf_ctx* ctx, int slot, const int16_t* y, ptrdiff_t stride_y, con
 int ilf_download(ilf_ctx* ctx, int slot, int16_t* y, ptrdiff_t stride_y, int16_t* cb,
                  ptrdiff_t stride_cb, int16_t* cr, ptrdiff_t stride_cr);
 int ilf_sync(ilf_ctx* ctx);
+/* Transfer pipeline.  A context has an upload, a compute and a download stream, ordered per slot by events: with
+ * several slots in rotation the upload of picture n+1, the kernels of picture n and the download of picture n-1
+ * overlap.  When the host planes are page-locked (ilf_host_alloc, ilf_host_register, cudaHostAlloc ...) ilf_upload and
+ * ilf_download_async copy straight from / into them and return without waiting; pageable planes are staged through the
+ * slot's pinned buffer (ilf_upload copies synchronously into it, ilf_download_async blocks).  ilf_wait(slot) returns
+ * when the slot's last download has landed; ilf_download = ilf_download_async + ilf_wait.  Page-locked arrays (planes,
+ * and side-information arrays of 4 KiB or more) are read asynchronously: leave them unchanged until the slot's next
+ * ilf_run has been followed by ilf_wait / ilf_sync. */
+int ilf_download_async(ilf_ctx* ctx, int slot, int16_t* y, ptrdiff_t stride_y, int16_t* cb,
+                       ptrdiff_t stride_cb, int16_t* cr, ptrdiff_t stride_cr);
+int ilf_wait(ilf_ctx* ctx, int slot);
+void* ilf_host_alloc(size_t bytes);             /* page-locked host memory (NULL on failure) */
+void ilf_host_free(void* p);
+int ilf_host_register(void* p, size_t bytes);   /* page-lock an existing allocation, e.g. a PelStorage of the DPB */
+int ilf_host_unregister(void* p);
 
 /* ---------------------------------------------------------------------------------------------
  * Deblocking side information: the packed per-4x4 CU/TU metadata grid.

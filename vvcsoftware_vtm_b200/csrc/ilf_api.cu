@@ -36,7 +36,15 @@ struct Slot {
   int result_buf[3] = {0, 0, 0};  // buffer holding the current picture, per plane
   bool sao_on[3] = {false, false, false};  // any CTU with SAO enabled, per component
   bool alf_on[3] = {false, false, false};
-  cudaEvent_t staged = nullptr;  // pinned staging buffer free again
+  // Transfer pipeline: H2D copies run on the context's upload stream, kernels on the compute stream, D2H copies on the
+  // download stream; the three are ordered per slot with these events, so upload of picture n+1, filtering of picture n
+  // and download of picture n-1 overlap when the caller cycles through several slots.
+  cudaEvent_t ev_up = nullptr;     // all H2D copies of the slot (planes + side information) issued so far are done
+  cudaEvent_t ev_run = nullptr;    // all kernels issued so far on the slot are done
+  cudaEvent_t ev_down = nullptr;   // the last D2H copy of the slot is done
+  cudaEvent_t ev_side[3] = {nullptr, nullptr, nullptr};  // the pinned side-information region of stage k is free again
+  size_t side_off[4] = {0, 0, 0, 0};                       // regions of pinned_side per stage
+  bool h2d_pending = false;        // H2D work was issued since the last kernel launch on this slot
 };
 
 }  // namespace
@@ -46,7 +54,9 @@ struct ilf_ctx {
   Geom g;
   bool is_band = false;
   ilf_band band;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;   // compute stream (kernels)
+  cudaStream_t s_up = nullptr;     // host -> device copies
+  cudaStream_t s_down = nullptr;   // device -> host copies
   std::vector<Slot> slots;
   SlotDev* slots_dev = nullptr;
   size_t plane_y = 0, plane_c = 0, buf_elems = 0;  // elements per plane / per 3-plane buffer
@@ -94,16 +104,32 @@ int16_t* plane_ptr(const ilf_ctx* ctx, const Slot& s, int buf, int plane) {
   return p;
 }
 
+// The slot descriptor travels on the upload stream like the side information it points to.
 int push_desc(ilf_ctx* ctx, int slot) {
-  CU(ctx, cudaMemcpyAsync(ctx->slots_dev + slot, &ctx->slots[slot].dev, sizeof(SlotDev), cudaMemcpyHostToDevice, ctx->stream));
+  Slot& s = ctx->slots[slot];
+  CU(ctx, cudaMemcpyAsync(ctx->slots_dev + slot, &s.dev, sizeof(SlotDev), cudaMemcpyHostToDevice, ctx->s_up));
+  CU(ctx, cudaEventRecord(s.ev_up, ctx->s_up));
+  s.h2d_pending = true;
   return ILF_OK;
 }
 
-// Side information goes host -> pinned staging -> device, asynchronously on the context's stream.
-int stage_side(ilf_ctx* ctx, Slot& s, void* dst, const void* src, size_t bytes, size_t& cursor) {
-  if (cursor + bytes > s.pinned_side_bytes) return fail(ctx, ILF_ERR_STATE, "side-information staging overflow");
+// Page-locked (cudaHostAlloc / cudaHostRegister / ilf_host_alloc) host memory can be the source or target of an
+// asynchronous copy directly; pageable memory goes through the slot's pinned staging buffer.
+bool is_pinned(const void* p) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return at.type == cudaMemoryTypeHost;
+}
+
+// Side information goes host -> pinned staging region of its stage -> device, asynchronously on the upload stream.
+int stage_side(ilf_ctx* ctx, Slot& s, void* dst, const void* src, size_t bytes, size_t& cursor, size_t limit) {
+  if (bytes >= 4096 && is_pinned(src)) {  // page-locked source: copy straight from the caller's array
+    CU(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->s_up));
+    return ILF_OK;
+  }
+  if (cursor + bytes > limit) return fail(ctx, ILF_ERR_STATE, "side-information staging overflow");
   memcpy(s.pinned_side + cursor, src, bytes);
-  CU(ctx, cudaMemcpyAsync(dst, s.pinned_side + cursor, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  CU(ctx, cudaMemcpyAsync(dst, s.pinned_side + cursor, bytes, cudaMemcpyHostToDevice, ctx->s_up));
   cursor += (bytes + 255) & ~size_t(255);
   return ILF_OK;
 }
@@ -161,13 +187,15 @@ int create_impl(ilf_ctx** out, const ilf_config* cfg, const ilf_band* band) {
 
   CU(ctx, cudaSetDevice(cfg->device));
   CU(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  CU(ctx, cudaStreamCreateWithFlags(&ctx->s_up, cudaStreamNonBlocking));
+  CU(ctx, cudaStreamCreateWithFlags(&ctx->s_down, cudaStreamNonBlocking));
   ctx->slots.resize(cfg->num_slots);
   CU(ctx, cudaMalloc(&ctx->slots_dev, sizeof(SlotDev) * cfg->num_slots));
   const size_t units = (size_t)g.units_w * g.units_h;
   for (int i = 0; i < cfg->num_slots; i++) {
     Slot& s = ctx->slots[i];
     CU(ctx, cudaMalloc(&s.planes, 3 * ctx->buf_elems * sizeof(int16_t)));
-    CU(ctx, cudaMemsetAsync(s.planes, 0, 3 * ctx->buf_elems * sizeof(int16_t), ctx->stream));
+    CU(ctx, cudaMemsetAsync(s.planes, 0, 3 * ctx->buf_elems * sizeof(int16_t), ctx->s_up));
     CU(ctx, cudaMalloc(&s.info, units * 4));
     CU(ctx, cudaMalloc(&s.info_c, units * 4));
     CU(ctx, cudaMalloc(&s.mv, units * 16));
@@ -179,16 +207,32 @@ int create_impl(ilf_ctx** out, const ilf_config* cfg, const ilf_band* band) {
     CU(ctx, cudaMalloc(&s.alf_ctu_enable, 3 * (size_t)ctx->num_ctus));
     CU(ctx, cudaMalloc(&s.alf_class, units));
     CU(ctx, cudaMallocHost(&s.pinned, ctx->buf_elems * sizeof(int16_t)));
-    s.pinned_side_bytes = units * (4 + 4 + 16) + 4096 + (size_t)ctx->num_ctus * (1 + sizeof(ilf_sao_ctu) + 3) + sizeof(ilf_deblock_params) + sizeof(ilf_alf_params) + 25 * 4 * 16 * sizeof(int) + 16 * 256;
+    auto up256 = [](size_t v) { return (v + 255) & ~size_t(255); };
+    s.side_off[0] = 0;
+    s.side_off[1] = up256(sizeof(ilf_deblock_params)) + 2 * up256(units * 4) + up256(units * 16) + up256(ctx->num_ctus);
+    s.side_off[2] = s.side_off[1] + up256(sizeof(ilf_sao_ctu) * ctx->num_ctus);
+    s.side_off[3] = s.side_off[2] + up256(sizeof(ilf_alf_params)) + up256(3 * (size_t)ctx->num_ctus) + up256(25 * 4 * 16 * sizeof(int));
+    s.pinned_side_bytes = s.side_off[3];
     CU(ctx, cudaMallocHost(&s.pinned_side, s.pinned_side_bytes));
-    CU(ctx, cudaEventCreateWithFlags(&s.staged, cudaEventDisableTiming));
+    CU(ctx, cudaEventCreateWithFlags(&s.ev_up, cudaEventDisableTiming));
+    CU(ctx, cudaEventCreateWithFlags(&s.ev_run, cudaEventDisableTiming));
+    CU(ctx, cudaEventCreateWithFlags(&s.ev_down, cudaEventDisableTiming));
+    for (int k = 0; k < 3; k++) CU(ctx, cudaEventCreateWithFlags(&s.ev_side[k], cudaEventDisableTiming));
     memset(&s.dev, 0, sizeof(s.dev));
     for (int b = 0; b < 3; b++)
       for (int p = 0; p < 3; p++) s.dev.buf[b][p] = plane_ptr(ctx, s, b, p);
     s.dev.alf_class = s.alf_class;
     if (int rc = push_desc(ctx, i)) return rc;
   }
+  CU(ctx, cudaStreamSynchronize(ctx->s_up));
+  for (Slot& s : ctx->slots) s.h2d_pending = false;
+  return ILF_OK;
+}
+
+int sync_all(ilf_ctx* ctx) {
+  CU(ctx, cudaStreamSynchronize(ctx->s_up));
   CU(ctx, cudaStreamSynchronize(ctx->stream));
+  CU(ctx, cudaStreamSynchronize(ctx->s_down));
   return ILF_OK;
 }
 
@@ -214,18 +258,18 @@ int ilf_create_band(ilf_ctx** out, const ilf_config* cfg, const ilf_band* band) 
 int ilf_destroy(ilf_ctx* ctx) {
   if (!ctx) return ILF_OK;
   cudaSetDevice(ctx->cfg.device);
-  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  for (cudaStream_t st : {ctx->s_up, ctx->stream, ctx->s_down}) if (st) cudaStreamSynchronize(st);
   for (Slot& s : ctx->slots) {
     cudaFree(s.planes); cudaFree(s.info); cudaFree(s.info_c); cudaFree(s.mv); cudaFree(s.ctu_slice); cudaFree(s.db_params);
     cudaFree(s.sao); cudaFree(s.alf); cudaFree(s.alf_coef); cudaFree(s.alf_ctu_enable); cudaFree(s.alf_class);
     if (s.pinned) cudaFreeHost(s.pinned);
     if (s.pinned_side) cudaFreeHost(s.pinned_side);
-    if (s.staged) cudaEventDestroy(s.staged);
+    for (cudaEvent_t e : {s.ev_up, s.ev_run, s.ev_down, s.ev_side[0], s.ev_side[1], s.ev_side[2]}) if (e) cudaEventDestroy(e);
   }
   cudaFree(ctx->slots_dev);
   for (auto& t : ctx->timed) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
   for (cudaEvent_t e : ctx->free_events) cudaEventDestroy(e);
-  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  for (cudaStream_t st : {ctx->s_up, ctx->stream, ctx->s_down}) if (st) cudaStreamDestroy(st);
   delete ctx;
   return ILF_OK;
 }
@@ -254,40 +298,66 @@ int ilf_upload(ilf_ctx* ctx, int slot, const int16_t* y, ptrdiff_t sy, const int
   Slot& s = ctx->slots[slot];
   const Geom& g = ctx->g;
   CU(ctx, cudaSetDevice(ctx->cfg.device));
-  CU(ctx, cudaEventSynchronize(s.staged));  // previous use of the staging buffer finished
+  // buffer 0 may still be read by kernels of the slot's previous picture, or by its download when no stage ran on a plane
+  CU(ctx, cudaStreamWaitEvent(ctx->s_up, s.ev_run, 0));
+  CU(ctx, cudaStreamWaitEvent(ctx->s_up, s.ev_down, 0));
   const int16_t* srcs[3] = {y, cb, cr};
   const ptrdiff_t strides[3] = {sy, scb, scr};
+  const bool direct = is_pinned(y) && is_pinned(cb) && is_pinned(cr);
+  if (!direct) {
+    CU(ctx, cudaEventSynchronize(s.ev_up));    // staging buffer: previous staged upload consumed ...
+    CU(ctx, cudaEventSynchronize(s.ev_down));  // ... and no staged download in flight
+  }
   int16_t* stage = s.pinned;
   for (int p = 0; p < 3; p++) {
     const int w = p ? g.width / 2 : g.width, h = p ? g.rows / 2 : g.rows, pitch = p ? g.pitch_c : g.pitch_y;
-    for (int r = 0; r < h; r++) memcpy(stage + (size_t)r * w, srcs[p] + (ptrdiff_t)r * strides[p], (size_t)w * 2);
-    CU(ctx, cudaMemcpy2DAsync(plane_ptr(ctx, s, 0, p), (size_t)pitch * 2, stage, (size_t)w * 2, (size_t)w * 2, h, cudaMemcpyHostToDevice, ctx->stream));
-    stage += (size_t)w * h;
+    if (direct) {
+      CU(ctx, cudaMemcpy2DAsync(plane_ptr(ctx, s, 0, p), (size_t)pitch * 2, srcs[p], (size_t)strides[p] * 2, (size_t)w * 2, h, cudaMemcpyHostToDevice, ctx->s_up));
+    } else {
+      for (int r = 0; r < h; r++) memcpy(stage + (size_t)r * w, srcs[p] + (ptrdiff_t)r * strides[p], (size_t)w * 2);
+      CU(ctx, cudaMemcpy2DAsync(plane_ptr(ctx, s, 0, p), (size_t)pitch * 2, stage, (size_t)w * 2, (size_t)w * 2, h, cudaMemcpyHostToDevice, ctx->s_up));
+      stage += (size_t)w * h;
+    }
   }
-  CU(ctx, cudaEventRecord(s.staged, ctx->stream));
+  CU(ctx, cudaEventRecord(s.ev_up, ctx->s_up));
+  s.h2d_pending = true;
   s.uploaded = true;
   s.has_db = s.has_sao = s.has_alf = false;
   s.result_buf[0] = s.result_buf[1] = s.result_buf[2] = 0;
   return ILF_OK;
 }
 
-int ilf_download(ilf_ctx* ctx, int slot, int16_t* y, ptrdiff_t sy, int16_t* cb, ptrdiff_t scb, int16_t* cr, ptrdiff_t scr) {
+// Issues the device -> host copy of the slot's current picture.  Into page-locked memory the copy is asynchronous
+// (ilf_wait / ilf_sync complete it); into pageable memory the call stages and blocks.
+int ilf_download_async(ilf_ctx* ctx, int slot, int16_t* y, ptrdiff_t sy, int16_t* cb, ptrdiff_t scb, int16_t* cr, ptrdiff_t scr) {
   if (int rc = check_slot(ctx, slot)) return rc;
   if (!y || !cb || !cr) return fail(ctx, ILF_ERR_ARG, "null plane pointer");
   Slot& s = ctx->slots[slot];
   if (!s.uploaded) return fail(ctx, ILF_ERR_STATE, "slot %d: download before upload", slot);
   const Geom& g = ctx->g;
   CU(ctx, cudaSetDevice(ctx->cfg.device));
-  CU(ctx, cudaEventSynchronize(s.staged));
+  CU(ctx, cudaStreamWaitEvent(ctx->s_down, s.ev_run, 0));
+  CU(ctx, cudaStreamWaitEvent(ctx->s_down, s.ev_up, 0));  // a picture that no stage touched is read from the upload buffer
   int16_t* dsts[3] = {y, cb, cr};
   const ptrdiff_t strides[3] = {sy, scb, scr};
+  const bool direct = is_pinned(y) && is_pinned(cb) && is_pinned(cr);
+  if (direct) {
+    for (int p = 0; p < 3; p++) {
+      const int w = p ? g.width / 2 : g.width, h = p ? g.rows / 2 : g.rows, pitch = p ? g.pitch_c : g.pitch_y;
+      CU(ctx, cudaMemcpy2DAsync(dsts[p], (size_t)strides[p] * 2, plane_ptr(ctx, s, s.result_buf[p], p), (size_t)pitch * 2, (size_t)w * 2, h, cudaMemcpyDeviceToHost, ctx->s_down));
+    }
+    CU(ctx, cudaEventRecord(s.ev_down, ctx->s_down));
+    return ILF_OK;
+  }
+  CU(ctx, cudaEventSynchronize(s.ev_up));  // the staging buffer may hold a staged upload that is still being copied
   int16_t* stage = s.pinned;
   for (int p = 0; p < 3; p++) {
     const int w = p ? g.width / 2 : g.width, h = p ? g.rows / 2 : g.rows, pitch = p ? g.pitch_c : g.pitch_y;
-    CU(ctx, cudaMemcpy2DAsync(stage, (size_t)w * 2, plane_ptr(ctx, s, s.result_buf[p], p), (size_t)pitch * 2, (size_t)w * 2, h, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaMemcpy2DAsync(stage, (size_t)w * 2, plane_ptr(ctx, s, s.result_buf[p], p), (size_t)pitch * 2, (size_t)w * 2, h, cudaMemcpyDeviceToHost, ctx->s_down));
     stage += (size_t)w * h;
   }
-  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  CU(ctx, cudaEventRecord(s.ev_down, ctx->s_down));
+  CU(ctx, cudaEventSynchronize(s.ev_down));
   stage = s.pinned;
   for (int p = 0; p < 3; p++) {
     const int w = p ? g.width / 2 : g.width, h = p ? g.rows / 2 : g.rows;
@@ -297,12 +367,32 @@ int ilf_download(ilf_ctx* ctx, int slot, int16_t* y, ptrdiff_t sy, int16_t* cb, 
   return ILF_OK;
 }
 
+int ilf_wait(ilf_ctx* ctx, int slot) {
+  if (int rc = check_slot(ctx, slot)) return rc;
+  CU(ctx, cudaSetDevice(ctx->cfg.device));
+  CU(ctx, cudaEventSynchronize(ctx->slots[slot].ev_down));
+  return ILF_OK;
+}
+
+int ilf_download(ilf_ctx* ctx, int slot, int16_t* y, ptrdiff_t sy, int16_t* cb, ptrdiff_t scb, int16_t* cr, ptrdiff_t scr) {
+  if (int rc = ilf_download_async(ctx, slot, y, sy, cb, scb, cr, scr)) return rc;
+  return ilf_wait(ctx, slot);
+}
+
 int ilf_sync(ilf_ctx* ctx) {
   if (!ctx) return ILF_ERR_ARG;
   CU(ctx, cudaSetDevice(ctx->cfg.device));
-  CU(ctx, cudaStreamSynchronize(ctx->stream));
-  return ILF_OK;
+  return sync_all(ctx);
 }
+
+void* ilf_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  return p;
+}
+void ilf_host_free(void* p) { if (p) cudaFreeHost(p); }
+int ilf_host_register(void* p, size_t bytes) { if (cudaHostRegister(p, bytes, cudaHostRegisterDefault) != cudaSuccess) { cudaGetLastError(); return ILF_ERR_CUDA; } return ILF_OK; }
+int ilf_host_unregister(void* p) { if (cudaHostUnregister(p) != cudaSuccess) { cudaGetLastError(); return ILF_ERR_CUDA; } return ILF_OK; }
 
 // Grids cover the rows the context holds (units_h = held rows / 4); ctu_slice covers the full picture.
 int ilf_set_deblock_info(ilf_ctx* ctx, int slot, const ilf_deblock_params* params, const uint32_t* info, const uint32_t* info_chroma,
@@ -313,17 +403,19 @@ int ilf_set_deblock_info(ilf_ctx* ctx, int slot, const ilf_deblock_params* param
   if (params->num_slices < 1 || params->num_slices > ILF_MAX_SLICES) return fail(ctx, ILF_ERR_ARG, "num_slices %d out of range", params->num_slices);
   Slot& s = ctx->slots[slot];
   CU(ctx, cudaSetDevice(ctx->cfg.device));
-  CU(ctx, cudaStreamSynchronize(ctx->stream));  // staging buffer reuse; side info is small next to the picture
+  CU(ctx, cudaEventSynchronize(s.ev_side[0]));  // the previous copy out of this staging region is done
+  CU(ctx, cudaStreamWaitEvent(ctx->s_up, s.ev_run, 0));  // kernels of the slot's previous picture may still read the device arrays
   const size_t units = (size_t)ctx->g.units_w * ctx->g.units_h;
-  size_t cur = 0;
-  if (int rc = stage_side(ctx, s, s.db_params, params, sizeof(*params), cur)) return rc;
-  if (int rc = stage_side(ctx, s, s.info, info, units * 4, cur)) return rc;
+  size_t cur = s.side_off[0];
+  const size_t lim = s.side_off[1];
+  if (int rc = stage_side(ctx, s, s.db_params, params, sizeof(*params), cur, lim)) return rc;
+  if (int rc = stage_side(ctx, s, s.info, info, units * 4, cur, lim)) return rc;
   s.has_ctree = info_chroma != nullptr;
-  if (info_chroma) if (int rc = stage_side(ctx, s, s.info_c, info_chroma, units * 4, cur)) return rc;
+  if (info_chroma) if (int rc = stage_side(ctx, s, s.info_c, info_chroma, units * 4, cur, lim)) return rc;
   s.mv_mode = mv16 ? 1 : (mv32 ? 2 : 0);
-  if (mv16) if (int rc = stage_side(ctx, s, s.mv, mv16, units * 8, cur)) return rc;
-  if (mv32) if (int rc = stage_side(ctx, s, s.mv, mv32, units * 16, cur)) return rc;
-  if (ctu_slice) if (int rc = stage_side(ctx, s, s.ctu_slice, ctu_slice, ctx->num_ctus, cur)) return rc;
+  if (mv16) if (int rc = stage_side(ctx, s, s.mv, mv16, units * 8, cur, lim)) return rc;
+  if (mv32) if (int rc = stage_side(ctx, s, s.mv, mv32, units * 16, cur, lim)) return rc;
+  if (ctu_slice) if (int rc = stage_side(ctx, s, s.ctu_slice, ctu_slice, ctx->num_ctus, cur, lim)) return rc;
   s.dev.info = s.info;
   s.dev.info_c = info_chroma ? s.info_c : nullptr;
   s.dev.mv16 = mv16 ? (const int16_t*)s.mv : nullptr;
@@ -331,6 +423,7 @@ int ilf_set_deblock_info(ilf_ctx* ctx, int slot, const ilf_deblock_params* param
   s.dev.ctu_slice = ctu_slice ? s.ctu_slice : nullptr;
   s.dev.db_params = s.db_params;
   s.has_db = true;
+  CU(ctx, cudaEventRecord(s.ev_side[0], ctx->s_up));
   return push_desc(ctx, slot);
 }
 
@@ -352,11 +445,13 @@ int ilf_set_sao_params(ilf_ctx* ctx, int slot, const ilf_sao_ctu* ctus) {
           return fail(ctx, ILF_ERR_UNSUPPORTED, "CTU %d comp %d: SAO offset %d outside [-128,127]", i, c, ctus[i].offset[c][k]);
     }
   CU(ctx, cudaSetDevice(ctx->cfg.device));
-  CU(ctx, cudaStreamSynchronize(ctx->stream));
-  size_t cur = 0;
-  if (int rc = stage_side(ctx, s, s.sao, ctus, sizeof(ilf_sao_ctu) * ctx->num_ctus, cur)) return rc;
+  CU(ctx, cudaEventSynchronize(s.ev_side[1]));
+  CU(ctx, cudaStreamWaitEvent(ctx->s_up, s.ev_run, 0));
+  size_t cur = s.side_off[1];
+  if (int rc = stage_side(ctx, s, s.sao, ctus, sizeof(ilf_sao_ctu) * ctx->num_ctus, cur, s.side_off[2])) return rc;
   s.dev.sao = s.sao;
   s.has_sao = true;
+  CU(ctx, cudaEventRecord(s.ev_side[1], ctx->s_up));
   return push_desc(ctx, slot);
 }
 
@@ -369,10 +464,12 @@ int ilf_set_alf_params(ilf_ctx* ctx, int slot, const ilf_alf_params* params, con
     for (int i = 0; i < ctx->num_ctus; i++) s.alf_on[c] |= ctu_enable[(size_t)c * ctx->num_ctus + i] != 0;
   }
   CU(ctx, cudaSetDevice(ctx->cfg.device));
-  CU(ctx, cudaStreamSynchronize(ctx->stream));
-  size_t cur = 0;
-  if (int rc = stage_side(ctx, s, s.alf, params, sizeof(*params), cur)) return rc;
-  if (int rc = stage_side(ctx, s, s.alf_ctu_enable, ctu_enable, 3 * (size_t)ctx->num_ctus, cur)) return rc;
+  CU(ctx, cudaEventSynchronize(s.ev_side[2]));
+  CU(ctx, cudaStreamWaitEvent(ctx->s_up, s.ev_run, 0));
+  size_t cur = s.side_off[2];
+  const size_t lim = s.side_off[3];
+  if (int rc = stage_side(ctx, s, s.alf, params, sizeof(*params), cur, lim)) return rc;
+  if (int rc = stage_side(ctx, s, s.alf_ctu_enable, ctu_enable, 3 * (size_t)ctx->num_ctus, cur, lim)) return rc;
   {
     // Coefficient order after transposition (filterBlk, AdaptiveLoopFilter.cpp:541-575), expanded once per picture so
     // that a 4x4 block fetches its 13 (7) coefficients with four 16-byte loads.
@@ -385,8 +482,9 @@ int ilf_set_alf_params(ilf_ctx* ctx, int slot, const ilf_alf_params* params, con
       for (int tr = 0; tr < 4; tr++)
         for (int k = 0; k < 16; k++)
           tab[cl][tr][k] = is7 ? (k < 13 ? params->luma_coeff[cl][perm7[tr][k]] : 0) : (k < 7 ? params->luma_coeff[cl][perm5[tr][k]] : 0);
-    if (int rc = stage_side(ctx, s, s.alf_coef, tab, sizeof(tab), cur)) return rc;
+    if (int rc = stage_side(ctx, s, s.alf_coef, tab, sizeof(tab), cur, lim)) return rc;
   }
+  CU(ctx, cudaEventRecord(s.ev_side[2], ctx->s_up));
   s.dev.alf_coef = s.alf_coef;
   s.dev.alf = s.alf;
   s.dev.alf_ctu_enable = s.alf_ctu_enable;
@@ -497,8 +595,14 @@ int ilf_run(ilf_ctx* ctx, int first_slot, int num_slots, unsigned stages) {
   // A full run always restarts from the uploaded input.
   if (stages & ILF_STAGE_DEBLOCK)
     for (int i = first_slot; i < first_slot + num_slots; i++) ctx->slots[i].result_buf[0] = ctx->slots[i].result_buf[1] = ctx->slots[i].result_buf[2] = 0;
+  for (int i = first_slot; i < first_slot + num_slots; i++) {
+    Slot& s = ctx->slots[i];
+    if (s.h2d_pending) { CU(ctx, cudaStreamWaitEvent(ctx->stream, s.ev_up, 0)); s.h2d_pending = false; }
+    CU(ctx, cudaStreamWaitEvent(ctx->stream, s.ev_down, 0));  // a download may still read the buffer this run overwrites
+  }
   for (int st = 0; st < 3; st++)
     if (stages & (1u << st)) if (int rc = run_stage(ctx, first_slot, num_slots, st)) return rc;
+  for (int i = first_slot; i < first_slot + num_slots; i++) CU(ctx, cudaEventRecord(ctx->slots[i].ev_run, ctx->stream));
   return ILF_OK;
 }
 
@@ -512,6 +616,7 @@ int ilf_alf_classify(ilf_ctx* ctx, int slot, uint8_t* out) {
   Slot& s = ctx->slots[slot];
   if (!s.uploaded) return fail(ctx, ILF_ERR_STATE, "slot %d: classify before upload", slot);
   CU(ctx, cudaSetDevice(ctx->cfg.device));
+  if (s.h2d_pending) { CU(ctx, cudaStreamWaitEvent(ctx->stream, s.ev_up, 0)); s.h2d_pending = false; }
   BatchCtl ctl;
   ctl.v[0] = (uint16_t)s.result_buf[0];
   launch_alf_luma(ctx->g, ctx->slots_dev, slot, 1, ctl, true, ctx->stream);

@@ -56,6 +56,13 @@ def load_library():
     lib.ilf_upload.argtypes = [vp, i, vp, pd, vp, pd, vp, pd]
     lib.ilf_download.argtypes = [vp, i, vp, pd, vp, pd, vp, pd]
     lib.ilf_sync.argtypes = [vp]
+    lib.ilf_download_async.argtypes = [vp, i, vp, pd, vp, pd, vp, pd]
+    lib.ilf_wait.argtypes = [vp, i]
+    lib.ilf_host_alloc.argtypes = [C.c_size_t]
+    lib.ilf_host_alloc.restype = vp
+    lib.ilf_host_free.argtypes = [vp]
+    lib.ilf_host_register.argtypes = [vp, C.c_size_t]
+    lib.ilf_host_unregister.argtypes = [vp]
     lib.ilf_set_deblock_info.argtypes = [vp, i, vp, vp, vp, vp, vp, vp]
     lib.ilf_set_sao_params.argtypes = [vp, i, vp]
     lib.ilf_set_alf_params.argtypes = [vp, i, vp, vp]
@@ -83,6 +90,18 @@ def _ptr(a):
 
 def _arr(a, dt):
     return None if a is None else np.ascontiguousarray(a, dtype=dt)
+
+
+def pinned_planes(width, height):
+    """{"y","cb","cr"} int16 arrays in page-locked host memory (ilf_host_alloc); keep the dict alive while in use."""
+    lib = load_library()
+    out = {}
+    for k, (h, w) in (("y", (height, width)), ("cb", (height // 2, width // 2)), ("cr", (height // 2, width // 2))):
+        p = lib.ilf_host_alloc(h * w * 2)
+        if not p:
+            raise IlfError("ilf_host_alloc failed")
+        out[k] = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_int16)), shape=(h, w))
+    return out
 
 
 class InLoopFilter:
@@ -130,6 +149,14 @@ class InLoopFilter:
         y, cb, cr = (_arr(a, np.int16) for a in (y, cb, cr))
         assert y.shape == (self.rows, self.width) and cb.shape == cr.shape == (self.rows // 2, self.width // 2)
         self._ck(self._lib.ilf_upload(self._h, slot, _ptr(y), y.shape[1], _ptr(cb), cb.shape[1], _ptr(cr), cr.shape[1]))
+
+    def download_async(self, slot, out):
+        """Start the device -> host copy of `slot` into `out` (dict of page-locked int16 arrays); wait(slot) completes it."""
+        y, cb, cr = out["y"], out["cb"], out["cr"]
+        self._ck(self._lib.ilf_download_async(self._h, slot, _ptr(y), y.shape[1], _ptr(cb), cb.shape[1], _ptr(cr), cr.shape[1]))
+
+    def wait(self, slot):
+        self._ck(self._lib.ilf_wait(self._h, slot))
 
     def download(self, slot, out=None):
         """Filtered picture of `slot` as {"y","cb","cr"}; `out` = dict of preallocated int16 arrays to fill (e.g. pinned)."""
