@@ -244,8 +244,8 @@ def run_b200(args, wl):
 
     w, h = wl["width"], wl["height"]
     mpx = w * h / 1e6
-    B = args.batch
     side = load_sideinfo(args.workload)
+    B = args.batch or len(side)
     planes = synth_planes(w, h, min(B, 4), seed=1000 + rank)
     f = v.InLoopFilter(w, h, 10, 10, 7, device=local, num_slots=B)
 
@@ -395,7 +395,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=None, choices=list(WORKLOADS))
-    ap.add_argument("--batch", type=int, default=16, help="pictures resident per GPU and filtered per step")
+    ap.add_argument("--batch", type=int, default=0, help="pictures resident per GPU and filtered per step (default: every picture of the workload's side information once, e.g. the 17 pictures of one 4K random-access GOP)")
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -1,8 +1,8 @@
 #!/bin/bash
 # One gpurun call: GPU parity tests, smoke, bench, ncu launch list and full captures.  Outputs under gpurun_out/.
 mkdir -p gpurun_out
-WL=${WL:-ra_1080p}
-BATCH=${BATCH:-16}
+WL=${WL:-ra_4k}
+BATCH=${BATCH:-0}
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/smi.txt 2>&1
 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/pytest_gpu.log
 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?" | tee -a gpurun_out/smoke.log

@@ -64,7 +64,7 @@ template <bool CLASSIFY_ONLY>
 __global__ void __launch_bounds__(NT) alf_luma_kernel(Geom g, const SlotDev* __restrict__ slots, int first_slot, BatchCtl bc) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   LumaSmem& s = *reinterpret_cast<LumaSmem*>(smem_raw);
-  const SlotDev& sd = slots[first_slot + blockIdx.z];
+  const SlotDev& sd = slots[first_slot + bc.slot[blockIdx.z]];
   const unsigned ctl = bc.v[blockIdx.z];
   if (ctl_skip(ctl, 0)) return;
   const int tid = threadIdx.x;
@@ -257,7 +257,7 @@ constexpr int CT_W = 64, CT_H = 16, CS_W = CT_W + 8, CS_H = CT_H + 4;
 
 __global__ void __launch_bounds__(NT) alf_chroma_kernel(Geom g, const SlotDev* __restrict__ slots, int first_slot, BatchCtl bc) {
   __shared__ __align__(16) int t[CS_H][CS_W];
-  const SlotDev& sd = slots[first_slot + (blockIdx.z >> 1)];
+  const SlotDev& sd = slots[first_slot + bc.slot[blockIdx.z >> 1]];
   const int plane = 1 + (blockIdx.z & 1);
   const unsigned ctl = bc.v[blockIdx.z >> 1];
   if (ctl_skip(ctl, plane)) return;

@@ -2,6 +2,7 @@
 // planes, pinned async transfers, side-information upload and stage launches.  No CPU fallback anywhere.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -177,6 +178,7 @@ int create_impl(ilf_ctx** out, const ilf_config* cfg, const ilf_band* band) {
     g.rows = std::min(cfg->height, out_end + halo) - g.row0;
   }
   g.units_h = g.rows / 4;
+  g.debug = getenv("ILF_DEBUG") ? atoi(getenv("ILF_DEBUG")) : 0;
   g.pitch_y = (cfg->width + 63) & ~63;
   g.pitch_c = (cfg->width / 2 + 63) & ~63;
   ctx->plane_y = (size_t)g.pitch_y * g.rows;
@@ -544,40 +546,58 @@ static int run_stage(ilf_ctx* ctx, int first, int n, int stage) {
   const double plane_bytes[3] = {2.0 * g.width * g.rows * 2, 2.0 * (g.width / 2) * (g.rows / 2) * 2, 2.0 * (g.width / 2) * (g.rows / 2) * 2};  // read + write
   for (int c0 = first; c0 < first + n; c0 += MAX_BATCH) {
     const int cn = std::min(MAX_BATCH, first + n - c0);
-    BatchCtl ctl;
-    bool any[3] = {false, false, false};
-    double bytes[3] = {0, 0, 0};
+    // control words of the slots of this chunk, then one compact launch list per kernel (active slots only)
+    uint16_t word[MAX_BATCH];
+    bool on[MAX_BATCH][3];
     for (int i = 0; i < cn; i++) {
       Slot& s = ctx->slots[c0 + i];
       unsigned v = 0;
       for (int p = 0; p < 3; p++) {
-        const bool on = stage == 0 ? true : (stage == 1 ? s.sao_on[p] : s.alf_on[p]);
+        on[i][p] = stage == 0 ? true : (stage == 1 ? s.sao_on[p] : s.alf_on[p]);
         v |= (unsigned)s.result_buf[p] << (2 * p);
-        if (!on) { v |= 1u << (6 + p); continue; }
+        if (!on[i][p]) { v |= 1u << (6 + p); continue; }
         s.result_buf[p] = s.result_buf[p] == 1 ? 2 : 1;
-        any[p] = true;
-        bytes[p] += plane_bytes[p];
       }
-      ctl.v[i] = (uint16_t)v;
+      word[i] = (uint16_t)v;
     }
+    auto compact = [&](bool use_y, bool use_c, BatchCtl& ctl, double& bytes) {
+      int m = 0;
+      bytes = 0;
+      for (int i = 0; i < cn; i++) {
+        const bool y = use_y && on[i][0], c = use_c && (on[i][1] || on[i][2]);
+        if (!y && !c) continue;
+        ctl.v[m] = word[i];
+        ctl.slot[m] = (uint8_t)i;
+        m++;
+        if (y) bytes += plane_bytes[0];
+        if (use_c) bytes += (on[i][1] ? plane_bytes[1] : 0) + (on[i][2] ? plane_bytes[2] : 0);
+      }
+      return m;
+    };
     if (ctx->timed.size() >= 4096) if (int rc = timed_collect(ctx)) return rc;
+    BatchCtl ctl;
+    double bytes = 0;
     if (stage == 0 || stage == 1) {
-      if (!(any[0] || any[1] || any[2])) continue;
-      if (int rc = timed_begin(ctx, stage, bytes[0] + bytes[1] + bytes[2])) return rc;
-      if (stage == 0) launch_deblock(g, ctx->slots_dev, c0, cn, ctl, mv_mode, ctx->stream);
-      else launch_sao(g, ctx->slots_dev, c0, cn, ctl, ctx->stream);
-      if (int rc = timed_end(ctx)) return rc;
-      ctx->launches++;
-    } else {
-      if (any[0]) {
-        if (int rc = timed_begin(ctx, ILF_KERNEL_ALF_LUMA, bytes[0])) return rc;
-        launch_alf_luma(g, ctx->slots_dev, c0, cn, ctl, false, ctx->stream);
+      const int m = compact(true, true, ctl, bytes);
+      if (m) {
+        if (int rc = timed_begin(ctx, stage, bytes)) return rc;
+        if (stage == 0) launch_deblock(g, ctx->slots_dev, c0, m, ctl, mv_mode, ctx->stream);
+        else launch_sao(g, ctx->slots_dev, c0, m, ctl, ctx->stream);
         if (int rc = timed_end(ctx)) return rc;
         ctx->launches++;
       }
-      if (any[1] || any[2]) {
-        if (int rc = timed_begin(ctx, ILF_KERNEL_ALF_CHROMA, bytes[1] + bytes[2])) return rc;
-        launch_alf_chroma(g, ctx->slots_dev, c0, cn, ctl, ctx->stream);
+    } else {
+      int m = compact(true, false, ctl, bytes);
+      if (m) {
+        if (int rc = timed_begin(ctx, ILF_KERNEL_ALF_LUMA, bytes)) return rc;
+        launch_alf_luma(g, ctx->slots_dev, c0, m, ctl, false, ctx->stream);
+        if (int rc = timed_end(ctx)) return rc;
+        ctx->launches++;
+      }
+      m = compact(false, true, ctl, bytes);
+      if (m) {
+        if (int rc = timed_begin(ctx, ILF_KERNEL_ALF_CHROMA, bytes)) return rc;
+        launch_alf_chroma(g, ctx->slots_dev, c0, m, ctl, ctx->stream);
         if (int rc = timed_end(ctx)) return rc;
         ctx->launches++;
       }
@@ -619,6 +639,7 @@ int ilf_alf_classify(ilf_ctx* ctx, int slot, uint8_t* out) {
   if (s.h2d_pending) { CU(ctx, cudaStreamWaitEvent(ctx->stream, s.ev_up, 0)); s.h2d_pending = false; }
   BatchCtl ctl;
   ctl.v[0] = (uint16_t)s.result_buf[0];
+  ctl.slot[0] = 0;
   launch_alf_luma(ctx->g, ctx->slots_dev, slot, 1, ctl, true, ctx->stream);
   ctx->launches += 1;
   CU(ctx, cudaGetLastError());

@@ -18,6 +18,7 @@ struct Geom {
   // [row0, row0 + rows) of the full picture; filtering decisions use full-picture coordinates.
   int row0, rows;           // luma rows held (row0 multiple of 8); whole picture: 0, height
   int out_row0, out_rows;   // luma rows this context must produce (its own CTU rows)
+  int debug;                // measurement aid (env ILF_DEBUG): bit 0 = kernels stage and write back only (no filtering)
 };
 
 // Per-slot device pointers; an array of these lives in device memory (one entry per slot) and kernels index
@@ -44,7 +45,8 @@ struct SlotDev {
 // no CTA touches it and its result stays where it was.
 constexpr int MAX_BATCH = 128;
 struct BatchCtl {
-  uint16_t v[MAX_BATCH];  // bits 2p..2p+1: source buffer of plane p; bit 6+p: skip plane p
+  uint16_t v[MAX_BATCH];     // bits 2p..2p+1: source buffer of plane p; bit 6+p: skip plane p
+  uint8_t slot[MAX_BATCH];   // slot (relative to first_slot) that grid layer blockIdx.z works on: launches cover active slots only
 };
 __host__ __device__ __forceinline__ int ctl_src(unsigned c, int plane) { return (c >> (2 * plane)) & 3; }
 __host__ __device__ __forceinline__ int ctl_dst(unsigned c, int plane) { return ctl_src(c, plane) == 1 ? 2 : 1; }
@@ -57,7 +59,7 @@ __device__ __forceinline__ int clip3i(int lo, int hi, int v) { return min(max(v,
 __device__ __forceinline__ uint2 ldg_u2(const void* p) { return __ldg(reinterpret_cast<const uint2*>(p)); }
 __device__ __forceinline__ uint4 ldg_u4(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
 
-// One launch covers slots [first_slot, first_slot + num_slots), num_slots <= MAX_BATCH; ctl.v[i] controls slot first_slot + i.
+// One launch covers `num_slots` <= MAX_BATCH grid layers; layer z works on slot first_slot + ctl.slot[z] under control word ctl.v[z].
 void launch_deblock(const Geom& g, const SlotDev* slots, int first_slot, int num_slots, const BatchCtl& ctl, int mv_mode, cudaStream_t st);
 void launch_sao(const Geom& g, const SlotDev* slots, int first_slot, int num_slots, const BatchCtl& ctl, cudaStream_t st);
 void launch_alf_luma(const Geom& g, const SlotDev* slots, int first_slot, int num_slots, const BatchCtl& ctl, bool classify_only, cudaStream_t st);

@@ -188,7 +188,7 @@ __device__ __forceinline__ uint32_t pack2(int a, int b) { return (uint32_t)(uint
 template <int MV>
 __global__ void __launch_bounds__(NTHREADS) deblock_kernel(Geom g, const SlotDev* __restrict__ slots, int first_slot, BatchCtl bc) {
   __shared__ __align__(16) Smem<MV> s;
-  const SlotDev& sd = slots[first_slot + blockIdx.z];
+  const SlotDev& sd = slots[first_slot + bc.slot[blockIdx.z]];
   const unsigned ctl = bc.v[blockIdx.z];
   const int src_b = ctl_src(ctl, 0), dst_b = ctl_dst(ctl, 0);  // deblocking starts from the uploaded picture: all planes in one buffer
   const int tid = threadIdx.x;
@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(NTHREADS) deblock_kernel(Geom g, const SlotDev
   const int max_y = (1 << g.bd_luma) - 1, max_c = (1 << g.bd_chroma) - 1;
 
   // ---- vertical edges, luma: task = 4 lines x 8 samples.  16 edge columns x 8 segment rows ----
-  {
+  if (!(g.debug & 1)) {
     const int e = tid & 15, sg = tid >> 4;
     const int q = sg * MW + 2 * e + 2;                 // Q unit in the window (x = 128 tx + 8 e -> unit 32 tx + 2 e)
     const int xg = x0 + 4 + 8 * e, yg = y0 + 4 * sg;   // first Q sample
@@ -265,7 +265,7 @@ __global__ void __launch_bounds__(NTHREADS) deblock_kernel(Geom g, const SlotDev
     }
   }
   // ---- vertical edges, chroma: task = one unit = 2 lines x 4 samples.  2 planes x 8 edge columns x 8 unit rows ----
-  {
+  if (!(g.debug & 1)) {
     const int pl = tid >> 6, k = (tid >> 3) & 7, sg = tid & 7;
     const int q = sg * MW + 4 * k + 2;               // chroma x = 64 tx + 8 k -> luma 128 tx + 16 k -> unit 32 tx + 4 k
     bool no_p, no_q;
@@ -284,7 +284,7 @@ __global__ void __launch_bounds__(NTHREADS) deblock_kernel(Geom g, const SlotDev
   __syncthreads();
 
   // ---- horizontal edges, luma: task = 4 columns x 8 rows.  4 edge rows x 32 segments (a warp = one edge row) ----
-  {
+  if (!(g.debug & 1)) {
     const int sg = tid & 31, h = tid >> 5;
     const int q = (2 * h + 1) * MW + sg + 1;         // unit column 32 tx - 1 + sg, unit row 8 ty + 2 h
     const int xg = x0 + 4 * sg, yg = y0 + 4 + 8 * h;
@@ -304,7 +304,7 @@ __global__ void __launch_bounds__(NTHREADS) deblock_kernel(Geom g, const SlotDev
     }
   }
   // ---- horizontal edges, chroma: task = one unit = 2 columns x 4 rows.  2 planes x 2 edge rows x 32 units ----
-  {
+  if (!(g.debug & 1)) {
     const int pl = tid >> 6, h = (tid >> 5) & 1, m = tid & 31;
     const int q = (4 * h + 1) * MW + m;               // chroma y = 16 ty + 8 h -> luma 32 ty + 16 h -> unit row 8 ty + 4 h
     bool no_p, no_q;

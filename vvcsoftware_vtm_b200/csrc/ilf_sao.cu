@@ -239,7 +239,7 @@ __device__ __forceinline__ void sao_strip(const Geom& g, const SlotDev& sd, unsi
 __global__ void __launch_bounds__(NTHREADS) sao_kernel(Geom g, const SlotDev* __restrict__ slots, int first_slot, BatchCtl bc,
                                                       int gy_y, int gy_c, int gx_c) {
   const unsigned ctl = bc.v[blockIdx.z];
-  const SlotDev& sd = slots[first_slot + blockIdx.z];
+  const SlotDev& sd = slots[first_slot + bc.slot[blockIdx.z]];
   // blockIdx.y enumerates row groups of Y, then Cb, then Cr.
   int by = blockIdx.y;
   if (by < gy_y) {

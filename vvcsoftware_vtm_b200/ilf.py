@@ -29,7 +29,7 @@ class IlfBand(C.Structure):
 
 
 def lib_path():
-    return os.path.join(_HERE, "libilf_b200.so")
+    return os.environ.get("ILF_B200_LIB") or os.path.join(_HERE, "libilf_b200.so")
 
 
 _LIB = None
