@@ -77,6 +77,44 @@ def synth_planes(width, height, n, seed):
     return out
 
 
+SAO_DT = np.dtype([("offset", "<i2", (3, 4)), ("type", "i1", (3,)), ("band_pos", "u1", (3,)), ("avail", "u1"), ("reserved", "u1")])
+ALF_DT = np.dtype([("luma_coeff", "<i2", (25, 13)), ("chroma_coeff", "<i2", (7,)), ("luma_filter_7x7", "<i2")])
+
+
+def all_on_sideinfo(side):
+    """Worst-case variant of the stream's side information: every CTU of every component has SAO on (the
+    five types cycled over the CTUs, small offsets) and ALF on (the stream's own filters; pictures whose slice had ALF
+    off borrow the coefficients of the stream's first ALF picture).  Deblocking information is unchanged (real)."""
+    donor = next((si for si in side if np.frombuffer(si["alf_params"].tobytes(), ALF_DT)["luma_coeff"].any()), None)
+    out = []
+    for j, si in enumerate(side):
+        d = dict(si)
+        sao = np.frombuffer(si["sao_ctus"].tobytes(), SAO_DT).copy()
+        n = sao.shape[0]
+        i = np.arange(n)
+        for c in range(3):
+            sao["type"][:, c] = (i + c + j) % 5
+            sao["band_pos"][:, c] = (i * 7 + 3 * c + j) % 32
+            for k in range(4):
+                sao["offset"][:, c, k] = ((i + 2 * k + c) % 7) - 3
+        d["sao_ctus"] = sao.view(np.uint8).reshape(n, 32)
+        alf = np.frombuffer(si["alf_params"].tobytes(), ALF_DT).copy()
+        if not alf["luma_coeff"].any():
+            if donor is not None:
+                alf = np.frombuffer(donor["alf_params"].tobytes(), ALF_DT).copy()
+            else:
+                alf["luma_coeff"][0, :, :12] = np.array([0, 1, -3, 1, 2, -4, 9, -4, 2, -6, 14, 40])[None, :]
+                alf["luma_coeff"][0, :, 12] = 512 - 2 * alf["luma_coeff"][0, :, :12].sum(axis=1)
+                alf["luma_filter_7x7"] = 1
+        cc = alf["chroma_coeff"][0].astype(np.int64)
+        if 2 * cc[:6].sum() + cc[6] != 512:  # chroma ALF was off in this slice: the stream carries no (meaningful) chroma filter
+            alf["chroma_coeff"][0] = [-2, 5, -9, 5, 3, 30, 512 - 2 * 32]
+        d["alf_params"] = np.frombuffer(alf.tobytes(), np.uint8)
+        d["alf_ctu_enable"] = np.ones_like(si["alf_ctu_enable"])
+        out.append(d)
+    return out
+
+
 class ClockSampler(threading.Thread):
     """Samples SM clock and throttle reasons of one GPU through NVML while the timed region runs."""
 
@@ -266,31 +304,41 @@ def run_b200(args, wl):
         torch.cuda.synchronize()
 
     # ---- device-resident throughput ----
-    for _ in range(max(args.warmup, 3)):
-        f.run(0, B, 7)
-    f.sync()
-    f.set_timing(True)
-    clocks = ClockSampler(local)
-    l0 = f.launch_count()
-    barrier()
-    clocks.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with torch.cuda.stream(stream):
-        ev0.record(stream)
-        for _ in range(args.steps):
+    def measure(side_set, steps):
+        """Time `steps` chain passes over the B resident pictures with the given side information (CUDA events on the
+        library's compute stream, barrier + synchronize on both sides, max over ranks)."""
+        for s in range(B):
+            set_side(s, side_set[s % len(side_set)])
+        f.sync()
+        for _ in range(max(args.warmup, 3)):
             f.run(0, B, 7)
-        ev1.record(stream)
-    barrier()
-    ms_total = ev0.elapsed_time(ev1)
+        f.sync()
+        f.set_timing(True)
+        l0 = f.launch_count()
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            ev0.record(stream)
+            for _ in range(steps):
+                f.run(0, B, 7)
+            ev1.record(stream)
+        barrier()
+        ms = ev0.elapsed_time(ev1)
+        n_launch = f.launch_count() - l0
+        kt = f.kernel_times()
+        f.set_timing(False)
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), kt, n_launch
+
+    clocks = ClockSampler(local, period=0.01)
+    clocks.start()
+    ms_on, kt_on, _ = measure(all_on_sideinfo(side), args.steps)      # worst case: every CTU filtered by every stage
+    ms_total, ktimes, launches = measure(side, args.steps)            # the stream's own decisions (headline)
     clk = clocks.finish()
-    launches = f.launch_count() - l0
-    ktimes = f.kernel_times()
-    f.set_timing(False)
-    t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
     value = world * B * args.steps * mpx / (ms_total * 1e-3)
+    value_on = world * B * args.steps * mpx / (ms_on * 1e-3)
 
     # ---- end to end through the public API: host planes + side information in, filtered host planes out ----
     # Host buffers are page-locked (what a host integration does with its picture buffers: ilf_host_alloc /
@@ -360,14 +408,27 @@ def run_b200(args, wl):
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-        per_kernel = {}
-        for k, (ms, n, nbytes) in ktimes.items():
-            if n:
-                # algorithmic bytes as counted by the library: 2 B x (read + write) x samples of the planes the launches processed
-                per_kernel[k] = {"avg_ms": round(ms / n, 4), "launches": n, "algo_mb_per_launch": round(nbytes / n / 1e6, 1), "algo_gbs": round(nbytes / (ms * 1e-3) / 1e9, 1)}
+        def kernel_table(kt):
+            tab = {}
+            for k, (ms, n, nbytes) in kt.items():
+                if n:
+                    # algorithmic bytes as counted by the library: 2 B x (read + write) x samples of the planes the launches processed
+                    tab[k] = {"avg_ms": round(ms / n, 4), "launches": n, "algo_mb_per_launch": round(nbytes / n / 1e6, 1), "algo_gbs": round(nbytes / (ms * 1e-3) / 1e9, 1),
+                              "frac": round(nbytes / (ms * 1e-3) / 1e9 / peak, 4)}
+            return tab
+
+        def chain(kt, ms_region):
+            """Whole chain against the roofline: bytes the launched kernels really had to move / time of the timed region."""
+            nbytes = sum(v[2] for v in kt.values())
+            gbs = nbytes / (ms_region * 1e-3) / 1e9
+            return {"algo_mb_per_step": round(nbytes / args.steps / 1e6, 1), "bytes_per_pixel": round(nbytes / (args.steps * B * mpx * 1e6), 2),
+                    "gbs": round(gbs, 1), "frac": round(gbs / peak, 4)}
+
+        per_kernel = kernel_table(ktimes)
         dom = max(per_kernel, key=lambda k: per_kernel[k]["avg_ms"])
         ach = per_kernel[dom]["algo_gbs"]
-        chain_gbs = CHAIN_BYTES_PER_PIXEL * value * 1e6 / 1e9 / world
+        pk_on = kernel_table(kt_on)
+        dom_on = max(pk_on, key=lambda k: pk_on[k]["avg_ms"])
         cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count()
         cpu = cpu_baseline(wl, cores, side, planes) if (world == 1 and not args.no_cpu_baseline) else None
         line = {"metric": "deblock+SAO+ALF Mpixel/s", "value": round(value, 1), "unit": "Mpixel/s", "n_gpus": world, "steps": args.steps,
@@ -377,7 +438,10 @@ def run_b200(args, wl):
                            "planes": "synthetic texture + 8x8 blockiness", "l2": f"working set {B * 2 * h2d / 1e6:.0f} MB per stage > 126 MB L2 (inputs larger than L2, no flush)",
                            "parallelism": f"independent pictures, {world} GPU(s), no collective"},
                 "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4), "traffic": None,
-                             "peak_source": peak_src, "chain_algo_gbs_per_gpu": round(chain_gbs, 1), "chain_frac": round(chain_gbs / peak, 4), "per_kernel": per_kernel},
+                             "peak_source": peak_src, "chain": chain(ktimes, ms_total), "per_kernel": per_kernel,
+                             "all_on": {"what": "same pictures and deblocking information, SAO and ALF forced on for every CTU of every component (18 B/pixel)",
+                                        "value": round(value_on, 1), "unit": "Mpixel/s", "ms_per_step": round(ms_on / args.steps, 4), "kernel": dom_on,
+                                        "chain": chain(kt_on, ms_on), "per_kernel": pk_on}},
                 "cpu_baseline": cpu,
                 "e2e": {"value": round(e2e_value, 1), "unit": "Mpixel/s", "h2d_bytes_per_step": B * h2d + side_b, "d2h_bytes_per_step": B * d2h,
                         "steps": e2e_steps, "path": "per picture InLoopFilter.upload + set_deblock_info/set_sao_params/set_alf_params + run + download_async (C ABI ilf_upload / ilf_set_* / ilf_run / ilf_download_async / ilf_wait), page-locked host buffers, slots cycled"},
@@ -391,7 +455,7 @@ def run_b200(args, wl):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=None, choices=list(WORKLOADS))

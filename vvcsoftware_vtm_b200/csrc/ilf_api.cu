@@ -98,11 +98,44 @@ int check_slot(ilf_ctx* ctx, int slot) {
   return ILF_OK;
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point lookup: the library does not link libcuda, so it still
+// loads (and exports its symbols) on a machine without a driver.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    cudaDriverEntryPointQueryResult q;
+    void* p = nullptr;
+    if (cudaGetDriverEntryPointByVersion("cuTensorMapEncodeTiled", &p, 12000, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+      cudaGetLastError();
+      return nullptr;
+    }
+    fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// Tensor (x, y, z) over `base`: w x h elements of `elem_bytes`, rows `pitch_bytes` apart, `nz` layers `layer_bytes` apart; box bw x bh x 1.
+int make_map3(ilf_ctx* ctx, CUtensorMap* out, CUtensorMapDataType dt, void* base, int w, int h, int nz, size_t pitch_bytes, size_t layer_bytes, int bw, int bh);
+
 int16_t* plane_ptr(const ilf_ctx* ctx, const Slot& s, int buf, int plane) {
   int16_t* p = s.planes + (size_t)buf * ctx->buf_elems;
   if (plane >= 1) p += ctx->plane_y;
   if (plane == 2) p += ctx->plane_c;
   return p;
+}
+
+int make_map3(ilf_ctx* ctx, CUtensorMap* out, CUtensorMapDataType dt, void* base, int w, int h, int nz, size_t pitch_bytes, size_t layer_bytes, int bw, int bh) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) return fail(ctx, ILF_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+  const cuuint64_t dims[3] = {(cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)nz};
+  const cuuint64_t strides[2] = {(cuuint64_t)pitch_bytes, (cuuint64_t)layer_bytes};
+  const cuuint32_t box[3] = {(cuuint32_t)bw, (cuuint32_t)bh, 1}, estr[3] = {1, 1, 1};
+  const CUresult r = enc(out, dt, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(ctx, ILF_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for a %dx%dx%d tensor, box %dx%d", (int)r, w, h, nz, bw, bh);
+  return ILF_OK;
 }
 
 // The slot descriptor travels on the upload stream like the side information it points to.
@@ -224,6 +257,12 @@ int create_impl(ilf_ctx** out, const ilf_config* cfg, const ilf_band* band) {
     for (int b = 0; b < 3; b++)
       for (int p = 0; p < 3; p++) s.dev.buf[b][p] = plane_ptr(ctx, s, b, p);
     s.dev.alf_class = s.alf_class;
+    for (int p = 0; p < 3; p++) {
+      const int pw = p ? cfg->width / 2 : cfg->width, ph = p ? g.rows / 2 : g.rows, pitch = p ? g.pitch_c : g.pitch_y;
+      if (int rc = make_map3(ctx, &s.dev.tm_sao[p], CU_TENSOR_MAP_DATA_TYPE_UINT16, plane_ptr(ctx, s, 0, p), pw, ph, 3, (size_t)pitch * 2, ctx->buf_elems * 2, RING_TILE_W,
+                             SAO_BAND_ROWS + 2))
+        return rc;
+    }
     if (int rc = push_desc(ctx, i)) return rc;
   }
   CU(ctx, cudaStreamSynchronize(ctx->s_up));

@@ -1,5 +1,6 @@
 // ilf_common.cuh -- shared device-side definitions of libilf_b200 (sm_100a).
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -23,7 +24,14 @@ struct Geom {
 
 // Per-slot device pointers; an array of these lives in device memory (one entry per slot) and kernels index
 // it with first_slot + blockIdx.z, so one launch covers a batch of pictures.
-struct SlotDev {
+// Tile geometry of the band-walking kernels (ilf_ring.cuh): the TMA box sizes are baked into the tensor maps that
+// ilf_create encodes, so they live here.
+constexpr int RING_TILE_W = 128;   // samples per tile row, all planes (256-byte box rows)
+constexpr int SAO_BAND_ROWS = 32;  // rows a SAO CTA owns; the box adds one halo row above and below
+
+struct alignas(64) SlotDev {
+  // TMA descriptors of the slot's planes, tensor (x, y, buffer): dims (plane width, held rows, 3)
+  CUtensorMap tm_sao[3];    // box RING_TILE_W x (SAO_BAND_ROWS + 2)
   int16_t* buf[3][3];       // [buffer: 0 = input, 1, 2 = work][plane]
   const uint32_t* info;     // deblock grid, luma tree
   const uint32_t* info_c;   // chroma tree layer or nullptr

@@ -4,14 +4,18 @@
 // offsetCTU :510-562, offsetBlock :292-508).  The source is the whole deblocked picture (the reference copies it to
 // m_tempBuf, :587), so every sample is independent.
 //
-// Work split: one thread owns a strip of 8 samples x 8 rows (one int16x8 vector per row).  It issues all of its
-// global loads first (8 rows + the row above and below for the vertical classes: 160 bytes in flight per thread),
-// then filters two samples per instruction (ilf_packed.cuh) and stores 8 vectors.  A strip lies inside one CTU, so
-// the CTU's parameters are fetched once per thread; the lanes of a warp that share a row group span exactly one CTU
-// width at the 128x128 CTU size (16 lanes luma, 8 lanes chroma), so a warp does not diverge on the SAO type.
-// Horizontal neighbours come from the adjacent lane by shuffle; the first/last lane of a row group fetches one
-// sample per row from the neighbouring CTU.  CTUs with SAO off are copied through; planes whose SAO is off for the
-// whole picture are not touched at all (BatchCtl skip bit).
+// Data movement: band walking over a TMA ring (ilf_ring.cuh).  A CTA owns a band of 32 rows of one plane (or a
+// horizontal segment of it when few pictures are in the batch) and walks it in tiles of 128 samples; the TMA unit
+// fetches each tile with one halo row above and below (box 128 x 34, always 256-byte aligned rows) into a ring of
+// shared-memory stages, several tiles ahead of the arithmetic.  The left / right neighbours of a tile's first / last
+// column are in the neighbouring tiles of the ring.  Nothing is read twice horizontally, 6 % vertically.
+//
+// Arithmetic: a thread owns 8 samples x 4 rows of the tile: it reads its rows and the two neighbouring rows as int16x8
+// vectors from shared memory, filters two samples per instruction (ilf_packed.cuh) and stores int16x8 vectors (16-byte
+// aligned) to the destination plane.  A strip lies inside one CTU, so the CTU's parameters are fetched once per
+// thread and tile; a warp spans one 128-sample CTU width, so it does not diverge on the SAO type at CTU size 128.
+// CTUs with SAO off are copied through; planes whose SAO is off for the whole picture are not touched at all
+// (BatchCtl skip bit).
 //
 // The row/column special cases of offsetBlock (:308-487) are the statement "an edge-offset sample is modified iff both
 // neighbours along the class direction are inside the CTU block or inside a neighbouring CTU whose availability flag
@@ -19,17 +23,24 @@
 // column and the columns in between, and only for CTUs that have an unavailable neighbour.
 #include "ilf_common.cuh"
 #include "ilf_packed.cuh"
+#include "ilf_ring.cuh"
 
 namespace ilf {
 namespace {
 
-constexpr int R = 8;          // rows per strip
+constexpr int R = 4;                       // rows per thread and tile
+constexpr int TW = RING_TILE_W;            // tile width (samples)
+constexpr int BR = SAO_BAND_ROWS;          // rows of a band
+constexpr int SR = BR + 2;                 // staged rows: one halo row above and below
+constexpr int STAGES = 6;                  // ring depth: previous, current, next tile + 3 tiles in flight
+constexpr int STAGE_BYTES = TW * SR * 2;   // 8704
 constexpr int NTHREADS = 128;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGES * 8;
 
 struct Row { uint32_t v[4]; };  // 8 samples
 
 __device__ __forceinline__ Row ld_row(const int16_t* p) {
-  const uint4 r = ldg_u4(p);
+  const uint4 r = *reinterpret_cast<const uint4*>(p);
   Row o; o.v[0] = r.x; o.v[1] = r.y; o.v[2] = r.z; o.v[3] = r.w;
   return o;
 }
@@ -59,19 +70,17 @@ struct EoCtx {
 };
 
 // Edge offset of the strip's rows for one class: first neighbour a = (x - SX, y - SY), second b = (x + SX, y + SY).
-// sft[0] = shifted row above the strip, sft[1 + r] = shifted row r, sft[nrows + 1] = shifted row below.
+// v[0] = row above the strip, v[1 + r] = row r, v[R + 1] = row below; sft[] = the same rows shifted by one sample.
 template <int SX, int SY>
-__device__ __forceinline__ void eo_rows(const EoCtx& e, const Row (&c)[R], const Row& above, const Row& below, const Shifted (&sft)[R + 2],
-                                        int16_t* __restrict__ out, int pitch) {
+__device__ __forceinline__ void eo_rows(const EoCtx& e, const Row (&v)[R + 2], const Shifted (&sft)[R + 2], int16_t* __restrict__ out, int pitch) {
 #pragma unroll
   for (int r = 0; r < R; r++) {
     if (r >= e.nrows) break;
+    const Row& c = v[r + 1];
     uint32_t a[4], b[4];
     if (SX == 0) {
-      const Row& ra = r == 0 ? above : c[r > 0 ? r - 1 : 0];
-      const Row& rb = (r + 1 < e.nrows) ? c[r + 1 < R ? r + 1 : R - 1] : below;
 #pragma unroll
-      for (int k = 0; k < 4; k++) { a[k] = ra.v[k]; b[k] = rb.v[k]; }
+      for (int k = 0; k < 4; k++) { a[k] = v[r].v[k]; b[k] = v[r + 2].v[k]; }
     } else {
       constexpr int ia_off = SY ? 0 : 1, ib_off = SY ? 2 : 1;
 #pragma unroll
@@ -82,7 +91,7 @@ __device__ __forceinline__ void eo_rows(const EoCtx& e, const Row (&c)[R], const
     }
     Row o;
 #pragma unroll
-    for (int k = 0; k < 4; k++) o.v[k] = pk::sao_apply2(c[r].v[k], pk::sao_eo_index2(c[r].v[k], a[k], b[k]), e.lut_lo, e.lut_hi, e.maxv);
+    for (int k = 0; k < 4; k++) o.v[k] = pk::sao_apply2(c.v[k], pk::sao_eo_index2(c.v[k], a[k], b[k]), e.lut_lo, e.lut_hi, e.maxv);
     if (e.need_mask) {
       const int gy = e.gy0 + r;
       const bool at_top = gy == e.ctu_y0, at_bottom = gy == e.last_row;
@@ -96,99 +105,37 @@ __device__ __forceinline__ void eo_rows(const EoCtx& e, const Row (&c)[R], const
         const bool l0 = e.rj == 2 * k ? ok_last : k0;
         const bool l1 = e.rj == 2 * k + 1 ? ok_last : ok_mid;
         const uint32_t m = (l0 ? 0xFFFFu : 0u) | (l1 ? 0xFFFF0000u : 0u);
-        o.v[k] = (o.v[k] & m) | (c[r].v[k] & ~m);
+        o.v[k] = (o.v[k] & m) | (c.v[k] & ~m);
       }
     }
     st_row(out + (size_t)r * pitch, o);
   }
 }
 
-template <int LPR>
-__device__ __forceinline__ void sao_strip(const Geom& g, const SlotDev& sd, unsigned ctl, int plane, int bx, int by) {
-  constexpr int RG = 32 / LPR;  // row groups per warp
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int seg_lane = lane % LPR, rgrp = lane / LPR;
+// One tile of the walk: `cur` is the tile's stage (SR rows x TW samples), `prev` / `next` the neighbouring tiles' stages (or
+// nullptr at the picture border, where the availability flags already exclude the missing neighbour).
+__device__ __forceinline__ void sao_tile(const Geom& g, const SlotDev& sd, int plane, int16_t* __restrict__ dst, int tx, int by0, const int16_t* cur,
+                                         const int16_t* prev, const int16_t* next) {
+  const int k = threadIdx.x & 15, rg = threadIdx.x >> 4;
   const int sh = plane ? 1 : 0;
   const int pw = g.width >> sh, ph_local = g.rows >> sh, ph_global = g.height >> sh;
   const int pitch = plane ? g.pitch_c : g.pitch_y;
-  const int x0 = (bx * LPR + seg_lane) * 8;
-  const int y0 = ((by * (NTHREADS / 32) + warp) * RG + rgrp) * R;  // local row of the strip's first row
-  const bool in = x0 < pw && y0 < ph_local;
-  const unsigned full = 0xffffffffu;
-
-  const int16_t* __restrict__ src = sd.buf[ctl_src(ctl, plane)][plane];
-  int16_t* __restrict__ dst = sd.buf[ctl_dst(ctl, plane)][plane];
-  const int nrows = in ? min(R, ph_local - y0) : 0;
+  const int x0 = tx * TW + 8 * k, y0 = by0 + R * rg;  // local row of the strip's first row
+  if (x0 >= pw || y0 >= ph_local) return;
+  const int nrows = min(R, ph_local - y0);
   const int gy0 = y0 + (g.row0 >> sh);  // picture row
   const int ctu_log2 = g.ctu_log2 - sh, ctu_sz = 1 << ctu_log2;
+  const int cx = x0 >> ctu_log2, cy = gy0 >> ctu_log2;
+  const uint4* __restrict__ prm = reinterpret_cast<const uint4*>(sd.sao + (size_t)cy * g.ctus_w + cx);
+  const uint4 pa = __ldg(prm), pb = __ldg(prm + 1);
+  // ilf_sao_ctu: offset[3][4] int16 (24 bytes), type[3] int8 at byte 24, band_pos[3] at 27, avail at 30
+  const int type = (int)(int8_t)((plane == 0 ? pb.z : plane == 1 ? pb.z >> 8 : pb.z >> 16) & 0xFF);
+  const int16_t* base = cur + (R * rg) * TW + 8 * k;  // staged row 0 of the strip = the row above it
+  int16_t* out = dst + (size_t)y0 * pitch + x0;
 
-  int type = ILF_SAO_OFF;
-  uint4 pa = make_uint4(0, 0, 0, 0), pb = pa;
-  int cx = 0, cy = 0;
-  if (in) {
-    cx = x0 >> ctu_log2; cy = gy0 >> ctu_log2;
-    const uint4* __restrict__ p = reinterpret_cast<const uint4*>(sd.sao + (size_t)cy * g.ctus_w + cx);
-    pa = __ldg(p); pb = __ldg(p + 1);
-    // ilf_sao_ctu: offset[3][4] int16 (24 bytes), type[3] int8 at byte 24, band_pos[3] at 27, avail at 30
-    type = (int)(int8_t)((plane == 0 ? pb.z : plane == 1 ? pb.z >> 8 : pb.z >> 16) & 0xFF);
-  }
-  const bool vert = type == ILF_SAO_EO_90 || type == ILF_SAO_EO_135 || type == ILF_SAO_EO_45;
-  const bool horz = type == ILF_SAO_EO_0 || type == ILF_SAO_EO_135 || type == ILF_SAO_EO_45;
-
-  // ---- all loads first ----
-  const int16_t* base = src + (size_t)y0 * pitch + x0;
-  Row c[R];
+  if (type == ILF_SAO_OFF) {  // plain copy
 #pragma unroll
-  for (int r = 0; r < R; r++) if (r < nrows) c[r] = ld_row(base + (ptrdiff_t)r * pitch);
-  Row above, below;
-  // a lane's rows above/below also feed its neighbours' diagonal taps, so load them when any lane of the warp needs them
-  // (the lanes of a row group share one CTU and one type at the 128x128 CTU size; smaller CTUs mix types in a warp)
-  const bool any_vert = __any_sync(full, vert);
-  if (any_vert && in) {
-    above = ld_row(base - (y0 > 0 ? pitch : 0));
-    below = ld_row(base + (ptrdiff_t)(y0 + nrows < ph_local ? nrows : nrows - 1) * pitch);
-  }
-  // halo samples of the first / last lane of a row group (neighbouring CTU column), rows -1 .. R
-  uint32_t hl[R + 2], hr[R + 2];
-  const bool any_horz = __any_sync(full, horz);
-  if (any_horz) {
-    const bool edge_l = seg_lane == 0 && horz && x0 > 0, edge_r = seg_lane == LPR - 1 && horz && x0 + 8 < pw;
-#pragma unroll
-    for (int r = -1; r <= R; r++) {
-      hl[r + 1] = 0; hr[r + 1] = 0;
-      const bool row_ok = (r >= 0 && r < nrows) || (vert && (r == -1 ? y0 > 0 : (r == nrows && y0 + nrows < ph_local)));  // `horz && vert` lanes only
-      if (edge_l && row_ok) hl[r + 1] = (uint16_t)__ldg(base + (ptrdiff_t)r * pitch - 1);
-      if (edge_r && row_ok) hr[r + 1] = (uint16_t)__ldg(base + (ptrdiff_t)r * pitch + 8);
-    }
-  }
-  if (__all_sync(full, !in)) return;
-
-  if (type == ILF_SAO_OFF && !any_horz) {  // plain copy
-#pragma unroll
-    for (int r = 0; r < R; r++) if (r < nrows) st_row(dst + (size_t)(y0 + r) * pitch + x0, c[r]);
-    return;
-  }
-
-  // ---- neighbour exchange inside the row group (all lanes take part) ----
-  // rows: index 0 = above, 1..R = c[0..R-1], R+1 = below (the row after the strip's last row)
-  Shifted sft[R + 2];
-  if (any_horz) {
-#pragma unroll
-    for (int i = 0; i < R + 2; i++) {
-      Row rr;
-      if (i == 0) rr = above;
-      else if (i == R + 1) rr = below;
-      else rr = c[i - 1];
-      if (i >= 1 && i <= R && i - 1 == nrows) rr = below;  // short strip at the picture bottom: "below" follows the last valid row
-      const uint32_t lft = __shfl_up_sync(full, rr.v[3] >> 16, 1, LPR);
-      const uint32_t rgt = __shfl_down_sync(full, rr.v[0] & 0xFFFFu, 1, LPR);
-      sft[i] = shift_row(rr, seg_lane == 0 ? hl[i] : lft, seg_lane == LPR - 1 ? hr[i] : rgt);
-    }
-  }
-  if (!in) return;
-  if (type == ILF_SAO_OFF) {
-#pragma unroll
-    for (int r = 0; r < R; r++) if (r < nrows) st_row(dst + (size_t)(y0 + r) * pitch + x0, c[r]);
+    for (int r = 0; r < R; r++) if (r < nrows) st_row(out + (size_t)r * pitch, ld_row(base + (r + 1) * TW));
     return;
   }
 
@@ -207,12 +154,28 @@ __device__ __forceinline__ void sao_strip(const Geom& g, const SlotDev& sd, unsi
 #pragma unroll
     for (int r = 0; r < R; r++) {
       if (r >= nrows) break;
+      const Row c = ld_row(base + (r + 1) * TW);
       Row o;
 #pragma unroll
-      for (int k = 0; k < 4; k++) o.v[k] = pk::sao_apply2(c[r].v[k], pk::sao_bo_index2(c[r].v[k], bd - 5, nband), lut_lo, lut_hi, maxv);
-      st_row(dst + (size_t)(y0 + r) * pitch + x0, o);
+      for (int q = 0; q < 4; q++) o.v[q] = pk::sao_apply2(c.v[q], pk::sao_bo_index2(c.v[q], bd - 5, nband), lut_lo, lut_hi, maxv);
+      st_row(out + (size_t)r * pitch, o);
     }
     return;
+  }
+
+  // ---- edge offset: the strip's rows, the rows above and below, and (except for the vertical class) their shifted copies ----
+  Row v[R + 2];
+  Shifted sft[R + 2];
+#pragma unroll
+  for (int i = 0; i < R + 2; i++) v[i] = ld_row(base + i * TW);
+  if (type != ILF_SAO_EO_90) {
+    const int16_t* lp = k > 0 ? base - 1 : (prev ? prev + (R * rg) * TW + TW - 1 : nullptr);
+    const int16_t* rp = k < 15 ? base + 8 : (next ? next + (R * rg) * TW : nullptr);
+#pragma unroll
+    for (int i = 0; i < R + 2; i++) {
+      const uint32_t lft = lp ? (uint16_t)lp[i * TW] : 0u, rgt = rp ? (uint16_t)rp[i * TW] : 0u;
+      sft[i] = shift_row(v[i], lft, rgt);
+    }
   }
 
   EoCtx e;
@@ -229,39 +192,70 @@ __device__ __forceinline__ void sao_strip(const Geom& g, const SlotDev& sd, unsi
   e.last_row = min(e.ctu_y0 + ctu_sz, ph_global) - 1;
   e.need_mask = avail != 0xFFu;
   e.gy0 = gy0; e.nrows = nrows;
-  int16_t* out = dst + (size_t)y0 * pitch + x0;
-  if (type == ILF_SAO_EO_0) eo_rows<1, 0>(e, c, above, below, sft, out, pitch);
-  else if (type == ILF_SAO_EO_90) eo_rows<0, 1>(e, c, above, below, sft, out, pitch);
-  else if (type == ILF_SAO_EO_135) eo_rows<1, 1>(e, c, above, below, sft, out, pitch);
-  else eo_rows<-1, 1>(e, c, above, below, sft, out, pitch);
+  if (type == ILF_SAO_EO_0) eo_rows<1, 0>(e, v, sft, out, pitch);
+  else if (type == ILF_SAO_EO_90) eo_rows<0, 1>(e, v, sft, out, pitch);
+  else if (type == ILF_SAO_EO_135) eo_rows<1, 1>(e, v, sft, out, pitch);
+  else eo_rows<-1, 1>(e, v, sft, out, pitch);
 }
 
-__global__ void __launch_bounds__(NTHREADS) sao_kernel(Geom g, const SlotDev* __restrict__ slots, int first_slot, BatchCtl bc,
-                                                      int gy_y, int gy_c, int gx_c) {
+__global__ void __launch_bounds__(NTHREADS) sao_kernel(Geom g, const SlotDev* __restrict__ slots, int first_slot, BatchCtl bc, int bands_y, int bands_c, int nseg) {
+  extern __shared__ __align__(128) unsigned char smem[];
   const unsigned ctl = bc.v[blockIdx.z];
   const SlotDev& sd = slots[first_slot + bc.slot[blockIdx.z]];
-  // blockIdx.y enumerates row groups of Y, then Cb, then Cr.
-  int by = blockIdx.y;
-  if (by < gy_y) {
-    if (ctl_skip(ctl, 0)) return;
-    sao_strip<16>(g, sd, ctl, 0, blockIdx.x, by);
-  } else {
-    by -= gy_y;
-    const int plane = by < gy_c ? 1 : 2;
-    if (plane == 2) by -= gy_c;
-    if (ctl_skip(ctl, plane) || (int)blockIdx.x >= gx_c) return;
-    sao_strip<8>(g, sd, ctl, plane, blockIdx.x, by);
+  // blockIdx.y enumerates the bands of Y, then Cb, then Cr; blockIdx.x the horizontal segments of a band
+  int band = blockIdx.y, plane = 0;
+  if (band >= bands_y) { band -= bands_y; plane = 1; if (band >= bands_c) { band -= bands_c; plane = 2; } }
+  if (ctl_skip(ctl, plane)) return;
+  const int pw = plane ? g.width >> 1 : g.width;
+  const int ntx = (pw + TW - 1) / TW;
+  const int ta = (int)blockIdx.x * ntx / nseg, tb = ((int)blockIdx.x + 1) * ntx / nseg;  // this CTA's tiles [ta, tb)
+  if (ta >= tb) return;
+  ring::Walk<STAGES> walk;
+  walk.first = max(ta - 1, 0); walk.last = min(tb, ntx - 1);  // tiles the walk loads: its own and one neighbour on each side
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  const int tid = threadIdx.x;
+  const int by0 = band * BR;
+  const int src_buf = ctl_src(ctl, plane);
+  int16_t* __restrict__ dst = sd.buf[ctl_dst(ctl, plane)][plane];
+  const CUtensorMap* map = &sd.tm_sao[plane];
+  auto stage_ptr = [&](int t) { return reinterpret_cast<int16_t*>(smem + walk.stage(t) * STAGE_BYTES); };
+  auto issue = [&](int t) {
+    uint64_t* bar = &full[walk.stage(t)];
+    ring::mbar_expect_tx(bar, STAGE_BYTES);
+    ring::tma_load_3d(stage_ptr(t), map, bar, t * TW, by0 - 1, src_buf);
+  };
+  if (tid == 0) {
+    for (int i = 0; i < STAGES; i++) ring::mbar_init(&full[i], 1);
+    ring::mbar_init_fence();
+  }
+  __syncthreads();
+  if (tid == 0)
+    for (int t = walk.first; t <= walk.last && t < walk.first + STAGES; t++) issue(t);
+  for (int tx = ta; tx < tb; tx++) {
+    if (tx == ta) {
+      if (tx > walk.first) ring::mbar_wait(&full[walk.stage(tx - 1)], walk.parity(tx - 1));
+      ring::mbar_wait(&full[walk.stage(tx)], walk.parity(tx));
+    }
+    if (tx + 1 <= walk.last) ring::mbar_wait(&full[walk.stage(tx + 1)], walk.parity(tx + 1));
+    sao_tile(g, sd, plane, dst, tx, by0, stage_ptr(tx), tx > 0 ? stage_ptr(tx - 1) : nullptr, tx + 1 < ntx ? stage_ptr(tx + 1) : nullptr);
+    __syncthreads();  // every thread is done with tile tx - 1: its stage can be refilled
+    if (tid == 0 && tx - 1 >= walk.first && tx - 1 + STAGES <= walk.last) issue(tx - 1 + STAGES);
   }
 }
 
 }  // namespace
 
 void launch_sao(const Geom& g, const SlotDev* slots, int first_slot, int num_slots, const BatchCtl& ctl, cudaStream_t st) {
-  // luma CTA: 128 samples x 64 rows (4 warps x 2 row groups x 8 rows); chroma CTA: 64 samples x 128 rows
-  const int gx_y = (g.width + 127) / 128, gy_y = (g.rows + 63) / 64;
-  const int gx_c = (g.width / 2 + 63) / 64, gy_c = (g.rows / 2 + 127) / 128;
-  dim3 grid(gx_y > gx_c ? gx_y : gx_c, gy_y + 2 * gy_c, num_slots);
-  sao_kernel<<<grid, NTHREADS, 0, st>>>(g, slots, first_slot, ctl, gy_y, gy_c, gx_c);
+  static bool attr_set = false;
+  if (!attr_set) { cudaFuncSetAttribute(sao_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES); attr_set = true; }
+  const int bands_y = (g.rows + BR - 1) / BR, bands_c = (g.rows / 2 + BR - 1) / BR;
+  // enough CTAs to fill the machine when the batch is small: split bands into horizontal segments
+  const int ntx = (g.width + TW - 1) / TW;
+  const int bands = (bands_y + 2 * bands_c) * num_slots;
+  int nseg = (148 * 4 + bands - 1) / bands;
+  nseg = nseg < 1 ? 1 : (nseg > ntx ? ntx : nseg);
+  dim3 grid(nseg, bands_y + 2 * bands_c, num_slots);
+  sao_kernel<<<grid, NTHREADS, SMEM_BYTES, st>>>(g, slots, first_slot, ctl, bands_y, bands_c, nseg);
 }
 
 }  // namespace ilf
