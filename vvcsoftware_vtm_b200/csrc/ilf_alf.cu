@@ -3,36 +3,79 @@
 // Replaces AdaptiveLoopFilter::ALFProcess after coefficient reconstruction (AdaptiveLoopFilter.cpp:89-138):
 //   deriveClassificationBlk :292-463   Laplacian activity/direction -> classIdx (0..24), transposeIdx (0..3)
 //   filterBlk<7/5>          :465-650   point-symmetric diamond FIR, (sum + 256) >> 9, clip to [0, 2^bd - 1]
-// The source is the whole SAO'd picture padded by 3 replicated samples (:90-92, Buffer.h:433-465); here the
-// padding is coordinate clamping while a tile + 3-sample halo is staged in shared memory.  CTUs whose enable
+// The source is the whole SAO'd picture padded by 3 replicated samples (:90-92, Buffer.h:433-465).  CTUs whose enable
 // flag is 0 are copied through (the stage reads one buffer and writes the other).
 //
-// Luma: one CTA (256 threads) per 128x32 tile; a thread owns one 4x4 block from classification to output.
-//   phase 1  stage the tile + 3-sample halo in shared memory as int32 (38 rows x 136 columns), all global loads first
-//   phase 2  1-D Laplacians of every sample, summed per 2x2 cell (two 16-bit sums per word); a task = 4 rows x 8 columns
+// Data movement (both kernels): band walking over a TMA ring (ilf_ring.cuh).  A CTA owns a band of 32 rows of a plane and
+// walks it in tiles of 128 samples; the TMA unit delivers each tile with its halo rows (box 128 x 38 luma, 128 x 36
+// chroma) into a ring of shared-memory stages ahead of the arithmetic.  Per tile the CTA builds a work tile: the staged
+// tile plus 4 halo columns from the neighbouring tiles of the ring, with the border padding applied (build_work_tile).
+//
+// Luma, per tile (256 threads, one thread = one 4x4 block from classification to output):
+//   phase 1  work tile (int16, two samples per 32-bit word)
+//   phase 2  1-D Laplacians two samples per instruction (|2c - a - b| = max(2c - s, s - 2c) with VIADD.16x2 / VIADDMNMX.S16x2),
+//            summed per 2x2 cell; a task walks one word column over 12 rows with a rolling 3-row window
 //   phase 3  each thread sums the 4x4 cells of its block's 8x8 window and derives class + transpose (kept in a register)
 //   phase 4  each thread filters its block with the (class, transpose) coefficient row of the per-picture table that
-//            ilf_set_alf_params precomputed (SlotDev::alf_coef), and stores four int16x4 rows
-// Tiles whose blocks are all in CTUs with ALF off are copied through without touching shared memory.
+//            ilf_set_alf_params precomputed (SlotDev::alf_coef): the 10 window rows are read once from shared memory
+//            (3 x 8 bytes each), unpacked once into registers and shared by the block's four output rows
+// Tiles whose blocks are all in CTUs with ALF off are copied through without classification.
 #include "ilf_common.cuh"
+#include "ilf_ring.cuh"
 
 namespace ilf {
 namespace {
 
-constexpr int LT_W = 128, LT_H = 32;         // luma tile
-constexpr int LS_W = LT_W + 8;               // staged columns: x0-4 .. x0+131
-constexpr int LS_P = LS_W + 4;               // smem pitch in samples (phase 2 reads one aligned int4 past the staged columns)
-constexpr int LS_H = LT_H + 6;               // staged rows:    y0-3 .. y0+34
-constexpr int CELL_W = LT_W / 2 + 2, CELL_H = LT_H / 2 + 2;  // 66 x 18 cells of 2x2 samples, first cell at (x0-2, y0-2)
+// ---- band walking (ilf_ring.cuh): shared by the chroma kernel (and the luma kernel) ----
+constexpr int TW = RING_TILE_W;     // tile width in samples
+constexpr int BR = ALF_BAND_ROWS;   // rows of a band
+constexpr int WP = TW + 16;         // work-tile pitch in samples: [8: left halo slot][128][8: right halo slot], 288-byte rows
+constexpr int WX0 = 8;              // work-tile column of the tile's first sample
+constexpr int RING_STAGES = 4;      // the tile being filtered + 3 tiles in flight
+
+// A stage of the ring IS the work tile: the TMA box starts 8 samples left of the tile (16-byte aligned) and is WP wide, so
+// it carries the tile's horizontal halo with it; these kernels are instruction-bound, the 12.5 % of re-read columns come
+// out of L2 and cost nothing.  Out-of-picture samples arrive as zeros; the filters read the picture "padded by
+// replication" (AdaptiveLoopFilter.cpp:90-92, Buffer.h:433-465), so tiles that touch a picture border repeat the nearest
+// picture sample into the halo: first along the rows (left / right border), then whole rows (top / bottom border).
+// vw = valid samples of this tile's rows, ytop = plane row of staged row 0, ph = plane rows.  CTA-uniform; every thread
+// of the CTA must call it.
+template <int SR, int HALO, int NTHREADS>
+__device__ __forceinline__ void pad_borders(int16_t* __restrict__ W, bool left, bool right, int vw, int ytop, int ph) {
+  const bool top = ytop < 0, bottom = ytop + SR > ph;
+  if (!(left || right || top || bottom)) return;
+  if (left || right) {
+    for (int r = threadIdx.x; r < SR; r += NTHREADS) {
+      int16_t* wrow = W + r * WP;
+      if (left) { const uint32_t e = (uint16_t)wrow[WX0]; *reinterpret_cast<uint2*>(wrow + WX0 - 4) = make_uint2(e | (e << 16), e | (e << 16)); }
+      if (right) { const uint32_t e = (uint16_t)wrow[WX0 + vw - 1]; *reinterpret_cast<uint2*>(wrow + WX0 + vw) = make_uint2(e | (e << 16), e | (e << 16)); }
+    }
+    __syncthreads();
+  }
+  if (top || bottom) {
+    const int r_last = ph - 1 - ytop;  // staged row of the last picture row
+    for (int i = threadIdx.x; i < 2 * HALO * (WP / 8); i += NTHREADS) {
+      const int q = i / (WP / 8), c = i - q * (WP / 8);
+      // q < HALO: rows above the picture <- staged row -ytop; else: the HALO rows below the picture <- staged row r_last
+      if (q < HALO) { if (top && q < -ytop) *reinterpret_cast<uint4*>(W + q * WP + 8 * c) = *reinterpret_cast<const uint4*>(W + (-ytop) * WP + 8 * c); }
+      else if (bottom && r_last + 1 + (q - HALO) < SR) *reinterpret_cast<uint4*>(W + (r_last + 1 + q - HALO) * WP + 8 * c) = *reinterpret_cast<const uint4*>(W + r_last * WP + 8 * c);
+    }
+    __syncthreads();
+  }
+}
+
+constexpr int L_SR = BR + 2 * ALF_HALO_Y;                      // 38 staged rows
+constexpr int L_STAGE_BYTES = WP * L_SR * 2;                   // 10944 bytes per box
+constexpr int L_STAGE_STRIDE = (L_STAGE_BYTES + 127) & ~127;   // TMA destinations are 128-byte aligned
+constexpr int CELL_W = TW / 2 + 2, CELL_H = BR / 2 + 2;        // 66 x 18 cells of 2x2 samples, first cell at (x0-2, y0-2)
+constexpr int L_CELL_BYTES = CELL_H * CELL_W * 8;
+constexpr int L_SMEM_BYTES = RING_STAGES * L_STAGE_STRIDE + L_CELL_BYTES + RING_STAGES * 8;
 constexpr int NT = 256;
+constexpr int LAP_ROWS = 12;                                   // sample rows a Laplacian task walks (6 cell rows)
+constexpr int LAP_TASKS = CELL_W * (CELL_H * 2 / LAP_ROWS);    // 66 word columns x 3 row groups
 
 __constant__ uint8_t c_th[16] = {0, 1, 2, 2, 2, 2, 2, 3, 3, 3, 3, 3, 3, 3, 3, 4};
 __constant__ uint8_t c_transpose[8] = {0, 1, 0, 2, 2, 3, 1, 3};
-
-struct LumaSmem {
-  int t[LS_H][LS_P];               // samples as int32
-  uint2 cell[CELL_H][CELL_W];      // {V | H << 16, D0 | D1 << 16} per 2x2 cell
-};
 
 // Class of one 4x4 block from its four window sums (AdaptiveLoopFilter.cpp:390-451).
 __device__ __forceinline__ int classify(int sum_v, int sum_h, int sum_d0, int sum_d1, int shift) {
@@ -55,279 +98,296 @@ __device__ __forceinline__ int classify(int sum_v, int sum_h, int sum_d0, int su
   return class_idx | (c_transpose[main_dir * 2 + (sec_dir >> 1)] << 5);
 }
 
-__device__ __forceinline__ void ld12(const int* p, int w[12]) {
-  const int4 a = *reinterpret_cast<const int4*>(p), b = *reinterpret_cast<const int4*>(p + 4), c = *reinterpret_cast<const int4*>(p + 8);
-  w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w; w[8] = c.x; w[9] = c.y; w[10] = c.z; w[11] = c.w;
+// One work-tile row of a block's window: p = sample x - 4 (8-byte aligned); v[i] = sample x - 4 + i
+__device__ __forceinline__ void load_win12(const int16_t* p, int v[12]) {
+  const uint2 a = *reinterpret_cast<const uint2*>(p), b = *reinterpret_cast<const uint2*>(p + 4), c = *reinterpret_cast<const uint2*>(p + 8);
+  v[0] = a.x & 0xFFFF; v[1] = a.x >> 16; v[2] = a.y & 0xFFFF; v[3] = a.y >> 16;
+  v[4] = b.x & 0xFFFF; v[5] = b.x >> 16; v[6] = b.y & 0xFFFF; v[7] = b.y >> 16;
+  v[8] = c.x & 0xFFFF; v[9] = c.x >> 16; v[10] = c.y & 0xFFFF; v[11] = c.y >> 16;
 }
 
 template <bool CLASSIFY_ONLY>
-__global__ void __launch_bounds__(NT) alf_luma_kernel(Geom g, const SlotDev* __restrict__ slots, int first_slot, BatchCtl bc) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  LumaSmem& s = *reinterpret_cast<LumaSmem*>(smem_raw);
+__global__ void __launch_bounds__(NT, 2) alf_luma_kernel(Geom g, const SlotDev* __restrict__ slots, int first_slot, BatchCtl bc, int nseg) {
+  extern __shared__ __align__(128) unsigned char smem[];
   const SlotDev& sd = slots[first_slot + bc.slot[blockIdx.z]];
   const unsigned ctl = bc.v[blockIdx.z];
   if (ctl_skip(ctl, 0)) return;
   const int tid = threadIdx.x;
-  const int x0 = blockIdx.x * LT_W, y0 = blockIdx.y * LT_H;  // local rows
-  const int16_t* __restrict__ src = sd.buf[ctl_src(ctl, 0)][0];
-  int16_t* __restrict__ dst = sd.buf[ctl_dst(ctl, 0)][0];
   const int rows = g.rows;
-
-  // this thread's 4x4 block: a warp = one row of 32 blocks
-  const int bj = tid & 31, bi = tid >> 5;
-  const int bx = x0 + 4 * bj, by = y0 + 4 * bi;
-  const bool blk_in = bx < g.width && by < rows;
-  bool en = false;
-  if (blk_in) en = CLASSIFY_ONLY ? true : (__ldg(sd.alf_ctu_enable + ((by + g.row0) >> g.ctu_log2) * g.ctus_w + (bx >> g.ctu_log2)) != 0);
-  if (!__syncthreads_or(en)) {
-    // every CTU under this tile has ALF off: copy through (int16x8 vectors, 2 per thread)
-    uint4 v[2];
-#pragma unroll
-    for (int i = 0; i < 2; i++) {
-      const int c = tid + i * NT, r = c >> 4, k = c & 15, x = x0 + 8 * k, y = y0 + r;
-      if (x < g.width && y < rows) v[i] = ldg_u4(src + (size_t)y * g.pitch_y + x);
-    }
-#pragma unroll
-    for (int i = 0; i < 2; i++) {
-      const int c = tid + i * NT, r = c >> 4, k = c & 15, x = x0 + 8 * k, y = y0 + r;
-      if (x < g.width && y < rows) *reinterpret_cast<uint4*>(dst + (size_t)y * g.pitch_y + x) = v[i];
-    }
-    return;
+  const int ntx = (g.width + TW - 1) / TW;
+  const int ta = (int)blockIdx.x * ntx / nseg, tb = ((int)blockIdx.x + 1) * ntx / nseg;
+  if (ta >= tb) return;
+  ring::Walk<RING_STAGES> walk;
+  walk.first = ta; walk.last = tb - 1;
+  uint2(*cell)[CELL_W] = reinterpret_cast<uint2(*)[CELL_W]>(smem + RING_STAGES * L_STAGE_STRIDE);  // {V | H << 16, D0 | D1 << 16} per 2x2 cell
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + RING_STAGES * L_STAGE_STRIDE + L_CELL_BYTES);
+  const int y0 = (int)blockIdx.y * BR;  // local rows
+  const int src_buf = ctl_src(ctl, 0);
+  int16_t* __restrict__ dst = sd.buf[ctl_dst(ctl, 0)][0];
+  const CUtensorMap* map = &sd.tm_alf[0];
+  auto stage_ptr = [&](int t) { return reinterpret_cast<int16_t*>(smem + walk.stage(t) * L_STAGE_STRIDE); };
+  auto issue = [&](int t) {
+    uint64_t* bar = &full[walk.stage(t)];
+    ring::mbar_expect_tx(bar, L_STAGE_BYTES);
+    ring::tma_load_3d(stage_ptr(t), map, bar, t * TW - WX0, y0 - ALF_HALO_Y, src_buf);
+  };
+  if (tid == 0) {
+    for (int i = 0; i < RING_STAGES; i++) ring::mbar_init(&full[i], 1);
+    ring::mbar_init_fence();
   }
+  __syncthreads();
+  if (tid == 0)
+    for (int t = walk.first; t <= walk.last && t < walk.first + RING_STAGES; t++) issue(t);
 
-  // ---- phase 1: stage tile + halo as int32; picture borders replicate (coordinate clamping = extendBorderPel) ----
-  {
-    constexpr int CHUNKS = LS_H * (LS_W / 4), ROUNDS = (CHUNKS + NT - 1) / NT;
-    const bool interior = x0 >= 4 && x0 + LT_W + 4 <= g.width && y0 >= 3 && y0 + LT_H + 3 <= rows;
-    uint2 raw[ROUNDS];
+  // this thread's 4x4 block of every tile: a warp = one row of 32 blocks
+  const int bj = tid & 31, bi = tid >> 5;
+  const int by = y0 + 4 * bi;
+  const uint8_t* __restrict__ en_row = sd.alf_ctu_enable + (size_t)((by + g.row0) >> g.ctu_log2) * g.ctus_w;
+  const int max_val = (1 << g.bd_luma) - 1;
+  const bool is7 = CLASSIFY_ONLY ? true : sd.alf->luma_filter_7x7 != 0;
+  const int shift = g.bd_luma + 4;
+
+  for (int tx = ta; tx < tb; tx++) {
+    ring::mbar_wait(&full[walk.stage(tx)], walk.parity(tx));
+    const int x0 = tx * TW, bx = x0 + 4 * bj;
+    const bool blk_in = bx < g.width && by < rows;
+    const bool en = blk_in && (CLASSIFY_ONLY || en_row[bx >> g.ctu_log2] != 0);
+    int16_t* W = stage_ptr(tx);
+    int16_t* out = dst + (size_t)by * g.pitch_y + bx;
+    if (!__syncthreads_or(en)) {
+      // every CTU under this tile has ALF off: copy through
+      if (blk_in) {
 #pragma unroll
-    for (int i = 0; i < ROUNDS; i++) {
-      const int c = tid + i * NT;
-      if (c < CHUNKS) {
-        const int r = c / (LS_W / 4), k = c % (LS_W / 4);
-        int y = y0 - 3 + r, x = x0 - 4 + 4 * k;
-        if (interior) raw[i] = ldg_u2(src + (size_t)y * g.pitch_y + x);
-        else {
-          y = min(max(y, 0), rows - 1);
-          const int16_t* rowp = src + (size_t)y * g.pitch_y;
-          if (x < 0) { const uint32_t e = (uint16_t)__ldg(rowp); raw[i] = make_uint2(e | (e << 16), e | (e << 16)); }
-          else if (x >= g.width) { const uint32_t e = (uint16_t)__ldg(rowp + g.width - 1); raw[i] = make_uint2(e | (e << 16), e | (e << 16)); }
-          else raw[i] = ldg_u2(rowp + x);
+        for (int o = 0; o < 4; o++) *reinterpret_cast<uint2*>(out + (size_t)o * g.pitch_y) = *reinterpret_cast<const uint2*>(W + (ALF_HALO_Y + 4 * bi + o) * WP + WX0 + 4 * bj);
+      }
+    } else {
+      // ---- phase 1: the stage is the work tile; border tiles get their padding ----
+      pad_borders<L_SR, ALF_HALO_Y, NT>(W, tx == 0, tx == ntx - 1, min(TW, g.width - x0), y0 - ALF_HALO_Y, rows);
+
+      // ---- phase 2: Laplacians per 2x2 cell, two samples per instruction.  Task = word column cc (samples x0-2+2cc, +1) over
+      //      the 12 sample rows of 6 cell rows: work-tile rows 12 rgp + 1 .. 12 rgp + 12, word 3 + cc ----
+      if (tid < LAP_TASKS) {
+        const int cc = tid % CELL_W, rgp = tid / CELL_W;
+        const uint32_t* wp = reinterpret_cast<const uint32_t*>(W) + (LAP_ROWS * rgp) * (WP / 2) + 3 + cc;
+        uint32_t cu, lu, ru, cm, lm, rm, cd, ld, rd;  // centre / left-shifted / right-shifted word of the rows above, at and below
+        { const uint32_t a = wp[-1], b = wp[0], c = wp[1]; cu = b; lu = __funnelshift_r(a, b, 16); ru = __funnelshift_r(b, c, 16); }
+        { const uint32_t a = wp[WP / 2 - 1], b = wp[WP / 2], c = wp[WP / 2 + 1]; cm = b; lm = __funnelshift_r(a, b, 16); rm = __funnelshift_r(b, c, 16); }
+        uint32_t av = 0, ah = 0, ad0 = 0, ad1 = 0;
+#pragma unroll
+        for (int i = 0; i < LAP_ROWS; i++) {
+          { const uint32_t* q = wp + (i + 2) * (WP / 2); const uint32_t a = q[-1], b = q[0], c = q[1]; cd = b; ld = __funnelshift_r(a, b, 16); rd = __funnelshift_r(b, c, 16); }
+          const uint32_t c2 = __vadd2(cm, cm), nc2 = __vsub2(0u, c2);
+          uint32_t s, t;
+          s = __vadd2(cu, cd); t = __vsub2(c2, s); const uint32_t v = __viaddmax_s16x2(s, nc2, t);     // |2c - up - down|
+          s = __vadd2(lm, rm); t = __vsub2(c2, s); const uint32_t h = __viaddmax_s16x2(s, nc2, t);     // |2c - left - right|
+          s = __vadd2(lu, rd); t = __vsub2(c2, s); const uint32_t d0 = __viaddmax_s16x2(s, nc2, t);    // |2c - up-left - down-right|
+          s = __vadd2(ru, ld); t = __vsub2(c2, s); const uint32_t d1 = __viaddmax_s16x2(s, nc2, t);    // |2c - up-right - down-left|
+          if ((i & 1) == 0) { av = v; ah = h; ad0 = d0; ad1 = d1; }
+          else {
+            av = __vadd2(av, v); ah = __vadd2(ah, h); ad0 = __vadd2(ad0, d0); ad1 = __vadd2(ad1, d1);
+            // both columns of the cell: {V, H} and {D0, D1} as 16-bit halves (a cell sum is < 2^15 up to 12 bit)
+            const uint32_t vh = __byte_perm(av, ah, 0x5410) + __byte_perm(av, ah, 0x7632);
+            const uint32_t dd = __byte_perm(ad0, ad1, 0x5410) + __byte_perm(ad0, ad1, 0x7632);
+            cell[(LAP_ROWS / 2) * rgp + (i >> 1)][cc] = make_uint2(vh, dd);
+          }
+          cu = cm; lu = lm; ru = rm; cm = cd; lm = ld; rm = rd;
+        }
+      }
+      __syncthreads();
+
+      // ---- phase 3: 4x4 cells of the block's 8x8 window -> class.  Two cells add without a carry between the 16-bit halves
+      //      (12-bit safe); wider sums are taken in 32 bits ----
+      int sv = 0, sh = 0, sd0 = 0, sd1 = 0;
+#pragma unroll
+      for (int r = 0; r < 4; r++) {
+        const uint4 c01 = *reinterpret_cast<const uint4*>(&cell[2 * bi + r][2 * bj]);      // cells 0, 1: {vh0, d0, vh1, d1}
+        const uint4 c23 = *reinterpret_cast<const uint4*>(&cell[2 * bi + r][2 * bj + 2]);
+        const uint32_t a0 = c01.x + c01.z, a1 = c23.x + c23.z, b0 = c01.y + c01.w, b1 = c23.y + c23.w;
+        sv += (a0 & 0xFFFF) + (a1 & 0xFFFF); sh += (a0 >> 16) + (a1 >> 16);
+        sd0 += (b0 & 0xFFFF) + (b1 & 0xFFFF); sd1 += (b0 >> 16) + (b1 >> 16);
+      }
+      const int cl = classify(sv, sh, sd0, sd1, shift);
+      if (CLASSIFY_ONLY) {
+        const int ux = bx >> 2, uy = by >> 2;
+        if (blk_in) sd.alf_class[(size_t)uy * g.units_w + ux] = (uint8_t)cl;
+      } else if (blk_in) {
+        // ---- phase 4: filter the block ----
+        const int16_t* wp = W + (4 * bi) * WP + WX0 + 4 * bj - 4;  // window row 0 (= block row 0 minus 3), sample x - 4
+        if (!en) {
+#pragma unroll
+          for (int o = 0; o < 4; o++) *reinterpret_cast<uint2*>(out + (size_t)o * g.pitch_y) = *reinterpret_cast<const uint2*>(wp + (3 + o) * WP + 4);
+        } else {
+          int f[16];
+          {
+            const int4* cp = reinterpret_cast<const int4*>(sd.alf_coef + ((cl & 31) * 4 + (cl >> 5)) * 16);
+            const int4 a = __ldg(cp), b = __ldg(cp + 1), c = __ldg(cp + 2), d = __ldg(cp + 3);
+            f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+            f[8] = c.x; f[9] = c.y; f[10] = c.z; f[11] = c.w; f[12] = d.x; f[13] = d.y; f[14] = d.z; f[15] = d.w;
+          }
+          // w[s][i] = sample (x - 4 + i, y - 3 + s); output sample j of output row o reads w[o + 3 + dy][j + 4 + dx]
+          int w[10][12];
+          if (is7) {
+#pragma unroll
+            for (int s = 0; s < 6; s++) load_win12(wp + s * WP, w[s]);
+#pragma unroll
+            for (int o = 0; o < 4; o++) {
+              load_win12(wp + (o + 6) * WP, w[o + 6]);
+              const int(&r0)[12] = w[o + 3];
+              int sum[4];
+#pragma unroll
+              for (int j = 0; j < 4; j++) {
+                sum[j] = 256 + f[12] * r0[j + 4] + f[11] * (r0[j + 5] + r0[j + 3]) + f[10] * (r0[j + 6] + r0[j + 2]) + f[9] * (r0[j + 7] + r0[j + 1]);
+                sum[j] += f[4] * (w[o + 4][j + 6] + w[o + 2][j + 2]) + f[5] * (w[o + 4][j + 5] + w[o + 2][j + 3]) + f[6] * (w[o + 4][j + 4] + w[o + 2][j + 4]) +
+                          f[7] * (w[o + 4][j + 3] + w[o + 2][j + 5]) + f[8] * (w[o + 4][j + 2] + w[o + 2][j + 6]);
+                sum[j] += f[1] * (w[o + 5][j + 5] + w[o + 1][j + 3]) + f[2] * (w[o + 5][j + 4] + w[o + 1][j + 4]) + f[3] * (w[o + 5][j + 3] + w[o + 1][j + 5]);
+                sum[j] += f[0] * (w[o + 6][j + 4] + w[o][j + 4]);
+                sum[j] = __vimin_s32_relu(sum[j] >> 9, max_val);
+              }
+              const uint32_t p0 = __byte_perm(sum[0], sum[1], 0x5410);
+              const uint32_t p1 = __byte_perm(sum[2], sum[3], 0x5410);
+              *reinterpret_cast<uint2*>(out + (size_t)o * g.pitch_y) = make_uint2(p0, p1);
+            }
+          } else {
+#pragma unroll
+            for (int s = 1; s < 5; s++) load_win12(wp + s * WP, w[s]);
+#pragma unroll
+            for (int o = 0; o < 4; o++) {
+              load_win12(wp + (o + 5) * WP, w[o + 5]);
+              const int(&r0)[12] = w[o + 3];
+              int sum[4];
+#pragma unroll
+              for (int j = 0; j < 4; j++) {
+                sum[j] = 256 + f[6] * r0[j + 4] + f[5] * (r0[j + 5] + r0[j + 3]) + f[4] * (r0[j + 6] + r0[j + 2]);
+                sum[j] += f[1] * (w[o + 4][j + 5] + w[o + 2][j + 3]) + f[2] * (w[o + 4][j + 4] + w[o + 2][j + 4]) + f[3] * (w[o + 4][j + 3] + w[o + 2][j + 5]);
+                sum[j] += f[0] * (w[o + 5][j + 4] + w[o + 1][j + 4]);
+                sum[j] = __vimin_s32_relu(sum[j] >> 9, max_val);
+              }
+              const uint32_t p0 = __byte_perm(sum[0], sum[1], 0x5410);
+              const uint32_t p1 = __byte_perm(sum[2], sum[3], 0x5410);
+              *reinterpret_cast<uint2*>(out + (size_t)o * g.pitch_y) = make_uint2(p0, p1);
+            }
+          }
         }
       }
     }
-#pragma unroll
-    for (int i = 0; i < ROUNDS; i++) {
-      const int c = tid + i * NT;
-      if (c < CHUNKS) {
-        const int r = c / (LS_W / 4), k = c % (LS_W / 4);
-        *reinterpret_cast<int4*>(&s.t[r][4 * k]) = make_int4((int)(int16_t)(raw[i].x & 0xFFFF), (int)(int16_t)(raw[i].x >> 16),
-                                                             (int)(int16_t)(raw[i].y & 0xFFFF), (int)(int16_t)(raw[i].y >> 16));
-      }
-    }
-  }
-  // coefficient row prefetch does not depend on shared memory; issued after the class is known (phase 4)
-  __syncthreads();
-
-  // ---- phase 2: Laplacians per 2x2 cell.  Task = 2 cell rows x 4 cell columns = sample rows 4 tr.., columns 8 tc.. of the
-  //      region that starts at (x0-2, y0-2), i.e. staged rows 1 + 4 tr .., staged columns 2 + 8 tc .. ----
-  if (tid < (CELL_H / 2) * ((CELL_W + 3) / 4)) {
-    constexpr int TPR = (CELL_W + 3) / 4;  // 17 tasks per row, the last one covers 2 cell columns
-    const int tr = tid / TPR, tc = tid % TPR;
-    const int ncell = tc == TPR - 1 ? CELL_W - 4 * (TPR - 1) : 4;
-    int up[12], cur[12], dn[12];
-    const int* base = &s.t[4 * tr][8 * tc];
-    ld12(base, up);
-    ld12(base + LS_P, cur);
-    uint32_t acc_vh[4], acc_d[4];
-#pragma unroll
-    for (int i = 0; i < 4; i++) {  // sample row i of the task; window index j + 2 <-> sample column j
-      ld12(base + (i + 2) * LS_P, dn);
-      if ((i & 1) == 0) {
-#pragma unroll
-        for (int k = 0; k < 4; k++) { acc_vh[k] = 0; acc_d[k] = 0; }
-      }
-#pragma unroll
-      for (int j = 0; j < 8; j++) {
-        const int c2 = cur[j + 2] << 1;
-        const int v = abs(c2 - up[j + 2] - dn[j + 2]);
-        const int h = abs(c2 - cur[j + 1] - cur[j + 3]);
-        const int d0 = abs(c2 - up[j + 1] - dn[j + 3]);
-        const int d1 = abs(c2 - up[j + 3] - dn[j + 1]);
-        acc_vh[j >> 1] += (uint32_t)v + ((uint32_t)h << 16);
-        acc_d[j >> 1] += (uint32_t)d0 + ((uint32_t)d1 << 16);
-      }
-      if (i & 1) {
-        const int cr = 2 * tr + (i >> 1);
-#pragma unroll
-        for (int k = 0; k < 4; k++)
-          if (k < ncell) s.cell[cr][4 * tc + k] = make_uint2(acc_vh[k], acc_d[k]);
-      }
-#pragma unroll
-      for (int k = 0; k < 12; k++) { up[k] = cur[k]; cur[k] = dn[k]; }
-    }
-  }
-  __syncthreads();
-
-  // ---- phase 3: 4x4 cells of the block's 8x8 window -> class.  A 2x2 cell sum is < 2^15 up to 12 bit, so two cells add
-  //      without a carry between the 16-bit halves; wider sums are taken in 32 bits ----
-  int sv = 0, sh = 0, sd0 = 0, sd1 = 0;
-#pragma unroll
-  for (int r = 0; r < 4; r++) {
-    const uint4 c01 = *reinterpret_cast<const uint4*>(&s.cell[2 * bi + r][2 * bj]);      // cells 0, 1: {vh0, d0, vh1, d1}
-    const uint4 c23 = *reinterpret_cast<const uint4*>(&s.cell[2 * bi + r][2 * bj + 2]);
-    const uint32_t a0 = c01.x + c01.z, a1 = c23.x + c23.z, b0 = c01.y + c01.w, b1 = c23.y + c23.w;
-    sv += (a0 & 0xFFFF) + (a1 & 0xFFFF); sh += (a0 >> 16) + (a1 >> 16);
-    sd0 += (b0 & 0xFFFF) + (b1 & 0xFFFF); sd1 += (b0 >> 16) + (b1 >> 16);
-  }
-  const int cl = classify(sv, sh, sd0, sd1, g.bd_luma + 4);
-  if (CLASSIFY_ONLY) {
-    const int ux = (x0 >> 2) + bj, uy = (y0 >> 2) + bi;
-    if (ux < g.units_w && uy < (rows >> 2)) sd.alf_class[(size_t)uy * g.units_w + ux] = (uint8_t)cl;
-    return;
-  }
-
-  // ---- phase 4: filter the block ----
-  if (!blk_in) return;
-  const int max_val = (1 << g.bd_luma) - 1;
-  const int tcx = 4 + 4 * bj;  // staged column of the block's first sample
-  if (!en) {
-#pragma unroll
-    for (int rr = 0; rr < 4; rr++) {
-      const int4 v = *reinterpret_cast<const int4*>(&s.t[3 + 4 * bi + rr][tcx]);
-      *reinterpret_cast<uint2*>(dst + (size_t)(by + rr) * g.pitch_y + bx) = make_uint2((uint32_t)v.x | ((uint32_t)v.y << 16), (uint32_t)v.z | ((uint32_t)v.w << 16));
-    }
-    return;
-  }
-  int f[16];
-  {
-    const int4* cp = reinterpret_cast<const int4*>(sd.alf_coef + ((cl & 31) * 4 + (cl >> 5)) * 16);
-    const int4 a = __ldg(cp), b = __ldg(cp + 1), c = __ldg(cp + 2), d = __ldg(cp + 3);
-    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
-    f[8] = c.x; f[9] = c.y; f[10] = c.z; f[11] = c.w; f[12] = d.x; f[13] = d.y; f[14] = d.z; f[15] = d.w;
-  }
-  const bool is7 = sd.alf->luma_filter_7x7 != 0;
-#pragma unroll
-  for (int rr = 0; rr < 4; rr++) {
-    const int trow = 3 + 4 * bi + rr;  // staged row of the output row
-    // rX[i] = staged columns tcx-4 .. tcx+7 (i = 0..11); output sample j reads i = j + 4 + dx
-    int sum[4], r0[12], rp[12], rm[12];
-    ld12(&s.t[trow][tcx - 4], r0);
-    if (is7) {
-#pragma unroll
-      for (int j = 0; j < 4; j++)
-        sum[j] = f[12] * r0[j + 4] + f[11] * (r0[j + 5] + r0[j + 3]) + f[10] * (r0[j + 6] + r0[j + 2]) + f[9] * (r0[j + 7] + r0[j + 1]);
-      ld12(&s.t[trow + 1][tcx - 4], rp); ld12(&s.t[trow - 1][tcx - 4], rm);
-#pragma unroll
-      for (int j = 0; j < 4; j++)
-        sum[j] += f[4] * (rp[j + 6] + rm[j + 2]) + f[5] * (rp[j + 5] + rm[j + 3]) + f[6] * (rp[j + 4] + rm[j + 4]) +
-                  f[7] * (rp[j + 3] + rm[j + 5]) + f[8] * (rp[j + 2] + rm[j + 6]);
-      ld12(&s.t[trow + 2][tcx - 4], rp); ld12(&s.t[trow - 2][tcx - 4], rm);
-#pragma unroll
-      for (int j = 0; j < 4; j++)
-        sum[j] += f[1] * (rp[j + 5] + rm[j + 3]) + f[2] * (rp[j + 4] + rm[j + 4]) + f[3] * (rp[j + 3] + rm[j + 5]);
-      {
-        const int4 a = *reinterpret_cast<const int4*>(&s.t[trow + 3][tcx]);
-        const int4 b = *reinterpret_cast<const int4*>(&s.t[trow - 3][tcx]);
-        sum[0] += f[0] * (a.x + b.x); sum[1] += f[0] * (a.y + b.y); sum[2] += f[0] * (a.z + b.z); sum[3] += f[0] * (a.w + b.w);
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 4; j++) sum[j] = f[6] * r0[j + 4] + f[5] * (r0[j + 5] + r0[j + 3]) + f[4] * (r0[j + 6] + r0[j + 2]);
-      ld12(&s.t[trow + 1][tcx - 4], rp); ld12(&s.t[trow - 1][tcx - 4], rm);
-#pragma unroll
-      for (int j = 0; j < 4; j++) sum[j] += f[1] * (rp[j + 5] + rm[j + 3]) + f[2] * (rp[j + 4] + rm[j + 4]) + f[3] * (rp[j + 3] + rm[j + 5]);
-      {
-        const int4 a = *reinterpret_cast<const int4*>(&s.t[trow + 2][tcx]);
-        const int4 b = *reinterpret_cast<const int4*>(&s.t[trow - 2][tcx]);
-        sum[0] += f[0] * (a.x + b.x); sum[1] += f[0] * (a.y + b.y); sum[2] += f[0] * (a.z + b.z); sum[3] += f[0] * (a.w + b.w);
-      }
-    }
-    int o4[4];
-#pragma unroll
-    for (int j = 0; j < 4; j++) o4[j] = clip3i(0, max_val, (sum[j] + 256) >> 9);
-    *reinterpret_cast<uint2*>(dst + (size_t)(by + rr) * g.pitch_y + bx) = make_uint2((uint32_t)o4[0] | ((uint32_t)o4[1] << 16), (uint32_t)o4[2] | ((uint32_t)o4[3] << 16));
+    __syncthreads();  // the stage and the cells are free
+    if (tid == 0 && tx + RING_STAGES <= walk.last) issue(tx + RING_STAGES);
   }
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Chroma: 5x5 diamond, one filter per picture, no classification.  Tile 64x16 per plane, 4 samples per thread.
+// Chroma: 5x5 diamond, one filter per picture, no classification (filterBlk<ALF_FILTER_5>, AdaptiveLoopFilter.cpp:465-650).
+// Band walking over a TMA ring: box 128 x 36 (2 halo rows each side); a thread filters 8 samples x 2 rows from the work
+// tile: 6 window rows of 12 samples are unpacked once into registers and serve both output rows.
 // ---------------------------------------------------------------------------------------------------------
-constexpr int CT_W = 64, CT_H = 16, CS_W = CT_W + 8, CS_H = CT_H + 4;
+constexpr int C_SR = BR + 2 * ALF_HALO_C;
+constexpr int C_STAGE_BYTES = WP * C_SR * 2;
+static_assert(C_STAGE_BYTES % 128 == 0, "TMA destinations are 128-byte aligned");
+constexpr int C_SMEM_BYTES = RING_STAGES * C_STAGE_BYTES + RING_STAGES * 8;
+constexpr int NTC = 256;
 
-__global__ void __launch_bounds__(NT) alf_chroma_kernel(Geom g, const SlotDev* __restrict__ slots, int first_slot, BatchCtl bc) {
-  __shared__ __align__(16) int t[CS_H][CS_W];
-  const SlotDev& sd = slots[first_slot + bc.slot[blockIdx.z >> 1]];
-  const int plane = 1 + (blockIdx.z & 1);
-  const unsigned ctl = bc.v[blockIdx.z >> 1];
+// p points at sample x of a work-tile row; v[i] = sample x - 2 + i, i = 0..11
+__device__ __forceinline__ void load_row12(const int16_t* p, int v[12]) {
+  const uint32_t a = *reinterpret_cast<const uint32_t*>(p - 2);
+  const uint4 b = *reinterpret_cast<const uint4*>(p);
+  const uint32_t c = *reinterpret_cast<const uint32_t*>(p + 8);
+  v[0] = a & 0xFFFF; v[1] = a >> 16;
+  v[2] = b.x & 0xFFFF; v[3] = b.x >> 16; v[4] = b.y & 0xFFFF; v[5] = b.y >> 16; v[6] = b.z & 0xFFFF; v[7] = b.z >> 16; v[8] = b.w & 0xFFFF; v[9] = b.w >> 16;
+  v[10] = c & 0xFFFF; v[11] = c >> 16;
+}
+
+__global__ void __launch_bounds__(NTC, 3) alf_chroma_kernel(Geom g, const SlotDev* __restrict__ slots, int first_slot, BatchCtl bc, int bands_c, int nseg) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const SlotDev& sd = slots[first_slot + bc.slot[blockIdx.z]];
+  const unsigned ctl = bc.v[blockIdx.z];
+  const int plane = 1 + ((int)blockIdx.y >= bands_c), band = (int)blockIdx.y - (plane - 1) * bands_c;
   if (ctl_skip(ctl, plane)) return;
   const int tid = threadIdx.x;
-  const int x0 = blockIdx.x * CT_W, y0 = blockIdx.y * CT_H;
   const int cw = g.width >> 1, crows = g.rows >> 1;
-  const int16_t* __restrict__ src = sd.buf[ctl_src(ctl, plane)][plane];
+  const int ntx = (cw + TW - 1) / TW;
+  const int ta = (int)blockIdx.x * ntx / nseg, tb = ((int)blockIdx.x + 1) * ntx / nseg;
+  if (ta >= tb) return;
+  ring::Walk<RING_STAGES> walk;
+  walk.first = ta; walk.last = tb - 1;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + RING_STAGES * C_STAGE_BYTES);
+  const int by0 = band * BR;
+  const int src_buf = ctl_src(ctl, plane);
   int16_t* __restrict__ dst = sd.buf[ctl_dst(ctl, plane)][plane];
-  const int r = tid >> 4, k = tid & 15;  // output: row r, columns 4k..4k+3 of the tile
-  const int x = x0 + 4 * k, y = y0 + r;
-  const bool in = x < cw && y < crows;
-  bool en = false;
-  if (in) {
-    const int ctu = ((((y << 1) + g.row0) >> g.ctu_log2) * g.ctus_w) + ((x << 1) >> g.ctu_log2);
-    en = sd.alf_ctu_enable[(size_t)plane * g.ctus_w * g.ctus_h + ctu] != 0;
-  }
-  const int any_en = __syncthreads_or(en);
-  if (!any_en) {
-    if (in) *reinterpret_cast<uint2*>(dst + (size_t)y * g.pitch_c + x) = ldg_u2(src + (size_t)y * g.pitch_c + x);
-    return;
-  }
-  for (int c = tid; c < CS_H * (CS_W / 4); c += NT) {
-    const int rr = c / (CS_W / 4), kk = c % (CS_W / 4);
-    const int yy = min(max(y0 - 2 + rr, 0), crows - 1);
-    const int xx = x0 - 4 + 4 * kk;
-    const int16_t* rowp = src + (size_t)yy * g.pitch_c;
-    int4 v;
-    if (xx < 0) { const int e = rowp[0]; v = make_int4(e, e, e, e); }
-    else if (xx >= cw) { const int e = rowp[cw - 1]; v = make_int4(e, e, e, e); }
-    else {
-      const uint2 raw = ldg_u2(rowp + xx);
-      v = make_int4((int)(int16_t)(raw.x & 0xFFFF), (int)(int16_t)(raw.x >> 16), (int)(int16_t)(raw.y & 0xFFFF), (int)(int16_t)(raw.y >> 16));
-    }
-    *reinterpret_cast<int4*>(&t[rr][4 * kk]) = v;
+  const CUtensorMap* map = &sd.tm_alf[plane];
+  auto stage_ptr = [&](int t) { return reinterpret_cast<int16_t*>(smem + walk.stage(t) * C_STAGE_BYTES); };
+  auto issue = [&](int t) {
+    uint64_t* bar = &full[walk.stage(t)];
+    ring::mbar_expect_tx(bar, C_STAGE_BYTES);
+    ring::tma_load_3d(stage_ptr(t), map, bar, t * TW - WX0, by0 - ALF_HALO_C, src_buf);
+  };
+  if (tid == 0) {
+    for (int i = 0; i < RING_STAGES; i++) ring::mbar_init(&full[i], 1);
+    ring::mbar_init_fence();
   }
   __syncthreads();
-  if (!in) return;
-  const int trow = 2 + r, tcx = 4 + 4 * k;
-  if (!en) {
-    const int4 v = *reinterpret_cast<const int4*>(&t[trow][tcx]);
-    uint2 o; o.x = (uint32_t)(uint16_t)v.x | ((uint32_t)(uint16_t)v.y << 16); o.y = (uint32_t)(uint16_t)v.z | ((uint32_t)(uint16_t)v.w << 16);
-    *reinterpret_cast<uint2*>(dst + (size_t)y * g.pitch_c + x) = o;
-    return;
-  }
+  if (tid == 0)
+    for (int t = walk.first; t <= walk.last && t < walk.first + RING_STAGES; t++) issue(t);
+
   int f[7];
 #pragma unroll
   for (int i = 0; i < 7; i++) f[i] = sd.alf->chroma_coeff[i];
-  auto load12 = [&](int* w, int row) {
-    const int4* p = reinterpret_cast<const int4*>(&t[row][tcx - 4]);
-    const int4 a = p[0], b = p[1], c = p[2];
-    w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w; w[8] = c.x; w[9] = c.y; w[10] = c.z; w[11] = c.w;
-  };
-  int r0[12], rp[12], rm[12], sum[4];
-  load12(r0, trow);
-#pragma unroll
-  for (int j = 0; j < 4; j++) sum[j] = f[6] * r0[j + 4] + f[5] * (r0[j + 5] + r0[j + 3]) + f[4] * (r0[j + 6] + r0[j + 2]);
-  load12(rp, trow + 1); load12(rm, trow - 1);
-#pragma unroll
-  for (int j = 0; j < 4; j++) sum[j] += f[1] * (rp[j + 5] + rm[j + 3]) + f[2] * (rp[j + 4] + rm[j + 4]) + f[3] * (rp[j + 3] + rm[j + 5]);
-  {
-    const int4 a = *reinterpret_cast<const int4*>(&t[trow + 2][tcx]);
-    const int4 b = *reinterpret_cast<const int4*>(&t[trow - 2][tcx]);
-    sum[0] += f[0] * (a.x + b.x); sum[1] += f[0] * (a.y + b.y); sum[2] += f[0] * (a.z + b.z); sum[3] += f[0] * (a.w + b.w);
-  }
   const int max_val = (1 << g.bd_chroma) - 1;
-  int o4[4];
+  const int k = tid & 15, rg = tid >> 4;  // 8 samples at column 8k, rows 2rg and 2rg + 1 of the band
+  const int y = by0 + 2 * rg;
+  const uint8_t* __restrict__ en_row = sd.alf_ctu_enable + (size_t)plane * g.ctus_w * g.ctus_h + (size_t)((((y << 1) + g.row0) >> g.ctu_log2) * g.ctus_w);
+
+  for (int tx = ta; tx < tb; tx++) {
+    ring::mbar_wait(&full[walk.stage(tx)], walk.parity(tx));
+    const int x0 = tx * TW, x = x0 + 8 * k;
+    const bool in = x < cw && y < crows;
+    const bool en = in && en_row[(x << 1) >> g.ctu_log2] != 0;
+    int16_t* W = stage_ptr(tx);
+    int16_t* out = dst + (size_t)y * g.pitch_c + x;
+    const int nrows = min(2, crows - y);
+    if (!__syncthreads_or(en)) {
+      // every CTU under this tile has chroma ALF off: copy through
+      if (in) {
 #pragma unroll
-  for (int j = 0; j < 4; j++) o4[j] = clip3i(0, max_val, (sum[j] + 256) >> 9);
-  uint2 o; o.x = (uint32_t)o4[0] | ((uint32_t)o4[1] << 16); o.y = (uint32_t)o4[2] | ((uint32_t)o4[3] << 16);
-  *reinterpret_cast<uint2*>(dst + (size_t)y * g.pitch_c + x) = o;
+        for (int o = 0; o < 2; o++)
+          if (o < nrows) *reinterpret_cast<uint4*>(out + (size_t)o * g.pitch_c) = *reinterpret_cast<const uint4*>(W + (ALF_HALO_C + 2 * rg + o) * WP + WX0 + 8 * k);
+      }
+    } else {
+      pad_borders<C_SR, ALF_HALO_C, NTC>(W, tx == 0, tx == ntx - 1, min(TW, cw - x0), by0 - ALF_HALO_C, crows);
+      if (in) {
+        const int16_t* wp = W + (2 * rg) * WP + WX0 + 8 * k;  // window row 0 (= output row 0 minus 2), sample x
+        if (!en) {
+#pragma unroll
+          for (int o = 0; o < 2; o++)
+            if (o < nrows) *reinterpret_cast<uint4*>(out + (size_t)o * g.pitch_c) = *reinterpret_cast<const uint4*>(wp + (2 + o) * WP);
+        } else {
+          int w[6][12];
+#pragma unroll
+          for (int r = 0; r < 6; r++) load_row12(wp + r * WP, w[r]);
+#pragma unroll
+          for (int o = 0; o < 2; o++) {
+            if (o >= nrows) break;
+            uint32_t pk2[4];
+#pragma unroll
+            for (int jj = 0; jj < 4; jj++) {
+              int sm[2];
+#pragma unroll
+              for (int h = 0; h < 2; h++) {
+                const int j = 2 * jj + h + 2;  // window index of the output sample
+                int sum = 256 + f[6] * w[o + 2][j] + f[5] * (w[o + 2][j + 1] + w[o + 2][j - 1]) + f[4] * (w[o + 2][j + 2] + w[o + 2][j - 2]);
+                sum += f[1] * (w[o + 3][j + 1] + w[o + 1][j - 1]) + f[2] * (w[o + 3][j] + w[o + 1][j]) + f[3] * (w[o + 3][j - 1] + w[o + 1][j + 1]);
+                sum += f[0] * (w[o + 4][j] + w[o][j]);
+                sm[h] = __vimin_s32_relu(sum >> 9, max_val);  // clip to [0, max]
+              }
+              pk2[jj] = __byte_perm(sm[0], sm[1], 0x5410);
+            }
+            *reinterpret_cast<uint4*>(out + (size_t)o * g.pitch_c) = make_uint4(pk2[0], pk2[1], pk2[2], pk2[3]);
+          }
+        }
+      }
+    }
+    __syncthreads();  // the stage is free
+    if (tid == 0 && tx + RING_STAGES <= walk.last) issue(tx + RING_STAGES);
+  }
 }
 
 }  // namespace
@@ -335,21 +395,28 @@ __global__ void __launch_bounds__(NT) alf_chroma_kernel(Geom g, const SlotDev* _
 void launch_alf_luma(const Geom& g, const SlotDev* slots, int first_slot, int num_slots, const BatchCtl& ctl, bool classify_only, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(alf_luma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LumaSmem));
-    cudaFuncSetAttribute(alf_luma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LumaSmem));
+    cudaFuncSetAttribute(alf_luma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, L_SMEM_BYTES);
+    cudaFuncSetAttribute(alf_luma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, L_SMEM_BYTES);
     attr_set = true;
   }
-  dim3 gl((g.width + LT_W - 1) / LT_W, (g.rows + LT_H - 1) / LT_H, num_slots);
-  if (classify_only) {
-    alf_luma_kernel<true><<<gl, NT, sizeof(LumaSmem), st>>>(g, slots, first_slot, ctl);
-    return;
-  }
-  alf_luma_kernel<false><<<gl, NT, sizeof(LumaSmem), st>>>(g, slots, first_slot, ctl);
+  const int bands_y = (g.rows + BR - 1) / BR, ntx = (g.width + TW - 1) / TW;
+  const int bands = bands_y * num_slots;
+  int nseg = (148 * 2 + bands - 1) / bands;
+  nseg = nseg < 1 ? 1 : (nseg > ntx ? ntx : nseg);
+  dim3 gl(nseg, bands_y, num_slots);
+  if (classify_only) alf_luma_kernel<true><<<gl, NT, L_SMEM_BYTES, st>>>(g, slots, first_slot, ctl, nseg);
+  else alf_luma_kernel<false><<<gl, NT, L_SMEM_BYTES, st>>>(g, slots, first_slot, ctl, nseg);
 }
 
 void launch_alf_chroma(const Geom& g, const SlotDev* slots, int first_slot, int num_slots, const BatchCtl& ctl, cudaStream_t st) {
-  dim3 gc((g.width / 2 + CT_W - 1) / CT_W, (g.rows / 2 + CT_H - 1) / CT_H, 2 * num_slots);
-  alf_chroma_kernel<<<gc, NT, 0, st>>>(g, slots, first_slot, ctl);
+  static bool attr_set = false;
+  if (!attr_set) { cudaFuncSetAttribute(alf_chroma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C_SMEM_BYTES); attr_set = true; }
+  const int bands_c = (g.rows / 2 + BR - 1) / BR, ntx = (g.width / 2 + TW - 1) / TW;
+  const int bands = 2 * bands_c * num_slots;
+  int nseg = (148 * 3 + bands - 1) / bands;
+  nseg = nseg < 1 ? 1 : (nseg > ntx ? ntx : nseg);
+  dim3 gc(nseg, 2 * bands_c, num_slots);
+  alf_chroma_kernel<<<gc, NTC, C_SMEM_BYTES, st>>>(g, slots, first_slot, ctl, bands_c, nseg);
 }
 
 }  // namespace ilf

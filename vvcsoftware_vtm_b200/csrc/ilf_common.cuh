@@ -28,10 +28,13 @@ struct Geom {
 // ilf_create encodes, so they live here.
 constexpr int RING_TILE_W = 128;   // samples per tile row, all planes (256-byte box rows)
 constexpr int SAO_BAND_ROWS = 32;  // rows a SAO CTA owns; the box adds one halo row above and below
+constexpr int ALF_BAND_ROWS = 32;  // rows an ALF CTA owns; the box adds 3 (luma, 7x7 + classification) or 2 (chroma, 5x5) halo rows on each side
+constexpr int ALF_HALO_Y = 3, ALF_HALO_C = 2;
 
 struct alignas(64) SlotDev {
   // TMA descriptors of the slot's planes, tensor (x, y, buffer): dims (plane width, held rows, 3)
   CUtensorMap tm_sao[3];    // box RING_TILE_W x (SAO_BAND_ROWS + 2)
+  CUtensorMap tm_alf[3];    // box (RING_TILE_W + 16) x (ALF_BAND_ROWS + 2 * halo), loaded 8 samples left of the tile
   int16_t* buf[3][3];       // [buffer: 0 = input, 1, 2 = work][plane]
   const uint32_t* info;     // deblock grid, luma tree
   const uint32_t* info_c;   // chroma tree layer or nullptr
