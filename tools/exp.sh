@@ -1,13 +1,11 @@
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -8
-timeout 300 python bench.py --no-cpu-baseline --e2e-steps 2 > gpurun_out/bench_new.json 2>gpurun_out/bench_new.err || tail -5 gpurun_out/bench_new.err
-python - <<'PY'
-import json
-d=json.load(open('gpurun_out/bench_new.json'))
-r=d['roofline']
-print('value', d['value'], 'ms', d['ms_per_step'], 'chain', r['chain'], 'e2e', d['e2e']['value'])
-for k,v in r['per_kernel'].items(): print('  ', k, v)
-a=r['all_on']
-print('ALL_ON value', a['value'], 'ms', a['ms_per_step'], 'chain', a['chain'])
-for k,v in a['per_kernel'].items(): print('  ', k, v)
+timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -5
+for dbg in 0 1; do
+  ILF_DEBUG=$dbg python bench.py --steps 30 --no-cpu-baseline --e2e-steps 1 > /tmp/b.json 2>/tmp/b.err || { echo FAILED; tail -3 /tmp/b.err; }
+  python - "dbg=$dbg" <<'PY'
+import json,sys
+d=json.load(open('/tmp/b.json'))
+pk=d['roofline']['per_kernel']
+print(sys.argv[1], 'value', d['value'], 'deblock', pk['deblock']['algo_gbs'])
 PY
+done

@@ -9,9 +9,9 @@
 constexpr int W = 3840, H = 2160, NS = 17;
 constexpr int PY = 3840, PC = 1920, UW = 960, UH = 540;
 constexpr size_t PLANE_Y = (size_t)PY * H, PLANE_C = (size_t)PC * (H / 2), BUF = PLANE_Y + 2 * PLANE_C;
-struct Cfg { int LP, CP, XO, CXO, META, S, OFF_C, OFF_INFO, OFF_MV, STAGE_BYTES, TX_BYTES; };
+struct Cfg { int LP, CP, XO, CXO, META, S, OFF_C, OFF_INFO, OFF_MV, STAGE_BYTES, TX_BYTES, ORDER; };
 static Cfg make_cfg(int lp, int cp, int xo, int cxo, int meta, int S) {
-  Cfg c; c.LP = lp; c.CP = cp; c.XO = xo; c.CXO = cxo; c.META = meta; c.S = S;
+  Cfg c; c.ORDER = 0; c.LP = lp; c.CP = cp; c.XO = xo; c.CXO = cxo; c.META = meta; c.S = S;
   c.OFF_C = lp * 32 * 2; c.OFF_INFO = c.OFF_C + 2 * cp * 16 * 2; c.OFF_MV = c.OFF_INFO + 36 * 8 * 4;
   c.TX_BYTES = meta ? c.OFF_MV + 36 * 8 * 8 : c.OFF_INFO;
   c.STAGE_BYTES = (c.TX_BYTES + 127) & ~127;
@@ -42,8 +42,15 @@ __global__ void __launch_bounds__(128) ring(const Maps* __restrict__ mp, int16_t
   }
   __syncthreads();
   const int per_slot = tiles_x * tiles_y;
-  auto issue = [&](int t, int stage) {
-    const int slot = t / per_slot, r = t % per_slot, ty = r / tiles_x, tx = r % tiles_x;
+  // ORDER 0: tiles in raster order, strided over the CTAs; 1: a CTA walks a band (row of tiles) left to right, bands dealt
+  // round-robin; 2: a CTA walks a column of tiles top to bottom
+  auto decode = [&](int i, int& slot, int& ty, int& tx) {
+    if (c.ORDER == 0) { const int t = blockIdx.x + i * gridDim.x; slot = t / per_slot; const int r = t % per_slot; ty = r / tiles_x; tx = r % tiles_x; }
+    else if (c.ORDER == 1) { const int b = blockIdx.x + (i / tiles_x) * gridDim.x; slot = b / tiles_y; ty = b % tiles_y; tx = i % tiles_x; }
+    else { const int b = blockIdx.x + (i / tiles_y) * gridDim.x; slot = b / tiles_x; tx = b % tiles_x; ty = i % tiles_y; }
+  };
+  auto issue = [&](int i, int stage) {
+    int slot, ty, tx; decode(i, slot, ty, tx);
     uint8_t* base = smem + stage * STAGE_BYTES;
     mbar_expect(&full[stage], TX_BYTES);
     tma_load3(base, &mp->y, &full[stage], tx * 128 + c.XO, ty * 32 - 4, slot);
@@ -55,13 +62,15 @@ __global__ void __launch_bounds__(128) ring(const Maps* __restrict__ mp, int16_t
     }
   };
   int n = 0;
-  for (int t = blockIdx.x; t < total; t += gridDim.x) n++;
+  if (c.ORDER == 0) { for (int t = blockIdx.x; t < total; t += gridDim.x) n++; }
+  else if (c.ORDER == 1) { for (int b = blockIdx.x; b < tiles_y * NS; b += gridDim.x) n += tiles_x; }
+  else { for (int b = blockIdx.x; b < tiles_x * NS; b += gridDim.x) n += tiles_y; }
   if (tid == 0)
-    for (int i = 0; i < S && i < n; i++) issue(blockIdx.x + i * gridDim.x, i);
+    for (int i = 0; i < S && i < n; i++) issue(i, i);
   const int k = tid & 31, r0 = tid >> 5, kc = tid & 15, rc0 = tid >> 4;
   for (int i = 0; i < n; i++) {
-    const int stage = i % S, t = blockIdx.x + i * gridDim.x;
-    const int slot = t / per_slot, r = t % per_slot, ty = r / tiles_x, tx = r % tiles_x;
+    const int stage = i % S;
+    int slot, ty, tx; decode(i, slot, ty, tx);
     mbar_wait(&full[stage], (i / S) & 1);
     uint8_t* base = smem + stage * STAGE_BYTES;
     int16_t* sy = reinterpret_cast<int16_t*>(base);
@@ -88,7 +97,7 @@ __global__ void __launch_bounds__(128) ring(const Maps* __restrict__ mp, int16_t
       if (x >= 0 && x < W / 2 && y >= 0 && y < H / 2) *(uint2*)(d + PLANE_Y + pl * PLANE_C + (size_t)y * PC + x) = *(uint2*)&sc[pl * CP * 16 + (rc0 + 8 * (q & 1)) * CP + sco + 4 * kc];
     }
     __syncthreads();  // every thread is done reading the stage
-    if (tid == 0 && i + S < n) issue(blockIdx.x + (i + S) * gridDim.x, stage);
+    if (tid == 0 && i + S < n) issue(i + S, stage);
   }
 }
 
@@ -109,8 +118,8 @@ static CUtensorMap make_map(EncodeFn enc, CUtensorMapDataType dt, int es_bytes, 
 int16_t *src, *dst; int16_t* h;
 static EncodeFn g_enc; static uint32_t* g_info; static uint2* g_mv; static CUtensorMapL2promotion g_l2 = CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
 template <int MODE>
-void run(int lp, int cp, int xo, int cxo, int meta, int S, int ctas_per_sm, double bytes) {
-  Cfg c = make_cfg(lp, cp, xo, cxo, meta, S);
+void run(int lp, int cp, int xo, int cxo, int meta, int S, int ctas_per_sm, double bytes, int order = 0) {
+  Cfg c = make_cfg(lp, cp, xo, cxo, meta, S); c.ORDER = order;
   const int STAGE_BYTES = c.STAGE_BYTES;
   Maps hm;
   hm.y = make_map(g_enc, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, src, W, H, PY * 2, BUF * 2, lp, 32);
@@ -141,7 +150,7 @@ void run(int lp, int cp, int xo, int cxo, int meta, int S, int ctas_per_sm, doub
     delete[] o;
   }
   int occ = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ring<MODE>, 128, smem); cudaFree(m);
-  printf("lp=%d cp=%d xo=%d meta=%d S=%d mode=%d ctas/SM=%d (occ %d) smem/SM=%dKB  %8.3f ms  %8.1f GB/s (algorithmic, samples only)  mismatches=%zu\n", lp, cp, xo, meta, S, MODE, ctas_per_sm, occ, ctas_per_sm * smem / 1024, ms / N,
+  printf("order=%d lp=%d cp=%d xo=%d meta=%d S=%d mode=%d ctas/SM=%d (occ %d) smem/SM=%dKB  %8.3f ms  %8.1f GB/s (algorithmic, samples only)  mismatches=%zu\n", order, lp, cp, xo, meta, S, MODE, ctas_per_sm, occ, ctas_per_sm * smem / 1024, ms / N,
          bytes / (ms / N * 1e-3) / 1e9, bad);
 }
 
@@ -157,26 +166,12 @@ int main() {
   cudaGetDriverEntryPointByVersion("cuTensorMapEncodeTiled", (void**)&enc, 12000, cudaEnableDefault, &q);
   g_enc = enc; g_info = info; g_mv = mv;
   const double bytes = 2.0 * NS * BUF * 2;
-  //      lp   cp  xo cxo meta S ctas
-  run<0>(136, 72, -8, -8, 1, 2, 4, bytes);
-  run<0>(136, 72, -8, -8, 0, 2, 4, bytes);
-  run<0>(136, 72, -8, -8, 0, 2, 6, bytes);
-  run<0>(136, 72, -8, -8, 0, 3, 4, bytes);
-  run<0>(128, 64, 0, 0, 0, 2, 4, bytes);
-  run<0>(128, 64, 0, 0, 0, 2, 6, bytes);
-  run<0>(128, 64, 0, 0, 0, 3, 5, bytes);
-  run<0>(128, 64, 0, 0, 0, 4, 4, bytes);
-  run<0>(144, 80, -8, -8, 0, 2, 4, bytes);
-  run<0>(136, 72, -8, -8, 1, 2, 2, bytes);
-  run<0>(136, 72, -8, -8, 1, 2, 3, bytes);
-  run<0>(136, 72, -8, -8, 1, 2, 5, bytes);
-  run<0>(136, 72, -8, -8, 1, 1, 8, bytes);
-  run<0>(136, 72, -8, -8, 1, 1, 12, bytes);
-  g_l2x = CU_TENSOR_MAP_L2_PROMOTION_NONE;
-  run<0>(136, 72, -8, -8, 1, 2, 4, bytes);
-  run<0>(136, 72, -8, -8, 1, 3, 4, bytes);
-  g_l2x = CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
-  run<0>(136, 72, -8, -8, 1, 2, 4, bytes);
-  run<0>(136, 72, -8, -8, 1, 3, 4, bytes);
+  for (int order = 0; order < 3; order++) {
+    run<0>(128, 64, 0, 0, 0, 2, 4, bytes, order);
+    run<0>(128, 64, 0, 0, 0, 4, 4, bytes, order);
+    run<0>(128, 64, 0, 0, 0, 3, 2, bytes, order);
+    run<0>(128, 64, 0, 0, 1, 3, 4, bytes, order);
+    run<0>(144, 80, -8, -8, 0, 3, 4, bytes, order);
+  }
   return 0;
 }

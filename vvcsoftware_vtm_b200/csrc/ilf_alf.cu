@@ -107,7 +107,7 @@ __device__ __forceinline__ void load_win12(const int16_t* p, int v[12]) {
 }
 
 template <bool CLASSIFY_ONLY>
-__global__ void __launch_bounds__(NT, 2) alf_luma_kernel(Geom g, const SlotDev* __restrict__ slots, int first_slot, BatchCtl bc, int nseg) {
+__global__ void __launch_bounds__(NT, 3) alf_luma_kernel(Geom g, const SlotDev* __restrict__ slots, int first_slot, BatchCtl bc, int nseg) {
   extern __shared__ __align__(128) unsigned char smem[];
   const SlotDev& sd = slots[first_slot + bc.slot[blockIdx.z]];
   const unsigned ctl = bc.v[blockIdx.z];

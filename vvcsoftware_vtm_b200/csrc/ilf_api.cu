@@ -168,6 +168,22 @@ int stage_side(ilf_ctx* ctx, Slot& s, void* dst, const void* src, size_t bytes, 
   return ILF_OK;
 }
 
+// Unit grids live on the device with a row pitch of units_pitch elements (multiple of 4); the caller's arrays are dense.
+int stage_grid(ilf_ctx* ctx, Slot& s, void* dst, const void* src, size_t elem_bytes, size_t& cursor, size_t limit) {
+  const Geom& g = ctx->g;
+  const size_t row = (size_t)g.units_w * elem_bytes, bytes = row * g.units_h;
+  if (g.units_pitch == g.units_w) return stage_side(ctx, s, dst, src, bytes, cursor, limit);
+  const void* from = src;
+  if (!(bytes >= 4096 && is_pinned(src))) {
+    if (cursor + bytes > limit) return fail(ctx, ILF_ERR_STATE, "side-information staging overflow");
+    memcpy(s.pinned_side + cursor, src, bytes);
+    from = s.pinned_side + cursor;
+    cursor += (bytes + 255) & ~size_t(255);
+  }
+  CU(ctx, cudaMemcpy2DAsync(dst, (size_t)g.units_pitch * elem_bytes, from, row, row, g.units_h, cudaMemcpyHostToDevice, ctx->s_up));
+  return ILF_OK;
+}
+
 int create_impl(ilf_ctx** out, const ilf_config* cfg, const ilf_band* band) {
   if (!out || !cfg) return fail(nullptr, ILF_ERR_ARG, "null argument");
   *out = nullptr;
@@ -211,6 +227,7 @@ int create_impl(ilf_ctx** out, const ilf_config* cfg, const ilf_band* band) {
     g.rows = std::min(cfg->height, out_end + halo) - g.row0;
   }
   g.units_h = g.rows / 4;
+  g.units_pitch = (g.units_w + 3) & ~3;
   g.debug = getenv("ILF_DEBUG") ? atoi(getenv("ILF_DEBUG")) : 0;
   g.pitch_y = (cfg->width + 63) & ~63;
   g.pitch_c = (cfg->width / 2 + 63) & ~63;
@@ -226,7 +243,7 @@ int create_impl(ilf_ctx** out, const ilf_config* cfg, const ilf_band* band) {
   CU(ctx, cudaStreamCreateWithFlags(&ctx->s_down, cudaStreamNonBlocking));
   ctx->slots.resize(cfg->num_slots);
   CU(ctx, cudaMalloc(&ctx->slots_dev, sizeof(SlotDev) * cfg->num_slots));
-  const size_t units = (size_t)g.units_w * g.units_h;
+  const size_t units = (size_t)g.units_pitch * g.units_h;  // device grids are pitched
   for (int i = 0; i < cfg->num_slots; i++) {
     Slot& s = ctx->slots[i];
     CU(ctx, cudaMalloc(&s.planes, 3 * ctx->buf_elems * sizeof(int16_t)));
@@ -234,6 +251,9 @@ int create_impl(ilf_ctx** out, const ilf_config* cfg, const ilf_band* band) {
     CU(ctx, cudaMalloc(&s.info, units * 4));
     CU(ctx, cudaMalloc(&s.info_c, units * 4));
     CU(ctx, cudaMalloc(&s.mv, units * 16));
+    CU(ctx, cudaMemsetAsync(s.info, 0, units * 4, ctx->s_up));
+    CU(ctx, cudaMemsetAsync(s.info_c, 0, units * 4, ctx->s_up));
+    CU(ctx, cudaMemsetAsync(s.mv, 0, units * 16, ctx->s_up));
     CU(ctx, cudaMalloc(&s.ctu_slice, ctx->num_ctus));
     CU(ctx, cudaMalloc(&s.db_params, sizeof(ilf_deblock_params)));
     CU(ctx, cudaMalloc(&s.sao, sizeof(ilf_sao_ctu) * ctx->num_ctus));
@@ -257,8 +277,18 @@ int create_impl(ilf_ctx** out, const ilf_config* cfg, const ilf_band* band) {
     for (int b = 0; b < 3; b++)
       for (int p = 0; p < 3; p++) s.dev.buf[b][p] = plane_ptr(ctx, s, b, p);
     s.dev.alf_class = s.alf_class;
+    {
+      const size_t grid_bytes = units * 4;
+      if (int rc = make_map3(ctx, &s.dev.tm_info, CU_TENSOR_MAP_DATA_TYPE_UINT32, s.info, g.units_w, g.units_h, 1, (size_t)g.units_pitch * 4, grid_bytes, 32, 8)) return rc;
+      if (int rc = make_map3(ctx, &s.dev.tm_info_c, CU_TENSOR_MAP_DATA_TYPE_UINT32, s.info_c, g.units_w, g.units_h, 1, (size_t)g.units_pitch * 4, grid_bytes, 32, 8)) return rc;
+      if (int rc = make_map3(ctx, &s.dev.tm_mv16, CU_TENSOR_MAP_DATA_TYPE_UINT32, s.mv, g.units_w * 2, g.units_h, 1, (size_t)g.units_pitch * 8, units * 8, 64, 8)) return rc;
+      if (int rc = make_map3(ctx, &s.dev.tm_mv32, CU_TENSOR_MAP_DATA_TYPE_UINT32, s.mv, g.units_w * 4, g.units_h, 1, (size_t)g.units_pitch * 16, units * 16, 128, 8)) return rc;
+    }
     for (int p = 0; p < 3; p++) {
       const int pw = p ? cfg->width / 2 : cfg->width, ph = p ? g.rows / 2 : g.rows, pitch = p ? g.pitch_c : g.pitch_y;
+      if (int rc = make_map3(ctx, &s.dev.tm_db[p], CU_TENSOR_MAP_DATA_TYPE_UINT16, plane_ptr(ctx, s, 0, p), pw, ph, 3, (size_t)pitch * 2, ctx->buf_elems * 2, p ? RING_TILE_W / 2 : RING_TILE_W,
+                             p ? DB_BAND_ROWS / 2 : DB_BAND_ROWS))
+        return rc;
       if (int rc = make_map3(ctx, &s.dev.tm_sao[p], CU_TENSOR_MAP_DATA_TYPE_UINT16, plane_ptr(ctx, s, 0, p), pw, ph, 3, (size_t)pitch * 2, ctx->buf_elems * 2, RING_TILE_W,
                              SAO_BAND_ROWS + 2))
         return rc;
@@ -449,16 +479,15 @@ int ilf_set_deblock_info(ilf_ctx* ctx, int slot, const ilf_deblock_params* param
   CU(ctx, cudaSetDevice(ctx->cfg.device));
   CU(ctx, cudaEventSynchronize(s.ev_side[0]));  // the previous copy out of this staging region is done
   CU(ctx, cudaStreamWaitEvent(ctx->s_up, s.ev_run, 0));  // kernels of the slot's previous picture may still read the device arrays
-  const size_t units = (size_t)ctx->g.units_w * ctx->g.units_h;
   size_t cur = s.side_off[0];
   const size_t lim = s.side_off[1];
   if (int rc = stage_side(ctx, s, s.db_params, params, sizeof(*params), cur, lim)) return rc;
-  if (int rc = stage_side(ctx, s, s.info, info, units * 4, cur, lim)) return rc;
+  if (int rc = stage_grid(ctx, s, s.info, info, 4, cur, lim)) return rc;
   s.has_ctree = info_chroma != nullptr;
-  if (info_chroma) if (int rc = stage_side(ctx, s, s.info_c, info_chroma, units * 4, cur, lim)) return rc;
+  if (info_chroma) if (int rc = stage_grid(ctx, s, s.info_c, info_chroma, 4, cur, lim)) return rc;
   s.mv_mode = mv16 ? 1 : (mv32 ? 2 : 0);
-  if (mv16) if (int rc = stage_side(ctx, s, s.mv, mv16, units * 8, cur, lim)) return rc;
-  if (mv32) if (int rc = stage_side(ctx, s, s.mv, mv32, units * 16, cur, lim)) return rc;
+  if (mv16) if (int rc = stage_grid(ctx, s, s.mv, mv16, 8, cur, lim)) return rc;
+  if (mv32) if (int rc = stage_grid(ctx, s, s.mv, mv32, 16, cur, lim)) return rc;
   if (ctu_slice) if (int rc = stage_side(ctx, s, s.ctu_slice, ctu_slice, ctx->num_ctus, cur, lim)) return rc;
   s.dev.info = s.info;
   s.dev.info_c = info_chroma ? s.info_c : nullptr;

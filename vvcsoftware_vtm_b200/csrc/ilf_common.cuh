@@ -13,6 +13,7 @@ struct Geom {
   int width, height;        // luma samples
   int pitch_y, pitch_c;     // plane pitches in samples (multiples of 64 -> 128-byte rows)
   int units_w, units_h;     // 4x4 luma units
+  int units_pitch;          // row pitch of the device-side unit grids (units_w rounded up to 4: TMA rows are multiples of 16 bytes)
   int ctu_log2, ctus_w, ctus_h;
   int bd_luma, bd_chroma;
   // Band mode (one picture split into CTU-row bands across GPUs): the slot's planes hold picture rows
@@ -27,12 +28,16 @@ struct Geom {
 // Tile geometry of the band-walking kernels (ilf_ring.cuh): the TMA box sizes are baked into the tensor maps that
 // ilf_create encodes, so they live here.
 constexpr int RING_TILE_W = 128;   // samples per tile row, all planes (256-byte box rows)
+constexpr int DB_BAND_ROWS = 32;   // luma rows a deblocking CTA owns (shifted up by 4 rows; chroma: 16 rows shifted by 2)
 constexpr int SAO_BAND_ROWS = 32;  // rows a SAO CTA owns; the box adds one halo row above and below
 constexpr int ALF_BAND_ROWS = 32;  // rows an ALF CTA owns; the box adds 3 (luma, 7x7 + classification) or 2 (chroma, 5x5) halo rows on each side
 constexpr int ALF_HALO_Y = 3, ALF_HALO_C = 2;
 
 struct alignas(64) SlotDev {
   // TMA descriptors of the slot's planes, tensor (x, y, buffer): dims (plane width, held rows, 3)
+  CUtensorMap tm_db[3];     // box RING_TILE_W x DB_BAND_ROWS (luma), RING_TILE_W/2 x DB_BAND_ROWS/2 (chroma)
+  CUtensorMap tm_info, tm_info_c;  // unit grids, tensor (unit x, unit y, 1) of uint32: box 32 x 8
+  CUtensorMap tm_mv16, tm_mv32;    // motion vectors as uint32 words (2 / 4 per unit): box 64 x 8 / 128 x 8
   CUtensorMap tm_sao[3];    // box RING_TILE_W x (SAO_BAND_ROWS + 2)
   CUtensorMap tm_alf[3];    // box (RING_TILE_W + 16) x (ALF_BAND_ROWS + 2 * halo), loaded 8 samples left of the tile
   int16_t* buf[3][3];       // [buffer: 0 = input, 1, 2 = work][plane]

@@ -3,32 +3,44 @@
 // Replaces LoopFilter::loopFilterPic (LoopFilter.cpp:149-230): "all vertical edges of the picture, then all
 // horizontal edges".  Filtered edges lie on the 8x8 luma grid (:313-324), each reads 4 and writes 3 samples
 // per side (:856-916), and the on/off + strong/weak decisions of a 4-line segment use lines 0 and 3 of that
-// segment only (:640-671).  Therefore the dependency closure of every 8x8 block SHIFTED by (-4,-4) is the
-// block itself: vertical-edge filtering of its 8 rows needs only its 8 columns, and the horizontal edge in
-// its middle needs only those 8 vertically filtered rows.  A CTA therefore stages one shifted tile
-// (128x32 luma + two 64x16 chroma tiles) in shared memory, runs the vertical pass and then the horizontal
-// pass on it, and writes it out: every sample is read from HBM once and written once, with no halo.
-// Chroma edges lie on the 8x8 chroma grid and reach 2/1 samples, so any shift in [2,6] closes them; the
-// chroma tile is shifted by (-4,-2) to keep 8-byte alignment of its rows.
+// segment only (:640-671).  Vertically, a band of 32 luma rows shifted up by 4 rows is therefore dependency-closed for
+// the horizontal edges in its middle once its vertical edges are done; horizontally the kernel WALKS the band: a
+// vertical edge on a tile boundary needs 4 samples of the tile to its left, and those are carried over.
+//
+// Data movement: band walking over a TMA ring (ilf_ring.cuh).  A CTA owns the band rows [32 ty - 4, 32 ty + 28) (chroma
+// [16 ty - 2, 16 ty + 14), units [8 ty - 1, 8 ty + 7)) and walks it in tiles of 128 luma columns.  One stage of the ring
+// holds everything a tile needs, fetched by five or six aligned TMA boxes several tiles ahead of the arithmetic: luma
+// 128 x 32, Cb and Cr 64 x 16, the unit grid 32 x 8 (and its chroma-tree layer), motion vectors 32 x 8.  Per tile:
+//   1. vertical edges x0 + 8e, e = 0..15 (luma) / cx0 + 8k, k = 0..7 (chroma).  Edge 0 lies on the tile boundary: its P
+//      side is the CARRY, the last 8 columns (luma and chroma) and the last unit column of the previous tile.
+//   2. horizontal edges over the columns whose vertical filtering is complete: [x0 - 4, x0 + 124) luma,
+//      [cx0 - 2, cx0 + 62) chroma -- the last carried unit column plus all but the last unit column of the tile.
+//   3. store the finished columns [x0 - 8, x0 + 120) (chroma [cx0 - 8, cx0 + 56)) as 16-byte vectors, carry + tile, and
+//      save the tile's last 8 columns / last unit column as the next carry.
+// Every sample crosses HBM once in and once out (the reference makes two picture passes); all global accesses are
+// 16-byte aligned.  A walk that starts inside the picture (small batches split bands into segments) first runs the
+// tile to its left without storing, which produces the carry; the last walk of a band ends with a flush step.
 //
 // Per-edge derivation on the device (xGetBoundaryStrengthSingle :419-541, QP/tc/beta :626-634, chroma QP
-// :811-829) from the packed per-4x4 grid described in include/ilf_b200.h, staged as a 33x8 unit window.
+// :811-829) from the packed per-4x4 grid described in include/ilf_b200.h.
 //
 // Work split: the unit of deblocking work is a SEGMENT (4 lines of one edge).  The 128 threads of a CTA take one
 // segment each in four phases -- luma vertical (16 edge columns x 8), chroma vertical (2 planes x 8 x 8 units),
 // luma horizontal (4 edge rows x 32), chroma horizontal (2 x 2 x 32) -- so edge flag, bS, QP, tc and beta are
 // derived once per segment, segments without an edge cost a few instructions, and no lane idles by construction.
+#include <cstdlib>
+
 #include "ilf_common.cuh"
+#include "ilf_ring.cuh"
 
 namespace ilf {
 namespace {
 
-constexpr int TW = 128, TH = 32;        // luma tile, origin shifted by (-4, -4)
-constexpr int LP = TW + 8;              // luma smem pitch (samples); 272-byte rows keep 16-byte alignment
-constexpr int CTW = 64, CTH = 16;       // chroma tile per plane, origin shifted by (-4, -2)
-constexpr int CP = CTW + 8;             // chroma smem pitch
-constexpr int MW = 33, MH = 8;          // staged metadata window in 4x4 units, origin (32 tx - 2, 8 ty - 1)
-constexpr int NTHREADS = 128;           // one task per thread in each of the four phases
+constexpr int TW = RING_TILE_W, TH = DB_BAND_ROWS;  // luma tile; the band is shifted up by 4 rows
+constexpr int CTW = TW / 2, CTH = TH / 2;           // chroma tile per plane; shifted up by 2 rows
+constexpr int UW = TW / 4, UH = TH / 4;             // units per tile: 32 x 8, rows shifted up by 1
+constexpr int NTHREADS = 128;                       // one task per thread in each of the four phases
+constexpr int DB_STAGES = 3;                        // ring depth: the tile being filtered + 2 in flight
 
 __constant__ uint8_t c_tc[66] = {0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  1,  1,  1,  1,
                                  1,  1,  1,  1,  1,  2,  2,  2,  2,  3,  3,  3,  3,  4,  4,  4,  5,  5,  6,  6,  7,  8,
@@ -41,39 +53,67 @@ __constant__ uint8_t c_chroma_scale[70] = {0,  1,  2,  3,  4,  5,  6,  7,  8,  9
                                            34, 34, 35, 35, 36, 36, 37, 37, 38, 39, 40, 41, 42, 43, 44, 45, 46, 47,
                                            48, 49, 50, 51, 52, 53, 54, 55, 56, 57, 58, 59, 60, 61, 62, 63};
 
-template <int MV> struct MvStore { uint32_t dummy; };
-template <> struct MvStore<1> { uint2 v[MH * MW]; };   // int16 x 4 per unit
-template <> struct MvStore<2> { int4 v[MH * MW]; };    // int32 x 4 per unit
+template <int MV> struct MvT { uint32_t dummy; };
+template <> struct MvT<1> { uint2 v; };   // int16 x 4 per unit
+template <> struct MvT<2> { int4 v; };    // int32 x 4 per unit
 
+// One stage of the ring = what the TMA unit delivers for a tile (dense boxes, each 128-byte aligned).
 template <int MV>
-struct Smem {
-  int16_t y[TH * LP];
-  int16_t c[2][CTH * CP];
-  uint32_t info[MH * MW];
-  uint32_t info_c[MH * MW];
-  MvStore<MV> mv;
+struct Stage {
+  int16_t y[TH][TW];
+  int16_t c[2][CTH][CTW];
+  uint32_t info[UH][UW];
+  uint32_t info_c[UH][UW];
+  MvT<MV> mv[MV ? UH : 1][MV ? UW : 1];
+};
+// What a tile inherits from the tile to its left.
+template <int MV>
+struct Carry {
+  int16_t y[TH][8];        // luma columns x0 - 8 .. x0 - 1
+  int16_t c[2][CTH][8];    // chroma columns cx0 - 8 .. cx0 - 1
+  uint32_t info[UH], info_c[UH];
+  MvT<MV> mv[UH];
+};
+template <int MV> __host__ __device__ constexpr int stage_stride() { return (int)((sizeof(Stage<MV>) + 127) & ~size_t(127)); }
+template <int MV> __host__ __device__ constexpr int stage_tx_bytes(bool ctree) {
+  return TH * TW * 2 + 2 * CTH * CTW * 2 + UH * UW * 4 + (ctree ? UH * UW * 4 : 0) + (MV == 1 ? UH * UW * 8 : (MV == 2 ? UH * UW * 16 : 0));
+}
+
+// The tile's unit window: column -1 is the carried unit column, 0 .. 31 the stage.
+template <int MV>
+struct Tile {
+  Stage<MV>* st;
+  Carry<MV>* cy;
+  bool ctree;
+  __device__ __forceinline__ uint32_t info(int r, int c) const { return c < 0 ? cy->info[r] : st->info[r][c]; }
+  __device__ __forceinline__ uint32_t cinfo(int r, int c) const {
+    if (!ctree) return info(r, c);
+    return c < 0 ? cy->info_c[r] : st->info_c[r][c];
+  }
+  __device__ __forceinline__ MvT<MV> mv(int r, int c) const { return c < 0 ? cy->mv[r] : st->mv[MV ? r : 0][MV ? c : 0]; }
+  // luma / chroma sample rows: column c of the tile, c in [-8, TW); negative columns live in the carry
+  __device__ __forceinline__ int16_t* y(int r, int c) const { return c < 0 ? &cy->y[r][c + 8] : &st->y[r][c]; }
+  __device__ __forceinline__ int16_t* ch(int pl, int r, int c) const { return c < 0 ? &cy->c[pl][r][c + 8] : &st->c[pl][r][c]; }
+  __device__ __forceinline__ int ypitch(int c) const { return c < 0 ? 8 : TW; }
+  __device__ __forceinline__ int cpitch(int c) const { return c < 0 ? 8 : CTW; }
 };
 
-template <int MV> __device__ __forceinline__ void mv_get(const Smem<MV>& s, int u, int m[4]);
-template <> __device__ __forceinline__ void mv_get<0>(const Smem<0>&, int, int m[4]) { m[0] = m[1] = m[2] = m[3] = 0; }
-template <> __device__ __forceinline__ void mv_get<1>(const Smem<1>& s, int u, int m[4]) {
-  const uint2 v = s.mv.v[u];
-  m[0] = (int)(int16_t)(v.x & 0xFFFF); m[1] = (int)(int16_t)(v.x >> 16); m[2] = (int)(int16_t)(v.y & 0xFFFF); m[3] = (int)(int16_t)(v.y >> 16);
+template <int MV> __device__ __forceinline__ void mv_get(const MvT<MV>& v, int m[4]);
+template <> __device__ __forceinline__ void mv_get<0>(const MvT<0>&, int m[4]) { m[0] = m[1] = m[2] = m[3] = 0; }
+template <> __device__ __forceinline__ void mv_get<1>(const MvT<1>& t, int m[4]) {
+  m[0] = (int)(int16_t)(t.v.x & 0xFFFF); m[1] = (int)(int16_t)(t.v.x >> 16); m[2] = (int)(int16_t)(t.v.y & 0xFFFF); m[3] = (int)(int16_t)(t.v.y >> 16);
 }
-template <> __device__ __forceinline__ void mv_get<2>(const Smem<2>& s, int u, int m[4]) {
-  const int4 v = s.mv.v[u];
-  m[0] = v.x; m[1] = v.y; m[2] = v.z; m[3] = v.w;
-}
+template <> __device__ __forceinline__ void mv_get<2>(const MvT<2>& t, int m[4]) { m[0] = t.v.x; m[1] = t.v.y; m[2] = t.v.z; m[3] = t.v.w; }
 
 // bS of one 4-sample segment (xGetBoundaryStrengthSingle, LoopFilter.cpp:419-541).  q, p index the staged window.
 template <int MV>
-__device__ __forceinline__ int boundary_strength(const Smem<MV>& s, uint32_t iq, uint32_t ip, int q, int p, uint32_t tu_bit, int thr) {
+__device__ __forceinline__ int boundary_strength(const Tile<MV>& t, uint32_t iq, uint32_t ip, int qr, int qc, int pr, int pc, uint32_t tu_bit, int thr) {
   if ((iq | ip) & ILF_BI_INTRA) return 2;
   if ((iq & tu_bit) && ((iq | ip) & ILF_BI_CBF)) return 1;
   const int rq0 = (iq >> 16) & 0xFF, rq1 = iq >> 24, rp0 = (ip >> 16) & 0xFF, rp1 = ip >> 24;
   int mq[4], mp[4];
-  mv_get<MV>(s, q, mq);
-  mv_get<MV>(s, p, mp);
+  mv_get<MV>(t.mv(qr, qc), mq);
+  mv_get<MV>(t.mv(pr, pc), mp);
   const bool d00 = abs(mq[0] - mp[0]) >= thr || abs(mq[1] - mp[1]) >= thr;
   if ((iq | ip) & ILF_BI_BSLICE) {
     if ((rp0 == rq0 && rp1 == rq1) || (rp0 == rq1 && rp1 == rq0)) {
@@ -115,33 +155,41 @@ __device__ __forceinline__ void filter_luma_line(int v[8], int tc, bool sw, bool
   if (no_q) { v[4] = m4; v[5] = m5; v[6] = m6; }
 }
 
+// Per-picture parameters and the tc / beta / chroma-QP tables, copied to shared memory once per CTA: the per-segment
+// derivations index them with per-thread values (constant memory would serialise) and must not wait on global loads.
+struct DbShared {
+  ilf_deblock_params prm;
+  const uint8_t* ctu_slice;  // nullptr: every CTU in slice 0
+  uint8_t tc[66 + 2], beta[64], chroma_scale[70 + 2];
+};
+
 struct EdgeParams {
   int bs;        // 0 = leave the segment alone
   int tc, beta;
   bool no_p, no_q;
 };
 
-__device__ __forceinline__ int slice_of(const Geom& g, const SlotDev& sd, int xg, int yg_local) {
-  return sd.ctu_slice ? (int)__ldg(sd.ctu_slice + (size_t)((yg_local + g.row0) >> g.ctu_log2) * g.ctus_w + (xg >> g.ctu_log2)) : 0;
+__device__ __forceinline__ int slice_of(const Geom& g, const DbShared& sh, int xg, int yg_local) {
+  return sh.ctu_slice ? (int)__ldg(sh.ctu_slice + (size_t)((yg_local + g.row0) >> g.ctu_log2) * g.ctus_w + (xg >> g.ctu_log2)) : 0;
 }
 
 // Parameters of one luma segment (xEdgeFilterLuma, LoopFilter.cpp:543-634): edge flag, bS, QP, tc, beta.  (xg, yg) = first Q sample.
+// (qr, qc) / (pr, pc) = unit row and column of the Q / P unit in the tile's window.
 template <int MV>
-__device__ __forceinline__ EdgeParams luma_edge_params(const Smem<MV>& s, const Geom& g, const SlotDev& sd, int q, int p, bool vertical, int xg, int yg) {
+__device__ __forceinline__ EdgeParams luma_edge_params(const Tile<MV>& t, const Geom& g, const DbShared& sh, int qr, int qc, int pr, int pc, bool vertical, int xg, int yg) {
   EdgeParams ep;
   ep.bs = 0; ep.tc = 0; ep.beta = 0; ep.no_p = ep.no_q = false;
-  const uint32_t iq = s.info[q], ip = s.info[p];
+  const uint32_t iq = t.info(qr, qc), ip = t.info(pr, pc);
   if (!(iq & (vertical ? ILF_BI_EDGE_V : ILF_BI_EDGE_H))) return ep;
-  const ilf_deblock_params* __restrict__ prm = sd.db_params;
-  const int bs = boundary_strength<MV>(s, iq, ip, q, p, vertical ? ILF_BI_TU_V : ILF_BI_TU_H, prm->mv_threshold);
+  const int bs = boundary_strength<MV>(t, iq, ip, qr, qc, pr, pc, vertical ? ILF_BI_TU_V : ILF_BI_TU_H, sh.prm.mv_threshold);
   if (!bs) return ep;
-  const int slice = slice_of(g, sd, xg, yg);
+  const int slice = slice_of(g, sh, xg, yg);
   const int qp = ((int)(int8_t)(ip >> 8) + (int)(int8_t)(iq >> 8) + 1) >> 1;
-  const int tc_off = prm->slices[slice].tc_offset_div2, beta_off = prm->slices[slice].beta_offset_div2;
+  const int tc_off = sh.prm.slices[slice].tc_offset_div2, beta_off = sh.prm.slices[slice].beta_offset_div2;
   const int scale = 1 << (g.bd_luma - 8);
   ep.bs = bs;
-  ep.tc = c_tc[clip3i(0, 65, qp + 2 * (bs - 1) + 2 * tc_off)] * scale;
-  ep.beta = c_beta[clip3i(0, 63, qp + 2 * beta_off)] * scale;
+  ep.tc = sh.tc[clip3i(0, 65, qp + 2 * (bs - 1) + 2 * tc_off)] * scale;
+  ep.beta = sh.beta[clip3i(0, 63, qp + 2 * beta_off)] * scale;
   ep.no_p = (ip & ILF_BI_NOFILT) != 0;
   ep.no_q = (iq & ILF_BI_NOFILT) != 0;
   return ep;
@@ -167,188 +215,230 @@ __device__ __forceinline__ bool filter_luma_segment(int (&L)[4][8], const EdgePa
 }
 
 // tc of a chroma segment for one component, or -1 when the segment is not filtered (xEdgeFilterChroma, LoopFilter.cpp:684-838).
-__device__ __forceinline__ int chroma_tc(const uint32_t* info, const Geom& g, const SlotDev& sd, int q, int p, bool vertical, int comp, int xg_luma, int yg_luma,
+__device__ __forceinline__ int chroma_tc(uint32_t iq, uint32_t ip, const Geom& g, const DbShared& sh, bool vertical, int comp, int xg_luma, int yg_luma,
                                          bool& no_p, bool& no_q) {
-  const uint32_t iq = info[q], ip = info[p];
   if (!(iq & (vertical ? ILF_BI_EDGE_V : ILF_BI_EDGE_H))) return -1;
   if (!((iq | ip) & ILF_BI_INTRA)) return -1;  // chroma is filtered for bS == 2 only (:769)
-  const ilf_deblock_params* __restrict__ prm = sd.db_params;
-  const int slice = slice_of(g, sd, xg_luma, yg_luma);
-  int qp = (((int)(int8_t)(ip >> 8) + (int)(int8_t)(iq >> 8) + 1) >> 1) + (comp == 0 ? prm->cb_qp_offset : prm->cr_qp_offset);
+  const int slice = slice_of(g, sh, xg_luma, yg_luma);
+  int qp = (((int)(int8_t)(ip >> 8) + (int)(int8_t)(iq >> 8) + 1) >> 1) + (comp == 0 ? sh.prm.cb_qp_offset : sh.prm.cr_qp_offset);
   if (qp >= 70) qp -= 6;
-  else if (qp >= 0) qp = c_chroma_scale[qp];
+  else if (qp >= 0) qp = sh.chroma_scale[qp];
   no_p = (ip & ILF_BI_NOFILT) != 0;
   no_q = (iq & ILF_BI_NOFILT) != 0;
-  return c_tc[clip3i(0, 65, qp + 2 + 2 * prm->slices[slice].tc_offset_div2)] * (1 << (g.bd_chroma - 8));
+  return sh.tc[clip3i(0, 65, qp + 2 + 2 * sh.prm.slices[slice].tc_offset_div2)] * (1 << (g.bd_chroma - 8));
 }
 
 __device__ __forceinline__ void unpack2(uint32_t w, int& a, int& b) { a = (int)(int16_t)(w & 0xFFFF); b = (int)(int16_t)(w >> 16); }
 __device__ __forceinline__ uint32_t pack2(int a, int b) { return (uint32_t)(uint16_t)a | ((uint32_t)b << 16); }
 
 template <int MV>
-__global__ void __launch_bounds__(NTHREADS) deblock_kernel(Geom g, const SlotDev* __restrict__ slots, int first_slot, BatchCtl bc) {
-  __shared__ __align__(16) Smem<MV> s;
+__global__ void __launch_bounds__(NTHREADS, 4) deblock_kernel(Geom g, const SlotDev* __restrict__ slots, int first_slot, BatchCtl bc, int nseg) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  constexpr int STRIDE = stage_stride<MV>();
+  constexpr int stages = DB_STAGES;
   const SlotDev& sd = slots[first_slot + bc.slot[blockIdx.z]];
   const unsigned ctl = bc.v[blockIdx.z];
   const int src_b = ctl_src(ctl, 0), dst_b = ctl_dst(ctl, 0);  // deblocking starts from the uploaded picture: all planes in one buffer
   const int tid = threadIdx.x;
-  const int tx = blockIdx.x, ty = blockIdx.y;
-  const int x0 = tx * TW - 4, y0 = ty * TH - 4;      // luma tile origin; rows are LOCAL (held-region) rows
-  const int cx0 = tx * CTW - 4, cy0 = ty * CTH - 2;  // chroma tile origin
-  const int ux0 = tx * (TW / 4) - 2, uy0 = ty * (TH / 4) - 1;  // metadata window origin (units)
+  const int ty = blockIdx.y;
+  const int y0 = ty * TH - 4, cy0 = ty * CTH - 2, uy0 = ty * UH - 1;  // band origin (local rows)
   const int rows = g.rows, crow = g.rows >> 1, cw = g.width >> 1;
-  const int units_h_local = rows >> 2;
-  const bool interior = x0 >= 0 && x0 + TW <= g.width && y0 >= 0 && y0 + TH <= rows;  // then the chroma tile and the unit window are inside too
-
-  // ---- stage: all global loads first (8-byte chunks: the -4 shift keeps 8-byte alignment), then the smem stores ----
-  {
-    const int16_t* __restrict__ src_y = sd.buf[src_b][0];
-    uint2 ly[8], lc[4];
-    const int k = tid & 31, r0 = tid >> 5;  // chunk column, first row; rows r0, r0 + 4, ...
-#pragma unroll
-    for (int i = 0; i < 8; i++) {
-      const int r = r0 + 4 * i, x = x0 + k * 4, y = y0 + r;
-      ly[i] = make_uint2(0u, 0u);
-      if (interior || (x >= 0 && x < g.width && y >= 0 && y < rows)) ly[i] = ldg_u2(src_y + (size_t)y * g.pitch_y + x);
-    }
-    const int kc = tid & 15, rc0 = tid >> 4;  // chroma: 16 chunks per row, rows rc0 and rc0 + 8, both planes
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-      const int pl = i >> 1, r = rc0 + 8 * (i & 1), x = cx0 + kc * 4, y = cy0 + r;
-      lc[i] = make_uint2(0u, 0u);
-      if (interior || (x >= 0 && x < cw && y >= 0 && y < crow)) lc[i] = ldg_u2(sd.buf[src_b][1 + pl] + (size_t)y * g.pitch_c + x);
-    }
-    // metadata window: 264 units
-    const bool has_ctree = sd.info_c != nullptr;
-#pragma unroll
-    for (int i = 0; i < 3; i++) {
-      const int m = tid + i * NTHREADS;
-      if (m < MH * MW) {
-        const int mx = m % MW, my = m / MW, ux = ux0 + mx, uy = uy0 + my;
-        const bool in = ux >= 0 && ux < g.units_w && uy >= 0 && uy < units_h_local;
-        const size_t u = (size_t)uy * g.units_w + ux;
-        s.info[m] = in ? __ldg(sd.info + u) : 0u;
-        if (has_ctree) s.info_c[m] = in ? __ldg(sd.info_c + u) : 0u;
-        if (MV == 1) reinterpret_cast<uint2*>(&s.mv)[m] = in ? ldg_u2(sd.mv16 + u * 4) : make_uint2(0u, 0u);
-        if (MV == 2) reinterpret_cast<uint4*>(&s.mv)[m] = in ? ldg_u4(sd.mv32 + u * 4) : make_uint4(0u, 0u, 0u, 0u);
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < 8; i++) *reinterpret_cast<uint2*>(&s.y[(r0 + 4 * i) * LP + k * 4]) = ly[i];
-#pragma unroll
-    for (int i = 0; i < 4; i++) *reinterpret_cast<uint2*>(&s.c[i >> 1][(rc0 + 8 * (i & 1)) * CP + kc * 4]) = lc[i];
+  const int ntx = (g.width + TW - 1) / TW;
+  const int ta = (int)blockIdx.x * ntx / nseg, tb = ((int)blockIdx.x + 1) * ntx / nseg;  // this walk stores the columns of tiles [ta, tb)
+  if (ta >= tb) return;
+  // tiles the walk loads: a walk that starts inside the picture runs tile ta - 1 first (no stores) to obtain its carry;
+  // the last walk of the band ends with a flush step (tile index ntx, nothing loaded)
+  const int first = max(ta - 1, 0), last = tb - 1;
+  const int t_end = tb == ntx ? ntx : tb - 1;  // last step of the walk
+  constexpr int CARRY_BYTES = (int)((sizeof(Carry<MV>) + 15) & ~size_t(15));
+  Carry<MV>* carry = reinterpret_cast<Carry<MV>*>(smem + stages * STRIDE);
+  Carry<MV>* carry1 = reinterpret_cast<Carry<MV>*>(smem + stages * STRIDE + CARRY_BYTES);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + stages * STRIDE + 2 * CARRY_BYTES);
+  DbShared& sh = *reinterpret_cast<DbShared*>(smem + stages * STRIDE + 2 * CARRY_BYTES + 8 * stages);
+  const bool has_ctree = sd.info_c != nullptr;
+  const bool no_meta = (g.debug & 3) == 3;  // measurement aid: copy-only without the unit grids
+  const uint32_t tx_bytes = no_meta ? (uint32_t)(TH * TW * 2 + 2 * CTH * CTW * 2) : (uint32_t)stage_tx_bytes<MV>(has_ctree);
+  auto issue = [&](int t, int si) {  // tile t into stage si
+    Stage<MV>* st = reinterpret_cast<Stage<MV>*>(smem + si * STRIDE);
+    uint64_t* bar = &full[si];
+    ring::mbar_expect_tx(bar, tx_bytes);
+    ring::tma_load_3d(&st->y[0][0], &sd.tm_db[0], bar, t * TW, y0, src_b);
+    ring::tma_load_3d(&st->c[0][0][0], &sd.tm_db[1], bar, t * CTW, cy0, src_b);
+    ring::tma_load_3d(&st->c[1][0][0], &sd.tm_db[2], bar, t * CTW, cy0, src_b);
+    if (no_meta) return;
+    ring::tma_load_3d(&st->info[0][0], &sd.tm_info, bar, t * UW, uy0, 0);
+    if (has_ctree) ring::tma_load_3d(&st->info_c[0][0], &sd.tm_info_c, bar, t * UW, uy0, 0);
+    if (MV == 1) ring::tma_load_3d(&st->mv[0][0], &sd.tm_mv16, bar, t * UW * 2, uy0, 0);
+    if (MV == 2) ring::tma_load_3d(&st->mv[0][0], &sd.tm_mv32, bar, t * UW * 4, uy0, 0);
+  };
+  if (tid == 0) {
+    for (int i = 0; i < stages; i++) ring::mbar_init(&full[i], 1);
+    ring::mbar_init_fence();
   }
+  // the first carry is empty: no unit flags, so nothing is filtered against it
+  for (int i = tid; i < (int)(sizeof(Carry<MV>) / 4); i += NTHREADS) reinterpret_cast<uint32_t*>(carry)[i] = 0u;
+  __syncthreads();
+  if (tid == 0)
+    for (int t = first; t <= last && t < first + stages; t++) issue(t, t - first);
+  // picture parameters and tables -> shared memory (overlaps the first loads)
+  for (int i = tid; i < (int)(sizeof(ilf_deblock_params) / 4); i += NTHREADS) reinterpret_cast<uint32_t*>(&sh.prm)[i] = __ldg(reinterpret_cast<const uint32_t*>(sd.db_params) + i);
+  if (tid < 66) sh.tc[tid] = c_tc[tid];
+  if (tid < 64) sh.beta[tid] = c_beta[tid];
+  if (tid < 70) sh.chroma_scale[tid] = c_chroma_scale[tid];
+  if (tid == 0) sh.ctu_slice = __ldg(&sd.db_params->num_slices) == 1 ? nullptr : sd.ctu_slice;  // one slice: no per-CTU lookup
   __syncthreads();
 
-  const uint32_t* cinfo = sd.info_c != nullptr ? s.info_c : s.info;
   const int max_y = (1 << g.bd_luma) - 1, max_c = (1 << g.bd_chroma) - 1;
+  int16_t* __restrict__ dst_y = sd.buf[dst_b][0];
+  int16_t* __restrict__ dst_cb = sd.buf[dst_b][1];
+  int16_t* __restrict__ dst_cr = sd.buf[dst_b][2];
 
-  // ---- vertical edges, luma: task = 4 lines x 8 samples.  16 edge columns x 8 segment rows ----
-  if (!(g.debug & 1)) {
-    const int e = tid & 15, sg = tid >> 4;
-    const int q = sg * MW + 2 * e + 2;                 // Q unit in the window (x = 128 tx + 8 e -> unit 32 tx + 2 e)
-    const int xg = x0 + 4 + 8 * e, yg = y0 + 4 * sg;   // first Q sample
-    const EdgeParams ep = luma_edge_params<MV>(s, g, sd, q, q - 1, true, xg, yg);
-    if (ep.bs) {
-      int16_t* sp = &s.y[(4 * sg) * LP + 8 * e];
-      int L[4][8];
+  int si = 0;           // stage of the current tile
+  uint32_t phase = 0;   // barrier phase of that stage
+  for (int tx = first; tx <= t_end; tx++) {
+    const bool flush = tx == ntx;     // nothing loaded: only the carry is finished and stored
+    const bool store = tx >= ta;      // the warm-up tile of a walk produces the carry only
+    Tile<MV> t;
+    t.st = reinterpret_cast<Stage<MV>*>(smem + si * STRIDE);
+    t.cy = ((tx - first) & 1) ? carry1 : carry;
+    t.ctree = has_ctree;
+    Carry<MV>* next_carry = ((tx - first) & 1) ? carry : carry1;
+    if (!flush) ring::mbar_wait(&full[si], phase);
+    const int x0 = tx * TW, cx0 = tx * CTW;
+
+    // ---- vertical edges, luma: task = 4 lines x 8 samples.  16 edge columns x 8 segment rows ----
+    if (!(g.debug & 1) && !flush) {
+      const int e = tid & 15, sg = tid >> 4;
+      const EdgeParams ep = luma_edge_params<MV>(t, g, sh, sg, 2 * e, sg, 2 * e - 1, true, x0 + 8 * e, y0 + 4 * sg);
+      if (ep.bs) {
+        int16_t* pp = t.y(4 * sg, 8 * e - 4);
+        int16_t* pq = t.y(4 * sg, 8 * e);
+        const int pitch_p = t.ypitch(8 * e - 4);
+        int L[4][8];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          const uint2 a = *reinterpret_cast<const uint2*>(pp + i * pitch_p), b = *reinterpret_cast<const uint2*>(pq + i * TW);
+          unpack2(a.x, L[i][0], L[i][1]); unpack2(a.y, L[i][2], L[i][3]); unpack2(b.x, L[i][4], L[i][5]); unpack2(b.y, L[i][6], L[i][7]);
+        }
+        if (filter_luma_segment(L, ep, max_y)) {
+#pragma unroll
+          for (int i = 0; i < 4; i++) {
+            *reinterpret_cast<uint2*>(pp + i * pitch_p) = make_uint2(pack2(L[i][0], L[i][1]), pack2(L[i][2], L[i][3]));
+            *reinterpret_cast<uint2*>(pq + i * TW) = make_uint2(pack2(L[i][4], L[i][5]), pack2(L[i][6], L[i][7]));
+          }
+        }
+      }
+    }
+    // ---- vertical edges, chroma: task = one unit = 2 lines x 4 samples.  2 planes x 8 edge columns x 8 unit rows ----
+    if (!(g.debug & 1) && !flush) {
+      const int pl = tid >> 6, k = (tid >> 3) & 7, sg = tid & 7;
+      bool no_p, no_q;
+      const int tc = chroma_tc(t.cinfo(sg, 4 * k), t.cinfo(sg, 4 * k - 1), g, sh, true, pl, 2 * (cx0 + 8 * k), 2 * (cy0 + 2 * sg), no_p, no_q);
+      if (tc >= 0) {
+        int16_t* pp = t.ch(pl, 2 * sg, 8 * k - 2);
+        int16_t* pq = t.ch(pl, 2 * sg, 8 * k);
+        const int pitch_p = t.cpitch(8 * k - 2);
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+          const int m2 = pp[i * pitch_p], m3 = pp[i * pitch_p + 1], m4 = pq[i * CTW], m5 = pq[i * CTW + 1];
+          const int delta = clip3i(-tc, tc, (((m4 - m3) << 2) + m2 - m5 + 4) >> 3);
+          if (!no_p) pp[i * pitch_p + 1] = (int16_t)clip3i(0, max_c, m3 + delta);
+          if (!no_q) pq[i * CTW] = (int16_t)clip3i(0, max_c, m4 - delta);
+        }
+      }
+    }
+    __syncthreads();
+
+    // ---- horizontal edges, luma: task = 4 columns x 8 rows.  4 edge rows x 32 unit columns -1 .. 30 (a warp = one edge row) ----
+    if (!(g.debug & 1)) {
+      const int u = (tid & 31) - 1, h = tid >> 5;
+      if (!flush || u < 0) {
+        const EdgeParams ep = luma_edge_params<MV>(t, g, sh, 2 * h + 1, u, 2 * h, u, false, x0 + 4 * u, y0 + 4 + 8 * h);
+        if (ep.bs) {
+          int16_t* sp = t.y(8 * h, 4 * u);
+          const int pitch = t.ypitch(4 * u);
+          int L[4][8];
+#pragma unroll
+          for (int i = 0; i < 8; i++) {
+            const uint2 raw = *reinterpret_cast<const uint2*>(sp + i * pitch);
+            unpack2(raw.x, L[0][i], L[1][i]); unpack2(raw.y, L[2][i], L[3][i]);
+          }
+          if (filter_luma_segment(L, ep, max_y)) {
+#pragma unroll
+            for (int i = 1; i < 7; i++) *reinterpret_cast<uint2*>(sp + i * pitch) = make_uint2(pack2(L[0][i], L[1][i]), pack2(L[2][i], L[3][i]));
+          }
+        }
+      }
+    }
+    // ---- horizontal edges, chroma: task = one unit = 2 columns x 4 rows.  2 planes x 2 edge rows x 32 unit columns -1 .. 30 ----
+    if (!(g.debug & 1)) {
+      const int pl = tid >> 6, h = (tid >> 5) & 1, u = (tid & 31) - 1;
+      if (!flush || u < 0) {
+        bool no_p, no_q;
+        const int tc = chroma_tc(t.cinfo(4 * h + 1, u), t.cinfo(4 * h, u), g, sh, false, pl, 2 * (cx0 + 2 * u), 2 * (cy0 + 2 + 8 * h), no_p, no_q);
+        if (tc >= 0) {
+          int16_t* sp = t.ch(pl, 8 * h, 2 * u);
+          const int pitch = t.cpitch(2 * u);
+          int a[4], b[4];
+#pragma unroll
+          for (int i = 0; i < 4; i++) unpack2(*reinterpret_cast<const uint32_t*>(sp + i * pitch), a[i], b[i]);
+          const int da = clip3i(-tc, tc, (((a[2] - a[1]) << 2) + a[0] - a[3] + 4) >> 3);
+          const int db = clip3i(-tc, tc, (((b[2] - b[1]) << 2) + b[0] - b[3] + 4) >> 3);
+          if (!no_p) *reinterpret_cast<uint32_t*>(sp + pitch) = pack2(clip3i(0, max_c, a[1] + da), clip3i(0, max_c, b[1] + db));
+          if (!no_q) *reinterpret_cast<uint32_t*>(sp + 2 * pitch) = pack2(clip3i(0, max_c, a[2] - da), clip3i(0, max_c, b[2] - db));
+        }
+      }
+    }
+    __syncthreads();
+
+    // ---- store the finished columns [x0 - 8, x0 + 120) (chroma [cx0 - 8, cx0 + 56)): 16-byte vectors, vector 0 from the carry ----
+    if (store) {
 #pragma unroll
       for (int i = 0; i < 4; i++) {
-        const uint4 raw = *reinterpret_cast<const uint4*>(sp + i * LP);
-        unpack2(raw.x, L[i][0], L[i][1]); unpack2(raw.y, L[i][2], L[i][3]); unpack2(raw.z, L[i][4], L[i][5]); unpack2(raw.w, L[i][6], L[i][7]);
+        const int v = tid & 15, r = (tid >> 4) + 8 * i;  // 16 vectors per row, 32 rows
+        const int x = x0 - 8 + 8 * v, y = y0 + r;
+        if (x >= 0 && x < g.width && y >= 0 && y < rows && (!flush || v == 0))
+          *reinterpret_cast<uint4*>(dst_y + (size_t)y * g.pitch_y + x) = *reinterpret_cast<const uint4*>(t.y(r, 8 * v - 8));
       }
-      if (filter_luma_segment(L, ep, max_y)) {
-#pragma unroll
-        for (int i = 0; i < 4; i++)
-          *reinterpret_cast<uint4*>(sp + i * LP) = make_uint4(pack2(L[i][0], L[i][1]), pack2(L[i][2], L[i][3]), pack2(L[i][4], L[i][5]), pack2(L[i][6], L[i][7]));
-      }
-    }
-  }
-  // ---- vertical edges, chroma: task = one unit = 2 lines x 4 samples.  2 planes x 8 edge columns x 8 unit rows ----
-  if (!(g.debug & 1)) {
-    const int pl = tid >> 6, k = (tid >> 3) & 7, sg = tid & 7;
-    const int q = sg * MW + 4 * k + 2;               // chroma x = 64 tx + 8 k -> luma 128 tx + 16 k -> unit 32 tx + 4 k
-    bool no_p, no_q;
-    const int tc = chroma_tc(cinfo, g, sd, q, q - 1, true, pl, 2 * (cx0 + 4 + 8 * k), 2 * (cy0 + 2 * sg), no_p, no_q);
-    if (tc >= 0) {
 #pragma unroll
       for (int i = 0; i < 2; i++) {
-        int16_t* sp = &s.c[pl][(2 * sg + i) * CP + 2 + 8 * k];
-        const int m2 = sp[0], m3 = sp[1], m4 = sp[2], m5 = sp[3];
-        const int delta = clip3i(-tc, tc, (((m4 - m3) << 2) + m2 - m5 + 4) >> 3);
-        if (!no_p) sp[1] = (int16_t)clip3i(0, max_c, m3 + delta);
-        if (!no_q) sp[2] = (int16_t)clip3i(0, max_c, m4 - delta);
+        const int v = tid & 7, r = (tid >> 3) & 15, pl = i;  // 8 vectors per row, 16 rows, 2 planes
+        const int x = cx0 - 8 + 8 * v, y = cy0 + r;
+        if (x >= 0 && x < cw && y >= 0 && y < crow && (!flush || v == 0))
+          *reinterpret_cast<uint4*>((pl ? dst_cr : dst_cb) + (size_t)y * g.pitch_c + x) = *reinterpret_cast<const uint4*>(t.ch(pl, r, 8 * v - 8));
       }
     }
-  }
-  __syncthreads();
-
-  // ---- horizontal edges, luma: task = 4 columns x 8 rows.  4 edge rows x 32 segments (a warp = one edge row) ----
-  if (!(g.debug & 1)) {
-    const int sg = tid & 31, h = tid >> 5;
-    const int q = (2 * h + 1) * MW + sg + 1;         // unit column 32 tx - 1 + sg, unit row 8 ty + 2 h
-    const int xg = x0 + 4 * sg, yg = y0 + 4 + 8 * h;
-    const EdgeParams ep = luma_edge_params<MV>(s, g, sd, q, q - MW, false, xg, yg);
-    if (ep.bs) {
-      int16_t* sp = &s.y[(8 * h) * LP + 4 * sg];
-      int L[4][8];
-#pragma unroll
-      for (int i = 0; i < 8; i++) {
-        const uint2 raw = *reinterpret_cast<const uint2*>(sp + i * LP);
-        unpack2(raw.x, L[0][i], L[1][i]); unpack2(raw.y, L[2][i], L[3][i]);
-      }
-      if (filter_luma_segment(L, ep, max_y)) {
-#pragma unroll
-        for (int i = 1; i < 7; i++) *reinterpret_cast<uint2*>(sp + i * LP) = make_uint2(pack2(L[0][i], L[1][i]), pack2(L[2][i], L[3][i]));
-      }
+    // ---- the tile's last 8 columns and last unit column become the next carry ----
+    if (!flush) {
+      if (tid < 32) *reinterpret_cast<uint4*>(&next_carry->y[tid][0]) = *reinterpret_cast<const uint4*>(&t.st->y[tid][TW - 8]);
+      else if (tid < 64) { const int pl = (tid - 32) >> 4, r = tid & 15; *reinterpret_cast<uint4*>(&next_carry->c[pl][r][0]) = *reinterpret_cast<const uint4*>(&t.st->c[pl][r][CTW - 8]); }
+      else if (tid < 64 + UH) { const int r = tid - 64; next_carry->info[r] = t.st->info[r][UW - 1]; next_carry->info_c[r] = has_ctree ? t.st->info_c[r][UW - 1] : 0u; }
+      else if (MV && tid >= 96 && tid < 96 + UH) { const int r = tid - 96; next_carry->mv[r] = t.st->mv[MV ? r : 0][MV ? UW - 1 : 0]; }
     }
-  }
-  // ---- horizontal edges, chroma: task = one unit = 2 columns x 4 rows.  2 planes x 2 edge rows x 32 units ----
-  if (!(g.debug & 1)) {
-    const int pl = tid >> 6, h = (tid >> 5) & 1, m = tid & 31;
-    const int q = (4 * h + 1) * MW + m;               // chroma y = 16 ty + 8 h -> luma 32 ty + 16 h -> unit row 8 ty + 4 h
-    bool no_p, no_q;
-    const int tc = chroma_tc(cinfo, g, sd, q, q - MW, false, pl, 2 * (cx0 + 2 * m), 2 * (cy0 + 2 + 8 * h), no_p, no_q);
-    if (tc >= 0) {
-      int16_t* sp = &s.c[pl][(8 * h) * CP + 2 * m];
-      int a[4], b[4];
-#pragma unroll
-      for (int i = 0; i < 4; i++) unpack2(*reinterpret_cast<const uint32_t*>(sp + i * CP), a[i], b[i]);
-      const int da = clip3i(-tc, tc, (((a[2] - a[1]) << 2) + a[0] - a[3] + 4) >> 3);
-      const int db = clip3i(-tc, tc, (((b[2] - b[1]) << 2) + b[0] - b[3] + 4) >> 3);
-      if (!no_p) *reinterpret_cast<uint32_t*>(sp + CP) = pack2(clip3i(0, max_c, a[1] + da), clip3i(0, max_c, b[1] + db));
-      if (!no_q) *reinterpret_cast<uint32_t*>(sp + 2 * CP) = pack2(clip3i(0, max_c, a[2] - da), clip3i(0, max_c, b[2] - db));
-    }
-  }
-  __syncthreads();
-
-  // ---- write back ----
-  {
-    int16_t* __restrict__ dst_y = sd.buf[dst_b][0];
-    const int k = tid & 31, r0 = tid >> 5;
-#pragma unroll
-    for (int i = 0; i < 8; i++) {
-      const int r = r0 + 4 * i, x = x0 + k * 4, y = y0 + r;
-      if (interior || (x >= 0 && x < g.width && y >= 0 && y < rows))
-        *reinterpret_cast<uint2*>(dst_y + (size_t)y * g.pitch_y + x) = *reinterpret_cast<const uint2*>(&s.y[r * LP + k * 4]);
-    }
-    const int kc = tid & 15, rc0 = tid >> 4;
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-      const int pl = i >> 1, r = rc0 + 8 * (i & 1), x = cx0 + kc * 4, y = cy0 + r;
-      if (interior || (x >= 0 && x < cw && y >= 0 && y < crow))
-        *reinterpret_cast<uint2*>(sd.buf[dst_b][1 + pl] + (size_t)y * g.pitch_c + x) = *reinterpret_cast<const uint2*>(&s.c[pl][r * CP + kc * 4]);
-    }
+    __syncthreads();  // the stage is free; the next carry is complete
+    if (tid == 0 && !flush && tx + stages <= last) issue(tx + stages, si);
+    if (++si == stages) { si = 0; phase ^= 1u; }
   }
 }
 
 }  // namespace
 
+template <int MV>
+static void launch_deblock_mv(const Geom& g, const SlotDev* slots, int first_slot, int num_slots, const BatchCtl& ctl, cudaStream_t st) {
+  const int smem = DB_STAGES * stage_stride<MV>() + 2 * (int)((sizeof(Carry<MV>) + 15) & ~size_t(15)) + DB_STAGES * 8 + (int)sizeof(DbShared);
+  static bool attr_set = false;
+  if (!attr_set) { cudaFuncSetAttribute(deblock_kernel<MV>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr_set = true; }
+  const int bands = (g.rows + 4 + TH - 1) / TH, ntx = (g.width + TW - 1) / TW;
+  int nseg = (148 * 4 + bands * num_slots - 1) / (bands * num_slots);
+  nseg = nseg < 1 ? 1 : (nseg > ntx ? ntx : nseg);
+  dim3 grid(nseg, bands, num_slots);
+  deblock_kernel<MV><<<grid, NTHREADS, smem, st>>>(g, slots, first_slot, ctl, nseg);
+}
+
 void launch_deblock(const Geom& g, const SlotDev* slots, int first_slot, int num_slots, const BatchCtl& ctl, int mv_mode, cudaStream_t st) {
-  dim3 grid((g.width + 4 + TW - 1) / TW, (g.rows + 4 + TH - 1) / TH, num_slots);
-  if (mv_mode == 0) deblock_kernel<0><<<grid, NTHREADS, 0, st>>>(g, slots, first_slot, ctl);
-  else if (mv_mode == 1) deblock_kernel<1><<<grid, NTHREADS, 0, st>>>(g, slots, first_slot, ctl);
-  else deblock_kernel<2><<<grid, NTHREADS, 0, st>>>(g, slots, first_slot, ctl);
+  if (mv_mode == 0) launch_deblock_mv<0>(g, slots, first_slot, num_slots, ctl, st);
+  else if (mv_mode == 1) launch_deblock_mv<1>(g, slots, first_slot, num_slots, ctl, st);
+  else launch_deblock_mv<2>(g, slots, first_slot, num_slots, ctl, st);
 }
 
 }  // namespace ilf
