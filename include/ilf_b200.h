@@ -248,19 +248,44 @@ int ilf_slot_output_planes(ilf_ctx* ctx, int slot, void* planes[3], int32_t pitc
 void* ilf_stream(ilf_ctx* ctx); /* cudaStream_t of the context */
 
 /* ---------------------------------------------------------------------------------------------
- * CTU-row band mode (one picture split across GPUs, BASELINE config 4).  A band context is created
- * with the FULL picture geometry plus the band's CTU-row range; it holds the band's rows and halo
- * rows above/below.  Halo rows come from the neighbouring band's context on another device through
- * ilf_band_exchange (cudaMemcpyPeerAsync over NVLink; staged through the host if peer access is
- * unavailable).  See DESIGN.md "multi-GPU".
+ * CTU-row band mode (one picture split across GPUs, BASELINE config 4).  A band context is
+ * created with the FULL picture geometry plus the band's CTU-row range; it holds the band's own rows and 16
+ * luma (8 chroma) halo rows above and below (clipped to the picture; 16 keeps the held region on the chroma edge grid).  The three stages are local stencils:
+ * the dependency chain of a band's own rows closes at 4 luma / 3 chroma INPUT rows per side, so the halo
+ * is exchanged once per picture, on the input, and every GPU filters its halo rows redundantly.  The
+ * results of the halo rows themselves are not valid and are never downloaded.
+ *
+ *   ilf_upload_band     host planes cover the band's OWN rows only (ilf_get_band_rows: own_first, own_rows)
+ *   ilf_band_export     handle of a slot's planes for the neighbouring band contexts
+ *   ilf_band_connect    opens a neighbour's planes: direct pointer in the same process (peer access is enabled
+ *                       when the devices differ), CUDA IPC mapping from another process (one process per GPU)
+ *   ilf_band_exchange   copies the halo rows of the slot's input picture out of the connected neighbours'
+ *                       input buffers, device to device (NVLink P2P between GPUs), on the context's upload
+ *                       stream; the slot's next ilf_run is ordered after it.  The CALLER makes sure that the
+ *                       neighbours' uploads have completed (ilf_sync on them; a barrier between processes)
+ *                       and that a neighbour does not upload its next picture before this exchange is done.
+ *   ilf_download_band   the band's own rows of the filtered picture
+ * Side information of a band context: unit grids cover the rows the context HOLDS (ilf_get_band: first_row,
+ * num_rows); ctu_slice, SAO parameters and ALF flags cover the full picture.
  * ------------------------------------------------------------------------------------------- */
 typedef struct {
   int32_t first_ctu_row; /* first CTU row owned by this band */
   int32_t num_ctu_rows;  /* CTU rows owned                    */
 } ilf_band;
 
+typedef struct { unsigned char opaque[192]; } ilf_band_handle;
+#define ILF_BAND_ABOVE 0
+#define ILF_BAND_BELOW 1
+
 int ilf_create_band(ilf_ctx** out, const ilf_config* cfg, const ilf_band* band);
 int ilf_get_band(const ilf_ctx* ctx, ilf_band* out, int32_t* first_row, int32_t* num_rows);
+int ilf_get_band_rows(const ilf_ctx* ctx, int32_t* own_first, int32_t* own_rows);
+int ilf_upload_band(ilf_ctx* ctx, int slot, const int16_t* y, ptrdiff_t stride_y, const int16_t* cb, ptrdiff_t stride_cb, const int16_t* cr,
+                    ptrdiff_t stride_cr);
+int ilf_download_band(ilf_ctx* ctx, int slot, int16_t* y, ptrdiff_t stride_y, int16_t* cb, ptrdiff_t stride_cb, int16_t* cr, ptrdiff_t stride_cr);
+int ilf_band_export(ilf_ctx* ctx, int slot, ilf_band_handle* out);
+int ilf_band_connect(ilf_ctx* ctx, int slot, int side, const ilf_band_handle* neighbour);
+int ilf_band_exchange(ilf_ctx* ctx, int slot);
 
 #ifdef __cplusplus
 }

@@ -64,3 +64,34 @@ def alf_params(rng, ctus_w, ctus_h, is7=True, p_on=0.8, big=False):
     a["luma_filter_7x7"][0] = 1 if is7 else 0
     en = (rng.random((3, ctus_w * ctus_h)) < p_on).astype(np.uint8)
     return a.tobytes(), en
+
+
+def deblock_info(rng, w, h, p_edge=0.5, p_intra=0.4, inter=False):
+    """Synthetic per-4x4 grid (include/ilf_b200.h): random 8x8 'coding blocks' -- edge / TU flags on the 8-sample grid
+    (never on the picture border), intra and cbf flags and QP per 8x8 block.  With inter=True the non-intra blocks carry
+    random reference ids and int16 motion vectors (constant per 8x8 block).  Returns (params_bytes, info, mv16)."""
+    uw, uh = w // 4, h // 4
+    bw, bh = (uw + 1) // 2, (uh + 1) // 2
+    up = lambda a: np.kron(a, np.ones((2, 2), a.dtype))[:uh, :uw]
+    intra = up((rng.random((bh, bw)) < p_intra).astype(np.uint32))
+    cbf = up((rng.random((bh, bw)) < 0.5).astype(np.uint32))
+    qp = up(rng.integers(20, 46, (bh, bw)).astype(np.uint32))
+    ev = up((rng.random((bh, bw)) < p_edge).astype(np.uint32))
+    eh = up((rng.random((bh, bw)) < p_edge).astype(np.uint32))
+    tv = up((rng.random((bh, bw)) < 0.7).astype(np.uint32))
+    th = up((rng.random((bh, bw)) < 0.7).astype(np.uint32))
+    xs, ys = np.arange(uw)[None, :], np.arange(uh)[:, None]
+    ev = ev * ((xs % 2 == 0) & (xs > 0))   # a unit's LEFT border is an edge only on the 8-sample grid, not at x = 0
+    eh = eh * ((ys % 2 == 0) & (ys > 0))
+    ref0 = up(rng.integers(0, 3, (bh, bw)).astype(np.uint32)) if inter else np.full((uh, uw), 0xFF, np.uint32)
+    ref1 = np.full((uh, uw), 0xFF, np.uint32)
+    info = (intra | (cbf << 1) | (ev.astype(np.uint32) << 2) | ((tv * ev).astype(np.uint32) << 3) | (eh.astype(np.uint32) << 4) |
+            ((th * eh).astype(np.uint32) << 5) | (qp << 8) | (ref0 << 16) | (ref1 << 24)).astype(np.uint32)
+    mv16 = None
+    if inter:
+        mv = rng.integers(-12, 13, (bh, bw, 4)).astype(np.int16)
+        mv16 = np.ascontiguousarray(np.kron(mv, np.ones((2, 2, 1), np.int16))[:uh, :uw])
+        mv16[..., 2:] = 0
+    prm = np.zeros(1, DB_DT)
+    prm["cb_qp_offset"], prm["cr_qp_offset"], prm["mv_threshold"], prm["num_slices"] = 1, -1, 4, 1
+    return prm.tobytes(), info, mv16

@@ -8,6 +8,8 @@
 #include <string>
 #include <vector>
 
+#include <unistd.h>
+
 #include "ilf_common.cuh"
 
 using namespace ilf;
@@ -46,6 +48,8 @@ struct Slot {
   cudaEvent_t ev_side[3] = {nullptr, nullptr, nullptr};  // the pinned side-information region of stage k is free again
   size_t side_off[4] = {0, 0, 0, 0};                       // regions of pinned_side per stage
   bool h2d_pending = false;        // H2D work was issued since the last kernel launch on this slot
+  // band mode: planes of the neighbouring bands' matching slot (above, below)
+  struct Neighbour { const int16_t* planes = nullptr; void* ipc_base = nullptr; int device = -1, row0 = 0, rows = 0, pitch_y = 0, pitch_c = 0; size_t plane_y = 0, plane_c = 0; } nb[2];
 };
 
 }  // namespace
@@ -168,6 +172,15 @@ int stage_side(ilf_ctx* ctx, Slot& s, void* dst, const void* src, size_t bytes, 
   return ILF_OK;
 }
 
+struct BandHandle {  // what ilf_band_export writes into ilf_band_handle::opaque
+  uint32_t magic;
+  int32_t pid, device, width, row0, rows, pitch_y, pitch_c;
+  uint64_t plane_y, plane_c, ptr;
+  cudaIpcMemHandle_t ipc;
+};
+static_assert(sizeof(BandHandle) <= sizeof(ilf_band_handle), "ilf_band_handle too small");
+constexpr uint32_t BAND_MAGIC = 0x424C4649u;
+
 // Unit grids live on the device with a row pitch of units_pitch elements (multiple of 4); the caller's arrays are dense.
 int stage_grid(ilf_ctx* ctx, Slot& s, void* dst, const void* src, size_t elem_bytes, size_t& cursor, size_t limit) {
   const Geom& g = ctx->g;
@@ -219,7 +232,9 @@ int create_impl(ilf_ctx** out, const ilf_config* cfg, const ilf_band* band) {
     }
     ctx->is_band = true;
     ctx->band = *band;
-    const int halo = 8;  // luma rows held beyond the band on each side (4 luma / 3 chroma rows are needed)
+    // luma rows held beyond the band on each side: 4 luma / 3 chroma rows are needed; 16 keeps the held region on the
+    // 16-luma-row grid of the chroma deblocking edges (8 chroma rows), which the kernels locate by LOCAL row
+    const int halo = 16;
     g.out_row0 = band->first_ctu_row << cfg->ctu_log2;
     const int out_end = std::min(cfg->height, (band->first_ctu_row + band->num_ctu_rows) << cfg->ctu_log2);
     g.out_rows = out_end - g.out_row0;
@@ -334,6 +349,7 @@ int ilf_destroy(ilf_ctx* ctx) {
   cudaSetDevice(ctx->cfg.device);
   for (cudaStream_t st : {ctx->s_up, ctx->stream, ctx->s_down}) if (st) cudaStreamSynchronize(st);
   for (Slot& s : ctx->slots) {
+    for (auto& nb : s.nb) if (nb.ipc_base) cudaIpcCloseMemHandle(nb.ipc_base);
     cudaFree(s.planes); cudaFree(s.info); cudaFree(s.info_c); cudaFree(s.mv); cudaFree(s.ctu_slice); cudaFree(s.db_params);
     cudaFree(s.sao); cudaFree(s.alf); cudaFree(s.alf_coef); cudaFree(s.alf_ctu_enable); cudaFree(s.alf_class);
     if (s.pinned) cudaFreeHost(s.pinned);
@@ -364,9 +380,8 @@ int ilf_get_band(const ilf_ctx* ctx, ilf_band* out, int32_t* first_row, int32_t*
   return ILF_OK;
 }
 
-// Host planes cover the rows the context HOLDS: the whole picture, or for a band context picture rows
-// [row0, row0 + rows) as reported by ilf_get_band (pointer = first held row).
-int ilf_upload(ilf_ctx* ctx, int slot, const int16_t* y, ptrdiff_t sy, const int16_t* cb, ptrdiff_t scb, const int16_t* cr, ptrdiff_t scr) {
+// Copies host rows [first, first + n) (LOCAL luma rows of the held region; chroma rows first/2 ..) into the slot's input buffer.
+static int upload_rows(ilf_ctx* ctx, int slot, const int16_t* y, ptrdiff_t sy, const int16_t* cb, ptrdiff_t scb, const int16_t* cr, ptrdiff_t scr, int first, int n) {
   if (int rc = check_slot(ctx, slot)) return rc;
   if (!y || !cb || !cr) return fail(ctx, ILF_ERR_ARG, "null plane pointer");
   Slot& s = ctx->slots[slot];
@@ -384,12 +399,13 @@ int ilf_upload(ilf_ctx* ctx, int slot, const int16_t* y, ptrdiff_t sy, const int
   }
   int16_t* stage = s.pinned;
   for (int p = 0; p < 3; p++) {
-    const int w = p ? g.width / 2 : g.width, h = p ? g.rows / 2 : g.rows, pitch = p ? g.pitch_c : g.pitch_y;
+    const int w = p ? g.width / 2 : g.width, h = p ? n / 2 : n, r0 = p ? first / 2 : first, pitch = p ? g.pitch_c : g.pitch_y;
+    int16_t* dst = plane_ptr(ctx, s, 0, p) + (size_t)r0 * pitch;
     if (direct) {
-      CU(ctx, cudaMemcpy2DAsync(plane_ptr(ctx, s, 0, p), (size_t)pitch * 2, srcs[p], (size_t)strides[p] * 2, (size_t)w * 2, h, cudaMemcpyHostToDevice, ctx->s_up));
+      CU(ctx, cudaMemcpy2DAsync(dst, (size_t)pitch * 2, srcs[p], (size_t)strides[p] * 2, (size_t)w * 2, h, cudaMemcpyHostToDevice, ctx->s_up));
     } else {
       for (int r = 0; r < h; r++) memcpy(stage + (size_t)r * w, srcs[p] + (ptrdiff_t)r * strides[p], (size_t)w * 2);
-      CU(ctx, cudaMemcpy2DAsync(plane_ptr(ctx, s, 0, p), (size_t)pitch * 2, stage, (size_t)w * 2, (size_t)w * 2, h, cudaMemcpyHostToDevice, ctx->s_up));
+      CU(ctx, cudaMemcpy2DAsync(dst, (size_t)pitch * 2, stage, (size_t)w * 2, (size_t)w * 2, h, cudaMemcpyHostToDevice, ctx->s_up));
       stage += (size_t)w * h;
     }
   }
@@ -401,9 +417,22 @@ int ilf_upload(ilf_ctx* ctx, int slot, const int16_t* y, ptrdiff_t sy, const int
   return ILF_OK;
 }
 
-// Issues the device -> host copy of the slot's current picture.  Into page-locked memory the copy is asynchronous
-// (ilf_wait / ilf_sync complete it); into pageable memory the call stages and blocks.
-int ilf_download_async(ilf_ctx* ctx, int slot, int16_t* y, ptrdiff_t sy, int16_t* cb, ptrdiff_t scb, int16_t* cr, ptrdiff_t scr) {
+// Host planes cover the rows the context HOLDS: the whole picture, or for a band context picture rows
+// [row0, row0 + rows) as reported by ilf_get_band (pointer = first held row).
+int ilf_upload(ilf_ctx* ctx, int slot, const int16_t* y, ptrdiff_t sy, const int16_t* cb, ptrdiff_t scb, const int16_t* cr, ptrdiff_t scr) {
+  if (!ctx) return ILF_ERR_ARG;
+  return upload_rows(ctx, slot, y, sy, cb, scb, cr, scr, 0, ctx->g.rows);
+}
+
+// Host planes cover the band's OWN rows (ilf_get_band_rows); the halo rows come from the neighbours (ilf_band_exchange).
+int ilf_upload_band(ilf_ctx* ctx, int slot, const int16_t* y, ptrdiff_t sy, const int16_t* cb, ptrdiff_t scb, const int16_t* cr, ptrdiff_t scr) {
+  if (!ctx) return ILF_ERR_ARG;
+  return upload_rows(ctx, slot, y, sy, cb, scb, cr, scr, ctx->g.out_row0 - ctx->g.row0, ctx->g.out_rows);
+}
+
+// Issues the device -> host copy of LOCAL rows [first, first + n) of the slot's current picture.  Into page-locked memory
+// the copy is asynchronous (ilf_wait / ilf_sync complete it); into pageable memory the call stages and blocks.
+static int download_rows(ilf_ctx* ctx, int slot, int16_t* y, ptrdiff_t sy, int16_t* cb, ptrdiff_t scb, int16_t* cr, ptrdiff_t scr, int first, int n) {
   if (int rc = check_slot(ctx, slot)) return rc;
   if (!y || !cb || !cr) return fail(ctx, ILF_ERR_ARG, "null plane pointer");
   Slot& s = ctx->slots[slot];
@@ -417,8 +446,8 @@ int ilf_download_async(ilf_ctx* ctx, int slot, int16_t* y, ptrdiff_t sy, int16_t
   const bool direct = is_pinned(y) && is_pinned(cb) && is_pinned(cr);
   if (direct) {
     for (int p = 0; p < 3; p++) {
-      const int w = p ? g.width / 2 : g.width, h = p ? g.rows / 2 : g.rows, pitch = p ? g.pitch_c : g.pitch_y;
-      CU(ctx, cudaMemcpy2DAsync(dsts[p], (size_t)strides[p] * 2, plane_ptr(ctx, s, s.result_buf[p], p), (size_t)pitch * 2, (size_t)w * 2, h, cudaMemcpyDeviceToHost, ctx->s_down));
+      const int w = p ? g.width / 2 : g.width, h = p ? n / 2 : n, r0 = p ? first / 2 : first, pitch = p ? g.pitch_c : g.pitch_y;
+      CU(ctx, cudaMemcpy2DAsync(dsts[p], (size_t)strides[p] * 2, plane_ptr(ctx, s, s.result_buf[p], p) + (size_t)r0 * pitch, (size_t)pitch * 2, (size_t)w * 2, h, cudaMemcpyDeviceToHost, ctx->s_down));
     }
     CU(ctx, cudaEventRecord(s.ev_down, ctx->s_down));
     return ILF_OK;
@@ -426,18 +455,111 @@ int ilf_download_async(ilf_ctx* ctx, int slot, int16_t* y, ptrdiff_t sy, int16_t
   CU(ctx, cudaEventSynchronize(s.ev_up));  // the staging buffer may hold a staged upload that is still being copied
   int16_t* stage = s.pinned;
   for (int p = 0; p < 3; p++) {
-    const int w = p ? g.width / 2 : g.width, h = p ? g.rows / 2 : g.rows, pitch = p ? g.pitch_c : g.pitch_y;
-    CU(ctx, cudaMemcpy2DAsync(stage, (size_t)w * 2, plane_ptr(ctx, s, s.result_buf[p], p), (size_t)pitch * 2, (size_t)w * 2, h, cudaMemcpyDeviceToHost, ctx->s_down));
+    const int w = p ? g.width / 2 : g.width, h = p ? n / 2 : n, r0 = p ? first / 2 : first, pitch = p ? g.pitch_c : g.pitch_y;
+    CU(ctx, cudaMemcpy2DAsync(stage, (size_t)w * 2, plane_ptr(ctx, s, s.result_buf[p], p) + (size_t)r0 * pitch, (size_t)pitch * 2, (size_t)w * 2, h, cudaMemcpyDeviceToHost, ctx->s_down));
     stage += (size_t)w * h;
   }
   CU(ctx, cudaEventRecord(s.ev_down, ctx->s_down));
   CU(ctx, cudaEventSynchronize(s.ev_down));
   stage = s.pinned;
   for (int p = 0; p < 3; p++) {
-    const int w = p ? g.width / 2 : g.width, h = p ? g.rows / 2 : g.rows;
+    const int w = p ? g.width / 2 : g.width, h = p ? n / 2 : n;
     for (int r = 0; r < h; r++) memcpy(dsts[p] + (ptrdiff_t)r * strides[p], stage + (size_t)r * w, (size_t)w * 2);
     stage += (size_t)w * h;
   }
+  return ILF_OK;
+}
+
+int ilf_download_async(ilf_ctx* ctx, int slot, int16_t* y, ptrdiff_t sy, int16_t* cb, ptrdiff_t scb, int16_t* cr, ptrdiff_t scr) {
+  if (!ctx) return ILF_ERR_ARG;
+  return download_rows(ctx, slot, y, sy, cb, scb, cr, scr, 0, ctx->g.rows);
+}
+
+int ilf_download_band(ilf_ctx* ctx, int slot, int16_t* y, ptrdiff_t sy, int16_t* cb, ptrdiff_t scb, int16_t* cr, ptrdiff_t scr) {
+  if (!ctx) return ILF_ERR_ARG;
+  if (int rc = download_rows(ctx, slot, y, sy, cb, scb, cr, scr, ctx->g.out_row0 - ctx->g.row0, ctx->g.out_rows)) return rc;
+  return ilf_wait(ctx, slot);
+}
+
+int ilf_get_band_rows(const ilf_ctx* ctx, int32_t* own_first, int32_t* own_rows) {
+  if (!ctx) return ILF_ERR_ARG;
+  if (own_first) *own_first = ctx->g.out_row0;
+  if (own_rows) *own_rows = ctx->g.out_rows;
+  return ILF_OK;
+}
+
+int ilf_band_export(ilf_ctx* ctx, int slot, ilf_band_handle* out) {
+  if (int rc = check_slot(ctx, slot)) return rc;
+  if (!out) return fail(ctx, ILF_ERR_ARG, "null handle");
+  Slot& s = ctx->slots[slot];
+  CU(ctx, cudaSetDevice(ctx->cfg.device));
+  BandHandle h;
+  memset(&h, 0, sizeof(h));
+  h.magic = BAND_MAGIC; h.pid = (int32_t)getpid(); h.device = ctx->cfg.device; h.width = ctx->g.width;
+  h.row0 = ctx->g.row0; h.rows = ctx->g.rows; h.pitch_y = ctx->g.pitch_y; h.pitch_c = ctx->g.pitch_c;
+  h.plane_y = ctx->plane_y; h.plane_c = ctx->plane_c; h.ptr = (uint64_t)(uintptr_t)s.planes;
+  CU(ctx, cudaIpcGetMemHandle(&h.ipc, s.planes));
+  memset(out, 0, sizeof(*out));
+  memcpy(out->opaque, &h, sizeof(h));
+  return ILF_OK;
+}
+
+int ilf_band_connect(ilf_ctx* ctx, int slot, int side, const ilf_band_handle* neighbour) {
+  if (int rc = check_slot(ctx, slot)) return rc;
+  if (!neighbour || (side != ILF_BAND_ABOVE && side != ILF_BAND_BELOW)) return fail(ctx, ILF_ERR_ARG, "bad neighbour handle or side");
+  BandHandle h;
+  memcpy(&h, neighbour->opaque, sizeof(h));
+  if (h.magic != BAND_MAGIC || h.width != ctx->g.width) return fail(ctx, ILF_ERR_ARG, "neighbour handle does not describe a band of this picture");
+  Slot& s = ctx->slots[slot];
+  Slot::Neighbour& nb = s.nb[side];
+  CU(ctx, cudaSetDevice(ctx->cfg.device));
+  if (nb.ipc_base) { cudaIpcCloseMemHandle(nb.ipc_base); nb.ipc_base = nullptr; }
+  if (h.pid == (int32_t)getpid()) {
+    if (h.device != ctx->cfg.device) {
+      int can = 0;
+      CU(ctx, cudaDeviceCanAccessPeer(&can, ctx->cfg.device, h.device));
+      if (can) {
+        cudaError_t e = cudaDeviceEnablePeerAccess(h.device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(ctx, ILF_ERR_CUDA, "cudaDeviceEnablePeerAccess(%d) failed: %s", h.device, cudaGetErrorString(e));
+        cudaGetLastError();
+      }  // without peer access the copies below are staged through the host by the driver (cudaMemcpyPeer semantics)
+    }
+    nb.planes = (const int16_t*)(uintptr_t)h.ptr;
+  } else {
+    void* base = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&base, h.ipc, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) return fail(ctx, ILF_ERR_CUDA, "cudaIpcOpenMemHandle failed: %s (no P2P path to device %d?)", cudaGetErrorString(e), h.device);
+    nb.ipc_base = base;
+    nb.planes = (const int16_t*)base;
+  }
+  nb.device = h.device; nb.row0 = h.row0; nb.rows = h.rows; nb.pitch_y = h.pitch_y; nb.pitch_c = h.pitch_c; nb.plane_y = (size_t)h.plane_y; nb.plane_c = (size_t)h.plane_c;
+  return ILF_OK;
+}
+
+int ilf_band_exchange(ilf_ctx* ctx, int slot) {
+  if (int rc = check_slot(ctx, slot)) return rc;
+  if (!ctx->is_band) return fail(ctx, ILF_ERR_STATE, "not a band context");
+  Slot& s = ctx->slots[slot];
+  const Geom& g = ctx->g;
+  CU(ctx, cudaSetDevice(ctx->cfg.device));
+  CU(ctx, cudaStreamWaitEvent(ctx->s_up, s.ev_run, 0));  // kernels of the slot's previous run may still read the halo rows
+  for (int side = 0; side < 2; side++) {
+    // picture rows of the halo on this side
+    const int h0 = side == ILF_BAND_ABOVE ? g.row0 : g.out_row0 + g.out_rows;
+    const int h1 = side == ILF_BAND_ABOVE ? g.out_row0 : g.row0 + g.rows;
+    if (h1 <= h0) continue;  // picture border
+    const Slot::Neighbour& nb = s.nb[side];
+    if (!nb.planes) return fail(ctx, ILF_ERR_STATE, "slot %d: no neighbour connected %s the band", slot, side == ILF_BAND_ABOVE ? "above" : "below");
+    if (h0 < nb.row0 || h1 > nb.row0 + nb.rows) return fail(ctx, ILF_ERR_ARG, "neighbour band does not hold picture rows [%d,%d)", h0, h1);
+    for (int p = 0; p < 3; p++) {
+      const int sh = p ? 1 : 0, w = g.width >> sh, pitch = p ? g.pitch_c : g.pitch_y, npitch = p ? nb.pitch_c : nb.pitch_y;
+      const int16_t* src = nb.planes + (p >= 1 ? nb.plane_y : 0) + (p == 2 ? nb.plane_c : 0) + (size_t)((h0 - nb.row0) >> sh) * npitch;  // neighbour's input buffer (buffer 0)
+      int16_t* dst = plane_ptr(ctx, s, 0, p) + (size_t)((h0 - g.row0) >> sh) * pitch;
+      CU(ctx, cudaMemcpy2DAsync(dst, (size_t)pitch * 2, src, (size_t)npitch * 2, (size_t)w * 2, (h1 - h0) >> sh, cudaMemcpyDefault, ctx->s_up));
+    }
+  }
+  CU(ctx, cudaEventRecord(s.ev_up, ctx->s_up));
+  s.h2d_pending = true;
   return ILF_OK;
 }
 

@@ -13,6 +13,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 STAGE_DEBLOCK, STAGE_SAO, STAGE_ALF, STAGE_ALL = 1, 2, 4, 7
 SAO_CTU_BYTES = 32
 MAX_SLICES = 64
+BAND_HANDLE_BYTES = 192
+BAND_ABOVE, BAND_BELOW = 0, 1
 
 
 class IlfError(RuntimeError):
@@ -53,6 +55,12 @@ def load_library():
     lib.ilf_last_error.restype = C.c_char_p
     lib.ilf_get_config.argtypes = [vp, C.POINTER(IlfConfig)]
     lib.ilf_get_band.argtypes = [vp, C.POINTER(IlfBand), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+    lib.ilf_get_band_rows.argtypes = [vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+    lib.ilf_upload_band.argtypes = [vp, i, vp, pd, vp, pd, vp, pd]
+    lib.ilf_download_band.argtypes = [vp, i, vp, pd, vp, pd, vp, pd]
+    lib.ilf_band_export.argtypes = [vp, i, C.c_char_p]
+    lib.ilf_band_connect.argtypes = [vp, i, i, C.c_char_p]
+    lib.ilf_band_exchange.argtypes = [vp, i]
     lib.ilf_upload.argtypes = [vp, i, vp, pd, vp, pd, vp, pd]
     lib.ilf_download.argtypes = [vp, i, vp, pd, vp, pd, vp, pd]
     lib.ilf_sync.argtypes = [vp]
@@ -123,6 +131,8 @@ class InLoopFilter:
         r0, nr = C.c_int32(), C.c_int32()
         self._lib.ilf_get_band(self._h, None, C.byref(r0), C.byref(nr))
         self.row0, self.rows = r0.value, nr.value   # picture rows held by this context
+        self._lib.ilf_get_band_rows(self._h, C.byref(r0), C.byref(nr))
+        self.own_row0, self.own_rows = r0.value, nr.value   # picture rows this context produces (band mode: its own CTU rows)
         self.width, self.height = width, height
         ctu = 1 << ctu_log2
         self.ctus_w, self.ctus_h = (width + ctu - 1) // ctu, (height + ctu - 1) // ctu
@@ -173,6 +183,33 @@ class InLoopFilter:
 
     def sync(self):
         self._ck(self._lib.ilf_sync(self._h))
+
+    # ---- CTU-row band mode (one picture across several GPUs) ---------------------------------------
+    def upload_band(self, slot, y, cb, cr):
+        """Upload the band's OWN rows (own_rows x width); halo rows come from the neighbours (band_exchange)."""
+        y, cb, cr = (_arr(a, np.int16) for a in (y, cb, cr))
+        assert y.shape == (self.own_rows, self.width) and cb.shape == cr.shape == (self.own_rows // 2, self.width // 2)
+        self._ck(self._lib.ilf_upload_band(self._h, slot, _ptr(y), y.shape[1], _ptr(cb), cb.shape[1], _ptr(cr), cr.shape[1]))
+
+    def download_band(self, slot):
+        y = np.empty((self.own_rows, self.width), np.int16)
+        cb = np.empty((self.own_rows // 2, self.width // 2), np.int16)
+        cr = np.empty_like(cb)
+        self._ck(self._lib.ilf_download_band(self._h, slot, _ptr(y), y.shape[1], _ptr(cb), cb.shape[1], _ptr(cr), cr.shape[1]))
+        return {"y": y, "cb": cb, "cr": cr}
+
+    def band_export(self, slot=0):
+        """Opaque handle (bytes) of the slot's planes for the neighbouring band contexts, in this or another process."""
+        buf = C.create_string_buffer(BAND_HANDLE_BYTES)
+        self._ck(self._lib.ilf_band_export(self._h, slot, buf))
+        return buf.raw
+
+    def band_connect(self, slot, side, handle):
+        assert len(handle) == BAND_HANDLE_BYTES
+        self._ck(self._lib.ilf_band_connect(self._h, slot, side, handle))
+
+    def band_exchange(self, slot=0):
+        self._ck(self._lib.ilf_band_exchange(self._h, slot))
 
     # ---- side information ------------------------------------------------------------------------
     def set_deblock_info(self, slot, params_bytes, info, info_chroma=None, mv16=None, mv32=None, ctu_slice=None):
