@@ -29,10 +29,19 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# NCCL prints its version banner on stdout at VERSION level; this script's stdout is ONE JSON line
+if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"
 
 WORKLOADS = {
     "ra_4k": dict(width=3840, height=2160, stream="ra_4k", desc="3840x2160 4:2:0 10-bit random access (VTM 2.1 encoder_randomaccess_vtm.cfg, QP37)"),
     "ra_1080p": dict(width=1920, height=1080, stream="ra_1080p", desc="1920x1080 4:2:0 10-bit random access (VTM 2.1 encoder_randomaccess_vtm.cfg, QP37)"),
+    # BASELINE config 5: 64 independent low-delay streams dealt round-robin to the GPUs (two encoded streams replicated to 64 logical ones)
+    "ld_1080p_x64": dict(width=1920, height=1080, stream="ld_1080p_s3001", npz=["ld_1080p_s3001", "ld_1080p_s3002"], streams=64, scaling="strong",
+                         desc="64 independent 1920x1080 4:2:0 10-bit low-delay streams (VTM 2.1 encoder_lowdelay_vtm.cfg, QP37), 9 pictures each, one stream per GPU at a time"),
+    # BASELINE config 4: one 8K picture in CTU-row bands across the GPUs, halo rows over NVLink P2P
+    "intra_8k_bands": dict(width=7680, height=4320, stream="intra_8k", npz=["intra_8k"], bands=True, scaling="strong",
+                           desc="7680x4320 4:2:0 10-bit intra picture (VTM 2.1 encoder_intra_vtm.cfg, QP37) split into CTU-row bands across the GPUs"),
 }
 # algorithmic bytes per luma pixel and launch: every sample of the planes a kernel owns read once + written once
 # (int16, 4:2:0: luma 2 B, both chroma planes 1 B per luma pixel); side information excluded.
@@ -45,6 +54,8 @@ def default_workload():
 
 
 def load_sideinfo(name):
+    if name in WORKLOADS and "npz" in WORKLOADS[name]:
+        name = WORKLOADS[name]["npz"][0]
     z = np.load(os.path.join(ROOT, "bench_data", name + ".npz"))
     pics = []
     for j in range(int(z["num_pictures"])):
@@ -264,6 +275,184 @@ def run_reference(args, wl):
 # ------------------------------------------------------------------------------------------------------------------
 # B200 arm
 # ------------------------------------------------------------------------------------------------------------------
+def hbm_peak():
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    return peak, ("MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)")
+
+
+def kernel_table(kt, peak):
+    tab = {}
+    for k, (ms, n, nbytes) in kt.items():
+        if n:
+            # algorithmic bytes as counted by the library: 2 B x (read + write) x samples of the planes the launches processed
+            tab[k] = {"avg_ms": round(ms / n, 4), "launches": n, "algo_mb_per_launch": round(nbytes / n / 1e6, 1), "algo_gbs": round(nbytes / (ms * 1e-3) / 1e9, 1),
+                      "frac": round(nbytes / (ms * 1e-3) / 1e9 / peak, 4)}
+    return tab
+
+
+def chain_table(kt, ms_region, steps, pixels_per_step, peak):
+    """Whole chain against the roofline: bytes the launched kernels really had to move / time of the timed region."""
+    nbytes = sum(v[2] for v in kt.values())
+    gbs = nbytes / (ms_region * 1e-3) / 1e9
+    return {"algo_mb_per_step": round(nbytes / steps / 1e6, 1), "bytes_per_pixel": round(nbytes / (steps * pixels_per_step), 2), "gbs": round(gbs, 1), "frac": round(gbs / peak, 4)}
+
+
+def run_bands(args, wl):
+    """BASELINE config 4: every rank owns a band of CTU rows of ONE picture (vvcsoftware_vtm_b200.bands), uploads its own rows,
+    pulls 16 halo rows per side from its neighbours' input planes (CUDA IPC mapping, device-to-device over NVLink P2P) and runs the
+    chain on its band.  A step = halo exchange + chain for `--batch` (default 4) resident pictures; strong scaling."""
+    import torch
+    import torch.distributed as dist
+    import vvcsoftware_vtm_b200 as v
+    from vvcsoftware_vtm_b200 import bands
+
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    v.load_library()
+    w, h = wl["width"], wl["height"]
+    mpx = w * h / 1e6
+    side = load_sideinfo(args.workload)
+    B = args.batch or 4
+    f = bands.make_band_context(w, h, 10, 10, 7, rank, world, local, num_slots=B)
+    y0, y1 = f.own_row0, f.own_row0 + f.own_rows
+    # synthetic planes: a 4K texture tiled 2 x 2 (every rank builds the picture and keeps its own rows)
+    q = synth_planes(w // 2, h // 2, 1, seed=8000)[0]
+    pic = [np.tile(p, (2, 2)) for p in q]
+    own = [np.ascontiguousarray(pic[0][y0:y1]), np.ascontiguousarray(pic[1][y0 // 2:y1 // 2]), np.ascontiguousarray(pic[2][y0 // 2:y1 // 2])]
+    del pic
+    pins = [torch.from_numpy(a).pin_memory() for a in own]
+    own = [t.numpy() for t in pins]
+
+    def set_side(slot, si):
+        s = bands.slice_side_info(si, f.row0, f.rows)
+        f.set_deblock_info(slot, s["db_params"].tobytes(), s["db_info"], s.get("db_info_c"), s.get("db_mv16"), None, s["ctu_slice"])
+        f.set_sao_params(slot, s["sao_ctus"])
+        f.set_alf_params(slot, s["alf_params"].tobytes(), s["alf_ctu_enable"])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for s in range(B):
+        f.upload_band(s, *own)
+    f.sync()
+    handles = [None] * world
+    for s in range(B):
+        mine = f.band_export(s)
+        if world > 1:
+            dist.all_gather_object(handles, mine)
+        else:
+            handles = [mine]
+        bands.connect_bands(f, s, rank, world, handles)
+    barrier()   # every rank's input planes are resident before anybody pulls halos
+    halo_rows = (f.own_row0 - f.row0) + (f.row0 + f.rows - (f.own_row0 + f.own_rows))
+    stream = torch.cuda.ExternalStream(f.stream(), device=torch.device("cuda", local))
+
+    def step():
+        for s in range(B):
+            f.band_exchange(s)
+        f.run(0, B, 7)
+
+    def measure(side_set, steps):
+        for s in range(B):
+            set_side(s, side_set[0])
+        f.sync()
+        for _ in range(max(args.warmup, 3)):
+            step()
+        f.sync()
+        f.set_timing(True)
+        l0 = f.launch_count()
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            ev0.record(stream)
+            for _ in range(steps):
+                step()
+            ev1.record(stream)
+        barrier()
+        ms = ev0.elapsed_time(ev1)
+        n_launch = f.launch_count() - l0
+        kt = f.kernel_times()
+        f.set_timing(False)
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), kt, n_launch
+
+    clocks = ClockSampler(local, period=0.01)
+    clocks.start()
+    ms_on, kt_on, _ = measure(all_on_sideinfo(side), args.steps)
+    ms_total, ktimes, launches = measure(side, args.steps)
+    clk = clocks.finish()
+    value = B * args.steps * mpx / (ms_total * 1e-3)       # the picture is shared: whole-job pixels = B pictures per step
+    value_on = B * args.steps * mpx / (ms_on * 1e-3)
+
+    # end to end: own rows up from page-locked memory, halos from the neighbours, chain, own rows down; one picture at a time,
+    # the ranks meet once per picture (uploads done -> halos may be pulled)
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    nbytes_own = sum(a.nbytes for a in own)
+
+    def e2e_pic():
+        f.upload_band(0, *own)
+        set_side(0, side[0])
+        f.sync()
+        if world > 1:
+            dist.barrier()
+        f.band_exchange(0)
+        f.run(0, 1, 7)
+        out = f.download_band(0)
+        if world > 1:
+            dist.barrier()   # nobody uploads the next picture while a neighbour still pulls halos
+        return out
+
+    e2e_pic()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_pic()
+    barrier()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = e2e_steps * mpx / float(t.item())
+
+    if rank == 0:
+        peak, peak_src = hbm_peak()
+        own_px = f.rows * w   # pixels rank 0 really filters per picture (own rows + redundant halo rows)
+        per_kernel = kernel_table(ktimes, peak)
+        dom = max(per_kernel, key=lambda k: per_kernel[k]["avg_ms"])
+        pk_on = kernel_table(kt_on, peak)
+        line = {"metric": "deblock+SAO+ALF Mpixel/s", "value": round(value, 1), "unit": "Mpixel/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": round(ms_total / args.steps, 4), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int16", "data": "synthetic",
+                "config": {"workload": wl["desc"], "pictures_per_step": B, "bands": bands.band_partition((h + 127) // 128, world), "halo_rows_per_side": 16,
+                           "halo_bytes_per_picture_rank0": halo_rows * w * 3, "exchange": "cudaMemcpy2DAsync device-to-device out of the neighbour's planes (CUDA IPC mapping, NVLink P2P), no collective",
+                           "side_info": f"real, bench_data/{wl['npz'][0]}.npz", "planes": "synthetic texture + 8x8 blockiness",
+                           "l2": "per rank working set of a stage: %d MB" % (B * 2 * own_px * 3 // 10 ** 6)},
+                "roofline": {"bound": "hbm", "kernel": dom, "achieved": per_kernel[dom]["algo_gbs"], "peak": peak, "unit": "GB/s", "frac": per_kernel[dom]["frac"], "traffic": None,
+                             "peak_source": peak_src, "note": "per-kernel numbers of rank 0 (its band incl. halo rows)",
+                             "chain": chain_table(ktimes, ms_total, args.steps, B * own_px, peak), "per_kernel": per_kernel,
+                             "all_on": {"value": round(value_on, 1), "unit": "Mpixel/s", "ms_per_step": round(ms_on / args.steps, 4),
+                                        "chain": chain_table(kt_on, ms_on, args.steps, B * own_px, peak), "per_kernel": pk_on}},
+                "cpu_baseline": None,
+                "e2e": {"value": round(e2e_value, 1), "unit": "Mpixel/s", "h2d_bytes_per_step": nbytes_own, "d2h_bytes_per_step": nbytes_own, "steps": e2e_steps,
+                        "path": "per picture and rank: upload_band (own rows, page-locked) + side information + barrier + band_exchange + run + download_band"},
+                "gpu_launches": launches, "clocks": clk}
+        print(json.dumps(line), flush=True)
+    f.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def run_b200(args, wl):
     import torch
     import torch.distributed as dist
@@ -282,7 +471,14 @@ def run_b200(args, wl):
 
     w, h = wl["width"], wl["height"]
     mpx = w * h / 1e6
-    side = load_sideinfo(args.workload)
+    if "streams" in wl:
+        # independent streams dealt round-robin to the ranks; every stream brings its own pictures (strong scaling)
+        from vvcsoftware_vtm_b200 import bands
+        sets = [load_sideinfo(n) for n in wl["npz"]]
+        mine = bands.deal_streams(wl["streams"], world)[rank]
+        side = [pic for st in mine for pic in sets[st % len(sets)]]
+    else:
+        side = load_sideinfo(args.workload)
     B = args.batch or len(side)
     planes = synth_planes(w, h, min(B, 4), seed=1000 + rank)
     f = v.InLoopFilter(w, h, 10, 10, 7, device=local, num_slots=B)
@@ -292,8 +488,9 @@ def run_b200(args, wl):
         f.set_sao_params(slot, si["sao_ctus"])
         f.set_alf_params(slot, si["alf_params"].tobytes(), si["alf_ctu_enable"])
 
+    pinned_planes_in = [[torch.from_numpy(np.ascontiguousarray(p)).pin_memory() for p in trip] for trip in planes]
     for s in range(B):
-        f.upload(s, *planes[s % len(planes)])
+        f.upload(s, *(t_.numpy() for t_ in pinned_planes_in[s % len(planes)]))
         set_side(s, side[s % len(side)])
     f.sync()
     stream = torch.cuda.ExternalStream(f.stream(), device=torch.device("cuda", local))
@@ -365,7 +562,8 @@ def run_b200(args, wl):
             else:
                 d[k] = v_
         pin_side.append(d)
-    outs = [v.pinned_planes(w, h) for _ in range(B)]
+    Be = min(B, 32)   # slots in rotation for the end-to-end leg
+    outs = [v.pinned_planes(w, h) for _ in range(Be)]
     h2d = sum(p.nbytes for p in planes[0])
     d2h = h2d
 
@@ -374,7 +572,7 @@ def run_b200(args, wl):
 
     def e2e_step():
         nb = 0
-        for s in range(B):
+        for s in range(Be):
             f.wait(s)                       # the slot's previous result has reached the host
             f.upload(s, *pin_in[s % len(pin_in)])
             si = pin_side[s % len(pin_side)]
@@ -398,52 +596,30 @@ def run_b200(args, wl):
     t = torch.tensor([dt], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * B * e2e_steps * mpx / float(t.item())
+    e2e_value = world * Be * e2e_steps * mpx / float(t.item())
 
     if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        peak = float(peaks.get("hbm_gbs", 6650.0))
-        peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-        def kernel_table(kt):
-            tab = {}
-            for k, (ms, n, nbytes) in kt.items():
-                if n:
-                    # algorithmic bytes as counted by the library: 2 B x (read + write) x samples of the planes the launches processed
-                    tab[k] = {"avg_ms": round(ms / n, 4), "launches": n, "algo_mb_per_launch": round(nbytes / n / 1e6, 1), "algo_gbs": round(nbytes / (ms * 1e-3) / 1e9, 1),
-                              "frac": round(nbytes / (ms * 1e-3) / 1e9 / peak, 4)}
-            return tab
-
-        def chain(kt, ms_region):
-            """Whole chain against the roofline: bytes the launched kernels really had to move / time of the timed region."""
-            nbytes = sum(v[2] for v in kt.values())
-            gbs = nbytes / (ms_region * 1e-3) / 1e9
-            return {"algo_mb_per_step": round(nbytes / args.steps / 1e6, 1), "bytes_per_pixel": round(nbytes / (args.steps * B * mpx * 1e6), 2),
-                    "gbs": round(gbs, 1), "frac": round(gbs / peak, 4)}
-
-        per_kernel = kernel_table(ktimes)
+        peak, peak_src = hbm_peak()
+        per_kernel = kernel_table(ktimes, peak)
         dom = max(per_kernel, key=lambda k: per_kernel[k]["avg_ms"])
         ach = per_kernel[dom]["algo_gbs"]
-        pk_on = kernel_table(kt_on)
+        pk_on = kernel_table(kt_on, peak)
         dom_on = max(pk_on, key=lambda k: pk_on[k]["avg_ms"])
         cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count()
         cpu = cpu_baseline(wl, cores, side, planes) if (world == 1 and not args.no_cpu_baseline) else None
         line = {"metric": "deblock+SAO+ALF Mpixel/s", "value": round(value, 1), "unit": "Mpixel/s", "n_gpus": world, "steps": args.steps,
-                "warmup": max(args.warmup, 3), "ms_per_step": round(ms_total / args.steps, 4), "higher_is_better": True, "scaling": "weak",
+                "warmup": max(args.warmup, 3), "ms_per_step": round(ms_total / args.steps, 4), "higher_is_better": True, "scaling": wl.get("scaling", "weak"),
                 "vs_baseline": None, "dtype": "int16", "data": "synthetic",
-                "config": {"workload": wl["desc"], "batch_pictures_per_gpu": B, "side_info": f"real, bench_data/{args.workload}.npz ({len(side)} pictures cycled)",
+                "config": {"workload": wl["desc"], "batch_pictures_per_gpu": B, "side_info": f"real, bench_data/{','.join(wl.get('npz', [args.workload]))}.npz ({len(side)} pictures per GPU)",
                            "planes": "synthetic texture + 8x8 blockiness", "l2": f"working set {B * 2 * h2d / 1e6:.0f} MB per stage > 126 MB L2 (inputs larger than L2, no flush)",
                            "parallelism": f"independent pictures, {world} GPU(s), no collective"},
                 "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4), "traffic": None,
-                             "peak_source": peak_src, "chain": chain(ktimes, ms_total), "per_kernel": per_kernel,
+                             "peak_source": peak_src, "chain": chain_table(ktimes, ms_total, args.steps, B * mpx * 1e6, peak), "per_kernel": per_kernel,
                              "all_on": {"what": "same pictures and deblocking information, SAO and ALF forced on for every CTU of every component (18 B/pixel)",
                                         "value": round(value_on, 1), "unit": "Mpixel/s", "ms_per_step": round(ms_on / args.steps, 4), "kernel": dom_on,
-                                        "chain": chain(kt_on, ms_on), "per_kernel": pk_on}},
+                                        "chain": chain_table(kt_on, ms_on, args.steps, B * mpx * 1e6, peak), "per_kernel": pk_on}},
                 "cpu_baseline": cpu,
-                "e2e": {"value": round(e2e_value, 1), "unit": "Mpixel/s", "h2d_bytes_per_step": B * h2d + side_b, "d2h_bytes_per_step": B * d2h,
+                "e2e": {"value": round(e2e_value, 1), "unit": "Mpixel/s", "h2d_bytes_per_step": Be * h2d + side_b, "d2h_bytes_per_step": Be * d2h, "pictures_per_step": Be,
                         "steps": e2e_steps, "path": "per picture InLoopFilter.upload + set_deblock_info/set_sao_params/set_alf_params + run + download_async (C ABI ilf_upload / ilf_set_* / ilf_run / ilf_download_async / ilf_wait), page-locked host buffers, slots cycled"},
                 "gpu_launches": launches, "clocks": clk}
         print(json.dumps(line), flush=True)
@@ -467,6 +643,8 @@ def main():
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
         run_reference(args, wl)
+    elif wl.get("bands"):
+        run_bands(args, wl)
     else:
         run_b200(args, wl)
 

@@ -30,7 +30,7 @@ struct Slot {
   int* alf_coef = nullptr;     // [25][4][16] transposed luma coefficient table
   uint8_t* alf_ctu_enable = nullptr;
   uint8_t* alf_class = nullptr;
-  int16_t* pinned = nullptr;   // host staging, one picture
+  int16_t* pinned = nullptr;   // host staging for pageable planes, one picture; allocated on first use
   uint8_t* pinned_side = nullptr;  // host staging for side information
   size_t pinned_side_bytes = 0;
   SlotDev dev;                 // host copy of the device descriptor
@@ -276,7 +276,6 @@ int create_impl(ilf_ctx** out, const ilf_config* cfg, const ilf_band* band) {
     CU(ctx, cudaMalloc(&s.alf_coef, 25 * 4 * 16 * sizeof(int)));
     CU(ctx, cudaMalloc(&s.alf_ctu_enable, 3 * (size_t)ctx->num_ctus));
     CU(ctx, cudaMalloc(&s.alf_class, units));
-    CU(ctx, cudaMallocHost(&s.pinned, ctx->buf_elems * sizeof(int16_t)));
     auto up256 = [](size_t v) { return (v + 255) & ~size_t(255); };
     s.side_off[0] = 0;
     s.side_off[1] = up256(sizeof(ilf_deblock_params)) + 2 * up256(units * 4) + up256(units * 16) + up256(ctx->num_ctus);
@@ -394,6 +393,7 @@ static int upload_rows(ilf_ctx* ctx, int slot, const int16_t* y, ptrdiff_t sy, c
   const ptrdiff_t strides[3] = {sy, scb, scr};
   const bool direct = is_pinned(y) && is_pinned(cb) && is_pinned(cr);
   if (!direct) {
+    if (!s.pinned) CU(ctx, cudaMallocHost(&s.pinned, ctx->buf_elems * sizeof(int16_t)));
     CU(ctx, cudaEventSynchronize(s.ev_up));    // staging buffer: previous staged upload consumed ...
     CU(ctx, cudaEventSynchronize(s.ev_down));  // ... and no staged download in flight
   }
@@ -452,6 +452,7 @@ static int download_rows(ilf_ctx* ctx, int slot, int16_t* y, ptrdiff_t sy, int16
     CU(ctx, cudaEventRecord(s.ev_down, ctx->s_down));
     return ILF_OK;
   }
+  if (!s.pinned) CU(ctx, cudaMallocHost(&s.pinned, ctx->buf_elems * sizeof(int16_t)));
   CU(ctx, cudaEventSynchronize(s.ev_up));  // the staging buffer may hold a staged upload that is still being copied
   int16_t* stage = s.pinned;
   for (int p = 0; p < 3; p++) {
