@@ -285,6 +285,21 @@ def hbm_peak():
     return peak, ("MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)")
 
 
+def ncu_traffic(kernel, batch):
+    """DRAM bytes per launch of `kernel` from the committed ncu capture (profiles/*_traffic.json, written by tools/ncu_summary.py),
+    if that capture was taken with the same batch; None otherwise."""
+    import glob
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json")), reverse=True):
+        try:
+            k = json.load(open(path))["kernels"].get(kernel)
+            if k and k["grid"].strip("()").split(",")[-1].strip() == str(batch):
+                return {"bytes_per_launch": round(k["dram_read_bytes"] + k["dram_write_bytes"]), "read": round(k["dram_read_bytes"]), "write": round(k["dram_write_bytes"]),
+                        "source": os.path.relpath(path, ROOT)}
+        except Exception:
+            pass
+    return None
+
+
 def kernel_table(kt, peak):
     tab = {}
     for k, (ms, n, nbytes) in kt.items():
@@ -613,7 +628,8 @@ def run_b200(args, wl):
                 "config": {"workload": wl["desc"], "batch_pictures_per_gpu": B, "side_info": f"real, bench_data/{','.join(wl.get('npz', [args.workload]))}.npz ({len(side)} pictures per GPU)",
                            "planes": "synthetic texture + 8x8 blockiness", "l2": f"working set {B * 2 * h2d / 1e6:.0f} MB per stage > 126 MB L2 (inputs larger than L2, no flush)",
                            "parallelism": f"independent pictures, {world} GPU(s), no collective"},
-                "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4), "traffic": None,
+                "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4),
+                             "traffic": (ncu_traffic(dom, B) or {}).get("bytes_per_launch"), "traffic_detail": ncu_traffic(dom, B),
                              "peak_source": peak_src, "chain": chain_table(ktimes, ms_total, args.steps, B * mpx * 1e6, peak), "per_kernel": per_kernel,
                              "all_on": {"what": "same pictures and deblocking information, SAO and ALF forced on for every CTU of every component (18 B/pixel)",
                                         "value": round(value_on, 1), "unit": "Mpixel/s", "ms_per_step": round(ms_on / args.steps, 4), "kernel": dom_on,

@@ -28,6 +28,19 @@ def main():
             for w in WANT:
                 if w in hdr:
                     fh.write(f"{w:90s} {r[hdr.index(w)]} {units[hdr.index(w)]}\n")
+    # DRAM traffic per launch of every captured kernel (bench.py copies the dominant kernel's figure into roofline.traffic)
+    import json
+    traffic = {}
+    for r in rows[2:]:
+        name = r[hdr.index("Kernel Name")].split("(")[0].split("::")[-1].split("<")[0]
+        def val(metric):
+            v = float(r[hdr.index(metric)].replace(",", ""))
+            u = units[hdr.index(metric)]
+            return v * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "usecond": 1.0, "msecond": 1e3, "nsecond": 1e-3}.get(u, 1.0)
+        traffic[name.replace("_kernel", "")] = {"grid": r[hdr.index("Grid Size")], "dram_read_bytes": val("dram__bytes_read.sum"), "dram_write_bytes": val("dram__bytes_write.sum"),
+                                                 "duration_us_under_ncu": val("gpu__time_duration.sum")}
+    with open(prefix + "_traffic.json", "w") as fh:
+        json.dump({"source": rep, "how": "ncu --set full --clock-control none, one launch per kernel of the bench's all-CTUs-on pass (17 resident 4K pictures)", "kernels": traffic}, fh, indent=1)
     tot = collections.defaultdict(lambda: [0, 0.0])
     with open(launches) as fh:
         lines = [l for l in fh if l.startswith('"')]

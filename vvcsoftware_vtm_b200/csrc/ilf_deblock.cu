@@ -40,7 +40,13 @@ constexpr int TW = RING_TILE_W, TH = DB_BAND_ROWS;  // luma tile; the band is sh
 constexpr int CTW = TW / 2, CTH = TH / 2;           // chroma tile per plane; shifted up by 2 rows
 constexpr int UW = TW / 4, UH = TH / 4;             // units per tile: 32 x 8, rows shifted up by 1
 constexpr int NTHREADS = 128;                       // one task per thread in each of the four phases
-constexpr int DB_STAGES = 3;                        // ring depth: the tile being filtered + 2 in flight
+#ifndef ILF_DB_STAGES
+#define ILF_DB_STAGES 3
+#endif
+#ifndef ILF_DB_MIN_CTAS
+#define ILF_DB_MIN_CTAS 4
+#endif
+constexpr int DB_STAGES = ILF_DB_STAGES;             // ring depth: the tile being filtered + (DB_STAGES - 1) in flight
 
 __constant__ uint8_t c_tc[66] = {0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  1,  1,  1,  1,
                                  1,  1,  1,  1,  1,  2,  2,  2,  2,  3,  3,  3,  3,  4,  4,  4,  5,  5,  6,  6,  7,  8,
@@ -232,7 +238,7 @@ __device__ __forceinline__ void unpack2(uint32_t w, int& a, int& b) { a = (int)(
 __device__ __forceinline__ uint32_t pack2(int a, int b) { return (uint32_t)(uint16_t)a | ((uint32_t)b << 16); }
 
 template <int MV>
-__global__ void __launch_bounds__(NTHREADS, 4) deblock_kernel(Geom g, const SlotDev* __restrict__ slots, int first_slot, BatchCtl bc, int nseg) {
+__global__ void __launch_bounds__(NTHREADS, ILF_DB_MIN_CTAS) deblock_kernel(Geom g, const SlotDev* __restrict__ slots, int first_slot, BatchCtl bc, int nseg) {
   extern __shared__ __align__(128) unsigned char smem[];
   constexpr int STRIDE = stage_stride<MV>();
   constexpr int stages = DB_STAGES;
