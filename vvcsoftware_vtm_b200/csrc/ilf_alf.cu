@@ -401,8 +401,7 @@ void launch_alf_luma(const Geom& g, const SlotDev* slots, int first_slot, int nu
   }
   const int bands_y = (g.rows + BR - 1) / BR, ntx = (g.width + TW - 1) / TW;
   const int bands = bands_y * num_slots;
-  int nseg = (148 * 2 + bands - 1) / bands;
-  nseg = nseg < 1 ? 1 : (nseg > ntx ? ntx : nseg);
+  const int nseg = pick_segments(bands, ntx, 148 * 3);
   dim3 gl(nseg, bands_y, num_slots);
   if (classify_only) alf_luma_kernel<true><<<gl, NT, L_SMEM_BYTES, st>>>(g, slots, first_slot, ctl, nseg);
   else alf_luma_kernel<false><<<gl, NT, L_SMEM_BYTES, st>>>(g, slots, first_slot, ctl, nseg);

@@ -75,6 +75,23 @@ __device__ __forceinline__ int clip3i(int lo, int hi, int v) { return min(max(v,
 __device__ __forceinline__ uint2 ldg_u2(const void* p) { return __ldg(reinterpret_cast<const uint2*>(p)); }
 __device__ __forceinline__ uint4 ldg_u4(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
 
+// Band-walking launches: a band (one CTA walking `ntx` tiles) can be cut into `nseg` horizontal segments so that a small batch
+// still fills the machine.  Picks the nseg whose CTA count comes closest to a whole number of waves of `resident` CTAs
+// (a partly filled last wave is idle hardware), discounted by the ring's start-up cost for short segments.
+inline int pick_segments(int bands_total, int ntx, int resident, float startup_tiles = 0.5f) {
+  int best = 1;
+  float best_score = -1.f;
+  for (int nseg = 1; nseg <= ntx; nseg++) {
+    const float len = (float)ntx / nseg;
+    if (nseg > 1 && len < 2.f) break;
+    const float waves = (float)bands_total * nseg / resident;
+    const float eff = waves / (float)(int)(waves + 0.999f);
+    const float score = eff * len / (len + startup_tiles);
+    if (score > best_score * 1.02f) { best_score = score; best = nseg; }  // prefer fewer, longer segments unless clearly better
+  }
+  return best;
+}
+
 // One launch covers `num_slots` <= MAX_BATCH grid layers; layer z works on slot first_slot + ctl.slot[z] under control word ctl.v[z].
 void launch_deblock(const Geom& g, const SlotDev* slots, int first_slot, int num_slots, const BatchCtl& ctl, int mv_mode, cudaStream_t st);
 void launch_sao(const Geom& g, const SlotDev* slots, int first_slot, int num_slots, const BatchCtl& ctl, cudaStream_t st);

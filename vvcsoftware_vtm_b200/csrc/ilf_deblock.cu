@@ -435,8 +435,7 @@ static void launch_deblock_mv(const Geom& g, const SlotDev* slots, int first_slo
   static bool attr_set = false;
   if (!attr_set) { cudaFuncSetAttribute(deblock_kernel<MV>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr_set = true; }
   const int bands = (g.rows + 4 + TH - 1) / TH, ntx = (g.width + TW - 1) / TW;
-  int nseg = (148 * 4 + bands * num_slots - 1) / (bands * num_slots);
-  nseg = nseg < 1 ? 1 : (nseg > ntx ? ntx : nseg);
+  const int nseg = pick_segments(bands * num_slots, ntx, 148 * ILF_DB_MIN_CTAS, 1.5f);  // a segment that starts inside the picture runs one extra tile
   dim3 grid(nseg, bands, num_slots);
   deblock_kernel<MV><<<grid, NTHREADS, smem, st>>>(g, slots, first_slot, ctl, nseg);
 }
