@@ -11,15 +11,16 @@
 // [16 ty - 2, 16 ty + 14), units [8 ty - 1, 8 ty + 7)) and walks it in tiles of 128 luma columns.  One stage of the ring
 // holds everything a tile needs, fetched by five or six aligned TMA boxes several tiles ahead of the arithmetic: luma
 // 128 x 32, Cb and Cr 64 x 16, the unit grid 32 x 8 (and its chroma-tree layer), motion vectors 32 x 8.  Per tile:
-//   1. vertical edges x0 + 8e, e = 0..15 (luma) / cx0 + 8k, k = 0..7 (chroma).  Edge 0 lies on the tile boundary: its P
-//      side is the CARRY, the last 8 columns (luma and chroma) and the last unit column of the previous tile.
-//   2. horizontal edges over the columns whose vertical filtering is complete: [x0 - 4, x0 + 124) luma,
-//      [cx0 - 2, cx0 + 62) chroma -- the last carried unit column plus all but the last unit column of the tile.
-//   3. store the finished columns [x0 - 8, x0 + 120) (chroma [cx0 - 8, cx0 + 56)) as 16-byte vectors, carry + tile, and
-//      save the tile's last 8 columns / last unit column as the next carry.
-// Every sample crosses HBM once in and once out (the reference makes two picture passes); all global accesses are
-// 16-byte aligned.  A walk that starts inside the picture (small batches split bands into segments) first runs the
-// tile to its left without storing, which produces the carry; the last walk of a band ends with a flush step.
+//   1. vertical edges x0 + 8e, e = 0..15 (luma) / cx0 + 8k, k = 0..7 (chroma), in shared memory.  Edge 0 lies on the tile
+//      boundary: its P side is the last four columns of the PREVIOUS tile, whose stage stays in the ring for one more step.
+//   2. horizontal edges over the columns whose vertical filtering is complete -- [x0 - 4, x0 + 124) luma,
+//      [cx0 - 2, cx0 + 62) chroma: the previous tile's last unit column plus all but the last unit column of this tile.
+//      A task (4 luma columns x 8 rows, or 2 chroma columns x 8 rows) loads its block, filters the edge in its middle when
+//      there is one, and stores the block straight to the destination plane: a warp's 32 tasks write 256 (128) contiguous
+//      bytes per row.  There is no separate write-back pass and only two CTA barriers per tile.
+// Every sample crosses HBM once in and once out (the reference makes two picture passes).  A walk that starts inside the
+// picture (small batches split bands into segments) first runs the tile to its left without storing; the last walk of a
+// band ends with a flush step for the last unit column.
 //
 // Per-edge derivation on the device (xGetBoundaryStrengthSingle :419-541, QP/tc/beta :626-634, chroma QP
 // :811-829) from the packed per-4x4 grid described in include/ilf_b200.h.
@@ -41,12 +42,12 @@ constexpr int CTW = TW / 2, CTH = TH / 2;           // chroma tile per plane; sh
 constexpr int UW = TW / 4, UH = TH / 4;             // units per tile: 32 x 8, rows shifted up by 1
 constexpr int NTHREADS = 128;                       // one task per thread in each of the four phases
 #ifndef ILF_DB_STAGES
-#define ILF_DB_STAGES 3
+#define ILF_DB_STAGES 4
 #endif
 #ifndef ILF_DB_MIN_CTAS
-#define ILF_DB_MIN_CTAS 4
+#define ILF_DB_MIN_CTAS 3
 #endif
-constexpr int DB_STAGES = ILF_DB_STAGES;             // ring depth: the tile being filtered + (DB_STAGES - 1) in flight
+constexpr int DB_STAGES = ILF_DB_STAGES;             // ring depth: previous tile, current tile, DB_STAGES - 2 in flight
 
 __constant__ uint8_t c_tc[66] = {0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  1,  1,  1,  1,
                                  1,  1,  1,  1,  1,  2,  2,  2,  2,  3,  3,  3,  3,  4,  4,  4,  5,  5,  6,  6,  7,  8,
@@ -72,36 +73,27 @@ struct Stage {
   uint32_t info_c[UH][UW];
   MvT<MV> mv[MV ? UH : 1][MV ? UW : 1];
 };
-// What a tile inherits from the tile to its left.
-template <int MV>
-struct Carry {
-  int16_t y[TH][8];        // luma columns x0 - 8 .. x0 - 1
-  int16_t c[2][CTH][8];    // chroma columns cx0 - 8 .. cx0 - 1
-  uint32_t info[UH], info_c[UH];
-  MvT<MV> mv[UH];
-};
 template <int MV> __host__ __device__ constexpr int stage_stride() { return (int)((sizeof(Stage<MV>) + 127) & ~size_t(127)); }
 template <int MV> __host__ __device__ constexpr int stage_tx_bytes(bool ctree) {
   return TH * TW * 2 + 2 * CTH * CTW * 2 + UH * UW * 4 + (ctree ? UH * UW * 4 : 0) + (MV == 1 ? UH * UW * 8 : (MV == 2 ? UH * UW * 16 : 0));
 }
 
-// The tile's unit window: column -1 is the carried unit column, 0 .. 31 the stage.
+// The tile's window: unit column -1 / sample columns -4 .. -1 (chroma -2, -1) are the last columns of the previous tile's
+// stage (nullptr at the start of a walk: no unit flags there, so nothing is filtered against it).
 template <int MV>
 struct Tile {
   Stage<MV>* st;
-  Carry<MV>* cy;
+  Stage<MV>* prev;
   bool ctree;
-  __device__ __forceinline__ uint32_t info(int r, int c) const { return c < 0 ? cy->info[r] : st->info[r][c]; }
+  __device__ __forceinline__ uint32_t info(int r, int c) const { return c < 0 ? (prev ? prev->info[r][UW - 1] : 0u) : st->info[r][c]; }
   __device__ __forceinline__ uint32_t cinfo(int r, int c) const {
     if (!ctree) return info(r, c);
-    return c < 0 ? cy->info_c[r] : st->info_c[r][c];
+    return c < 0 ? (prev ? prev->info_c[r][UW - 1] : 0u) : st->info_c[r][c];
   }
-  __device__ __forceinline__ MvT<MV> mv(int r, int c) const { return c < 0 ? cy->mv[r] : st->mv[MV ? r : 0][MV ? c : 0]; }
-  // luma / chroma sample rows: column c of the tile, c in [-8, TW); negative columns live in the carry
-  __device__ __forceinline__ int16_t* y(int r, int c) const { return c < 0 ? &cy->y[r][c + 8] : &st->y[r][c]; }
-  __device__ __forceinline__ int16_t* ch(int pl, int r, int c) const { return c < 0 ? &cy->c[pl][r][c + 8] : &st->c[pl][r][c]; }
-  __device__ __forceinline__ int ypitch(int c) const { return c < 0 ? 8 : TW; }
-  __device__ __forceinline__ int cpitch(int c) const { return c < 0 ? 8 : CTW; }
+  __device__ __forceinline__ MvT<MV> mv(int r, int c) const { return c < 0 ? prev->mv[MV ? r : 0][MV ? UW - 1 : 0] : st->mv[MV ? r : 0][MV ? c : 0]; }
+  // sample pointers: column c of the tile; negative columns live at the end of the previous tile's rows (same pitch)
+  __device__ __forceinline__ int16_t* y(int r, int c) const { return c < 0 ? &prev->y[r][TW + c] : &st->y[r][c]; }
+  __device__ __forceinline__ int16_t* ch(int pl, int r, int c) const { return c < 0 ? &prev->c[pl][r][CTW + c] : &st->c[pl][r][c]; }
 };
 
 template <int MV> __device__ __forceinline__ void mv_get(const MvT<MV>& v, int m[4]);
@@ -252,15 +244,12 @@ __global__ void __launch_bounds__(NTHREADS, ILF_DB_MIN_CTAS) deblock_kernel(Geom
   const int ntx = (g.width + TW - 1) / TW;
   const int ta = (int)blockIdx.x * ntx / nseg, tb = ((int)blockIdx.x + 1) * ntx / nseg;  // this walk stores the columns of tiles [ta, tb)
   if (ta >= tb) return;
-  // tiles the walk loads: a walk that starts inside the picture runs tile ta - 1 first (no stores) to obtain its carry;
-  // the last walk of the band ends with a flush step (tile index ntx, nothing loaded)
+  // tiles the walk loads: a walk that starts inside the picture runs tile ta - 1 first (no stores) so that tile ta finds its
+  // left neighbour vertically filtered; the last walk of the band ends with a flush step (tile index ntx, nothing loaded)
   const int first = max(ta - 1, 0), last = tb - 1;
   const int t_end = tb == ntx ? ntx : tb - 1;  // last step of the walk
-  constexpr int CARRY_BYTES = (int)((sizeof(Carry<MV>) + 15) & ~size_t(15));
-  Carry<MV>* carry = reinterpret_cast<Carry<MV>*>(smem + stages * STRIDE);
-  Carry<MV>* carry1 = reinterpret_cast<Carry<MV>*>(smem + stages * STRIDE + CARRY_BYTES);
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + stages * STRIDE + 2 * CARRY_BYTES);
-  DbShared& sh = *reinterpret_cast<DbShared*>(smem + stages * STRIDE + 2 * CARRY_BYTES + 8 * stages);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + stages * STRIDE);
+  DbShared& sh = *reinterpret_cast<DbShared*>(smem + stages * STRIDE + 8 * stages);
   const bool has_ctree = sd.info_c != nullptr;
   const bool no_meta = (g.debug & 3) == 3;  // measurement aid: copy-only without the unit grids
   const uint32_t tx_bytes = no_meta ? (uint32_t)(TH * TW * 2 + 2 * CTH * CTW * 2) : (uint32_t)stage_tx_bytes<MV>(has_ctree);
@@ -281,8 +270,6 @@ __global__ void __launch_bounds__(NTHREADS, ILF_DB_MIN_CTAS) deblock_kernel(Geom
     for (int i = 0; i < stages; i++) ring::mbar_init(&full[i], 1);
     ring::mbar_init_fence();
   }
-  // the first carry is empty: no unit flags, so nothing is filtered against it
-  for (int i = tid; i < (int)(sizeof(Carry<MV>) / 4); i += NTHREADS) reinterpret_cast<uint32_t*>(carry)[i] = 0u;
   __syncthreads();
   if (tid == 0)
     for (int t = first; t <= last && t < first + stages; t++) issue(t, t - first);
@@ -298,131 +285,141 @@ __global__ void __launch_bounds__(NTHREADS, ILF_DB_MIN_CTAS) deblock_kernel(Geom
   int16_t* __restrict__ dst_y = sd.buf[dst_b][0];
   int16_t* __restrict__ dst_cb = sd.buf[dst_b][1];
   int16_t* __restrict__ dst_cr = sd.buf[dst_b][2];
+  const bool filt = !(g.debug & 1);
 
   int si = 0;           // stage of the current tile
   uint32_t phase = 0;   // barrier phase of that stage
+  Stage<MV>* prev = nullptr;
   for (int tx = first; tx <= t_end; tx++) {
-    const bool flush = tx == ntx;     // nothing loaded: only the carry is finished and stored
-    const bool store = tx >= ta;      // the warm-up tile of a walk produces the carry only
+    const bool flush = tx == ntx;     // nothing loaded: only the previous tile's last unit column is finished and stored
     Tile<MV> t;
     t.st = reinterpret_cast<Stage<MV>*>(smem + si * STRIDE);
-    t.cy = ((tx - first) & 1) ? carry1 : carry;
+    t.prev = prev;
     t.ctree = has_ctree;
-    Carry<MV>* next_carry = ((tx - first) & 1) ? carry : carry1;
     if (!flush) ring::mbar_wait(&full[si], phase);
+    if (tx < ta) {
+      // the tile left of the walk: only its last four columns and last unit column are needed, as they were loaded (the
+      // vertical edge at column 120 does not reach them, and they are filtered and stored by this walk's first step)
+      prev = t.st;
+      if (++si == stages) { si = 0; phase ^= 1u; }
+      continue;
+    }
     const int x0 = tx * TW, cx0 = tx * CTW;
 
     // ---- vertical edges, luma: task = 4 lines x 8 samples.  16 edge columns x 8 segment rows ----
-    if (!(g.debug & 1) && !flush) {
+    if (filt && !flush && ((tid & 15) > 0 || prev)) {
       const int e = tid & 15, sg = tid >> 4;
       const EdgeParams ep = luma_edge_params<MV>(t, g, sh, sg, 2 * e, sg, 2 * e - 1, true, x0 + 8 * e, y0 + 4 * sg);
       if (ep.bs) {
         int16_t* pp = t.y(4 * sg, 8 * e - 4);
         int16_t* pq = t.y(4 * sg, 8 * e);
-        const int pitch_p = t.ypitch(8 * e - 4);
         int L[4][8];
 #pragma unroll
         for (int i = 0; i < 4; i++) {
-          const uint2 a = *reinterpret_cast<const uint2*>(pp + i * pitch_p), b = *reinterpret_cast<const uint2*>(pq + i * TW);
+          const uint2 a = *reinterpret_cast<const uint2*>(pp + i * TW), b = *reinterpret_cast<const uint2*>(pq + i * TW);
           unpack2(a.x, L[i][0], L[i][1]); unpack2(a.y, L[i][2], L[i][3]); unpack2(b.x, L[i][4], L[i][5]); unpack2(b.y, L[i][6], L[i][7]);
         }
         if (filter_luma_segment(L, ep, max_y)) {
 #pragma unroll
           for (int i = 0; i < 4; i++) {
-            *reinterpret_cast<uint2*>(pp + i * pitch_p) = make_uint2(pack2(L[i][0], L[i][1]), pack2(L[i][2], L[i][3]));
+            *reinterpret_cast<uint2*>(pp + i * TW) = make_uint2(pack2(L[i][0], L[i][1]), pack2(L[i][2], L[i][3]));
             *reinterpret_cast<uint2*>(pq + i * TW) = make_uint2(pack2(L[i][4], L[i][5]), pack2(L[i][6], L[i][7]));
           }
         }
       }
     }
     // ---- vertical edges, chroma: task = one unit = 2 lines x 4 samples.  2 planes x 8 edge columns x 8 unit rows ----
-    if (!(g.debug & 1) && !flush) {
+    if (filt && !flush && (((tid >> 3) & 7) > 0 || prev)) {
       const int pl = tid >> 6, k = (tid >> 3) & 7, sg = tid & 7;
       bool no_p, no_q;
       const int tc = chroma_tc(t.cinfo(sg, 4 * k), t.cinfo(sg, 4 * k - 1), g, sh, true, pl, 2 * (cx0 + 8 * k), 2 * (cy0 + 2 * sg), no_p, no_q);
       if (tc >= 0) {
         int16_t* pp = t.ch(pl, 2 * sg, 8 * k - 2);
         int16_t* pq = t.ch(pl, 2 * sg, 8 * k);
-        const int pitch_p = t.cpitch(8 * k - 2);
 #pragma unroll
         for (int i = 0; i < 2; i++) {
-          const int m2 = pp[i * pitch_p], m3 = pp[i * pitch_p + 1], m4 = pq[i * CTW], m5 = pq[i * CTW + 1];
+          const int m2 = pp[i * CTW], m3 = pp[i * CTW + 1], m4 = pq[i * CTW], m5 = pq[i * CTW + 1];
           const int delta = clip3i(-tc, tc, (((m4 - m3) << 2) + m2 - m5 + 4) >> 3);
-          if (!no_p) pp[i * pitch_p + 1] = (int16_t)clip3i(0, max_c, m3 + delta);
+          if (!no_p) pp[i * CTW + 1] = (int16_t)clip3i(0, max_c, m3 + delta);
           if (!no_q) pq[i * CTW] = (int16_t)clip3i(0, max_c, m4 - delta);
         }
       }
     }
     __syncthreads();
+    // every thread is past the previous step's horizontal pass: the stage before the previous one is free
+    if (tid == 0) {
+      const int tf = tx - 2;  // tile whose stage is refilled
+      if (tf >= first && tf + stages <= last) issue(tf + stages, (si + stages - 2) % stages);
+    }
 
-    // ---- horizontal edges, luma: task = 4 columns x 8 rows.  4 edge rows x 32 unit columns -1 .. 30 (a warp = one edge row) ----
-    if (!(g.debug & 1)) {
+    // ---- horizontal edges, luma: task = 4 columns x 8 rows, filtered and stored.  4 edge rows x unit columns -1 .. 30
+    //      (a warp = one edge row: 256 contiguous bytes per stored row) ----
+    {
       const int u = (tid & 31) - 1, h = tid >> 5;
-      if (!flush || u < 0) {
-        const EdgeParams ep = luma_edge_params<MV>(t, g, sh, 2 * h + 1, u, 2 * h, u, false, x0 + 4 * u, y0 + 4 + 8 * h);
-        if (ep.bs) {
-          int16_t* sp = t.y(8 * h, 4 * u);
-          const int pitch = t.ypitch(4 * u);
-          int L[4][8];
+      if (u < 0 ? prev != nullptr : !flush) {
+        const int16_t* sp = t.y(8 * h, 4 * u);
+        uint2 raw[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) raw[i] = *reinterpret_cast<const uint2*>(sp + i * TW);
+        if (filt) {
+          const EdgeParams ep = luma_edge_params<MV>(t, g, sh, 2 * h + 1, u, 2 * h, u, false, x0 + 4 * u, y0 + 4 + 8 * h);
+          if (ep.bs) {
+            int L[4][8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) { unpack2(raw[i].x, L[0][i], L[1][i]); unpack2(raw[i].y, L[2][i], L[3][i]); }
+            if (filter_luma_segment(L, ep, max_y)) {
+#pragma unroll
+              for (int i = 1; i < 7; i++) raw[i] = make_uint2(pack2(L[0][i], L[1][i]), pack2(L[2][i], L[3][i]));
+            }
+          }
+        }
+        const int x = x0 + 4 * u;
+        if (x < g.width) {
+          int16_t* op = dst_y + (size_t)(y0 + 8 * h) * g.pitch_y + x;
 #pragma unroll
           for (int i = 0; i < 8; i++) {
-            const uint2 raw = *reinterpret_cast<const uint2*>(sp + i * pitch);
-            unpack2(raw.x, L[0][i], L[1][i]); unpack2(raw.y, L[2][i], L[3][i]);
-          }
-          if (filter_luma_segment(L, ep, max_y)) {
-#pragma unroll
-            for (int i = 1; i < 7; i++) *reinterpret_cast<uint2*>(sp + i * pitch) = make_uint2(pack2(L[0][i], L[1][i]), pack2(L[2][i], L[3][i]));
+            const int y = y0 + 8 * h + i;
+            if (y >= 0 && y < rows) *reinterpret_cast<uint2*>(op + (size_t)i * g.pitch_y) = raw[i];
           }
         }
       }
     }
-    // ---- horizontal edges, chroma: task = one unit = 2 columns x 4 rows.  2 planes x 2 edge rows x 32 unit columns -1 .. 30 ----
-    if (!(g.debug & 1)) {
+    // ---- horizontal edges, chroma: task = 2 columns x 8 rows (the edge lies between rows 1 and 2), filtered and stored.
+    //      2 planes x 2 row groups x unit columns -1 .. 30 ----
+    {
       const int pl = tid >> 6, h = (tid >> 5) & 1, u = (tid & 31) - 1;
-      if (!flush || u < 0) {
-        bool no_p, no_q;
-        const int tc = chroma_tc(t.cinfo(4 * h + 1, u), t.cinfo(4 * h, u), g, sh, false, pl, 2 * (cx0 + 2 * u), 2 * (cy0 + 2 + 8 * h), no_p, no_q);
-        if (tc >= 0) {
-          int16_t* sp = t.ch(pl, 8 * h, 2 * u);
-          const int pitch = t.cpitch(2 * u);
-          int a[4], b[4];
+      if (u < 0 ? prev != nullptr : !flush) {
+        const int16_t* sp = t.ch(pl, 8 * h, 2 * u);
+        uint32_t raw[8];
 #pragma unroll
-          for (int i = 0; i < 4; i++) unpack2(*reinterpret_cast<const uint32_t*>(sp + i * pitch), a[i], b[i]);
-          const int da = clip3i(-tc, tc, (((a[2] - a[1]) << 2) + a[0] - a[3] + 4) >> 3);
-          const int db = clip3i(-tc, tc, (((b[2] - b[1]) << 2) + b[0] - b[3] + 4) >> 3);
-          if (!no_p) *reinterpret_cast<uint32_t*>(sp + pitch) = pack2(clip3i(0, max_c, a[1] + da), clip3i(0, max_c, b[1] + db));
-          if (!no_q) *reinterpret_cast<uint32_t*>(sp + 2 * pitch) = pack2(clip3i(0, max_c, a[2] - da), clip3i(0, max_c, b[2] - db));
+        for (int i = 0; i < 8; i++) raw[i] = *reinterpret_cast<const uint32_t*>(sp + i * CTW);
+        if (filt) {
+          bool no_p, no_q;
+          const int tc = chroma_tc(t.cinfo(4 * h + 1, u), t.cinfo(4 * h, u), g, sh, false, pl, 2 * (cx0 + 2 * u), 2 * (cy0 + 2 + 8 * h), no_p, no_q);
+          if (tc >= 0) {
+            int a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) unpack2(raw[i], a[i], b[i]);
+            const int da = clip3i(-tc, tc, (((a[2] - a[1]) << 2) + a[0] - a[3] + 4) >> 3);
+            const int db = clip3i(-tc, tc, (((b[2] - b[1]) << 2) + b[0] - b[3] + 4) >> 3);
+            if (!no_p) raw[1] = pack2(clip3i(0, max_c, a[1] + da), clip3i(0, max_c, b[1] + db));
+            if (!no_q) raw[2] = pack2(clip3i(0, max_c, a[2] - da), clip3i(0, max_c, b[2] - db));
+          }
+        }
+        const int x = cx0 + 2 * u;
+        if (x < cw) {
+          int16_t* op = (pl ? dst_cr : dst_cb) + (size_t)(cy0 + 8 * h) * g.pitch_c + x;
+#pragma unroll
+          for (int i = 0; i < 8; i++) {
+            const int y = cy0 + 8 * h + i;
+            if (y >= 0 && y < crow) *reinterpret_cast<uint32_t*>(op + (size_t)i * g.pitch_c) = raw[i];
+          }
         }
       }
     }
-    __syncthreads();
-
-    // ---- store the finished columns [x0 - 8, x0 + 120) (chroma [cx0 - 8, cx0 + 56)): 16-byte vectors, vector 0 from the carry ----
-    if (store) {
-#pragma unroll
-      for (int i = 0; i < 4; i++) {
-        const int v = tid & 15, r = (tid >> 4) + 8 * i;  // 16 vectors per row, 32 rows
-        const int x = x0 - 8 + 8 * v, y = y0 + r;
-        if (x >= 0 && x < g.width && y >= 0 && y < rows && (!flush || v == 0))
-          *reinterpret_cast<uint4*>(dst_y + (size_t)y * g.pitch_y + x) = *reinterpret_cast<const uint4*>(t.y(r, 8 * v - 8));
-      }
-#pragma unroll
-      for (int i = 0; i < 2; i++) {
-        const int v = tid & 7, r = (tid >> 3) & 15, pl = i;  // 8 vectors per row, 16 rows, 2 planes
-        const int x = cx0 - 8 + 8 * v, y = cy0 + r;
-        if (x >= 0 && x < cw && y >= 0 && y < crow && (!flush || v == 0))
-          *reinterpret_cast<uint4*>((pl ? dst_cr : dst_cb) + (size_t)y * g.pitch_c + x) = *reinterpret_cast<const uint4*>(t.ch(pl, r, 8 * v - 8));
-      }
-    }
-    // ---- the tile's last 8 columns and last unit column become the next carry ----
-    if (!flush) {
-      if (tid < 32) *reinterpret_cast<uint4*>(&next_carry->y[tid][0]) = *reinterpret_cast<const uint4*>(&t.st->y[tid][TW - 8]);
-      else if (tid < 64) { const int pl = (tid - 32) >> 4, r = tid & 15; *reinterpret_cast<uint4*>(&next_carry->c[pl][r][0]) = *reinterpret_cast<const uint4*>(&t.st->c[pl][r][CTW - 8]); }
-      else if (tid < 64 + UH) { const int r = tid - 64; next_carry->info[r] = t.st->info[r][UW - 1]; next_carry->info_c[r] = has_ctree ? t.st->info_c[r][UW - 1] : 0u; }
-      else if (MV && tid >= 96 && tid < 96 + UH) { const int r = tid - 96; next_carry->mv[r] = t.st->mv[MV ? r : 0][MV ? UW - 1 : 0]; }
-    }
-    __syncthreads();  // the stage is free; the next carry is complete
-    if (tid == 0 && !flush && tx + stages <= last) issue(tx + stages, si);
+    // no barrier here: the next step's vertical pass touches the next stage and the last four columns of this one, the
+    // horizontal pass above reads neither
+    prev = t.st;
     if (++si == stages) { si = 0; phase ^= 1u; }
   }
 }
@@ -431,7 +428,7 @@ __global__ void __launch_bounds__(NTHREADS, ILF_DB_MIN_CTAS) deblock_kernel(Geom
 
 template <int MV>
 static void launch_deblock_mv(const Geom& g, const SlotDev* slots, int first_slot, int num_slots, const BatchCtl& ctl, cudaStream_t st) {
-  const int smem = DB_STAGES * stage_stride<MV>() + 2 * (int)((sizeof(Carry<MV>) + 15) & ~size_t(15)) + DB_STAGES * 8 + (int)sizeof(DbShared);
+  const int smem = DB_STAGES * stage_stride<MV>() + DB_STAGES * 8 + (int)sizeof(DbShared);
   static bool attr_set = false;
   if (!attr_set) { cudaFuncSetAttribute(deblock_kernel<MV>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr_set = true; }
   const int bands = (g.rows + 4 + TH - 1) / TH, ntx = (g.width + TW - 1) / TW;
