@@ -4,8 +4,8 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 constexpr int ITER = 512, CH = 8, UNR = 8;
-enum { IMAD, LOP3, IADD3, VADD2, VSUB2, VMAXS2, VMINU2, VIADDMAX, PRMT, SHF, IABS, DP2A, SHL, ISETP_SEL, VIMNMX, LEA, NKIND };
-const char* names[NKIND] = {"IMAD", "LOP3", "IADD3", "VIADD.16x2(add)", "VIADD.16x2(sub)", "VIMNMX.S16x2", "VIMNMX.U16x2", "VIADDMNMX.16x2", "PRMT", "SHF", "IABS", "IDP.2A", "SHL(imm)", "ISETP+SEL", "VIMNMX(32)", "LEA"};
+enum { IMAD, LOP3, IADD3, VADD2, VSUB2, VMAXS2, VMINU2, VIADDMAX, PRMT, SHF, IABS, DP2A, SHL, ISETP_SEL, VIMNMX, LEA, FFMA, FFMA2, FADDRM, I2F, F2I, FMNMX, HFMA2, IMADHI, NKIND };
+const char* names[NKIND] = {"IMAD", "LOP3", "IADD3", "VIADD.16x2(add)", "VIADD.16x2(sub)", "VIMNMX.S16x2", "VIMNMX.U16x2", "VIADDMNMX.16x2", "PRMT", "SHF", "IABS", "IDP.2A", "SHL(imm)", "ISETP+SEL", "VIMNMX(32)", "LEA", "FFMA", "FFMA2(f32x2)", "FADD.RM", "I2F", "F2I", "FMNMX", "HFMA2", "IMAD.SHL/big"};
 template <int K>
 __device__ __forceinline__ void op(uint32_t& x, uint32_t a, uint32_t b) {
   if (K == IMAD) x = x * a + b;
@@ -24,6 +24,18 @@ __device__ __forceinline__ void op(uint32_t& x, uint32_t a, uint32_t b) {
   else if (K == ISETP_SEL) x = ((int)x > (int)a) ? b : x;
   else if (K == VIMNMX) x = (uint32_t)max((int)x, (int)a);
   else if (K == LEA) x = (x << 2) + a;
+  else if (K == FFMA2) {
+    uint32_t y = x ^ 0x3f800000u;
+    asm volatile("{ .reg .b64 t, u, v; mov.b64 t, {%0, %1}; mov.b64 u, {%2, %2}; mov.b64 v, {%3, %3}; fma.rn.f32x2 t, t, u, v; mov.b64 {%0, %1}, t; }" : "+r"(x), "+r"(y) : "r"(a), "r"(b));
+    x ^= y & 1;
+  }
+  else if (K == FFMA) x = __float_as_uint(fmaf(__uint_as_float(x), __uint_as_float(a), __uint_as_float(b)));
+  else if (K == FADDRM) x = __float_as_uint(__fadd_rd(__uint_as_float(x), __uint_as_float(a)));
+  else if (K == I2F) x = __float_as_uint((float)(int)x) + a;
+  else if (K == F2I) x = (uint32_t)__float2int_rd(__uint_as_float(x | 0x40000000u));
+  else if (K == FMNMX) x = __float_as_uint(fminf(__uint_as_float(x), __uint_as_float(a)));
+  else if (K == HFMA2) asm volatile("fma.rn.f16x2 %0, %0, %1, %2;" : "+r"(x) : "r"(a), "r"(b));
+  else if (K == IMADHI) x = x * 0x10001u + b;
 }
 template <int K0, int K1>
 __global__ void __launch_bounds__(512) bench(uint32_t* out, uint32_t a, uint32_t b, long long* cyc) {
@@ -68,6 +80,6 @@ int main() {
   cudaMalloc(&out, blocks * 512 * 4); cudaMalloc(&cyc, blocks * 8);
   printf("warp-instructions per clock64 tick per SMSP (16 resident warps per SMSP)\n");
   row<IMAD>(); row<LOP3>(); row<IADD3>(); row<VADD2>(); row<VSUB2>(); row<VMAXS2>(); row<VMINU2>(); row<VIADDMAX>(); row<PRMT>(); row<SHF>(); row<IABS>(); row<DP2A>();
-  row<SHL>(); row<ISETP_SEL>(); row<VIMNMX>(); row<LEA>();
+  row<SHL>(); row<ISETP_SEL>(); row<VIMNMX>(); row<LEA>(); row<FFMA>(); row<FFMA2>(); row<FADDRM>(); row<I2F>(); row<F2I>(); row<FMNMX>(); row<HFMA2>(); row<IMADHI>();
   return 0;
 }

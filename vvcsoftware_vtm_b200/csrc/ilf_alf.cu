@@ -71,8 +71,10 @@ constexpr int CELL_W = TW / 2 + 2, CELL_H = BR / 2 + 2;        // 66 x 18 cells 
 constexpr int L_CELL_BYTES = CELL_H * CELL_W * 8;
 constexpr int L_SMEM_BYTES = RING_STAGES * L_STAGE_STRIDE + L_CELL_BYTES + RING_STAGES * 8;
 constexpr int NT = 256;
-constexpr int LAP_ROWS = 12;                                   // sample rows a Laplacian task walks (6 cell rows)
-constexpr int LAP_TASKS = CELL_W * (CELL_H * 2 / LAP_ROWS);    // 66 word columns x 3 row groups
+constexpr int LAP_ROWS = 6;                                    // sample rows a Laplacian task walks (3 cell rows)
+constexpr int LAP_COLS = CELL_W / 2;                           // a task covers two word columns (two cells per cell row)
+constexpr int LAP_TASKS = LAP_COLS * (CELL_H * 2 / LAP_ROWS);  // 33 column pairs x 6 row groups
+static_assert(CELL_W % 2 == 0 && (CELL_H * 2) % LAP_ROWS == 0 && LAP_TASKS <= 256, "Laplacian task grid");
 
 __constant__ uint8_t c_th[16] = {0, 1, 2, 2, 2, 2, 2, 3, 3, 3, 3, 3, 3, 3, 3, 4};
 __constant__ uint8_t c_transpose[8] = {0, 1, 0, 2, 2, 3, 1, 3};
@@ -146,6 +148,7 @@ __global__ void __launch_bounds__(NT, 3) alf_luma_kernel(Geom g, const SlotDev* 
   const int max_val = (1 << g.bd_luma) - 1;
   const bool is7 = CLASSIFY_ONLY ? true : sd.alf->luma_filter_7x7 != 0;
   const int shift = g.bd_luma + 4;
+  const uint32_t lap_k = 0x10001u << (g.bd_luma + 1), lap_k2 = lap_k << 1, lap_k4 = lap_k << 2;  // Laplacian lane bias K, 2K, 4K
 
   for (int tx = ta; tx < tb; tx++) {
     ring::mbar_wait(&full[walk.stage(tx)], walk.parity(tx));
@@ -164,33 +167,48 @@ __global__ void __launch_bounds__(NT, 3) alf_luma_kernel(Geom g, const SlotDev* 
       // ---- phase 1: the stage is the work tile; border tiles get their padding ----
       pad_borders<L_SR, ALF_HALO_Y, NT>(W, tx == 0, tx == ntx - 1, min(TW, g.width - x0), y0 - ALF_HALO_Y, rows);
 
-      // ---- phase 2: Laplacians per 2x2 cell, two samples per instruction.  Task = word column cc (samples x0-2+2cc, +1) over
-      //      the 12 sample rows of 6 cell rows: work-tile rows 12 rgp + 1 .. 12 rgp + 12, word 3 + cc ----
+      // ---- phase 2: Laplacians per 2x2 cell, two samples per instruction.  Task = two word columns (cells 2q, 2q + 1: samples
+      //      x0-2+4q .. x0+1+4q) over the 6 sample rows of 3 cell rows: work-tile rows 6 rgp + 1 .. 6 rgp + 6, words 3 + 2q, 4 + 2q.
+      //      Everything is plain 32-bit arithmetic on biased lanes (no lane ever borrows or carries): with K = 2^(bd+1),
+      //      t' = 2c + K - a - b lies in (0, 2K), and max(t', 2K - t') = K + |2c - a - b|; the 4K a cell collects is taken off
+      //      when its two columns are combined.  (__vsub2 / __vneg2 are multi-instruction emulations on sm_100a.) ----
       if (tid < LAP_TASKS) {
-        const int cc = tid % CELL_W, rgp = tid / CELL_W;
-        const uint32_t* wp = reinterpret_cast<const uint32_t*>(W) + (LAP_ROWS * rgp) * (WP / 2) + 3 + cc;
-        uint32_t cu, lu, ru, cm, lm, rm, cd, ld, rd;  // centre / left-shifted / right-shifted word of the rows above, at and below
-        { const uint32_t a = wp[-1], b = wp[0], c = wp[1]; cu = b; lu = __funnelshift_r(a, b, 16); ru = __funnelshift_r(b, c, 16); }
-        { const uint32_t a = wp[WP / 2 - 1], b = wp[WP / 2], c = wp[WP / 2 + 1]; cm = b; lm = __funnelshift_r(a, b, 16); rm = __funnelshift_r(b, c, 16); }
-        uint32_t av = 0, ah = 0, ad0 = 0, ad1 = 0;
+        const int q = tid % LAP_COLS, rgp = tid / LAP_COLS;
+        const uint32_t* wp = reinterpret_cast<const uint32_t*>(W) + (LAP_ROWS * rgp) * (WP / 2) + 2 + 2 * q;
+        // per column j: centre / left-shifted / right-shifted word of the rows above (u), at (m) and below (d)
+        uint32_t cu[2], lu[2], ru[2], cm[2], lm[2], rm[2], cd[2], ld[2], rd[2];
+        auto load_row = [&](int r, uint32_t (&c)[2], uint32_t (&l)[2], uint32_t (&rr)[2]) {
+          const uint2 a = *reinterpret_cast<const uint2*>(wp + r * (WP / 2)), b = *reinterpret_cast<const uint2*>(wp + r * (WP / 2) + 2);
+          const uint32_t f12 = __funnelshift_r(a.y, b.x, 16);
+          c[0] = a.y; c[1] = b.x; l[0] = __funnelshift_r(a.x, a.y, 16); rr[0] = f12; l[1] = f12; rr[1] = __funnelshift_r(b.x, b.y, 16);
+        };
+        load_row(0, cu, lu, ru);
+        load_row(1, cm, lm, rm);
+        uint32_t av[2], ah[2], ad0[2], ad1[2];
 #pragma unroll
         for (int i = 0; i < LAP_ROWS; i++) {
-          { const uint32_t* q = wp + (i + 2) * (WP / 2); const uint32_t a = q[-1], b = q[0], c = q[1]; cd = b; ld = __funnelshift_r(a, b, 16); rd = __funnelshift_r(b, c, 16); }
-          const uint32_t c2 = __vadd2(cm, cm), nc2 = __vsub2(0u, c2);
-          uint32_t s, t;
-          s = __vadd2(cu, cd); t = __vsub2(c2, s); const uint32_t v = __viaddmax_s16x2(s, nc2, t);     // |2c - up - down|
-          s = __vadd2(lm, rm); t = __vsub2(c2, s); const uint32_t h = __viaddmax_s16x2(s, nc2, t);     // |2c - left - right|
-          s = __vadd2(lu, rd); t = __vsub2(c2, s); const uint32_t d0 = __viaddmax_s16x2(s, nc2, t);    // |2c - up-left - down-right|
-          s = __vadd2(ru, ld); t = __vsub2(c2, s); const uint32_t d1 = __viaddmax_s16x2(s, nc2, t);    // |2c - up-right - down-left|
-          if ((i & 1) == 0) { av = v; ah = h; ad0 = d0; ad1 = d1; }
-          else {
-            av = __vadd2(av, v); ah = __vadd2(ah, h); ad0 = __vadd2(ad0, d0); ad1 = __vadd2(ad1, d1);
-            // both columns of the cell: {V, H} and {D0, D1} as 16-bit halves (a cell sum is < 2^15 up to 12 bit)
-            const uint32_t vh = __byte_perm(av, ah, 0x5410) + __byte_perm(av, ah, 0x7632);
-            const uint32_t dd = __byte_perm(ad0, ad1, 0x5410) + __byte_perm(ad0, ad1, 0x7632);
-            cell[(LAP_ROWS / 2) * rgp + (i >> 1)][cc] = make_uint2(vh, dd);
+          load_row(i + 2, cd, ld, rd);
+#pragma unroll
+          for (int j = 0; j < 2; j++) {
+            const uint32_t c2k = cm[j] + cm[j] + lap_k;
+            uint32_t t;
+            t = c2k - cu[j] - cd[j]; const uint32_t v = __vmaxu2(t, lap_k2 - t);     // K + |2c - up - down|
+            t = c2k - lm[j] - rm[j]; const uint32_t h = __vmaxu2(t, lap_k2 - t);     // K + |2c - left - right|
+            t = c2k - lu[j] - rd[j]; const uint32_t d0 = __vmaxu2(t, lap_k2 - t);    // K + |2c - up-left - down-right|
+            t = c2k - ru[j] - ld[j]; const uint32_t d1 = __vmaxu2(t, lap_k2 - t);    // K + |2c - up-right - down-left|
+            if ((i & 1) == 0) { av[j] = v; ah[j] = h; ad0[j] = d0; ad1[j] = d1; }
+            else { av[j] += v; ah[j] += h; ad0[j] += d0; ad1[j] += d1; }
+            cu[j] = cm[j]; lu[j] = lm[j]; ru[j] = rm[j]; cm[j] = cd[j]; lm[j] = ld[j]; rm[j] = rd[j];
           }
-          cu = cm; lu = lm; ru = rm; cm = cd; lm = ld; rm = rd;
+          if (i & 1) {
+            // both columns of each cell: {V, H} and {D0, D1} as 16-bit halves (a cell sum is < 2^15 up to 12 bit)
+            uint4 o;
+            o.x = __byte_perm(av[0], ah[0], 0x5410) + __byte_perm(av[0], ah[0], 0x7632) - lap_k4;
+            o.y = __byte_perm(ad0[0], ad1[0], 0x5410) + __byte_perm(ad0[0], ad1[0], 0x7632) - lap_k4;
+            o.z = __byte_perm(av[1], ah[1], 0x5410) + __byte_perm(av[1], ah[1], 0x7632) - lap_k4;
+            o.w = __byte_perm(ad0[1], ad1[1], 0x5410) + __byte_perm(ad0[1], ad1[1], 0x7632) - lap_k4;
+            *reinterpret_cast<uint4*>(&cell[(LAP_ROWS / 2) * rgp + (i >> 1)][2 * q]) = o;
+          }
         }
       }
       __syncthreads();
