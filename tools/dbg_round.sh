@@ -1,0 +1,12 @@
+run() { label=$1; shift; env "$@" python bench.py --steps 30 --warmup 3 --e2e-steps 1 --no-cpu-baseline > /tmp/b.json 2>/tmp/b.err || { echo "$label FAILED"; tail -3 /tmp/b.err; return; }
+python - "$label" <<'PY'
+import json,sys
+d=json.load(open('/tmp/b.json')); pk=d['roofline']['per_kernel']; ao=d['roofline']['all_on']['per_kernel']
+print(f"{sys.argv[1]:24s} real " + " ".join(f"{k}={v['avg_ms']:.4f}" for k,v in pk.items()) + "  | all-on " + " ".join(f"{k}={v['avg_ms']:.4f}({v['algo_gbs']:.0f})" for k,v in ao.items()))
+PY
+}
+run base X=1
+run debug1 ILF_DEBUG=1
+run debug3 ILF_DEBUG=3
+echo == copy2d; tools/ubench/copy2d
+echo == tma_ring; tools/ubench/tma_ring

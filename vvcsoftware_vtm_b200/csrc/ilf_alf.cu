@@ -31,7 +31,14 @@ constexpr int TW = RING_TILE_W;     // tile width in samples
 constexpr int BR = ALF_BAND_ROWS;   // rows of a band
 constexpr int WP = TW + 16;         // work-tile pitch in samples: [8: left halo slot][128][8: right halo slot], 288-byte rows
 constexpr int WX0 = 8;              // work-tile column of the tile's first sample
-constexpr int RING_STAGES = 4;      // the tile being filtered + 3 tiles in flight
+#ifndef ALF_RING
+#define ALF_RING 4
+#endif
+#ifndef ALF_L_CTAS
+#define ALF_L_CTAS 3
+#endif
+constexpr int RING_STAGES = ALF_RING;  // the tile being filtered + the tiles in flight
+constexpr int L_CTAS = ALF_L_CTAS;     // resident luma CTAs per SM the kernel is built for
 
 // A stage of the ring IS the work tile: the TMA box starts 8 samples left of the tile (16-byte aligned) and is WP wide, so
 // it carries the tile's horizontal halo with it; these kernels are instruction-bound, the 12.5 % of re-read columns come
@@ -109,7 +116,7 @@ __device__ __forceinline__ void load_win12(const int16_t* p, int v[12]) {
 }
 
 template <bool CLASSIFY_ONLY>
-__global__ void __launch_bounds__(NT, 3) alf_luma_kernel(Geom g, const SlotDev* __restrict__ slots, int first_slot, BatchCtl bc, int nseg) {
+__global__ void __launch_bounds__(NT, L_CTAS) alf_luma_kernel(Geom g, const SlotDev* __restrict__ slots, int first_slot, BatchCtl bc, int nseg) {
   extern __shared__ __align__(128) unsigned char smem[];
   const SlotDev& sd = slots[first_slot + bc.slot[blockIdx.z]];
   const unsigned ctl = bc.v[blockIdx.z];
@@ -419,7 +426,7 @@ void launch_alf_luma(const Geom& g, const SlotDev* slots, int first_slot, int nu
   }
   const int bands_y = (g.rows + BR - 1) / BR, ntx = (g.width + TW - 1) / TW;
   const int bands = bands_y * num_slots;
-  const int nseg = pick_segments(bands, ntx, 148 * 3);
+  const int nseg = pick_segments(bands, ntx, 148 * L_CTAS);
   dim3 gl(nseg, bands_y, num_slots);
   if (classify_only) alf_luma_kernel<true><<<gl, NT, L_SMEM_BYTES, st>>>(g, slots, first_slot, ctl, nseg);
   else alf_luma_kernel<false><<<gl, NT, L_SMEM_BYTES, st>>>(g, slots, first_slot, ctl, nseg);

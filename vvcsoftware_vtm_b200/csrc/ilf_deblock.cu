@@ -13,14 +13,15 @@
 // 128 x 32, Cb and Cr 64 x 16, the unit grid 32 x 8 (and its chroma-tree layer), motion vectors 32 x 8.  Per tile:
 //   1. vertical edges x0 + 8e, e = 0..15 (luma) / cx0 + 8k, k = 0..7 (chroma), in shared memory.  Edge 0 lies on the tile
 //      boundary: its P side is the last four columns of the PREVIOUS tile, whose stage stays in the ring for one more step.
-//   2. horizontal edges over the columns whose vertical filtering is complete -- [x0 - 4, x0 + 124) luma,
-//      [cx0 - 2, cx0 + 62) chroma: the previous tile's last unit column plus all but the last unit column of this tile.
-//      A task (4 luma columns x 8 rows, or 2 chroma columns x 8 rows) loads its block, filters the edge in its middle when
-//      there is one, and stores the block straight to the destination plane: a warp's 32 tasks write 256 (128) contiguous
-//      bytes per row.  There is no separate write-back pass and only two CTA barriers per tile.
+//   2. horizontal edges over columns whose vertical filtering is complete.  The tile's last four luma (one chroma) columns
+//      wait for the next tile's edge 0; the pass lags by 16 columns instead -- [x0 - 16, x0 + 112) luma, [cx0 - 16, cx0 + 48)
+//      chroma, the previous tile's last columns coming from its stage -- so that every stored warp row starts on a 32-byte
+//      sector.  A task (4 luma columns x 8 rows, or 2 chroma columns x 8 rows) loads its block, filters the edge in its middle
+//      when there is one, and stores the block straight to the destination plane: a warp's 32 tasks write 256 (128)
+//      contiguous bytes per row.  There is no separate write-back pass and only two CTA barriers per tile.
 // Every sample crosses HBM once in and once out (the reference makes two picture passes).  A walk that starts inside the
-// picture (small batches split bands into segments) first runs the tile to its left without storing; the last walk of a
-// band ends with a flush step for the last unit column.
+// picture (small batches split bands into segments) first runs the vertical edges of the tile to its left without storing;
+// the last walk of a band ends with a flush step for the lagging columns.
 //
 // Per-edge derivation on the device (xGetBoundaryStrengthSingle :419-541, QP/tc/beta :626-634, chroma QP
 // :811-829) from the packed per-4x4 grid described in include/ilf_b200.h.
@@ -48,6 +49,16 @@ constexpr int NTHREADS = 128;                       // one task per thread in ea
 #define ILF_DB_MIN_CTAS 3
 #endif
 constexpr int DB_STAGES = ILF_DB_STAGES;             // ring depth: previous tile, current tile, DB_STAGES - 2 in flight
+// The horizontal pass of a step stores 128 luma / 64 chroma columns that END before the tile does: the tile's last columns
+// wait for the next tile's first vertical edge.  Lagging by 16 samples (4 luma units / 8 chroma unit halves) instead of the
+// minimum (4 luma / 2 chroma samples) makes every stored warp row start on a 32-byte sector: no partly written sectors.
+#ifndef ILF_DB_LAG_Y
+#define ILF_DB_LAG_Y 4
+#endif
+#ifndef ILF_DB_LAG_C
+#define ILF_DB_LAG_C 8
+#endif
+constexpr int LAG_Y = ILF_DB_LAG_Y, LAG_C = ILF_DB_LAG_C;  // in units of 4 luma / 2 chroma columns
 
 __constant__ uint8_t c_tc[66] = {0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  1,  1,  1,  1,
                                  1,  1,  1,  1,  1,  2,  2,  2,  2,  3,  3,  3,  3,  4,  4,  4,  5,  5,  6,  6,  7,  8,
@@ -85,12 +96,12 @@ struct Tile {
   Stage<MV>* st;
   Stage<MV>* prev;
   bool ctree;
-  __device__ __forceinline__ uint32_t info(int r, int c) const { return c < 0 ? (prev ? prev->info[r][UW - 1] : 0u) : st->info[r][c]; }
+  __device__ __forceinline__ uint32_t info(int r, int c) const { return c < 0 ? (prev ? prev->info[r][UW + c] : 0u) : st->info[r][c]; }
   __device__ __forceinline__ uint32_t cinfo(int r, int c) const {
     if (!ctree) return info(r, c);
-    return c < 0 ? (prev ? prev->info_c[r][UW - 1] : 0u) : st->info_c[r][c];
+    return c < 0 ? (prev ? prev->info_c[r][UW + c] : 0u) : st->info_c[r][c];
   }
-  __device__ __forceinline__ MvT<MV> mv(int r, int c) const { return c < 0 ? prev->mv[MV ? r : 0][MV ? UW - 1 : 0] : st->mv[MV ? r : 0][MV ? c : 0]; }
+  __device__ __forceinline__ MvT<MV> mv(int r, int c) const { return c < 0 ? prev->mv[MV ? r : 0][MV ? UW + c : 0] : st->mv[MV ? r : 0][MV ? c : 0]; }
   // sample pointers: column c of the tile; negative columns live at the end of the previous tile's rows (same pitch)
   __device__ __forceinline__ int16_t* y(int r, int c) const { return c < 0 ? &prev->y[r][TW + c] : &st->y[r][c]; }
   __device__ __forceinline__ int16_t* ch(int pl, int r, int c) const { return c < 0 ? &prev->c[pl][r][CTW + c] : &st->c[pl][r][c]; }
@@ -291,19 +302,15 @@ __global__ void __launch_bounds__(NTHREADS, ILF_DB_MIN_CTAS) deblock_kernel(Geom
   uint32_t phase = 0;   // barrier phase of that stage
   Stage<MV>* prev = nullptr;
   for (int tx = first; tx <= t_end; tx++) {
-    const bool flush = tx == ntx;     // nothing loaded: only the previous tile's last unit column is finished and stored
+    const bool flush = tx == ntx;     // nothing loaded: only the previous tile's lagging columns are finished and stored
     Tile<MV> t;
     t.st = reinterpret_cast<Stage<MV>*>(smem + si * STRIDE);
     t.prev = prev;
     t.ctree = has_ctree;
     if (!flush) ring::mbar_wait(&full[si], phase);
-    if (tx < ta) {
-      // the tile left of the walk: only its last four columns and last unit column are needed, as they were loaded (the
-      // vertical edge at column 120 does not reach them, and they are filtered and stored by this walk's first step)
-      prev = t.st;
-      if (++si == stages) { si = 0; phase ^= 1u; }
-      continue;
-    }
+    // tx < ta: the tile left of the walk.  Its last columns are stored by this walk's first step, so its vertical edges
+    // are filtered here like any other tile's (all but edge 0, which does not reach those columns); nothing is stored.
+    const bool pre = tx < ta;
     const int x0 = tx * TW, cx0 = tx * CTW;
 
     // ---- vertical edges, luma: task = 4 lines x 8 samples.  16 edge columns x 8 segment rows ----
@@ -345,6 +352,11 @@ __global__ void __launch_bounds__(NTHREADS, ILF_DB_MIN_CTAS) deblock_kernel(Geom
         }
       }
     }
+    if (pre) {
+      prev = t.st;
+      if (++si == stages) { si = 0; phase ^= 1u; }
+      continue;
+    }
     __syncthreads();
     // every thread is past the previous step's horizontal pass: the stage before the previous one is free
     if (tid == 0) {
@@ -352,10 +364,10 @@ __global__ void __launch_bounds__(NTHREADS, ILF_DB_MIN_CTAS) deblock_kernel(Geom
       if (tf >= first && tf + stages <= last) issue(tf + stages, (si + stages - 2) % stages);
     }
 
-    // ---- horizontal edges, luma: task = 4 columns x 8 rows, filtered and stored.  4 edge rows x unit columns -1 .. 30
+    // ---- horizontal edges, luma: task = 4 columns x 8 rows, filtered and stored.  4 edge rows x unit columns -LAG_Y .. 31 - LAG_Y
     //      (a warp = one edge row: 256 contiguous bytes per stored row) ----
     {
-      const int u = (tid & 31) - 1, h = tid >> 5;
+      const int u = (tid & 31) - LAG_Y, h = tid >> 5;
       if (u < 0 ? prev != nullptr : !flush) {
         const int16_t* sp = t.y(8 * h, 4 * u);
         uint2 raw[8];
@@ -385,9 +397,9 @@ __global__ void __launch_bounds__(NTHREADS, ILF_DB_MIN_CTAS) deblock_kernel(Geom
       }
     }
     // ---- horizontal edges, chroma: task = 2 columns x 8 rows (the edge lies between rows 1 and 2), filtered and stored.
-    //      2 planes x 2 row groups x unit columns -1 .. 30 ----
+    //      2 planes x 2 row groups x unit columns -LAG_C .. 31 - LAG_C ----
     {
-      const int pl = tid >> 6, h = (tid >> 5) & 1, u = (tid & 31) - 1;
+      const int pl = tid >> 6, h = (tid >> 5) & 1, u = (tid & 31) - LAG_C;
       if (u < 0 ? prev != nullptr : !flush) {
         const int16_t* sp = t.ch(pl, 8 * h, 2 * u);
         uint32_t raw[8];
