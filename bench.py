@@ -29,9 +29,20 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-# NCCL prints its version banner on stdout at VERSION level; this script's stdout is ONE JSON line
+# This script's stdout is ONE JSON line.  Libraries write to file descriptor 1 behind Python's back (NCCL prints its version
+# banner there at VERSION level, whatever the environment says), so descriptor 1 is pointed at stderr for the whole run
+# and the line goes to a private copy of the original stdout.
 if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
     os.environ["NCCL_DEBUG"] = "WARN"
+_RESULT_OUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+sys.stdout = sys.stderr
+
+
+def emit(line):
+    _RESULT_OUT.write(json.dumps(line) + "\n")
+    _RESULT_OUT.flush()
+
 
 WORKLOADS = {
     "ra_4k": dict(width=3840, height=2160, stream="ra_4k", desc="3840x2160 4:2:0 10-bit random access (VTM 2.1 encoder_randomaccess_vtm.cfg, QP37)"),
@@ -269,7 +280,7 @@ def run_reference(args, wl):
             "data": "synthetic", "config": {"workload": wl["desc"]},
             "cpu_baseline": {"value": round(val, 1), "unit": "Mpixel/s", "cores": c, "kind": kind, "sample": smp},
             "e2e": {"value": round(val, 1), "unit": "Mpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -462,7 +473,7 @@ def run_bands(args, wl):
                 "e2e": {"value": round(e2e_value, 1), "unit": "Mpixel/s", "h2d_bytes_per_step": nbytes_own, "d2h_bytes_per_step": nbytes_own, "steps": e2e_steps,
                         "path": "per picture and rank: upload_band (own rows, page-locked) + side information + barrier + band_exchange + run + download_band"},
                 "gpu_launches": launches, "clocks": clk}
-        print(json.dumps(line), flush=True)
+        emit(line)
     f.close()
     if world > 1:
         dist.destroy_process_group()
@@ -638,7 +649,7 @@ def run_b200(args, wl):
                 "e2e": {"value": round(e2e_value, 1), "unit": "Mpixel/s", "h2d_bytes_per_step": Be * h2d + side_b, "d2h_bytes_per_step": Be * d2h, "pictures_per_step": Be,
                         "steps": e2e_steps, "path": "per picture InLoopFilter.upload + set_deblock_info/set_sao_params/set_alf_params + run + download_async (C ABI ilf_upload / ilf_set_* / ilf_run / ilf_download_async / ilf_wait), page-locked host buffers, slots cycled"},
                 "gpu_launches": launches, "clocks": clk}
-        print(json.dumps(line), flush=True)
+        emit(line)
     f.close()
     if world > 1:
         dist.destroy_process_group()
