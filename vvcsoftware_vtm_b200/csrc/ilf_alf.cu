@@ -118,6 +118,7 @@ __device__ __forceinline__ void load_win12(const int16_t* p, int v[12]) {
 template <bool CLASSIFY_ONLY>
 __global__ void __launch_bounds__(NT, L_CTAS) alf_luma_kernel(Geom g, const SlotDev* __restrict__ slots, int first_slot, BatchCtl bc, int nseg) {
   extern __shared__ __align__(128) unsigned char smem[];
+  pdl_launch_dependents();
   const SlotDev& sd = slots[first_slot + bc.slot[blockIdx.z]];
   const unsigned ctl = bc.v[blockIdx.z];
   if (ctl_skip(ctl, 0)) return;
@@ -145,6 +146,7 @@ __global__ void __launch_bounds__(NT, L_CTAS) alf_luma_kernel(Geom g, const Slot
     ring::mbar_init_fence();
   }
   __syncthreads();
+  pdl_wait();  // the stage before this one has written the planes read from here on
   if (tid == 0)
     for (int t = walk.first; t <= walk.last && t < walk.first + RING_STAGES; t++) issue(t);
 
@@ -323,6 +325,7 @@ __device__ __forceinline__ void load_row12(const int16_t* p, int v[12]) {
 
 __global__ void __launch_bounds__(NTC, 3) alf_chroma_kernel(Geom g, const SlotDev* __restrict__ slots, int first_slot, BatchCtl bc, int bands_c, int nseg) {
   extern __shared__ __align__(128) unsigned char smem[];
+  pdl_launch_dependents();
   const SlotDev& sd = slots[first_slot + bc.slot[blockIdx.z]];
   const unsigned ctl = bc.v[blockIdx.z];
   const int plane = 1 + ((int)blockIdx.y >= bands_c), band = (int)blockIdx.y - (plane - 1) * bands_c;
@@ -350,6 +353,7 @@ __global__ void __launch_bounds__(NTC, 3) alf_chroma_kernel(Geom g, const SlotDe
     ring::mbar_init_fence();
   }
   __syncthreads();
+  pdl_wait();  // the stage before this one has written the planes read from here on
   if (tid == 0)
     for (int t = walk.first; t <= walk.last && t < walk.first + RING_STAGES; t++) issue(t);
 
@@ -428,8 +432,8 @@ void launch_alf_luma(const Geom& g, const SlotDev* slots, int first_slot, int nu
   const int bands = bands_y * num_slots;
   const int nseg = pick_segments(bands, ntx, 148 * L_CTAS);
   dim3 gl(nseg, bands_y, num_slots);
-  if (classify_only) alf_luma_kernel<true><<<gl, NT, L_SMEM_BYTES, st>>>(g, slots, first_slot, ctl, nseg);
-  else alf_luma_kernel<false><<<gl, NT, L_SMEM_BYTES, st>>>(g, slots, first_slot, ctl, nseg);
+  if (classify_only) launch_pdl(alf_luma_kernel<true>, gl, dim3(NT), L_SMEM_BYTES, st, g, slots, first_slot, ctl, nseg);
+  else launch_pdl(alf_luma_kernel<false>, gl, dim3(NT), L_SMEM_BYTES, st, g, slots, first_slot, ctl, nseg);
 }
 
 void launch_alf_chroma(const Geom& g, const SlotDev* slots, int first_slot, int num_slots, const BatchCtl& ctl, cudaStream_t st) {
@@ -440,7 +444,7 @@ void launch_alf_chroma(const Geom& g, const SlotDev* slots, int first_slot, int 
   int nseg = (148 * 3 + bands - 1) / bands;
   nseg = nseg < 1 ? 1 : (nseg > ntx ? ntx : nseg);
   dim3 gc(nseg, 2 * bands_c, num_slots);
-  alf_chroma_kernel<<<gc, NTC, C_SMEM_BYTES, st>>>(g, slots, first_slot, ctl, bands_c, nseg);
+  launch_pdl(alf_chroma_kernel, gc, dim3(NTC), C_SMEM_BYTES, st, g, slots, first_slot, ctl, bands_c, nseg);
 }
 
 }  // namespace ilf

@@ -43,11 +43,12 @@ struct Slot {
   // download stream; the three are ordered per slot with these events, so upload of picture n+1, filtering of picture n
   // and download of picture n-1 overlap when the caller cycles through several slots.
   cudaEvent_t ev_up = nullptr;     // all H2D copies of the slot (planes + side information) issued so far are done
-  cudaEvent_t ev_run = nullptr;    // all kernels issued so far on the slot are done
+  cudaEvent_t ev_run = nullptr;    // all kernels issued so far on the slot are done (an event of the context's run ring, shared by the slots of a run)
   cudaEvent_t ev_down = nullptr;   // the last D2H copy of the slot is done
   cudaEvent_t ev_side[3] = {nullptr, nullptr, nullptr};  // the pinned side-information region of stage k is free again
   size_t side_off[4] = {0, 0, 0, 0};                       // regions of pinned_side per stage
   bool h2d_pending = false;        // H2D work was issued since the last kernel launch on this slot
+  bool d2h_pending = false;        // a D2H copy was issued since the last kernel launch on this slot
   // band mode: planes of the neighbouring bands' matching slot (above, below)
   struct Neighbour { const int16_t* planes = nullptr; void* ipc_base = nullptr; int device = -1, row0 = 0, rows = 0, pitch_y = 0, pitch_c = 0; size_t plane_y = 0, plane_c = 0; } nb[2];
 };
@@ -72,6 +73,11 @@ struct ilf_ctx {
   struct TimedLaunch { int kernel; cudaEvent_t a, b; };
   std::vector<TimedLaunch> timed;
   std::vector<cudaEvent_t> free_events;
+  // one event per ilf_run marks the end of its kernels for every slot of the run; a ring is enough because waiting on a
+  // re-recorded event only waits longer (same stream)
+  static constexpr int RUN_RING = 64;
+  cudaEvent_t run_ring[RUN_RING] = {};
+  unsigned run_pos = 0;
   double kernel_ms[ILF_NUM_KERNELS] = {0, 0, 0, 0};
   double kernel_bytes[ILF_NUM_KERNELS] = {0, 0, 0, 0};
   long long kernel_launches[ILF_NUM_KERNELS] = {0, 0, 0, 0};
@@ -256,6 +262,7 @@ int create_impl(ilf_ctx** out, const ilf_config* cfg, const ilf_band* band) {
   CU(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   CU(ctx, cudaStreamCreateWithFlags(&ctx->s_up, cudaStreamNonBlocking));
   CU(ctx, cudaStreamCreateWithFlags(&ctx->s_down, cudaStreamNonBlocking));
+  for (cudaEvent_t& e : ctx->run_ring) CU(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   ctx->slots.resize(cfg->num_slots);
   CU(ctx, cudaMalloc(&ctx->slots_dev, sizeof(SlotDev) * cfg->num_slots));
   const size_t units = (size_t)g.units_pitch * g.units_h;  // device grids are pitched
@@ -284,7 +291,7 @@ int create_impl(ilf_ctx** out, const ilf_config* cfg, const ilf_band* band) {
     s.pinned_side_bytes = s.side_off[3];
     CU(ctx, cudaMallocHost(&s.pinned_side, s.pinned_side_bytes));
     CU(ctx, cudaEventCreateWithFlags(&s.ev_up, cudaEventDisableTiming));
-    CU(ctx, cudaEventCreateWithFlags(&s.ev_run, cudaEventDisableTiming));
+    s.ev_run = ctx->run_ring[0];  // never recorded yet: waiting on it is a no-op
     CU(ctx, cudaEventCreateWithFlags(&s.ev_down, cudaEventDisableTiming));
     for (int k = 0; k < 3; k++) CU(ctx, cudaEventCreateWithFlags(&s.ev_side[k], cudaEventDisableTiming));
     memset(&s.dev, 0, sizeof(s.dev));
@@ -353,8 +360,9 @@ int ilf_destroy(ilf_ctx* ctx) {
     cudaFree(s.sao); cudaFree(s.alf); cudaFree(s.alf_coef); cudaFree(s.alf_ctu_enable); cudaFree(s.alf_class);
     if (s.pinned) cudaFreeHost(s.pinned);
     if (s.pinned_side) cudaFreeHost(s.pinned_side);
-    for (cudaEvent_t e : {s.ev_up, s.ev_run, s.ev_down, s.ev_side[0], s.ev_side[1], s.ev_side[2]}) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : {s.ev_up, s.ev_down, s.ev_side[0], s.ev_side[1], s.ev_side[2]}) if (e) cudaEventDestroy(e);
   }
+  for (cudaEvent_t e : ctx->run_ring) if (e) cudaEventDestroy(e);
   cudaFree(ctx->slots_dev);
   for (auto& t : ctx->timed) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
   for (cudaEvent_t e : ctx->free_events) cudaEventDestroy(e);
@@ -450,6 +458,7 @@ static int download_rows(ilf_ctx* ctx, int slot, int16_t* y, ptrdiff_t sy, int16
       CU(ctx, cudaMemcpy2DAsync(dsts[p], (size_t)strides[p] * 2, plane_ptr(ctx, s, s.result_buf[p], p) + (size_t)r0 * pitch, (size_t)pitch * 2, (size_t)w * 2, h, cudaMemcpyDeviceToHost, ctx->s_down));
     }
     CU(ctx, cudaEventRecord(s.ev_down, ctx->s_down));
+    s.d2h_pending = true;
     return ILF_OK;
   }
   if (!s.pinned) CU(ctx, cudaMallocHost(&s.pinned, ctx->buf_elems * sizeof(int16_t)));
@@ -461,7 +470,7 @@ static int download_rows(ilf_ctx* ctx, int slot, int16_t* y, ptrdiff_t sy, int16
     stage += (size_t)w * h;
   }
   CU(ctx, cudaEventRecord(s.ev_down, ctx->s_down));
-  CU(ctx, cudaEventSynchronize(s.ev_down));
+  CU(ctx, cudaEventSynchronize(s.ev_down));  // synchronous: nothing left pending
   stage = s.pinned;
   for (int p = 0; p < 3; p++) {
     const int w = p ? g.width / 2 : g.width, h = p ? n / 2 : n;
@@ -812,11 +821,13 @@ int ilf_run(ilf_ctx* ctx, int first_slot, int num_slots, unsigned stages) {
   for (int i = first_slot; i < first_slot + num_slots; i++) {
     Slot& s = ctx->slots[i];
     if (s.h2d_pending) { CU(ctx, cudaStreamWaitEvent(ctx->stream, s.ev_up, 0)); s.h2d_pending = false; }
-    CU(ctx, cudaStreamWaitEvent(ctx->stream, s.ev_down, 0));  // a download may still read the buffer this run overwrites
+    if (s.d2h_pending) { CU(ctx, cudaStreamWaitEvent(ctx->stream, s.ev_down, 0)); s.d2h_pending = false; }  // a download may still read the buffer this run overwrites
   }
   for (int st = 0; st < 3; st++)
     if (stages & (1u << st)) if (int rc = run_stage(ctx, first_slot, num_slots, st)) return rc;
-  for (int i = first_slot; i < first_slot + num_slots; i++) CU(ctx, cudaEventRecord(ctx->slots[i].ev_run, ctx->stream));
+  cudaEvent_t done = ctx->run_ring[ctx->run_pos++ % ilf_ctx::RUN_RING];
+  CU(ctx, cudaEventRecord(done, ctx->stream));
+  for (int i = first_slot; i < first_slot + num_slots; i++) ctx->slots[i].ev_run = done;
   return ILF_OK;
 }
 

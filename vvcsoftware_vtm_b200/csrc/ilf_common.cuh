@@ -3,6 +3,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "ilf_b200.h"
 
@@ -90,6 +91,24 @@ inline int pick_segments(int bands_total, int ntx, int resident, float startup_t
     if (score > best_score * 1.02f) { best_score = score; best = nseg; }  // prefer fewer, longer segments unless clearly better
   }
   return best;
+}
+
+// Programmatic dependent launch: the stages of a chain are consecutive kernels on one stream.  Every kernel lets its
+// successor be scheduled as soon as all of its own CTAs have started (pdl_launch_dependents, first instruction), and waits
+// for its predecessor to have completed and flushed (pdl_wait) before it touches picture planes -- its prologue (barrier
+// initialisation, tables, descriptors) and the predecessor's last wave overlap.  ILF_NO_PDL=1 launches the plain way.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  static const bool plain = getenv("ILF_NO_PDL") && atoi(getenv("ILF_NO_PDL")) != 0;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = plain ? 0 : 1;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
 // One launch covers `num_slots` <= MAX_BATCH grid layers; layer z works on slot first_slot + ctl.slot[z] under control word ctl.v[z].

@@ -245,6 +245,7 @@ __global__ void __launch_bounds__(NTHREADS, ILF_DB_MIN_CTAS) deblock_kernel(Geom
   extern __shared__ __align__(128) unsigned char smem[];
   constexpr int STRIDE = stage_stride<MV>();
   constexpr int stages = DB_STAGES;
+  pdl_launch_dependents();
   const SlotDev& sd = slots[first_slot + bc.slot[blockIdx.z]];
   const unsigned ctl = bc.v[blockIdx.z];
   const int src_b = ctl_src(ctl, 0), dst_b = ctl_dst(ctl, 0);  // deblocking starts from the uploaded picture: all planes in one buffer
@@ -282,6 +283,7 @@ __global__ void __launch_bounds__(NTHREADS, ILF_DB_MIN_CTAS) deblock_kernel(Geom
     ring::mbar_init_fence();
   }
   __syncthreads();
+  pdl_wait();  // the previous chain's last stage has finished with the buffers this stage reads and writes
   if (tid == 0)
     for (int t = first; t <= last && t < first + stages; t++) issue(t, t - first);
   // picture parameters and tables -> shared memory (overlaps the first loads)
@@ -446,7 +448,7 @@ static void launch_deblock_mv(const Geom& g, const SlotDev* slots, int first_slo
   const int bands = (g.rows + 4 + TH - 1) / TH, ntx = (g.width + TW - 1) / TW;
   const int nseg = pick_segments(bands * num_slots, ntx, 148 * ILF_DB_MIN_CTAS, 1.5f);  // a segment that starts inside the picture runs one extra tile
   dim3 grid(nseg, bands, num_slots);
-  deblock_kernel<MV><<<grid, NTHREADS, smem, st>>>(g, slots, first_slot, ctl, nseg);
+  launch_pdl(deblock_kernel<MV>, grid, dim3(NTHREADS), smem, st, g, slots, first_slot, ctl, nseg);
 }
 
 void launch_deblock(const Geom& g, const SlotDev* slots, int first_slot, int num_slots, const BatchCtl& ctl, int mv_mode, cudaStream_t st) {

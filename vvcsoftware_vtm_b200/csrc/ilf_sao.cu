@@ -200,6 +200,7 @@ __device__ __forceinline__ void sao_tile(const Geom& g, const SlotDev& sd, int p
 
 __global__ void __launch_bounds__(NTHREADS) sao_kernel(Geom g, const SlotDev* __restrict__ slots, int first_slot, BatchCtl bc, int bands_y, int bands_c, int nseg) {
   extern __shared__ __align__(128) unsigned char smem[];
+  pdl_launch_dependents();
   const unsigned ctl = bc.v[blockIdx.z];
   const SlotDev& sd = slots[first_slot + bc.slot[blockIdx.z]];
   // blockIdx.y enumerates the bands of Y, then Cb, then Cr; blockIdx.x the horizontal segments of a band
@@ -229,6 +230,7 @@ __global__ void __launch_bounds__(NTHREADS) sao_kernel(Geom g, const SlotDev* __
     ring::mbar_init_fence();
   }
   __syncthreads();
+  pdl_wait();  // deblocking has written the planes read from here on
   if (tid == 0)
     for (int t = walk.first; t <= walk.last && t < walk.first + STAGES; t++) issue(t);
   for (int tx = ta; tx < tb; tx++) {
@@ -255,7 +257,7 @@ void launch_sao(const Geom& g, const SlotDev* slots, int first_slot, int num_slo
   int nseg = (148 * 4 + bands - 1) / bands;
   nseg = nseg < 1 ? 1 : (nseg > ntx ? ntx : nseg);
   dim3 grid(nseg, bands_y + 2 * bands_c, num_slots);
-  sao_kernel<<<grid, NTHREADS, SMEM_BYTES, st>>>(g, slots, first_slot, ctl, bands_y, bands_c, nseg);
+  launch_pdl(sao_kernel, grid, dim3(NTHREADS), SMEM_BYTES, st, g, slots, first_slot, ctl, bands_y, bands_c, nseg);
 }
 
 }  // namespace ilf
