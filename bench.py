@@ -56,7 +56,7 @@ WORKLOADS = {
 }
 # algorithmic bytes per luma pixel and launch: every sample of the planes a kernel owns read once + written once
 # (int16, 4:2:0: luma 2 B, both chroma planes 1 B per luma pixel); side information excluded.
-ALGO_BYTES_PER_PIXEL = {"deblock": 6.0, "sao": 6.0, "alf_luma": 4.0, "alf_chroma": 2.0}
+ALGO_BYTES_PER_PIXEL = {"deblock": 6.0, "sao": 6.0, "alf": 6.0}
 CHAIN_BYTES_PER_PIXEL = 18.0
 
 

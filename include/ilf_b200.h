@@ -234,8 +234,8 @@ int ilf_alf_classify(ilf_ctx* ctx, int slot, uint8_t* out);
  * ------------------------------------------------------------------------------------------- */
 #define ILF_KERNEL_DEBLOCK 0
 #define ILF_KERNEL_SAO 1
-#define ILF_KERNEL_ALF_LUMA 2
-#define ILF_KERNEL_ALF_CHROMA 3
+#define ILF_KERNEL_ALF_LUMA 2   /* the whole ALF stage: luma and chroma bands are CTAs of ONE launch (luma only when ILF_ALF_SPLIT=1) */
+#define ILF_KERNEL_ALF_CHROMA 3 /* the separate chroma launch of ILF_ALF_SPLIT=1 (measurement aid); otherwise unused */
 #define ILF_NUM_KERNELS 4
 int ilf_set_timing(ilf_ctx* ctx, int enable); /* enable != 0: clear the accumulators and time every launch */
 /* algo_bytes: bytes the launches had to move = 2 bytes x (read + write) x samples of the planes they processed

@@ -115,13 +115,10 @@ __device__ __forceinline__ void load_win12(const int16_t* p, int v[12]) {
   v[8] = c.x & 0xFFFF; v[9] = c.x >> 16; v[10] = c.y & 0xFFFF; v[11] = c.y >> 16;
 }
 
+// Luma CTA: band blockIdx.y, horizontal segment blockIdx.x of nseg.
 template <bool CLASSIFY_ONLY>
-__global__ void __launch_bounds__(NT, L_CTAS) alf_luma_kernel(Geom g, const SlotDev* __restrict__ slots, int first_slot, BatchCtl bc, int nseg) {
-  extern __shared__ __align__(128) unsigned char smem[];
-  pdl_launch_dependents();
-  const SlotDev& sd = slots[first_slot + bc.slot[blockIdx.z]];
-  const unsigned ctl = bc.v[blockIdx.z];
-  if (ctl_skip(ctl, 0)) return;
+__device__ __forceinline__ void alf_luma_cta(unsigned char* smem, const Geom& g, const SlotDev& sd, unsigned ctl, int nseg) {
+  if (ctl_skip(ctl, 0) || (int)blockIdx.x >= nseg) return;
   const int tid = threadIdx.x;
   const int rows = g.rows;
   const int ntx = (g.width + TW - 1) / TW;
@@ -323,13 +320,10 @@ __device__ __forceinline__ void load_row12(const int16_t* p, int v[12]) {
   v[10] = c & 0xFFFF; v[11] = c >> 16;
 }
 
-__global__ void __launch_bounds__(NTC, 3) alf_chroma_kernel(Geom g, const SlotDev* __restrict__ slots, int first_slot, BatchCtl bc, int bands_c, int nseg) {
-  extern __shared__ __align__(128) unsigned char smem[];
-  pdl_launch_dependents();
-  const SlotDev& sd = slots[first_slot + bc.slot[blockIdx.z]];
-  const unsigned ctl = bc.v[blockIdx.z];
-  const int plane = 1 + ((int)blockIdx.y >= bands_c), band = (int)blockIdx.y - (plane - 1) * bands_c;
-  if (ctl_skip(ctl, plane)) return;
+// Chroma CTA: band `cband` (0 .. 2 bands_c - 1: Cb bands, then Cr bands), horizontal segment blockIdx.x of nseg.
+__device__ __forceinline__ void alf_chroma_cta(unsigned char* smem, const Geom& g, const SlotDev& sd, unsigned ctl, int cband, int bands_c, int nseg) {
+  const int plane = 1 + (cband >= bands_c), band = cband - (plane - 1) * bands_c;
+  if (ctl_skip(ctl, plane) || (int)blockIdx.x >= nseg) return;
   const int tid = threadIdx.x;
   const int cw = g.width >> 1, crows = g.rows >> 1;
   const int ntx = (cw + TW - 1) / TW;
@@ -419,32 +413,57 @@ __global__ void __launch_bounds__(NTC, 3) alf_chroma_kernel(Geom g, const SlotDe
   }
 }
 
+// One launch for the whole ALF stage: grid rows [0, bands_y) are luma bands, [bands_y, bands_y + 2 bands_c) chroma bands.
+// The instruction-bound luma CTAs and the memory-bound chroma CTAs share the SMs instead of running back to back.
+// PLANES: 1 = luma only, 2 = chroma only (split launches, ILF_ALF_SPLIT=1), 3 = both.
+template <int PLANES>
+__global__ void __launch_bounds__(NT, L_CTAS) alf_kernel(Geom g, const SlotDev* __restrict__ slots, int first_slot, BatchCtl bc, int bands_y, int bands_c, int nseg_y, int nseg_c) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  pdl_launch_dependents();
+  const SlotDev& sd = slots[first_slot + bc.slot[blockIdx.z]];
+  const unsigned ctl = bc.v[blockIdx.z];
+  if (PLANES == 1 || (PLANES == 3 && (int)blockIdx.y < bands_y)) alf_luma_cta<false>(smem, g, sd, ctl, nseg_y);
+  else alf_chroma_cta(smem, g, sd, ctl, (int)blockIdx.y - (PLANES == 3 ? bands_y : 0), bands_c, nseg_c);
+}
+__global__ void __launch_bounds__(NT, L_CTAS) alf_classify_kernel(Geom g, const SlotDev* __restrict__ slots, int first_slot, BatchCtl bc, int nseg) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  pdl_launch_dependents();
+  alf_luma_cta<true>(smem, g, slots[first_slot + bc.slot[blockIdx.z]], bc.v[blockIdx.z], nseg);
+}
+static_assert(NT == NTC, "luma and chroma CTAs share one launch");
+
 }  // namespace
 
-void launch_alf_luma(const Geom& g, const SlotDev* slots, int first_slot, int num_slots, const BatchCtl& ctl, bool classify_only, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(alf_luma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, L_SMEM_BYTES);
-    cudaFuncSetAttribute(alf_luma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, L_SMEM_BYTES);
-    attr_set = true;
-  }
-  const int bands_y = (g.rows + BR - 1) / BR, ntx = (g.width + TW - 1) / TW;
-  const int bands = bands_y * num_slots;
-  const int nseg = pick_segments(bands, ntx, 148 * L_CTAS);
-  dim3 gl(nseg, bands_y, num_slots);
-  if (classify_only) launch_pdl(alf_luma_kernel<true>, gl, dim3(NT), L_SMEM_BYTES, st, g, slots, first_slot, ctl, nseg);
-  else launch_pdl(alf_luma_kernel<false>, gl, dim3(NT), L_SMEM_BYTES, st, g, slots, first_slot, ctl, nseg);
+static int alf_nseg(int bands_total, int ntx, bool luma) {
+  if (luma) return pick_segments(bands_total, ntx, 148 * L_CTAS);
+  int nseg = (148 * 3 + bands_total - 1) / bands_total;
+  return nseg < 1 ? 1 : (nseg > ntx ? ntx : nseg);
 }
 
-void launch_alf_chroma(const Geom& g, const SlotDev* slots, int first_slot, int num_slots, const BatchCtl& ctl, cudaStream_t st) {
+// planes: bit 0 = luma, bit 1 = chroma (the slots' control words say which planes of which slot really run)
+void launch_alf(const Geom& g, const SlotDev* slots, int first_slot, int num_slots, const BatchCtl& ctl, int planes, cudaStream_t st) {
   static bool attr_set = false;
-  if (!attr_set) { cudaFuncSetAttribute(alf_chroma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C_SMEM_BYTES); attr_set = true; }
-  const int bands_c = (g.rows / 2 + BR - 1) / BR, ntx = (g.width / 2 + TW - 1) / TW;
-  const int bands = 2 * bands_c * num_slots;
-  int nseg = (148 * 3 + bands - 1) / bands;
-  nseg = nseg < 1 ? 1 : (nseg > ntx ? ntx : nseg);
-  dim3 gc(nseg, 2 * bands_c, num_slots);
-  launch_pdl(alf_chroma_kernel, gc, dim3(NTC), C_SMEM_BYTES, st, g, slots, first_slot, ctl, bands_c, nseg);
+  if (!attr_set) {
+    cudaFuncSetAttribute(alf_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, L_SMEM_BYTES);
+    cudaFuncSetAttribute(alf_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, C_SMEM_BYTES);
+    cudaFuncSetAttribute(alf_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, L_SMEM_BYTES > C_SMEM_BYTES ? L_SMEM_BYTES : C_SMEM_BYTES);
+    attr_set = true;
+  }
+  const int bands_y = (g.rows + BR - 1) / BR, bands_c = (g.rows / 2 + BR - 1) / BR;
+  const int nseg_y = alf_nseg(bands_y * num_slots, (g.width + TW - 1) / TW, true);
+  const int nseg_c = alf_nseg(2 * bands_c * num_slots, (g.width / 2 + TW - 1) / TW, false);
+  if (planes == 1) launch_pdl(alf_kernel<1>, dim3(nseg_y, bands_y, num_slots), dim3(NT), L_SMEM_BYTES, st, g, slots, first_slot, ctl, bands_y, bands_c, nseg_y, nseg_c);
+  else if (planes == 2) launch_pdl(alf_kernel<2>, dim3(nseg_c, 2 * bands_c, num_slots), dim3(NT), C_SMEM_BYTES, st, g, slots, first_slot, ctl, bands_y, bands_c, nseg_y, nseg_c);
+  else launch_pdl(alf_kernel<3>, dim3(nseg_y > nseg_c ? nseg_y : nseg_c, bands_y + 2 * bands_c, num_slots), dim3(NT), L_SMEM_BYTES > C_SMEM_BYTES ? L_SMEM_BYTES : C_SMEM_BYTES, st, g,
+                  slots, first_slot, ctl, bands_y, bands_c, nseg_y, nseg_c);
+}
+
+void launch_alf_classify(const Geom& g, const SlotDev* slots, int first_slot, int num_slots, const BatchCtl& ctl, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) { cudaFuncSetAttribute(alf_classify_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L_SMEM_BYTES); attr_set = true; }
+  const int bands_y = (g.rows + BR - 1) / BR;
+  const int nseg = alf_nseg(bands_y * num_slots, (g.width + TW - 1) / TW, true);
+  launch_pdl(alf_classify_kernel, dim3(nseg, bands_y, num_slots), dim3(NT), L_SMEM_BYTES, st, g, slots, first_slot, ctl, nseg);
 }
 
 }  // namespace ilf

@@ -790,19 +790,32 @@ static int run_stage(ilf_ctx* ctx, int first, int n, int stage) {
         ctx->launches++;
       }
     } else {
-      int m = compact(true, false, ctl, bytes);
-      if (m) {
-        if (int rc = timed_begin(ctx, ILF_KERNEL_ALF_LUMA, bytes)) return rc;
-        launch_alf_luma(g, ctx->slots_dev, c0, m, ctl, false, ctx->stream);
-        if (int rc = timed_end(ctx)) return rc;
-        ctx->launches++;
-      }
-      m = compact(false, true, ctl, bytes);
-      if (m) {
-        if (int rc = timed_begin(ctx, ILF_KERNEL_ALF_CHROMA, bytes)) return rc;
-        launch_alf_chroma(g, ctx->slots_dev, c0, m, ctl, ctx->stream);
-        if (int rc = timed_end(ctx)) return rc;
-        ctx->launches++;
+      // One launch for luma and chroma (their CTAs share the SMs); ILF_ALF_SPLIT=1 launches them one after the other, which
+      // is how the per-plane durations of DESIGN.md were measured.  Merged, the whole stage is accounted under ALF_LUMA.
+      static const bool split = getenv("ILF_ALF_SPLIT") && atoi(getenv("ILF_ALF_SPLIT")) != 0;
+      if (!split) {
+        const int m = compact(true, true, ctl, bytes);
+        if (m) {
+          if (int rc = timed_begin(ctx, ILF_KERNEL_ALF_LUMA, bytes)) return rc;
+          launch_alf(g, ctx->slots_dev, c0, m, ctl, 3, ctx->stream);
+          if (int rc = timed_end(ctx)) return rc;
+          ctx->launches++;
+        }
+      } else {
+        int m = compact(true, false, ctl, bytes);
+        if (m) {
+          if (int rc = timed_begin(ctx, ILF_KERNEL_ALF_LUMA, bytes)) return rc;
+          launch_alf(g, ctx->slots_dev, c0, m, ctl, 1, ctx->stream);
+          if (int rc = timed_end(ctx)) return rc;
+          ctx->launches++;
+        }
+        m = compact(false, true, ctl, bytes);
+        if (m) {
+          if (int rc = timed_begin(ctx, ILF_KERNEL_ALF_CHROMA, bytes)) return rc;
+          launch_alf(g, ctx->slots_dev, c0, m, ctl, 2, ctx->stream);
+          if (int rc = timed_end(ctx)) return rc;
+          ctx->launches++;
+        }
       }
     }
     CU(ctx, cudaGetLastError());
@@ -845,7 +858,7 @@ int ilf_alf_classify(ilf_ctx* ctx, int slot, uint8_t* out) {
   BatchCtl ctl;
   ctl.v[0] = (uint16_t)s.result_buf[0];
   ctl.slot[0] = 0;
-  launch_alf_luma(ctx->g, ctx->slots_dev, slot, 1, ctl, true, ctx->stream);
+  launch_alf_classify(ctx->g, ctx->slots_dev, slot, 1, ctl, ctx->stream);
   ctx->launches += 1;
   CU(ctx, cudaGetLastError());
   CU(ctx, cudaMemcpyAsync(out, s.alf_class, (size_t)ctx->g.units_w * ctx->g.units_h, cudaMemcpyDeviceToHost, ctx->stream));
