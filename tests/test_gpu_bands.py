@@ -22,10 +22,10 @@ def _run_whole(v, w, h, bd, ctu_log2, pic, si):
         return f.download(0)
 
 
-def _run_banded(v, w, h, bd, ctu_log2, pic, si, n):
+def _run_banded(v, w, h, bd, ctu_log2, pic, si, n, devices=1):
     ctu = 1 << ctu_log2
     part = bands.band_partition((h + ctu - 1) // ctu, n)
-    ctxs = [v.InLoopFilter(w, h, bd, bd, ctu_log2, band=b) for b in part]
+    ctxs = [v.InLoopFilter(w, h, bd, bd, ctu_log2, band=b, device=r % devices) for r, b in enumerate(part)]
     try:
         for f in ctxs:
             assert (f.own_row0, f.own_rows, f.row0, f.rows) == bands.band_rows(h, ctu_log2, part[ctxs.index(f)])
@@ -77,5 +77,21 @@ def test_bands_equal_reference_capture(ilf_lib):
     si = {"db_params": c["db_params"].tobytes(), "db_info": c["db_info"], "db_info_c": c.get("db_info_c"), "db_mv32": c["db_mv32"], "ctu_slice": c["ctu_slice"],
           "sao_ctus": c["sao_ctus"], "alf_params": c["alf_params"].tobytes(), "alf_ctu_enable": c["alf_ctu_enable"]}
     got = _run_banded(ilf_lib, g["width"], g["height"], g["bd_luma"], g["ctu_log2"], pic, si, 2)
+    for k in K:
+        assert np.array_equal(got[k], c["alf_" + k]), f"plane {k}: banded result differs from the reference's picture"
+
+
+def test_bands_on_two_devices_in_one_process(ilf_lib):
+    """Band contexts on different GPUs of ONE process: the halo exchange goes through peer access (NVLink P2P) instead of
+    CUDA IPC, and every device needs its own kernel attributes.  Skipped on a one-GPU box."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    c = G.load_golden([p for p in G.golden_files() if "ra_416x240_05" in p][0])
+    g = c["geom"]
+    pic = {k: c["pre_" + k] for k in K}
+    si = {"db_params": c["db_params"].tobytes(), "db_info": c["db_info"], "db_info_c": c.get("db_info_c"), "db_mv32": c["db_mv32"], "ctu_slice": c["ctu_slice"],
+          "sao_ctus": c["sao_ctus"], "alf_params": c["alf_params"].tobytes(), "alf_ctu_enable": c["alf_ctu_enable"]}
+    got = _run_banded(ilf_lib, g["width"], g["height"], g["bd_luma"], g["ctu_log2"], pic, si, 2, devices=2)
     for k in K:
         assert np.array_equal(got[k], c["alf_" + k]), f"plane {k}: banded result differs from the reference's picture"

@@ -93,6 +93,15 @@ inline int pick_segments(int bands_total, int ntx, int resident, float startup_t
   return best;
 }
 
+// cudaFuncSetAttribute is per device: a process may hold contexts on several GPUs, so "already raised" is tracked per device.
+inline bool first_launch_on_device(bool (&seen)[64]) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || seen[dev]) return false;
+  seen[dev] = true;
+  return true;
+}
+
 // Programmatic dependent launch: the stages of a chain are consecutive kernels on one stream.  Every kernel lets its
 // successor be scheduled as soon as all of its own CTAs have started (pdl_launch_dependents, first instruction), and waits
 // for its predecessor to have completed and flushed (pdl_wait) before it touches picture planes -- its prologue (barrier
