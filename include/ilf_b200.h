@@ -226,6 +226,23 @@ int ilf_alf(ilf_ctx* ctx, int slot);
 int ilf_alf_classify(ilf_ctx* ctx, int slot, uint8_t* out);
 
 /* ---------------------------------------------------------------------------------------------
+ * Encoder SAO statistics on the device-resident picture: replaces
+ * EncSampleAdaptiveOffset::getStatistics (EncoderLib/EncSampleAdaptiveOffset.cpp:278-331, getBlkStats :1122-1487) for the
+ * path without SaoCtuBoundary.  ilf_set_original uploads the source picture of the slot (cs.getOrgBuf()) and the per-CTU
+ * availability flags (ILF_AVAIL_L / _A / _AL of EncSampleAdaptiveOffset::deriveLoopFilterBoundaryAvailibility; right,
+ * below and above-right follow from the picture bounds as in :307-309); ilf_sao_stats launches one kernel over the
+ * CURRENT state of the slots' pictures (after ilf_deblock: the deblocked picture, which is what the encoder measures);
+ * ilf_get_sao_stats copies a slot's result to the host: out[num_ctus][3][5][64] int64, per CTU, component and SAO type
+ * diff[32] followed by count[32] -- the memory layout of SAOStatData (EncSampleAdaptiveOffset.h:53-57).
+ * Not available on band contexts.
+ * ------------------------------------------------------------------------------------------- */
+#define ILF_SAO_STATS_WORDS (5 * 64)
+int ilf_set_original(ilf_ctx* ctx, int slot, const int16_t* y, ptrdiff_t stride_y, const int16_t* cb, ptrdiff_t stride_cb, const int16_t* cr,
+                     ptrdiff_t stride_cr, const uint8_t* ctu_avail /* [ctus_h*ctus_w] */);
+int ilf_sao_stats(ilf_ctx* ctx, int first_slot, int num_slots);
+int ilf_get_sao_stats(ilf_ctx* ctx, int slot, int64_t* out);
+
+/* ---------------------------------------------------------------------------------------------
  * Measurement helpers (bench.py).  Accumulated device time per kernel in milliseconds since
  * ilf_set_timing(ctx, 1) (CUDA event pairs around every launch on the context's stream, collected
  * without synchronising inside ilf_run), number of kernel launches issued since ilf_create, and
@@ -236,7 +253,8 @@ int ilf_alf_classify(ilf_ctx* ctx, int slot, uint8_t* out);
 #define ILF_KERNEL_SAO 1
 #define ILF_KERNEL_ALF_LUMA 2   /* the whole ALF stage: luma and chroma bands are CTAs of ONE launch (luma only when ILF_ALF_SPLIT=1) */
 #define ILF_KERNEL_ALF_CHROMA 3 /* the separate chroma launch of ILF_ALF_SPLIT=1 (measurement aid); otherwise unused */
-#define ILF_NUM_KERNELS 4
+#define ILF_KERNEL_SAO_STATS 4  /* ilf_sao_stats */
+#define ILF_NUM_KERNELS 5
 int ilf_set_timing(ilf_ctx* ctx, int enable); /* enable != 0: clear the accumulators and time every launch */
 /* algo_bytes: bytes the launches had to move = 2 bytes x (read + write) x samples of the planes they processed
  * (planes whose stage is off for the whole picture are skipped and not counted).  Synchronises the stream. */

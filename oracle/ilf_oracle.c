@@ -433,3 +433,106 @@ int ilf_oracle_alf(const int16_t* const src[3], const ptrdiff_t sstride[3], int1
     }
   return 0;
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * Encoder SAO statistics: EncSampleAdaptiveOffset::getStatistics
+ * (EncoderLib/EncSampleAdaptiveOffset.cpp:278-331) + getBlkStats (:1122-1487), the path the encoder takes
+ * without SaoCtuBoundary (isCalculatePreDeblockSamples == false): per CTU, component and SAO type, the count
+ * of samples per class and the sum of (original - deblocked) per class.  The region of a CTU block that
+ * contributes depends on the type, on the neighbour availability and on the "skip lines" of createEncData
+ * (:122-128: right 5 / bottom 4 luma, 3 / 2 chroma -- applied when the right / below CTU exists).
+ * out[ctu][comp][type][0..31] = diff, [32..63] = count (the memory layout of SAOStatData, EncSampleAdaptiveOffset.h:53-57).
+ * avail[ctu]: ILF_AVAIL_L / _A / _AL of deriveLoopFilterBoundaryAvailibility (:1489-); right / below /
+ * above-right come from the picture bounds, as in :307-309.
+ * ---------------------------------------------------------------------------------------------- */
+static void sao_stats_block(const Pel* src, ptrdiff_t ss, const Pel* org, ptrdiff_t os, int w, int h, int bd, int skip_r, int skip_b, int L, int R, int A,
+                            int B, int AL, int AR, int64_t* out /* [5][64] */) {
+  memset(out, 0, sizeof(int64_t) * 5 * 64);
+  for (int type = 0; type < 5; type++) {
+    int64_t* diff = out + type * 64;
+    int64_t* count = diff + 32;
+    int start_x, end_x, start_y, end_y;
+    switch (type) {
+      case ILF_SAO_EO_0: /* :1146-1163 */
+        start_x = L ? 0 : 1; end_x = R ? w - skip_r : w - 1; end_y = B ? h - skip_b : h;
+        for (int y = 0; y < end_y; y++)
+          for (int x = start_x; x < end_x; x++) {
+            const Pel* s = src + y * ss + x;
+            const int c = 2 + sgn(s[0] - s[-1]) + sgn(s[0] - s[1]);
+            diff[c] += org[y * os + x] - s[0]; count[c]++;
+          }
+        break;
+      case ILF_SAO_EO_90: /* :1192-1230 */
+        start_x = 0; end_x = R ? w - skip_r : w; start_y = A ? 0 : 1; end_y = B ? h - skip_b : h - 1;
+        for (int y = start_y; y < end_y; y++)
+          for (int x = start_x; x < end_x; x++) {
+            const Pel* s = src + y * ss + x;
+            const int c = 2 + sgn(s[0] - s[-ss]) + sgn(s[0] - s[ss]);
+            diff[c] += org[y * os + x] - s[0]; count[c]++;
+          }
+        break;
+      case ILF_SAO_EO_135: { /* :1258-1312: the first line has its own column range */
+        start_x = L ? 0 : 1; end_x = R ? w - skip_r : w - 1; end_y = B ? h - skip_b : h - 1;
+        const int fs = AL ? 0 : 1, fe = A ? end_x : 1;
+        for (int y = 0; y < end_y; y++) {
+          const int x0 = y == 0 ? fs : start_x, x1 = y == 0 ? fe : end_x;
+          for (int x = x0; x < x1; x++) {
+            const Pel* s = src + y * ss + x;
+            const int c = 2 + sgn(s[0] - s[-ss - 1]) + sgn(s[0] - s[ss + 1]);
+            diff[c] += org[y * os + x] - s[0]; count[c]++;
+          }
+        }
+        break;
+      }
+      case ILF_SAO_EO_45: { /* :1340-1395 */
+        start_x = L ? 0 : 1; end_x = R ? w - skip_r : w - 1; end_y = B ? h - skip_b : h - 1;
+        const int fs = A ? start_x : end_x, fe = (!R && AR) ? w : end_x;
+        for (int y = 0; y < end_y; y++) {
+          const int x0 = y == 0 ? fs : start_x, x1 = y == 0 ? fe : end_x;
+          for (int x = x0; x < x1; x++) {
+            const Pel* s = src + y * ss + x;
+            const int c = 2 + sgn(s[0] - s[-ss + 1]) + sgn(s[0] - s[ss - 1]);
+            diff[c] += org[y * os + x] - s[0]; count[c]++;
+          }
+        }
+        break;
+      }
+      default: /* ILF_SAO_BO :1437-1456 */
+        end_x = R ? w - skip_r : w; end_y = B ? h - skip_b : h;
+        for (int y = 0; y < end_y; y++)
+          for (int x = 0; x < end_x; x++) {
+            const int c = src[y * ss + x] >> (bd - 5);
+            diff[c] += org[y * os + x] - src[y * ss + x]; count[c]++;
+          }
+        break;
+    }
+  }
+}
+
+int ilf_oracle_sao_stats(const int16_t* const rec[3], const ptrdiff_t rec_stride[3], const int16_t* const org[3], const ptrdiff_t org_stride[3], int width,
+                         int height, int bd_luma, int bd_chroma, int ctu_log2, const uint8_t* avail, int64_t* out) {
+  const int ctu = 1 << ctu_log2, cw = (width + ctu - 1) / ctu, ch = (height + ctu - 1) / ctu;
+  for (int cy = 0; cy < ch; cy++)
+    for (int cx = 0; cx < cw; cx++) {
+      const int a = avail[cy * cw + cx];
+      const int x0 = cx * ctu, y0 = cy * ctu;
+      const int R = x0 + ctu < width, B = y0 + ctu < height, AR = y0 > 0 && R; /* :307-309 */
+      for (int comp = 0; comp < 3; comp++) {
+        const int sh = comp ? 1 : 0;
+        const int bw = ((x0 + ctu > width ? width - x0 : ctu)) >> sh, bh = ((y0 + ctu > height ? height - y0 : ctu)) >> sh;
+        sao_stats_block(rec[comp] + (ptrdiff_t)(y0 >> sh) * rec_stride[comp] + (x0 >> sh), rec_stride[comp],
+                        org[comp] + (ptrdiff_t)(y0 >> sh) * org_stride[comp] + (x0 >> sh), org_stride[comp], bw, bh, comp ? bd_chroma : bd_luma, comp ? 3 : 5,
+                        comp ? 2 : 4, (a & ILF_AVAIL_L) != 0, R, (a & ILF_AVAIL_A) != 0, B, (a & ILF_AVAIL_AL) != 0, AR,
+                        out + ((size_t)(cy * cw + cx) * 3 + comp) * 5 * 64);
+      }
+    }
+  return 0;
+}
+
+/* One block with explicit flags, for the unit comparison with the reference's getBlkStats (tests/test_oracle_units.py). */
+int ilf_oracle_sao_stats_block(const int16_t* src, ptrdiff_t ss, const int16_t* org, ptrdiff_t os, int w, int h, int bd, int is_chroma, unsigned avail6,
+                               int64_t* out) {
+  sao_stats_block(src, ss, org, os, w, h, bd, is_chroma ? 3 : 5, is_chroma ? 2 : 4, avail6 & 1, (avail6 >> 1) & 1, (avail6 >> 2) & 1, (avail6 >> 3) & 1,
+                  (avail6 >> 4) & 1, (avail6 >> 5) & 1, out);
+  return 0;
+}

@@ -103,3 +103,33 @@ def alf_classify(y, bd_luma):
     f.argtypes = [C.c_void_p, C.c_ssize_t, C.c_int, C.c_int, C.c_int, C.c_void_p]
     assert f(_p(y), w, w, h, bd_luma, _p(out)) == 0
     return out
+
+
+def sao_stats(rec, org, bd_luma, bd_chroma, ctu_log2, avail):
+    """EncSampleAdaptiveOffset::getStatistics (no SaoCtuBoundary): int64 array [num_ctus, 3, 5, 64] (diff[32], count[32])."""
+    r, rp, rs = _planes3(rec)
+    o, op, os_ = _planes3(org)
+    h, w = r[0].shape
+    ctu = 1 << ctu_log2
+    n = ((w + ctu - 1) // ctu) * ((h + ctu - 1) // ctu)
+    av = _c(avail, np.uint8)
+    assert av.size == n
+    out = np.zeros((n, 3, 5, 64), dtype=np.int64)
+    f = lib().ilf_oracle_sao_stats
+    f.restype = C.c_int
+    f.argtypes = [C.c_void_p] * 4 + [C.c_int] * 5 + [C.c_void_p, C.c_void_p]
+    assert f(rp, rs, op, os_, w, h, bd_luma, bd_chroma, ctu_log2, _p(av), _p(out)) == 0
+    return out
+
+
+def sao_stats_block(src, org, x0, y0, w, h, bd, is_chroma, avail6):
+    """One block of 2-D arrays src/org at (x0, y0), explicit flags (bit0 L, 1 R, 2 A, 3 B, 4 AL, 5 AR): int64 [5, 64]."""
+    src = np.ascontiguousarray(src, np.int16); org = np.ascontiguousarray(org, np.int16)
+    out = np.zeros((5, 64), dtype=np.int64)
+    f = lib().ilf_oracle_sao_stats_block
+    f.restype = C.c_int
+    f.argtypes = [C.c_void_p, C.c_ssize_t, C.c_void_p, C.c_ssize_t, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint, C.c_void_p]
+    sp = src.ctypes.data + 2 * (y0 * src.shape[1] + x0)
+    gp = org.ctypes.data + 2 * (y0 * org.shape[1] + x0)
+    assert f(sp, src.shape[1], gp, org.shape[1], w, h, bd, int(is_chroma), avail6, _p(out)) == 0
+    return out

@@ -4,12 +4,19 @@
 //   SampleAdaptiveOffset::offsetBlock                 SampleAdaptiveOffset.cpp:292-508
 //   AdaptiveLoopFilter::deriveClassificationBlk       AdaptiveLoopFilter.cpp:292-463 (scalar) / x86 SIMD
 //   AdaptiveLoopFilter::filterBlk<5|7>                AdaptiveLoopFilter.cpp:465-650 (scalar) / x86 SIMD
+//   EncSampleAdaptiveOffset::getBlkStats              EncoderLib/EncSampleAdaptiveOffset.cpp:1122-1487
 // Linked against oracle/_ref/libvtm.a (unmodified reference objects).  Nothing here is product code.
 #include <cstring>
 #include <vector>
 
 #include "CommonLib/AdaptiveLoopFilter.h"
 #include "CommonLib/SampleAdaptiveOffset.h"
+#include "EncoderLib/CABACWriter.h"
+// getBlkStats and the skip-line tables are private members of the reference class: open them for this test door only
+// (every header the class needs is already included above, so nothing else is parsed under the define)
+#define private public
+#include "EncoderLib/EncSampleAdaptiveOffset.h"
+#undef private
 
 namespace
 {
@@ -86,6 +93,34 @@ int ref_alf_filter( int simd, int is7, int chroma, const int16_t* src, int src_s
   const ComponentID comp = chroma ? COMPONENT_Cb : COMPONENT_Y;
   if( simd ) { if( is7 ) simdAlf.m_filter7x7Blk( rows.data(), dstU, srcU, blk, comp, cf.data(), clp ); else simdAlf.m_filter5x5Blk( rows.data(), dstU, srcU, blk, comp, cf.data(), clp ); }
   else { if( is7 ) AdaptiveLoopFilter::filterBlk<ALF_FILTER_7>( rows.data(), dstU, srcU, blk, comp, cf.data(), clp ); else AdaptiveLoopFilter::filterBlk<ALF_FILTER_5>( rows.data(), dstU, srcU, blk, comp, cf.data(), clp ); }
+  return 0;
+}
+
+// One CTU block of one component through the reference's own statistics function, skip lines as createEncData sets them
+// without SaoCtuBoundary (EncSampleAdaptiveOffset.cpp:122-128).  avail6: bit0 L, bit1 R, bit2 A, bit3 B, bit4 AL, bit5 AR.
+// src/org point at the block's first sample inside larger pictures.  out[5][64]: diff[32] then count[32] per type.
+int ref_sao_blk_stats( int is_chroma, int bit_depth, const int16_t* src, const int16_t* org, int src_stride, int org_stride, int w, int h, unsigned avail6, int64_t* out )
+{
+  struct EncDoor : public EncSampleAdaptiveOffset
+  {
+    void lineBufs( int w ) { if( m_signLineBuf1.size() < size_t( w + 2 ) ) { m_signLineBuf1.resize( w + 2 ); m_signLineBuf2.resize( w + 2 ); } }
+  };
+  static EncDoor* enc = nullptr;
+  if( !enc )
+  {
+    enc = new EncDoor;
+    enc->create( 256, 256, CHROMA_420, 128, 128, 4, 0, 0 );
+    enc->createEncData( false, 4 );
+  }
+  enc->lineBufs( w );
+  SAOStatData stats[NUM_SAO_NEW_TYPES];
+  enc->getBlkStats( is_chroma ? COMPONENT_Cb : COMPONENT_Y, bit_depth, stats, const_cast<Pel*>( src ), const_cast<Pel*>( org ), src_stride, org_stride, w, h,
+                    avail6 & 1, ( avail6 >> 1 ) & 1, ( avail6 >> 2 ) & 1, ( avail6 >> 3 ) & 1, ( avail6 >> 4 ) & 1, ( avail6 >> 5 ) & 1, false );
+  for( int t = 0; t < NUM_SAO_NEW_TYPES; t++ )
+  {
+    memcpy( out + t * 64, stats[t].diff, sizeof( int64_t ) * 32 );
+    memcpy( out + t * 64 + 32, stats[t].count, sizeof( int64_t ) * 32 );
+  }
   return 0;
 }
 }

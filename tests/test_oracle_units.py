@@ -107,3 +107,25 @@ def test_alf_filter_oracle_equals_reference(simd, is7, units, oracle):
                                  pw, ph, bd, cls.ctypes.data, coeff.ctypes.data)
             want = dst[4:-4, 4:-4]
             assert np.array_equal(got[k], want), f"{kind} {k}: {(got[k] != want).sum()} samples differ"
+
+
+@pytest.mark.parametrize("bd,is_chroma,w,h,seed", [(10, 0, 128, 128, 1), (10, 1, 64, 64, 2), (8, 0, 64, 56, 3), (12, 1, 32, 28, 4), (10, 0, 32, 112, 5)])
+def test_sao_statistics_block_vs_reference(units, oracle, bd, is_chroma, w, h, seed):
+    """Encoder SAO statistics (SURVEY.md 8f): the oracle's block function == EncSampleAdaptiveOffset::getBlkStats of the
+    reference for every combination of the six availability flags, on noisy and on flat (many ties) content."""
+    units.ref_sao_blk_stats.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint, C.c_void_p]
+    rng = np.random.default_rng(seed)
+    H, W = h + 16, w + 16
+    for kind in ("noise", "flat"):
+        if kind == "noise":
+            src = rng.integers(0, 1 << bd, (H, W)).astype(np.int16)
+        else:
+            src = (rng.integers(0, 1 << (bd - 2), (H // 4 + 1, W // 4 + 1)).repeat(4, 0).repeat(4, 1)[:H, :W] * 4 + rng.integers(0, 2, (H, W))).astype(np.int16)
+        org = np.clip(src.astype(np.int32) + rng.integers(-9, 10, (H, W)), 0, (1 << bd) - 1).astype(np.int16)
+        for avail6 in range(64):
+            want = np.zeros((5, 64), np.int64)
+            sp = src.ctypes.data + 2 * (8 * W + 8)
+            gp = org.ctypes.data + 2 * (8 * W + 8)
+            assert units.ref_sao_blk_stats(is_chroma, bd, sp, gp, W, W, w, h, avail6, want.ctypes.data) == 0
+            got = oracle.sao_stats_block(src, org, 8, 8, w, h, bd, is_chroma, avail6)
+            assert np.array_equal(got, want), f"{kind} avail6={avail6:06b}: types differing {np.nonzero((got != want).any(axis=1))[0]}"

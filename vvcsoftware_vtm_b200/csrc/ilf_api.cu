@@ -30,6 +30,10 @@ struct Slot {
   int* alf_coef = nullptr;     // [25][4][16] transposed luma coefficient table
   uint8_t* alf_ctu_enable = nullptr;
   uint8_t* alf_class = nullptr;
+  int16_t* org = nullptr;      // source picture of the encoder (3 planes, same layout as one buffer of `planes`); allocated by ilf_set_original
+  uint8_t* stats_avail = nullptr;
+  long long* stats = nullptr;  // [num_ctus][3][5][64]
+  bool has_org = false;
   int16_t* pinned = nullptr;   // host staging for pageable planes, one picture; allocated on first use
   uint8_t* pinned_side = nullptr;  // host staging for side information
   size_t pinned_side_bytes = 0;
@@ -78,9 +82,9 @@ struct ilf_ctx {
   static constexpr int RUN_RING = 64;
   cudaEvent_t run_ring[RUN_RING] = {};
   unsigned run_pos = 0;
-  double kernel_ms[ILF_NUM_KERNELS] = {0, 0, 0, 0};
-  double kernel_bytes[ILF_NUM_KERNELS] = {0, 0, 0, 0};
-  long long kernel_launches[ILF_NUM_KERNELS] = {0, 0, 0, 0};
+  double kernel_ms[ILF_NUM_KERNELS] = {0, 0, 0, 0, 0};
+  double kernel_bytes[ILF_NUM_KERNELS] = {0, 0, 0, 0, 0};
+  long long kernel_launches[ILF_NUM_KERNELS] = {0, 0, 0, 0, 0};
   int num_ctus = 0;
 };
 
@@ -358,6 +362,7 @@ int ilf_destroy(ilf_ctx* ctx) {
     for (auto& nb : s.nb) if (nb.ipc_base) cudaIpcCloseMemHandle(nb.ipc_base);
     cudaFree(s.planes); cudaFree(s.info); cudaFree(s.info_c); cudaFree(s.mv); cudaFree(s.ctu_slice); cudaFree(s.db_params);
     cudaFree(s.sao); cudaFree(s.alf); cudaFree(s.alf_coef); cudaFree(s.alf_ctu_enable); cudaFree(s.alf_class);
+    cudaFree(s.org); cudaFree(s.stats_avail); cudaFree(s.stats);
     if (s.pinned) cudaFreeHost(s.pinned);
     if (s.pinned_side) cudaFreeHost(s.pinned_side);
     for (cudaEvent_t e : {s.ev_up, s.ev_down, s.ev_side[0], s.ev_side[1], s.ev_side[2]}) if (e) cudaEventDestroy(e);
@@ -862,6 +867,80 @@ int ilf_alf_classify(ilf_ctx* ctx, int slot, uint8_t* out) {
   ctx->launches += 1;
   CU(ctx, cudaGetLastError());
   CU(ctx, cudaMemcpyAsync(out, s.alf_class, (size_t)ctx->g.units_w * ctx->g.units_h, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  return ILF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Encoder SAO statistics (include/ilf_b200.h; EncSampleAdaptiveOffset::getStatistics)
+// ---------------------------------------------------------------------------------------------------------------
+int ilf_set_original(ilf_ctx* ctx, int slot, const int16_t* y, ptrdiff_t sy, const int16_t* cb, ptrdiff_t scb, const int16_t* cr, ptrdiff_t scr, const uint8_t* ctu_avail) {
+  if (int rc = check_slot(ctx, slot)) return rc;
+  if (ctx->is_band) return fail(ctx, ILF_ERR_STATE, "SAO statistics are not available on band contexts");
+  if (!y || !cb || !cr || !ctu_avail) return fail(ctx, ILF_ERR_ARG, "null pointer");
+  Slot& s = ctx->slots[slot];
+  const Geom& g = ctx->g;
+  CU(ctx, cudaSetDevice(ctx->cfg.device));
+  if (!s.org) {
+    CU(ctx, cudaMalloc(&s.org, ctx->buf_elems * sizeof(int16_t)));
+    CU(ctx, cudaMalloc(&s.stats_avail, ctx->num_ctus));
+    CU(ctx, cudaMalloc(&s.stats, (size_t)ctx->num_ctus * 3 * ILF_SAO_STATS_WORDS * sizeof(long long)));
+    s.dev.org[0] = s.org; s.dev.org[1] = s.org + ctx->plane_y; s.dev.org[2] = s.org + ctx->plane_y + ctx->plane_c;
+    s.dev.stats_avail = s.stats_avail;
+    s.dev.stats = s.stats;
+  }
+  CU(ctx, cudaStreamWaitEvent(ctx->s_up, s.ev_run, 0));  // a statistics kernel of the previous picture may still read the planes
+  const int16_t* srcs[3] = {y, cb, cr};
+  const ptrdiff_t strides[3] = {sy, scb, scr};
+  for (int p = 0; p < 3; p++) {
+    const int w = p ? g.width / 2 : g.width, h = p ? g.height / 2 : g.height, pitch = p ? g.pitch_c : g.pitch_y;
+    // pageable sources are staged by the runtime (the call returns when the source may be reused); page-locked ones are asynchronous
+    CU(ctx, cudaMemcpy2DAsync(const_cast<int16_t*>(s.dev.org[p]), (size_t)pitch * 2, srcs[p], (size_t)strides[p] * 2, (size_t)w * 2, h, cudaMemcpyHostToDevice, ctx->s_up));
+  }
+  CU(ctx, cudaMemcpyAsync(s.stats_avail, ctu_avail, ctx->num_ctus, cudaMemcpyHostToDevice, ctx->s_up));
+  if (!is_pinned(ctu_avail)) CU(ctx, cudaStreamSynchronize(ctx->s_up));  // the caller may reuse ctu_avail
+  s.has_org = true;
+  return push_desc(ctx, slot);
+}
+
+int ilf_sao_stats(ilf_ctx* ctx, int first_slot, int num_slots) {
+  if (!ctx) return ILF_ERR_ARG;
+  if (first_slot < 0 || num_slots < 1 || first_slot + num_slots > (int)ctx->slots.size()) return fail(ctx, ILF_ERR_ARG, "slot range [%d,+%d) out of range", first_slot, num_slots);
+  CU(ctx, cudaSetDevice(ctx->cfg.device));
+  const Geom& g = ctx->g;
+  for (int i = first_slot; i < first_slot + num_slots; i++) {
+    Slot& s = ctx->slots[i];
+    if (!s.uploaded || !s.has_org) return fail(ctx, ILF_ERR_STATE, "slot %d: statistics need ilf_upload and ilf_set_original", i);
+    if (s.h2d_pending) { CU(ctx, cudaStreamWaitEvent(ctx->stream, s.ev_up, 0)); s.h2d_pending = false; }
+  }
+  for (int c0 = first_slot; c0 < first_slot + num_slots; c0 += MAX_BATCH) {
+    const int cn = std::min(MAX_BATCH, first_slot + num_slots - c0);
+    BatchCtl ctl;
+    for (int i = 0; i < cn; i++) {
+      const Slot& s = ctx->slots[c0 + i];
+      ctl.v[i] = (uint16_t)(s.result_buf[0] | (s.result_buf[1] << 2) | (s.result_buf[2] << 4));
+      ctl.slot[i] = (uint8_t)i;
+    }
+    // algorithmic bytes: the deblocked and the original picture are read once (2 B x 1.5 samples x 2 pictures per luma pixel)
+    if (int rc = timed_begin(ctx, ILF_KERNEL_SAO_STATS, 6.0 * g.width * g.height * cn)) return rc;
+    launch_sao_stats(g, ctx->slots_dev, c0, cn, ctl, ctx->stream);
+    if (int rc = timed_end(ctx)) return rc;
+    ctx->launches++;
+    CU(ctx, cudaGetLastError());
+  }
+  cudaEvent_t done = ctx->run_ring[ctx->run_pos++ % ilf_ctx::RUN_RING];
+  CU(ctx, cudaEventRecord(done, ctx->stream));
+  for (int i = first_slot; i < first_slot + num_slots; i++) ctx->slots[i].ev_run = done;
+  return ILF_OK;
+}
+
+int ilf_get_sao_stats(ilf_ctx* ctx, int slot, int64_t* out) {
+  if (int rc = check_slot(ctx, slot)) return rc;
+  if (!out) return fail(ctx, ILF_ERR_ARG, "null output");
+  Slot& s = ctx->slots[slot];
+  if (!s.stats) return fail(ctx, ILF_ERR_STATE, "slot %d: no statistics (ilf_set_original / ilf_sao_stats first)", slot);
+  CU(ctx, cudaSetDevice(ctx->cfg.device));
+  CU(ctx, cudaMemcpyAsync(out, s.stats, (size_t)ctx->num_ctus * 3 * ILF_SAO_STATS_WORDS * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
   CU(ctx, cudaStreamSynchronize(ctx->stream));
   return ILF_OK;
 }

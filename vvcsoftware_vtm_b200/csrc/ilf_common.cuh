@@ -53,6 +53,9 @@ struct alignas(64) SlotDev {
   const int* alf_coef;            // [25 classes][4 transposes][16] luma coefficients, transposition applied (set by ilf_set_alf_params)
   const uint8_t* alf_ctu_enable;  // [3][num_ctus]
   uint8_t* alf_class;             // [units_h][units_w] scratch / output of ilf_alf_classify
+  const int16_t* org[3];          // source picture of the encoder (ilf_set_original), plane pitches as buf
+  const uint8_t* stats_avail;     // [num_ctus] ILF_AVAIL_* of the statistics pass
+  long long* stats;               // [num_ctus][3][5][64] SAO statistics (ilf_sao_stats)
 };
 
 // Per-launch control word of every slot of a batch (kernel parameter, indexed with blockIdx.z).  Each plane of a
@@ -124,6 +127,7 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
 void launch_deblock(const Geom& g, const SlotDev* slots, int first_slot, int num_slots, const BatchCtl& ctl, int mv_mode, cudaStream_t st);
 void launch_sao(const Geom& g, const SlotDev* slots, int first_slot, int num_slots, const BatchCtl& ctl, cudaStream_t st);
 void launch_alf(const Geom& g, const SlotDev* slots, int first_slot, int num_slots, const BatchCtl& ctl, int planes /* bit 0 luma, bit 1 chroma */, cudaStream_t st);
+void launch_sao_stats(const Geom& g, const SlotDev* slots, int first_slot, int num_slots, const BatchCtl& ctl, cudaStream_t st);
 void launch_alf_classify(const Geom& g, const SlotDev* slots, int first_slot, int num_slots, const BatchCtl& ctl, cudaStream_t st);
 
 }  // namespace ilf

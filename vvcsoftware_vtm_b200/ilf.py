@@ -35,6 +35,7 @@ def lib_path():
 
 
 _LIB = None
+NUM_KERNELS = 5   # ILF_NUM_KERNELS
 
 
 def load_library():
@@ -78,7 +79,10 @@ def load_library():
     for n in ("ilf_deblock", "ilf_sao", "ilf_alf"):
         getattr(lib, n).argtypes = [vp, i]
     lib.ilf_alf_classify.argtypes = [vp, i, vp]
-    lib.ilf_kernel_times.argtypes = [vp, C.POINTER(C.c_double * 4), C.POINTER(C.c_longlong * 4), C.POINTER(C.c_double * 4)]
+    lib.ilf_set_original.argtypes = [vp, i, vp, pd, vp, pd, vp, pd, vp]
+    lib.ilf_sao_stats.argtypes = [vp, i, i]
+    lib.ilf_get_sao_stats.argtypes = [vp, i, vp]
+    lib.ilf_kernel_times.argtypes = [vp, C.POINTER(C.c_double * NUM_KERNELS), C.POINTER(C.c_longlong * NUM_KERNELS), C.POINTER(C.c_double * NUM_KERNELS)]
     lib.ilf_set_timing.argtypes = [vp, i]
     lib.ilf_launch_count.argtypes = [vp]
     lib.ilf_launch_count.restype = C.c_longlong
@@ -248,15 +252,33 @@ class InLoopFilter:
         self._ck(self._lib.ilf_alf_classify(self._h, slot, _ptr(out)))
         return out
 
+    # ---- encoder SAO statistics (EncSampleAdaptiveOffset::getStatistics) ---------------------------------
+    def set_original(self, slot, y, cb, cr, ctu_avail):
+        """Source picture of the slot and the per-CTU ILF_AVAIL_L/_A/_AL flags of the statistics pass."""
+        y, cb, cr = (_arr(a, np.int16) for a in (y, cb, cr))
+        av = _arr(ctu_avail, np.uint8)
+        self._ck(self._lib.ilf_set_original(self._h, slot, _ptr(y), y.strides[0] // 2, _ptr(cb), cb.strides[0] // 2, _ptr(cr), cr.strides[0] // 2, _ptr(av)))
+
+    def sao_stats(self, first_slot=0, num_slots=1):
+        self._ck(self._lib.ilf_sao_stats(self._h, first_slot, num_slots))
+
+    def get_sao_stats(self, slot=0):
+        """int64 [num_ctus, 3, 5, 64]: per CTU, component and SAO type diff[32] then count[32] (SAOStatData)."""
+        ctu = 1 << self.cfg.ctu_log2
+        n = ((self.width + ctu - 1) // ctu) * ((self.height + ctu - 1) // ctu)
+        out = np.empty((n, 3, 5, 64), np.int64)
+        self._ck(self._lib.ilf_get_sao_stats(self._h, slot, _ptr(out)))
+        return out
+
     # ---- measurement -----------------------------------------------------------------------------
     def set_timing(self, on):
         self._ck(self._lib.ilf_set_timing(self._h, int(on)))
 
-    KERNELS = ("deblock", "sao", "alf", "alf_chroma")   # "alf" = the whole ALF stage (one launch); with ILF_ALF_SPLIT=1: luma only, "alf_chroma" the second launch
+    KERNELS = ("deblock", "sao", "alf", "alf_chroma", "sao_stats")   # "alf" = the whole ALF stage (one launch); with ILF_ALF_SPLIT=1: luma only, "alf_chroma" the second launch
 
     def kernel_times(self):
         """{kernel: (total ms, launches, algorithmic bytes)} since set_timing(True); synchronises the context's stream."""
-        ms = (C.c_double * 4)(); n = (C.c_longlong * 4)(); nb = (C.c_double * 4)()
+        ms = (C.c_double * NUM_KERNELS)(); n = (C.c_longlong * NUM_KERNELS)(); nb = (C.c_double * NUM_KERNELS)()
         self._ck(self._lib.ilf_kernel_times(self._h, C.byref(ms), C.byref(n), C.byref(nb)))
         return {k: (ms[i], n[i], nb[i]) for i, k in enumerate(self.KERNELS)}
 
