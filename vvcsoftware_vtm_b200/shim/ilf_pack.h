@@ -15,6 +15,7 @@
 #ifndef ILF_PACK_H
 #define ILF_PACK_H
 
+#include <cstddef>
 #include <cstdint>
 #include <vector>
 
@@ -60,5 +61,12 @@ void ilfPackSao( CodingStructure& cs, SAOBlkParam* saoBlkParams, const uint32_t 
 // ALF: reconstructs the coefficients (mutating alfSliceParam like the reference) and flattens.
 void ilfReconstructAlfCoeff( AlfSliceParam& alfSliceParam, bool isLuma, short* coeffFinal /* [25*13], luma only */, bool redo );
 void ilfPackAlf( CodingStructure& cs, AlfSliceParam& alfSliceParam, IlfPackedAlf& out );
+
+
+// Encoder SAO statistics of cs's picture through the shim's context (ilf_shim.cpp): `src` is the deblocked picture the
+// encoder measures (uploaded only when the device does not already hold it from loopFilterPic), `org` the source picture,
+// ctuAvail the ILF_AVAIL_L/_A/_AL flags per CTU; out[numCtus][3][5][64] in SAOStatData layout (diff[32], count[32]).
+struct ilfPlanes { const int16_t* p[3]; ptrdiff_t stride[3]; };
+void ilfShimSaoStatistics( CodingStructure& cs, const ilfPlanes& org, const ilfPlanes& src, const uint8_t* ctuAvail, int64_t* out );
 
 #endif

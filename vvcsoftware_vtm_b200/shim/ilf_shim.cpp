@@ -40,6 +40,8 @@ struct ShimState
   ilf_ctx*       ctx = nullptr;
   ilf_config     cfg;
   const Picture* resident = nullptr;  // picture whose current state lives on the device and not (yet) in the host reco buffer
+  const Picture* mirrored = nullptr;  // picture whose host reco buffer equals the slot's current device state (just downloaded) ...
+  int            mirroredPoc = -1;    // ... and its POC (Picture objects are recycled)
   bool           timing   = false;
   long long      usDeblock = 0, usSao = 0, usAlf = 0;
   int            picCount = 0;
@@ -105,6 +107,7 @@ void upload( ShimState& s, CodingStructure& cs )
   const CPelBuf     y = reco.get( COMPONENT_Y ), cb = reco.get( COMPONENT_Cb ), cr = reco.get( COMPONENT_Cr );
   ck( s, ilf_upload( s.ctx, 0, y.buf, y.stride, cb.buf, cb.stride, cr.buf, cr.stride ), "ilf_upload" );
   s.resident = cs.picture;
+  s.mirrored = nullptr;
 }
 
 void download( ShimState& s, CodingStructure& cs )
@@ -112,7 +115,9 @@ void download( ShimState& s, CodingStructure& cs )
   PelUnitBuf reco = cs.getRecoBuf();
   PelBuf     y = reco.get( COMPONENT_Y ), cb = reco.get( COMPONENT_Cb ), cr = reco.get( COMPONENT_Cr );
   ck( s, ilf_download( s.ctx, 0, y.buf, y.stride, cb.buf, cb.stride, cr.buf, cr.stride ), "ilf_download" );
-  s.resident = nullptr;
+  s.resident    = nullptr;
+  s.mirrored    = cs.picture;
+  s.mirroredPoc = cs.slice->getPOC();
 }
 
 long long usSince( clk::time_point t0 ) { return std::chrono::duration_cast<std::chrono::microseconds>( clk::now() - t0 ).count(); }
@@ -185,4 +190,24 @@ void AdaptiveLoopFilter::ALFProcess( CodingStructure& cs, AlfSliceParam& alfSlic
   if( s.resident == cs.picture ) download( s, cs );
   s.usAlf = usSince( t0 );
   report( s, cs );
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Encoder SAO statistics (called by EncSampleAdaptiveOffset::SAOProcess in ilf_shim_enc.cpp).  EncGOP::compressGOP calls
+// loopFilterPic and then the SAO search on the same picture (EncGOP.cpp:2122-2137): the deblocked picture is still in the
+// slot, so only the source picture crosses PCIe here.
+void ilfShimSaoStatistics( CodingStructure& cs, const ilfPlanes& org, const ilfPlanes& src, const uint8_t* ctuAvail, int64_t* out )
+{
+  const auto t0 = clk::now();
+  ShimState& s  = contextFor( cs );
+  if( !( s.mirrored == cs.picture && s.mirroredPoc == cs.slice->getPOC() ) )
+  {
+    ck( s, ilf_upload( s.ctx, 0, src.p[0], src.stride[0], src.p[1], src.stride[1], src.p[2], src.stride[2] ), "ilf_upload" );
+    s.resident = nullptr;
+    s.mirrored = nullptr;
+  }
+  ck( s, ilf_set_original( s.ctx, 0, org.p[0], org.stride[0], org.p[1], org.stride[1], org.p[2], org.stride[2], ctuAvail ), "ilf_set_original" );
+  ck( s, ilf_sao_stats( s.ctx, 0, 1 ), "ilf_sao_stats" );
+  ck( s, ilf_get_sao_stats( s.ctx, 0, out ), "ilf_get_sao_stats" );
+  if( s.timing ) fprintf( stderr, "[ILFTIME] poc=%d sao_stats_us=%lld impl=b200\n", cs.slice->getPOC(), usSince( t0 ) );
 }
