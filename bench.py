@@ -576,6 +576,26 @@ def run_b200(args, wl):
     value = world * B * args.steps * mpx / (ms_total * 1e-3)
     value_on = world * B * args.steps * mpx / (ms_on * 1e-3)
 
+    # ---- the "next" row of SURVEY.md 8f that is built: encoder SAO statistics on the resident deblocked pictures ----
+    # (not part of `value`: the decoder chain does not run it; reported as its own kernel against the HBM roofline)
+    rng_o = np.random.default_rng(7)
+    cw_, ch_ = (wl["width"] + 127) // 128, (wl["height"] + 127) // 128
+    av = np.full(cw_ * ch_, 0x15, np.uint8)
+    av[np.arange(cw_ * ch_) % cw_ == 0] &= ~np.uint8(0x11)
+    av[:cw_] &= ~np.uint8(0x14)
+    for s_ in range(B):
+        org = [np.clip(p.astype(np.int32) + rng_o.integers(-6, 7, p.shape), 0, 1023).astype(np.int16) for p in planes[s_ % len(planes)]]
+        f.set_original(s_, org[0], org[1], org[2], av)
+    f.run(0, B, 1)                     # deblocked pictures in the slots, as in the encoder
+    for _ in range(3):
+        f.sao_stats(0, B)
+    f.sync()
+    f.set_timing(True)
+    for _ in range(args.steps):
+        f.sao_stats(0, B)
+    kt_stats = f.kernel_times()["sao_stats"]
+    f.set_timing(False)
+
     # ---- end to end through the public API: host planes + side information in, filtered host planes out ----
     # Host buffers are page-locked (what a host integration does with its picture buffers: ilf_host_alloc /
     # ilf_host_register), every picture crosses PCIe in both directions inside the timed region, and the slots are
@@ -660,6 +680,9 @@ def run_b200(args, wl):
                              "all_on": {"what": "same pictures and deblocking information, SAO and ALF forced on for every CTU of every component (18 B/pixel)",
                                         "value": round(value_on, 1), "unit": "Mpixel/s", "ms_per_step": round(ms_on / args.steps, 4), "kernel": dom_on,
                                         "chain": chain_table(kt_on, ms_on, args.steps, B * mpx * 1e6, peak), "per_kernel": pk_on}},
+                "next_rows": {"sao_stats": dict(kernel_table({"sao_stats": kt_stats}, peak)["sao_stats"],
+                                                what="encoder SAO statistics (EncSampleAdaptiveOffset::getStatistics) of the resident deblocked pictures, one launch per step; algorithmic bytes = deblocked + original picture read once (6 B/pixel)",
+                                                mpixel_per_s=round(B * mpx / (kt_stats[0] / max(kt_stats[1], 1) * 1e-3), 1))},
                 "cpu_baseline": cpu,
                 "e2e": {"value": round(e2e_value, 1), "unit": "Mpixel/s", "h2d_bytes_per_step": Be * h2d + side_b, "d2h_bytes_per_step": Be * d2h, "pictures_per_step": Be,
                         "steps": e2e_steps, "path": "per picture InLoopFilter.upload + set_deblock_info/set_sao_params/set_alf_params + run + download_async (C ABI ilf_upload / ilf_set_* / ilf_run / ilf_download_async / ilf_wait), page-locked host buffers, slots cycled"},
