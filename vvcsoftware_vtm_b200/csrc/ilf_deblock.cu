@@ -41,7 +41,12 @@ namespace {
 constexpr int TW = RING_TILE_W, TH = DB_BAND_ROWS;  // luma tile; the band is shifted up by 4 rows
 constexpr int CTW = TW / 2, CTH = TH / 2;           // chroma tile per plane; shifted up by 2 rows
 constexpr int UW = TW / 4, UH = TH / 4;             // units per tile: 32 x 8, rows shifted up by 1
-constexpr int NTHREADS = 128;                       // one task per thread in each of the four phases
+// ILF_DB_SPLIT=1: 256 threads, the first 128 run the luma phases and the second 128 the chroma phases of a tile side by side
+// (the per-tile critical path is what limits a CTA's throughput); 0: 128 threads run luma then chroma.
+#ifndef ILF_DB_SPLIT
+#define ILF_DB_SPLIT 0
+#endif
+constexpr int NTHREADS = ILF_DB_SPLIT ? 256 : 128;  // 128 tasks in each of the four phases
 #ifndef ILF_DB_STAGES
 #define ILF_DB_STAGES 4
 #endif
@@ -250,6 +255,8 @@ __global__ void __launch_bounds__(NTHREADS, ILF_DB_MIN_CTAS) deblock_kernel(Geom
   const unsigned ctl = bc.v[blockIdx.z];
   const int src_b = ctl_src(ctl, 0), dst_b = ctl_dst(ctl, 0);  // deblocking starts from the uploaded picture: all planes in one buffer
   const int tid = threadIdx.x;
+  const int lt = tid & 127;  // task index within a phase
+  const bool do_luma = !ILF_DB_SPLIT || tid < 128, do_chroma = !ILF_DB_SPLIT || tid >= 128;
   const int ty = blockIdx.y;
   const int y0 = ty * TH - 4, cy0 = ty * CTH - 2, uy0 = ty * UH - 1;  // band origin (local rows)
   const int rows = g.rows, crow = g.rows >> 1, cw = g.width >> 1;
@@ -316,8 +323,8 @@ __global__ void __launch_bounds__(NTHREADS, ILF_DB_MIN_CTAS) deblock_kernel(Geom
     const int x0 = tx * TW, cx0 = tx * CTW;
 
     // ---- vertical edges, luma: task = 4 lines x 8 samples.  16 edge columns x 8 segment rows ----
-    if (filt && !flush && ((tid & 15) > 0 || prev)) {
-      const int e = tid & 15, sg = tid >> 4;
+    if (do_luma && filt && !flush && ((lt & 15) > 0 || prev)) {
+      const int e = lt & 15, sg = lt >> 4;
       const EdgeParams ep = luma_edge_params<MV>(t, g, sh, sg, 2 * e, sg, 2 * e - 1, true, x0 + 8 * e, y0 + 4 * sg);
       if (ep.bs) {
         int16_t* pp = t.y(4 * sg, 8 * e - 4);
@@ -338,8 +345,8 @@ __global__ void __launch_bounds__(NTHREADS, ILF_DB_MIN_CTAS) deblock_kernel(Geom
       }
     }
     // ---- vertical edges, chroma: task = one unit = 2 lines x 4 samples.  2 planes x 8 edge columns x 8 unit rows ----
-    if (filt && !flush && (((tid >> 3) & 7) > 0 || prev)) {
-      const int pl = tid >> 6, k = (tid >> 3) & 7, sg = tid & 7;
+    if (do_chroma && filt && !flush && (((lt >> 3) & 7) > 0 || prev)) {
+      const int pl = lt >> 6, k = (lt >> 3) & 7, sg = lt & 7;
       bool no_p, no_q;
       const int tc = chroma_tc(t.cinfo(sg, 4 * k), t.cinfo(sg, 4 * k - 1), g, sh, true, pl, 2 * (cx0 + 8 * k), 2 * (cy0 + 2 * sg), no_p, no_q);
       if (tc >= 0) {
@@ -369,8 +376,8 @@ __global__ void __launch_bounds__(NTHREADS, ILF_DB_MIN_CTAS) deblock_kernel(Geom
     // ---- horizontal edges, luma: task = 4 columns x 8 rows, filtered and stored.  4 edge rows x unit columns -LAG_Y .. 31 - LAG_Y
     //      (a warp = one edge row: 256 contiguous bytes per stored row) ----
     {
-      const int u = (tid & 31) - LAG_Y, h = tid >> 5;
-      if (u < 0 ? prev != nullptr : !flush) {
+      const int u = (lt & 31) - LAG_Y, h = lt >> 5;
+      if (do_luma && (u < 0 ? prev != nullptr : !flush)) {
         const int16_t* sp = t.y(8 * h, 4 * u);
         uint2 raw[8];
 #pragma unroll
@@ -401,8 +408,8 @@ __global__ void __launch_bounds__(NTHREADS, ILF_DB_MIN_CTAS) deblock_kernel(Geom
     // ---- horizontal edges, chroma: task = 2 columns x 8 rows (the edge lies between rows 1 and 2), filtered and stored.
     //      2 planes x 2 row groups x unit columns -LAG_C .. 31 - LAG_C ----
     {
-      const int pl = tid >> 6, h = (tid >> 5) & 1, u = (tid & 31) - LAG_C;
-      if (u < 0 ? prev != nullptr : !flush) {
+      const int pl = lt >> 6, h = (lt >> 5) & 1, u = (lt & 31) - LAG_C;
+      if (do_chroma && (u < 0 ? prev != nullptr : !flush)) {
         const int16_t* sp = t.ch(pl, 8 * h, 2 * u);
         uint32_t raw[8];
 #pragma unroll

@@ -91,7 +91,9 @@ ILF_PK uint32_t sao_bo_index2(uint32_t c, int shift, uint32_t nband) {
 // out = clip(c + lut[idx], 0, max) per lane; lut = 5 signed bytes (lut_lo = bytes 0..3, lut_hi = byte 4), idx lanes 0..4.
 ILF_PK uint32_t sao_apply2(uint32_t c, uint32_t idx, uint32_t lut_lo, uint32_t lut_hi, uint32_t maxv) {
   // selector nibbles: byte0 <- lut[idx0], byte1 <- sign(lut[idx0]), byte2 <- lut[idx1], byte3 <- sign(lut[idx1])
-  const uint32_t sel = ((idx | (idx >> 8)) & 0x0707u) * 0x11u + 0x8080u;
+  // idx lanes hold 0..4 only: gather their low bytes with one PRMT (bytes 0 and 2 -> 0 and 1), then spread each index over its
+  // two nibbles with a multiply (FMA pipe; the SAO kernel is ALU-pipe bound)
+  const uint32_t sel = prmt(idx, 0u, 0x4420u) * 0x11u + 0x8080u;
   const uint32_t off = prmt(lut_lo, lut_hi, sel);
   return addmin2_relu(c, off, maxv);
 }

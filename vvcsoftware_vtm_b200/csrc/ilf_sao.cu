@@ -233,15 +233,21 @@ __global__ void __launch_bounds__(NTHREADS) sao_kernel(Geom g, const SlotDev* __
   pdl_wait();  // deblocking has written the planes read from here on
   if (tid == 0)
     for (int t = walk.first; t <= walk.last && t < walk.first + STAGES; t++) issue(t);
+  // stage index and barrier phase of tiles tx - 1, tx, tx + 1, advanced by one per step (no division by the ring depth)
+  struct Pos { int st; uint32_t par; __device__ __forceinline__ void next() { if (++st == STAGES) { st = 0; par ^= 1u; } } };
+  Pos pp = {walk.stage(ta) - 1, 0u}, pc = {walk.stage(ta), 0u}, pn = {walk.stage(ta), 0u};   // ta - first is 0 or 1: all in the first lap
+  pn.next();
+  auto sptr = [&](const Pos& p) { return reinterpret_cast<int16_t*>(smem + p.st * STAGE_BYTES); };
   for (int tx = ta; tx < tb; tx++) {
     if (tx == ta) {
-      if (tx > walk.first) ring::mbar_wait(&full[walk.stage(tx - 1)], walk.parity(tx - 1));
-      ring::mbar_wait(&full[walk.stage(tx)], walk.parity(tx));
+      if (tx > walk.first) ring::mbar_wait(&full[pp.st], pp.par);
+      ring::mbar_wait(&full[pc.st], pc.par);
     }
-    if (tx + 1 <= walk.last) ring::mbar_wait(&full[walk.stage(tx + 1)], walk.parity(tx + 1));
-    sao_tile(g, sd, plane, dst, tx, by0, stage_ptr(tx), tx > 0 ? stage_ptr(tx - 1) : nullptr, tx + 1 < ntx ? stage_ptr(tx + 1) : nullptr);
+    if (tx + 1 <= walk.last) ring::mbar_wait(&full[pn.st], pn.par);
+    sao_tile(g, sd, plane, dst, tx, by0, sptr(pc), tx > 0 ? sptr(pp) : nullptr, tx + 1 < ntx ? sptr(pn) : nullptr);
     __syncthreads();  // every thread is done with tile tx - 1: its stage can be refilled
     if (tid == 0 && tx - 1 >= walk.first && tx - 1 + STAGES <= walk.last) issue(tx - 1 + STAGES);
+    pp = pc; pc = pn; pn.next();
   }
 }
 
