@@ -137,6 +137,24 @@ def all_on_sideinfo(side):
     return out
 
 
+
+def bind_to_gpu_numa(index):
+    """Run this rank on the CPU cores NVML names as local to GPU `index` (its NUMA node): page-locked buffers are then
+    allocated next to the GPU's PCIe root and the e2e copies do not cross the socket interconnect.  Best effort."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * i + b for i, wd in enumerate(words) for b in range(64) if (wd >> b) & 1}
+        allowed = cpus & os.sched_getaffinity(0)
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+        return len(allowed)
+    except Exception:
+        return 0
+
+
 class ClockSampler(threading.Thread):
     """Samples SM clock and throttle reasons of one GPU through NVML while the timed region runs."""
 
@@ -342,6 +360,8 @@ def run_bands(args, wl):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
+    if world > 1:
+        bind_to_gpu_numa(local)
     v.load_library()
     w, h = wl["width"], wl["height"]
     mpx = w * h / 1e6
@@ -498,6 +518,8 @@ def run_b200(args, wl):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; libilf_b200 has no CPU fallback")
     torch.cuda.set_device(local)
+    if world > 1:
+        bind_to_gpu_numa(local)
     v.load_library()
 
     w, h = wl["width"], wl["height"]
