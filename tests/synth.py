@@ -95,3 +95,43 @@ def deblock_info(rng, w, h, p_edge=0.5, p_intra=0.4, inter=False):
     prm = np.zeros(1, DB_DT)
     prm["cb_qp_offset"], prm["cr_qp_offset"], prm["mv_threshold"], prm["num_slices"] = 1, -1, 4, 1
     return prm.tobytes(), info, mv16
+
+
+def deblock_info_stress(rng, w, h, ctu_log2=7, mv32=False):
+    """Side information that real streams of the committed configurations rarely or never carry: several slices with their
+    own beta / tc offsets (ctu_slice map), no-filter units (PCM / lossless), B-slice units with two reference ids and four
+    motion-vector components, a separate chroma-tree layer, QPs over the whole range, optionally 32-bit motion vectors.
+    Returns a dict with the keys of the bench side information."""
+    uw, uh = w // 4, h // 4
+    bw, bh = (uw + 1) // 2, (uh + 1) // 2
+    up = lambda a: np.kron(a, np.ones((2, 2), a.dtype))[:uh, :uw]
+    xs, ys = np.arange(uw)[None, :], np.arange(uh)[:, None]
+
+    def layer(p_intra):
+        intra = up((rng.random((bh, bw)) < p_intra).astype(np.uint32))
+        cbf = up((rng.random((bh, bw)) < 0.5).astype(np.uint32))
+        qp = up(rng.integers(0, 64, (bh, bw)).astype(np.uint32))
+        ev = up((rng.random((bh, bw)) < 0.6).astype(np.uint32)) * ((xs % 2 == 0) & (xs > 0))
+        eh = up((rng.random((bh, bw)) < 0.6).astype(np.uint32)) * ((ys % 2 == 0) & (ys > 0))
+        tv = up((rng.random((bh, bw)) < 0.7).astype(np.uint32))
+        th = up((rng.random((bh, bw)) < 0.7).astype(np.uint32))
+        nofilt = up((rng.random((bh, bw)) < 0.08).astype(np.uint32))
+        bsl = up((rng.random((bh, bw)) < 0.6).astype(np.uint32))
+        ids = np.array([0, 1, 2, 0xFF], np.uint32)
+        ref0 = up(ids[rng.integers(0, 3, (bh, bw))])
+        ref1 = up(ids[rng.integers(0, 4, (bh, bw))]) * bsl + np.uint32(0xFF) * (1 - bsl)
+        return (intra | (cbf << 1) | (ev.astype(np.uint32) << 2) | ((tv * ev).astype(np.uint32) << 3) | (eh.astype(np.uint32) << 4) |
+                ((th * eh).astype(np.uint32) << 5) | (nofilt << 6) | (bsl << 7) | (qp << 8) | (ref0 << 16) | (ref1.astype(np.uint32) << 24)).astype(np.uint32)
+
+    info, info_c = layer(0.3), layer(0.6)
+    span = 40000 if mv32 else 14
+    mv = np.kron(rng.integers(-span, span + 1, (bh, bw, 4)), np.ones((2, 2, 1), np.int64))[:uh, :uw]
+    ctu = 1 << ctu_log2
+    cw, ch = (w + ctu - 1) // ctu, (h + ctu - 1) // ctu
+    prm = np.zeros(1, DB_DT)
+    prm["cb_qp_offset"], prm["cr_qp_offset"], prm["mv_threshold"], prm["num_slices"] = rng.integers(-6, 7), rng.integers(-6, 7), 16 if mv32 else 4, 3
+    prm["slices"][0, :3, 0] = rng.integers(-6, 7, 3)
+    prm["slices"][0, :3, 1] = rng.integers(-6, 7, 3)
+    d = {"db_params": prm.tobytes(), "db_info": info, "db_info_c": info_c, "ctu_slice": np.sort(rng.integers(0, 3, cw * ch)).astype(np.uint8)}
+    d["db_mv32" if mv32 else "db_mv16"] = np.ascontiguousarray(mv.astype(np.int32 if mv32 else np.int16))
+    return d

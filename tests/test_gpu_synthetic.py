@@ -65,3 +65,23 @@ def test_alf_random_coefficients(w, h, bd, is7, seed, ilf_lib, oracle):
             cls = f.alf_classify(0)
         d = _diff(got, want)
         assert not any(d.values()), f"{kind}: mismatching samples {d}"
+
+
+@pytest.mark.parametrize("w,h,bd,ctu_log2,mv32,seed", [(416, 240, 10, 7, False, 31), (200, 136, 8, 5, True, 32), (264, 200, 12, 6, False, 33), (1920, 1080, 10, 7, True, 34)])
+def test_deblock_stress_side_information(w, h, bd, ctu_log2, mv32, seed, ilf_lib, oracle):
+    """Deblocking with side information the committed streams do not produce: three slices with their own beta / tc offsets,
+    no-filter (PCM / lossless) units, two reference lists with four MV components, a chroma-tree layer, the whole QP range,
+    chroma QP offsets, 32-bit MVs with the 1/16-pel threshold -- CUDA == oracle, bit-exact."""
+    rng = np.random.default_rng(seed)
+    for kind in ("mix", "noise"):
+        pic = synth.picture(rng, w, h, bd, kind)
+        si = synth.deblock_info_stress(rng, w, h, ctu_log2, mv32)
+        want = oracle.deblock(pic, bd, bd, ctu_log2, si["db_params"], si["db_info"], si["db_info_c"], si.get("db_mv16"), si.get("db_mv32"), si["ctu_slice"])
+        with ilf_lib.InLoopFilter(w, h, bd, bd, ctu_log2) as f:
+            f.upload(0, *(pic[k] for k in K))
+            f.set_deblock_info(0, si["db_params"], si["db_info"], si["db_info_c"], si.get("db_mv16"), si.get("db_mv32"), si["ctu_slice"])
+            f.loop_filter_pic(0)
+            got = f.download(0)
+        d = _diff(got, want)
+        assert not any(d.values()), f"{kind}: mismatching samples {d}"
+        assert any((got[k] != pic[k]).any() for k in K)      # and something was filtered
