@@ -273,7 +273,9 @@ def run_reference(args, wl):
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count()
     w, h = wl["width"], wl["height"]
     mpx = w * h / 1e6
-    sample_pics = 5  # bounded sample per step: the first 5 pictures in decoding order (I + 4 B of one RA GOP)
+    # bounded sample per step: the first pictures of the stream in decoding order (I + B pictures of one RA GOP) on every core;
+    # fewer of them when many steps are asked for, so that the whole run stays within a few minutes (a step costs a decode)
+    sample_pics = 5 if args.steps <= 20 else (3 if args.steps <= 50 else 2)
     if reference_chain_run(wl["stream"], w, h, 1, 1) is None:
         # the reference binary did not travel: time the C restatement instead
         pics = load_sideinfo(args.workload)
