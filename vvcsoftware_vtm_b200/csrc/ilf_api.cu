@@ -38,6 +38,8 @@ struct Slot {
   uint8_t* pinned_side = nullptr;  // host staging for side information
   size_t pinned_side_bytes = 0;
   SlotDev dev;                 // host copy of the device descriptor
+  SlotDev pushed;              // what the device copy holds (valid once pushed_valid): unchanged descriptors are not sent again
+  bool pushed_valid = false;
   bool uploaded = false, has_db = false, has_sao = false, has_alf = false, has_ctree = false;
   int mv_mode = 0;             // 0 none, 1 int16, 2 int32
   int result_buf[3] = {0, 0, 0};  // buffer holding the current picture, per plane
@@ -155,7 +157,12 @@ int make_map3(ilf_ctx* ctx, CUtensorMap* out, CUtensorMapDataType dt, void* base
 // The slot descriptor travels on the upload stream like the side information it points to.
 int push_desc(ilf_ctx* ctx, int slot) {
   Slot& s = ctx->slots[slot];
-  CU(ctx, cudaMemcpyAsync(ctx->slots_dev + slot, &s.dev, sizeof(SlotDev), cudaMemcpyHostToDevice, ctx->s_up));
+  // the pointers of a slot settle after its first picture: most calls find the device copy up to date
+  if (!(s.pushed_valid && memcmp(&s.dev, &s.pushed, sizeof(SlotDev)) == 0)) {
+    memcpy(&s.pushed, &s.dev, sizeof(SlotDev));  // padding included, so that the comparison above is exact
+    CU(ctx, cudaMemcpyAsync(ctx->slots_dev + slot, &s.pushed, sizeof(SlotDev), cudaMemcpyHostToDevice, ctx->s_up));
+    s.pushed_valid = true;
+  }
   CU(ctx, cudaEventRecord(s.ev_up, ctx->s_up));
   s.h2d_pending = true;
   return ILF_OK;
