@@ -50,10 +50,24 @@ struct PackCtx
 {
   CodingStructure*              cs;
   IlfPackedDeblock*             out;
-  EdgeScratch                   scratch[2];  // [tree layer]
+  EdgeScratch*                  scratch;     // [tree layer]; kept between pictures so that the arrays keep their pages
   std::map<const Picture*, int> refIds;
   std::map<const Slice*, int>   sliceIds;
   bool                          pcmFilter, tqBypass, highPrecMv;
+  // reference-picture ids of the slice the walk is in, [list][refIdx] (one map lookup per reference and slice, not per unit)
+  const Slice*                  tabSlice = nullptr;
+  uint32_t                      refTab[2][MAX_NUM_REF];
+  const uint32_t*               refsOf( const Slice& s )
+  {
+    if( &s != tabSlice )
+    {
+      tabSlice = &s;
+      for( int l = 0; l < 2; l++ )
+        for( int i = 0; i < MAX_NUM_REF; i++ )
+          refTab[l][i] = i < s.getNumRefIdx( RefPicList( l ) ) && s.getRefPic( RefPicList( l ), i ) ? uint32_t( refId( s.getRefPic( RefPicList( l ), i ) ) ) : ILF_REF_NONE;
+    }
+    return &refTab[0][0];
+  }
 
   int sliceId( const Slice* s )
   {
@@ -151,28 +165,38 @@ void packCU( PackCtx& pc, const CodingUnit& cu, int layer )
     }
     if( cu.predMode != MODE_INTRA && layer == 0 )
     {
+      const uint32_t*  refTab = pc.refsOf( slice );
+      const CMotionBuf mb     = cu.cs->getMotionBuf( Area( ux0 * 4, uy0 * 4, ( ux1 - ux0 ) * 4, ( uy1 - uy0 ) * 4 ) );  // one MotionInfo per 4x4 unit
+      int32_t*         mv32   = pc.out->wantMv32 ? pc.out->mv32.data() : nullptr;
+      int16_t*         mv16   = pc.out->mv16.data();
+      bool             fits   = true;
       for( int y = uy0; y < uy1; y++ )
+      {
+        const MotionInfo* row = mb.buf + size_t( y - uy0 ) * mb.stride;
         for( int x = ux0; x < ux1; x++ )
         {
-          const MotionInfo& mi  = cu.cs->getMotionInfo( Position( x * 4, y * 4 ) );
+          const MotionInfo& mi  = row[x - ux0];
           const size_t      idx = size_t( y ) * unitsW + x;
           uint32_t          refs[2] = { ILF_REF_NONE, ILF_REF_NONE };
           for( int l = 0; l < 2; l++ )
           {
-            int32_t* dst = &pc.out->mv32[idx * 4 + l * 2];
             if( mi.refIdx[l] >= 0 )  // LoopFilter.cpp:456-466
             {
-              refs[l] = uint32_t( pc.refId( slice.getRefPic( RefPicList( l ), mi.refIdx[l] ) ) );
+              refs[l] = refTab[l * MAX_NUM_REF + mi.refIdx[l]];
               Mv mv   = mi.mv[l];
               if( pc.highPrecMv ) mv.setHighPrec();  // :470-477
-              dst[0] = mv.getHor();
-              dst[1] = mv.getVer();
-              if( mv.getHor() < -32768 || mv.getHor() > 32767 || mv.getVer() < -32768 || mv.getVer() > 32767 ) pc.out->mvFits16 = false;
-              pc.out->anyInter = true;
+              const int hor = mv.getHor(), ver = mv.getVer();
+              if( mv32 ) { mv32[idx * 4 + l * 2] = hor; mv32[idx * 4 + l * 2 + 1] = ver; }
+              mv16[idx * 4 + l * 2]     = int16_t( hor );
+              mv16[idx * 4 + l * 2 + 1] = int16_t( ver );
+              fits &= hor >= -32768 && hor <= 32767 && ver >= -32768 && ver <= 32767;
             }
           }
           info[idx] = ( info[idx] & 0x0000FFFFu ) | ( refs[0] << 16 ) | ( refs[1] << 24 );
         }
+      }
+      pc.out->anyInter = true;
+      if( !fits ) pc.out->mvFits16 = false;
     }
   }
 
@@ -215,8 +239,8 @@ void ilfPackDeblock( CodingStructure& cs, IlfPackedDeblock& out )
   out.ctusH  = pcv.heightInCtus;
   const size_t n = size_t( out.unitsW ) * out.unitsH;
   out.info.assign( n, 0xFFFF0000u );
-  out.mv32.assign( n * 4, 0 );
-  out.mv16.clear();
+  if( out.wantMv32 ) out.mv32.assign( n * 4, 0 ); else out.mv32.clear();
+  out.mv16.assign( n * 4, 0 );   // written in place by the walk; meaningful only while mvFits16
   out.mvFits16 = true;
   out.anyInter = false;
   out.ctuSlice.assign( size_t( out.ctusW ) * out.ctusH, 0 );
@@ -227,7 +251,9 @@ void ilfPackDeblock( CodingStructure& cs, IlfPackedDeblock& out )
   const bool dual = CS::isDualITree( cs );
   if( dual ) out.infoChroma.assign( n, 0xFFFF0000u ); else out.infoChroma.clear();
 
+  static EdgeScratch scratchStore[2];
   PackCtx pc;
+  pc.scratch    = scratchStore;
   pc.cs         = &cs;
   pc.out        = &out;
   pc.pcmFilter  = cs.sps->getUsePCM() && cs.sps->getPCMFilterDisableFlag();
@@ -250,11 +276,6 @@ void ilfPackDeblock( CodingStructure& cs, IlfPackedDeblock& out )
     }
   if( out.params.num_slices == 0 ) pc.sliceId( cs.slice );
 
-  if( out.mvFits16 && out.anyInter )
-  {
-    out.mv16.resize( n * 4 );
-    for( size_t i = 0; i < n * 4; i++ ) out.mv16[i] = int16_t( out.mv32[i] );
-  }
 }
 
 // ------------------------------------------------------------------------------------------------------------

@@ -31,8 +31,9 @@ struct IlfPackedDeblock
   ilf_deblock_params    params;
   std::vector<uint32_t> info;        // luma-tree layer
   std::vector<uint32_t> infoChroma;  // chroma-tree layer, empty when the picture has no dual-tree slice
-  std::vector<int32_t>  mv32;        // 4 per unit
-  std::vector<int16_t>  mv16;        // same values, filled when mvFits16
+  bool                  wantMv32 = true;  // in: also fill mv32 (the shim asks for it only after a picture did not fit 16 bits)
+  std::vector<int32_t>  mv32;        // 4 per unit (when wantMv32)
+  std::vector<int16_t>  mv16;        // same values as int16, valid while mvFits16
   bool                  mvFits16 = true;
   bool                  anyInter = false;
   std::vector<uint8_t>  ctuSlice;

@@ -21,6 +21,8 @@
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <utility>
+#include <vector>
 
 #include "CommonLib/AdaptiveLoopFilter.h"
 #include "CommonLib/CodingStructure.h"
@@ -43,6 +45,8 @@ struct ShimState
   const Picture* mirrored = nullptr;  // picture whose host reco buffer equals the slot's current device state (just downloaded) ...
   int            mirroredPoc = -1;    // ... and its POC (Picture objects are recycled)
   bool           timing   = false;
+  bool           pin      = true;     // page-lock the reference's picture planes on first sight (ILF_SHIM_PIN=0: stage through the library)
+  std::vector<std::pair<const char*, size_t>> pinned, unpinnable, seenOnce;
   long long      usDeblock = 0, usSao = 0, usAlf = 0;
   int            picCount = 0;
   ~ShimState()
@@ -59,6 +63,7 @@ ShimState& state()
   {
     init     = true;
     s.timing = getenv( "ILF_TIMING" ) && atoi( getenv( "ILF_TIMING" ) ) != 0;
+    s.pin    = !( getenv( "ILF_SHIM_PIN" ) && atoi( getenv( "ILF_SHIM_PIN" ) ) == 0 );
   }
   return s;
 }
@@ -101,9 +106,32 @@ ShimState& contextFor( const CodingStructure& cs )
   return s;
 }
 
+// The decoded-picture buffer is allocated once and recycled (Picture::create).  Page-locking a plane costs about as much as
+// five staged copies of it (cudaHostRegister runs at ~1 GB/s), so a plane is registered when it comes around the SECOND time:
+// from then on the library copies straight from / into it (ilf_b200.h "transfer pipeline") instead of staging 25 MB per 4K
+// picture through its own pinned buffer.  A range that cannot be registered stays pageable.
+void pinPlane( ShimState& s, const Pel* buf, int stride, int w, int h )
+{
+  if( !s.pin ) return;
+  const char*  lo    = reinterpret_cast<const char*>( buf );
+  const size_t bytes = ( size_t( h - 1 ) * stride + w ) * sizeof( Pel );
+  for( auto& r : s.pinned ) if( lo >= r.first && lo + bytes <= r.first + r.second ) return;
+  for( auto& r : s.unpinnable ) if( lo == r.first && bytes == r.second ) return;
+  bool again = false;
+  for( auto& r : s.seenOnce ) again |= lo == r.first && bytes == r.second;
+  if( !again ) { s.seenOnce.emplace_back( lo, bytes ); return; }
+  if( ilf_host_register( const_cast<char*>( lo ), bytes ) == ILF_OK ) s.pinned.emplace_back( lo, bytes );
+  else s.unpinnable.emplace_back( lo, bytes );
+}
+void pinPlanes( ShimState& s, const CPelUnitBuf& u )
+{
+  for( int c = 0; c < 3; c++ ) { const CPelBuf b = u.get( ComponentID( c ) ); pinPlane( s, b.buf, b.stride, b.width, b.height ); }
+}
+
 void upload( ShimState& s, CodingStructure& cs )
 {
   const CPelUnitBuf reco = cs.getRecoBuf();
+  pinPlanes( s, reco );
   const CPelBuf     y = reco.get( COMPONENT_Y ), cb = reco.get( COMPONENT_Cb ), cr = reco.get( COMPONENT_Cr );
   ck( s, ilf_upload( s.ctx, 0, y.buf, y.stride, cb.buf, cb.stride, cr.buf, cr.stride ), "ilf_upload" );
   s.resident = cs.picture;
@@ -113,6 +141,7 @@ void upload( ShimState& s, CodingStructure& cs )
 void download( ShimState& s, CodingStructure& cs )
 {
   PelUnitBuf reco = cs.getRecoBuf();
+  pinPlanes( s, reco );
   PelBuf     y = reco.get( COMPONENT_Y ), cb = reco.get( COMPONENT_Cb ), cr = reco.get( COMPONENT_Cr );
   ck( s, ilf_download( s.ctx, 0, y.buf, y.stride, cb.buf, cb.stride, cr.buf, cr.stride ), "ilf_download" );
   s.resident    = nullptr;
@@ -137,16 +166,30 @@ void LoopFilter::loopFilterPic( CodingStructure& cs )
 {
   const auto t0 = clk::now();
   ShimState& s  = contextFor( cs );
-  IlfPackedDeblock db;
+  const auto tc = clk::now();
+  static IlfPackedDeblock db;  // kept between pictures: the arrays keep their pages
+  db.wantMv32 = false;
   ilfPackDeblock( cs, db );  // the walk over CUs/TUs/motion of LoopFilter.cpp:167-222, 243-541, flattened
+  if( db.anyInter && !db.mvFits16 )
+  {
+    db.wantMv32 = true;  // a motion vector beyond 16 bits: walk again for the 32-bit array
+    ilfPackDeblock( cs, db );
+  }
+  const auto tp = clk::now();
   upload( s, cs );
+  const auto tu = clk::now();
   ck( s, ilf_set_deblock_info( s.ctx, 0, &db.params, db.info.data(), db.infoChroma.empty() ? nullptr : db.infoChroma.data(),
                                ( db.anyInter && db.mvFits16 ) ? db.mv16.data() : nullptr, ( db.anyInter && !db.mvFits16 ) ? db.mv32.data() : nullptr, db.ctuSlice.data() ),
       "ilf_set_deblock_info" );
   ck( s, ilf_deblock( s.ctx, 0 ), "ilf_deblock" );
+  const auto tk = clk::now();
   const bool laterStage = !cs.pcv->isEncoder && ( cs.sps->getUseSAO() || cs.sps->getUseALF() );
   if( !laterStage ) download( s, cs );
   s.usDeblock = usSince( t0 );
+  if( s.timing && getenv( "ILF_TIMING" ) && atoi( getenv( "ILF_TIMING" ) ) > 1 )
+    fprintf( stderr, "[ILFTIME2] context_us=%lld pack_us=%lld upload_us=%lld set+launch_us=%lld rest_us=%lld\n",
+             (long long) std::chrono::duration_cast<std::chrono::microseconds>( tc - t0 ).count(), (long long) std::chrono::duration_cast<std::chrono::microseconds>( tp - tc ).count(),
+             (long long) std::chrono::duration_cast<std::chrono::microseconds>( tu - tp ).count(), (long long) std::chrono::duration_cast<std::chrono::microseconds>( tk - tu ).count(), usSince( tk ) );
   if( !laterStage ) report( s, cs );
 }
 
