@@ -140,8 +140,7 @@ void upload( ShimState& s, CodingStructure& cs )
 
 void download( ShimState& s, CodingStructure& cs )
 {
-  PelUnitBuf reco = cs.getRecoBuf();
-  pinPlanes( s, reco );
+  PelUnitBuf reco = cs.getRecoBuf();  // (page-locked or not as upload() left it)
   PelBuf     y = reco.get( COMPONENT_Y ), cb = reco.get( COMPONENT_Cb ), cr = reco.get( COMPONENT_Cr );
   ck( s, ilf_download( s.ctx, 0, y.buf, y.stride, cb.buf, cb.stride, cr.buf, cr.stride ), "ilf_download" );
   s.resident    = nullptr;
