@@ -120,6 +120,14 @@ void DecLib::executeLoopFilters()
   }
 
   using clk = std::chrono::steady_clock;
+  if( getenv( "ILF_PACK_TIMING" ) )  // how long does the product packer take on this picture? (host-side cost of the drop-in)
+  {
+    static IlfPackedDeblock db;
+    db.wantMv32 = false;
+    const auto p0 = clk::now();
+    ilfPackDeblock( cs, db );
+    fprintf( stderr, "[PACKTIME] poc=%d pack_us=%lld\n", cs.slice->getPOC(), (long long) std::chrono::duration_cast<std::chrono::microseconds>( clk::now() - p0 ).count() );
+  }
   const auto t0 = clk::now();
   m_cLoopFilter.loopFilterPic( cs );
   const auto t1 = clk::now();

@@ -69,7 +69,16 @@ struct PackCtx
     return &refTab[0][0];
   }
 
+  const Slice* lastSlice = nullptr;
+  int          lastSliceId = 0;
   int sliceId( const Slice* s )
+  {
+    if( s == lastSlice ) return lastSliceId;
+    lastSlice   = s;
+    lastSliceId = sliceIdSlow( s );
+    return lastSliceId;
+  }
+  int sliceIdSlow( const Slice* s )
   {
     auto it = sliceIds.find( s );
     if( it != sliceIds.end() ) return it->second;
@@ -112,16 +121,10 @@ void packCU( PackCtx& pc, const CodingUnit& cu, int layer )
   {
     const Position& pos = cu.blocks[cu.chType].pos();
     internalEdge        = true;
-    if( pos.x > 0 )
-    {
-      const CodingUnit* l = cu.cs->getCU( pos.offset( -1, 0 ), cu.chType );
-      leftEdge            = slice.getLFCrossSliceBoundaryFlag() || CU::isSameSlice( cu, *l );
-    }
-    if( pos.y > 0 )
-    {
-      const CodingUnit* a = cu.cs->getCU( pos.offset( 0, -1 ), cu.chType );
-      topEdge             = slice.getLFCrossSliceBoundaryFlag() || CU::isSameSlice( cu, *a );
-    }
+    // the neighbour is looked up only when the answer depends on it (the flag is 1 in every reference configuration)
+    const bool across = slice.getLFCrossSliceBoundaryFlag();
+    if( pos.x > 0 ) leftEdge = across || CU::isSameSlice( cu, *cu.cs->getCU( pos.offset( -1, 0 ), cu.chType ) );
+    if( pos.y > 0 ) topEdge = across || CU::isSameSlice( cu, *cu.cs->getCU( pos.offset( 0, -1 ), cu.chType ) );
   }
 
   // TU edges (:250-255), PU edges (:257-266), affine sub-block edges (:268-284)
@@ -144,7 +147,6 @@ void packCU( PackCtx& pc, const CodingUnit& cu, int layer )
     for( int e = 1; e < int( cu.Y().width ) / 4; e++ ) es.mark( 0, Area( cu.Y().x + e * 4, cu.Y().y, 4, cu.Y().height ), internalEdge, true );
     for( int e = 1; e < int( cu.Y().height ) / 4; e++ ) es.mark( 1, Area( cu.Y().x, cu.Y().y + e * 4, cu.Y().width, 4 ), internalEdge, true );
   }
-
   // Per-unit CU / TU / motion fields (looked up by position in xGetBoundaryStrengthSingle / xEdgeFilter*).
   const bool     noFilt = ( pc.pcmFilter && cu.ipcm ) || ( pc.tqBypass && cu.transQuantBypass );
   const uint32_t cuBits = ( cu.predMode == MODE_INTRA ? ILF_BI_INTRA : 0u ) | ( noFilt ? ILF_BI_NOFILT : 0u ) |
@@ -178,20 +180,21 @@ void packCU( PackCtx& pc, const CodingUnit& cu, int layer )
           const MotionInfo& mi  = row[x - ux0];
           const size_t      idx = size_t( y ) * unitsW + x;
           uint32_t          refs[2] = { ILF_REF_NONE, ILF_REF_NONE };
+          int               v[4] = { 0, 0, 0, 0 };
           for( int l = 0; l < 2; l++ )
           {
             if( mi.refIdx[l] >= 0 )  // LoopFilter.cpp:456-466
             {
               refs[l] = refTab[l * MAX_NUM_REF + mi.refIdx[l]];
-              Mv mv   = mi.mv[l];
-              if( pc.highPrecMv ) mv.setHighPrec();  // :470-477
-              const int hor = mv.getHor(), ver = mv.getVer();
-              if( mv32 ) { mv32[idx * 4 + l * 2] = hor; mv32[idx * 4 + l * 2 + 1] = ver; }
-              mv16[idx * 4 + l * 2]     = int16_t( hor );
-              mv16[idx * 4 + l * 2 + 1] = int16_t( ver );
-              fits &= hor >= -32768 && hor <= 32767 && ver >= -32768 && ver <= 32767;
+              // Mv::setHighPrec (:470-477, Mv.h:259-265) multiplies a low-precision vector by 4, sign-symmetrically
+              const int sc = ( pc.highPrecMv && !mi.mv[l].highPrec ) ? ( 1 << VCEG_AZ07_MV_ADD_PRECISION_BIT_FOR_STORE ) : 1;
+              v[2 * l]     = mi.mv[l].hor * sc;
+              v[2 * l + 1] = mi.mv[l].ver * sc;
             }
           }
+          if( mv32 ) { mv32[idx * 4] = v[0]; mv32[idx * 4 + 1] = v[1]; mv32[idx * 4 + 2] = v[2]; mv32[idx * 4 + 3] = v[3]; }
+          mv16[idx * 4] = int16_t( v[0] ); mv16[idx * 4 + 1] = int16_t( v[1] ); mv16[idx * 4 + 2] = int16_t( v[2] ); mv16[idx * 4 + 3] = int16_t( v[3] );
+          fits &= ( unsigned( v[0] + 32768 ) | unsigned( v[1] + 32768 ) | unsigned( v[2] + 32768 ) | unsigned( v[3] + 32768 ) ) < 65536u;
           info[idx] = ( info[idx] & 0x0000FFFFu ) | ( refs[0] << 16 ) | ( refs[1] << 24 );
         }
       }
@@ -199,7 +202,6 @@ void packCU( PackCtx& pc, const CodingUnit& cu, int layer )
       if( !fits ) pc.out->mvFits16 = false;
     }
   }
-
   // Which columns / rows of the CU does the reference actually filter (LoopFilter.cpp:313-354)?
   for( int dir = 0; dir < 2; dir++ )
   {
@@ -265,7 +267,6 @@ void ilfPackDeblock( CodingStructure& cs, IlfPackedDeblock& out )
   out.params.cb_qp_offset = cs.pps->getQpOffset( COMPONENT_Cb );
   out.params.cr_qp_offset = cs.pps->getQpOffset( COMPONENT_Cr );
   out.params.mv_threshold = pc.highPrecMv ? ( 4 << VCEG_AZ07_MV_ADD_PRECISION_BIT_FOR_STORE ) : 4;
-
   for( unsigned y = 0; y < pcv.heightInCtus; y++ )
     for( unsigned x = 0; x < pcv.widthInCtus; x++ )
     {
