@@ -1,8 +1,13 @@
 // ilf_pack.cpp -- see ilf_pack.h.  Host C++11 against the reference's data model.
 #include "ilf_pack.h"
 
+#include <algorithm>
+#include <cstdlib>
 #include <cstring>
+#include <exception>
 #include <map>
+#include <mutex>
+#include <thread>
 
 #include "CommonLib/CodingStructure.h"
 #include "CommonLib/Picture.h"
@@ -46,59 +51,35 @@ struct EdgeScratch
   }
 };
 
-struct PackCtx
+// Read-only while the walk runs: the picture's slices with their dense ids and reference-picture ids [list][refIdx]
+// (one map lookup per reference and slice, not per unit), filled serially before the CTU rows are dealt to the workers.
+struct PackShared
 {
-  CodingStructure*              cs;
-  IlfPackedDeblock*             out;
-  EdgeScratch*                  scratch;     // [tree layer]; kept between pictures so that the arrays keep their pages
-  std::map<const Picture*, int> refIds;
-  std::map<const Slice*, int>   sliceIds;
-  bool                          pcmFilter, tqBypass, highPrecMv;
-  // reference-picture ids of the slice the walk is in, [list][refIdx] (one map lookup per reference and slice, not per unit)
-  const Slice*                  tabSlice = nullptr;
-  uint32_t                      refTab[2][MAX_NUM_REF];
-  const uint32_t*               refsOf( const Slice& s )
+  std::vector<const Slice*> slices;
+  std::vector<uint32_t>     refTabs;  // [slice][2][MAX_NUM_REF]
+  int find( const Slice* s ) const
   {
-    if( &s != tabSlice )
-    {
-      tabSlice = &s;
-      for( int l = 0; l < 2; l++ )
-        for( int i = 0; i < MAX_NUM_REF; i++ )
-          refTab[l][i] = i < s.getNumRefIdx( RefPicList( l ) ) && s.getRefPic( RefPicList( l ), i ) ? uint32_t( refId( s.getRefPic( RefPicList( l ), i ) ) ) : ILF_REF_NONE;
-    }
-    return &refTab[0][0];
+    for( size_t i = 0; i < slices.size(); i++ ) if( slices[i] == s ) return int( i );
+    THROW( "ilf_b200: a coding unit refers to a slice that is not in Picture::slices" );
   }
+};
 
-  const Slice* lastSlice = nullptr;
-  int          lastSliceId = 0;
+struct PackCtx  // one per worker
+{
+  CodingStructure*  cs;
+  IlfPackedDeblock* out;
+  EdgeScratch*      scratch;     // [tree layer]; kept between pictures so that the arrays keep their pages
+  const PackShared* sh;
+  bool              pcmFilter, tqBypass, highPrecMv;
+  bool              anyInter = false, mvFits16 = true;
+  const Slice*      lastSlice = nullptr;
+  int               lastSliceId = 0;
   int sliceId( const Slice* s )
   {
-    if( s == lastSlice ) return lastSliceId;
-    lastSlice   = s;
-    lastSliceId = sliceIdSlow( s );
+    if( s != lastSlice ) { lastSlice = s; lastSliceId = sh->find( s ); }
     return lastSliceId;
   }
-  int sliceIdSlow( const Slice* s )
-  {
-    auto it = sliceIds.find( s );
-    if( it != sliceIds.end() ) return it->second;
-    const int id = int( sliceIds.size() );
-    CHECK( id >= ILF_MAX_SLICES, "ilf_b200: more slices per picture than ILF_MAX_SLICES" );
-    sliceIds[s]                              = id;
-    out->params.slices[id].beta_offset_div2 = int8_t( s->getDeblockingFilterBetaOffsetDiv2() );
-    out->params.slices[id].tc_offset_div2   = int8_t( s->getDeblockingFilterTcOffsetDiv2() );
-    out->params.num_slices                  = id + 1;
-    return id;
-  }
-  int refId( const Picture* p )
-  {
-    auto it = refIds.find( p );
-    if( it != refIds.end() ) return it->second;
-    const int id = int( refIds.size() );
-    CHECK( id >= 255, "ilf_b200: too many distinct reference pictures" );
-    refIds[p] = id;
-    return id;
-  }
+  const uint32_t* refsOf( const Slice& s ) { return &sh->refTabs[size_t( sliceId( &s ) ) * 2 * MAX_NUM_REF]; }
 };
 
 // One call of LoopFilter::xDeblockCU for both edge directions, reduced to its effect on the grid.
@@ -198,8 +179,8 @@ void packCU( PackCtx& pc, const CodingUnit& cu, int layer )
           info[idx] = ( info[idx] & 0x0000FFFFu ) | ( refs[0] << 16 ) | ( refs[1] << 24 );
         }
       }
-      pc.out->anyInter = true;
-      if( !fits ) pc.out->mvFits16 = false;
+      pc.anyInter = true;
+      if( !fits ) pc.mvFits16 = false;
     }
   }
   // Which columns / rows of the CU does the reference actually filter (LoopFilter.cpp:313-354)?
@@ -254,29 +235,74 @@ void ilfPackDeblock( CodingStructure& cs, IlfPackedDeblock& out )
   if( dual ) out.infoChroma.assign( n, 0xFFFF0000u ); else out.infoChroma.clear();
 
   static EdgeScratch scratchStore[2];
-  PackCtx pc;
-  pc.scratch    = scratchStore;
-  pc.cs         = &cs;
-  pc.out        = &out;
-  pc.pcmFilter  = cs.sps->getUsePCM() && cs.sps->getPCMFilterDisableFlag();
-  pc.tqBypass   = cs.pps->getTransquantBypassEnabledFlag();
-  pc.highPrecMv = cs.sps->getSpsNext().getUseHighPrecMv();
-  pc.scratch[0].init( out.unitsW, out.unitsH );
-  if( dual ) pc.scratch[1].init( out.unitsW, out.unitsH );
+  scratchStore[0].init( out.unitsW, out.unitsH );
+  if( dual ) scratchStore[1].init( out.unitsW, out.unitsH );
 
+  const bool highPrecMv   = cs.sps->getSpsNext().getUseHighPrecMv();
   out.params.cb_qp_offset = cs.pps->getQpOffset( COMPONENT_Cb );
   out.params.cr_qp_offset = cs.pps->getQpOffset( COMPONENT_Cr );
-  out.params.mv_threshold = pc.highPrecMv ? ( 4 << VCEG_AZ07_MV_ADD_PRECISION_BIT_FOR_STORE ) : 4;
-  for( unsigned y = 0; y < pcv.heightInCtus; y++ )
-    for( unsigned x = 0; x < pcv.widthInCtus; x++ )
-    {
-      const UnitArea ctuArea( pcv.chrFormat, Area( x << pcv.maxCUWidthLog2, y << pcv.maxCUHeightLog2, pcv.maxCUWidth, pcv.maxCUWidth ) );
-      for( auto& cu : cs.traverseCUs( CS::getArea( cs, ctuArea, CH_L ), CH_L ) ) packCU( pc, cu, 0 );
-      if( dual )
-        for( auto& cu : cs.traverseCUs( CS::getArea( cs, ctuArea, CH_C ), CH_C ) ) packCU( pc, cu, 1 );
-    }
-  if( out.params.num_slices == 0 ) pc.sliceId( cs.slice );
+  out.params.mv_threshold = highPrecMv ? ( 4 << VCEG_AZ07_MV_ADD_PRECISION_BIT_FOR_STORE ) : 4;
 
+  // slices and their reference pictures (dense ids: only identity matters, xGetBoundaryStrengthSingle :456-466)
+  PackShared sh;
+  std::map<const Picture*, int> refIds;
+  for( const Slice* sl : cs.picture->slices ) sh.slices.push_back( sl );
+  if( sh.slices.empty() ) sh.slices.push_back( cs.slice );
+  CHECK( sh.slices.size() > ILF_MAX_SLICES, "ilf_b200: more slices per picture than ILF_MAX_SLICES" );
+  out.params.num_slices = int( sh.slices.size() );
+  sh.refTabs.assign( sh.slices.size() * 2 * MAX_NUM_REF, ILF_REF_NONE );
+  for( size_t i = 0; i < sh.slices.size(); i++ )
+  {
+    const Slice& sl = *sh.slices[i];
+    out.params.slices[i].beta_offset_div2 = int8_t( sl.getDeblockingFilterBetaOffsetDiv2() );
+    out.params.slices[i].tc_offset_div2   = int8_t( sl.getDeblockingFilterTcOffsetDiv2() );
+    if( sl.isIntra() ) continue;
+    for( int l = 0; l < 2; l++ )
+      for( int r = 0; r < MAX_NUM_REF && r < sl.getNumRefIdx( RefPicList( l ) ); r++ )
+      {
+        const Picture* rp = sl.getRefPic( RefPicList( l ), r );
+        if( !rp ) continue;
+        auto it = refIds.find( rp );
+        if( it == refIds.end() ) { CHECK( refIds.size() >= 255, "ilf_b200: too many distinct reference pictures" ); it = refIds.emplace( rp, int( refIds.size() ) ).first; }
+        sh.refTabs[( i * 2 + l ) * MAX_NUM_REF + r] = uint32_t( it->second );
+      }
+  }
+
+  // The CTU rows are dealt to a few workers: coding units are disjoint, so every worker writes its own units of the grids.
+  static const int maxThreads = getenv( "ILF_PACK_THREADS" ) ? std::max( 1, atoi( getenv( "ILF_PACK_THREADS" ) ) ) : 4;
+  const int nThreads = ( pcv.sizeInCtus >= 64 ) ? std::min<int>( maxThreads, int( pcv.heightInCtus ) ) : 1;
+  std::vector<PackCtx> ctx( nThreads );
+  auto work = [&]( int t )
+  {
+    PackCtx& pc   = ctx[t];
+    pc.cs         = &cs;
+    pc.out        = &out;
+    pc.scratch    = scratchStore;
+    pc.sh         = &sh;
+    pc.pcmFilter  = cs.sps->getUsePCM() && cs.sps->getPCMFilterDisableFlag();
+    pc.tqBypass   = cs.pps->getTransquantBypassEnabledFlag();
+    pc.highPrecMv = highPrecMv;
+    for( unsigned y = t; y < pcv.heightInCtus; y += nThreads )
+      for( unsigned x = 0; x < pcv.widthInCtus; x++ )
+      {
+        const UnitArea ctuArea( pcv.chrFormat, Area( x << pcv.maxCUWidthLog2, y << pcv.maxCUHeightLog2, pcv.maxCUWidth, pcv.maxCUWidth ) );
+        for( auto& cu : cs.traverseCUs( CS::getArea( cs, ctuArea, CH_L ), CH_L ) ) packCU( pc, cu, 0 );
+        if( dual )
+          for( auto& cu : cs.traverseCUs( CS::getArea( cs, ctuArea, CH_C ), CH_C ) ) packCU( pc, cu, 1 );
+      }
+  };
+  if( nThreads == 1 ) work( 0 );
+  else
+  {
+    std::vector<std::thread> pool;
+    std::exception_ptr       err;
+    std::mutex               errLock;
+    for( int t = 0; t < nThreads; t++ )
+      pool.emplace_back( [&, t]() { try { work( t ); } catch( ... ) { std::lock_guard<std::mutex> g( errLock ); err = std::current_exception(); } } );
+    for( auto& th : pool ) th.join();
+    if( err ) std::rethrow_exception( err );
+  }
+  for( const PackCtx& pc : ctx ) { out.anyInter |= pc.anyInter; out.mvFits16 &= pc.mvFits16; }
 }
 
 // ------------------------------------------------------------------------------------------------------------
