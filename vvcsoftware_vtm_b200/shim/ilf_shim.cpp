@@ -107,7 +107,7 @@ ShimState& contextFor( const CodingStructure& cs )
 }
 
 // The decoded-picture buffer is allocated once and recycled (Picture::create).  Page-locking a plane costs about as much as
-// five staged copies of it (cudaHostRegister runs at ~1 GB/s), so a plane is registered when it comes around the SECOND time:
+// five staged copies of it (cudaHostRegister runs at ~1 GB/s), so a plane is registered when it comes around the THIRD time:
 // from then on the library copies straight from / into it (ilf_b200.h "transfer pipeline") instead of staging 25 MB per 4K
 // picture through its own pinned buffer.  A range that cannot be registered stays pageable.
 void pinPlane( ShimState& s, const Pel* buf, int stride, int w, int h )
@@ -117,15 +117,27 @@ void pinPlane( ShimState& s, const Pel* buf, int stride, int w, int h )
   const size_t bytes = ( size_t( h - 1 ) * stride + w ) * sizeof( Pel );
   for( auto& r : s.pinned ) if( lo >= r.first && lo + bytes <= r.first + r.second ) return;
   for( auto& r : s.unpinnable ) if( lo == r.first && bytes == r.second ) return;
-  bool again = false;
-  for( auto& r : s.seenOnce ) again |= lo == r.first && bytes == r.second;
-  if( !again ) { s.seenOnce.emplace_back( lo, bytes ); return; }
+  int seen = 0;
+  for( auto& r : s.seenOnce ) seen += lo == r.first && bytes == r.second;
+  if( seen < 2 ) { s.seenOnce.emplace_back( lo, bytes ); return; }   // third appearance: the buffer is clearly being recycled
   if( ilf_host_register( const_cast<char*>( lo ), bytes ) == ILF_OK ) s.pinned.emplace_back( lo, bytes );
   else s.unpinnable.emplace_back( lo, bytes );
 }
 void pinPlanes( ShimState& s, const CPelUnitBuf& u )
 {
   for( int c = 0; c < 3; c++ ) { const CPelBuf b = u.get( ComponentID( c ) ); pinPlane( s, b.buf, b.stride, b.width, b.height ); }
+}
+
+// The packer's arrays live between pictures (static in loopFilterPic); once their storage is page-locked the library copies
+// them to the device without staging (2 MB + 4 MB per 4K picture).  Re-registered when a vector moved (geometry change).
+void pinArray( ShimState& s, std::pair<const char*, size_t>& slot, const void* p, size_t bytes )
+{
+  if( !s.pin || !p || !bytes ) return;
+  const char* lo = reinterpret_cast<const char*>( p );
+  if( slot.first == lo && slot.second >= bytes ) return;
+  if( slot.first ) ilf_host_unregister( const_cast<char*>( slot.first ) );
+  slot = { nullptr, 0 };
+  if( ilf_host_register( const_cast<char*>( lo ), bytes ) == ILF_OK ) slot = { lo, bytes };
 }
 
 void upload( ShimState& s, CodingStructure& cs )
@@ -174,6 +186,10 @@ void LoopFilter::loopFilterPic( CodingStructure& cs )
     db.wantMv32 = true;  // a motion vector beyond 16 bits: walk again for the 32-bit array
     ilfPackDeblock( cs, db );
   }
+  static std::pair<const char*, size_t> pinInfo, pinInfoC, pinMv;
+  pinArray( s, pinInfo, db.info.data(), db.info.capacity() * sizeof( uint32_t ) );
+  pinArray( s, pinInfoC, db.infoChroma.data(), db.infoChroma.capacity() * sizeof( uint32_t ) );
+  pinArray( s, pinMv, db.mv16.data(), db.mv16.capacity() * sizeof( int16_t ) );
   const auto tp = clk::now();
   upload( s, cs );
   const auto tu = clk::now();
