@@ -7,11 +7,11 @@
 // flag is 0 are copied through (the stage reads one buffer and writes the other).
 //
 // Data movement (both kernels): band walking over a TMA ring (ilf_ring.cuh).  A CTA owns a band of 32 rows of a plane and
-// walks it in tiles of 128 samples; the TMA unit delivers each tile with its halo rows (box 128 x 38 luma, 128 x 36
+// walks it in tiles of TW = 64 samples; the TMA unit delivers each tile with its halo (box 80 x 38 luma, 80 x 36
 // chroma) into a ring of shared-memory stages ahead of the arithmetic.  Per tile the CTA builds a work tile: the staged
 // tile plus 4 halo columns from the neighbouring tiles of the ring, with the border padding applied (build_work_tile).
 //
-// Luma, per tile (256 threads, one thread = one 4x4 block from classification to output):
+// Luma, per tile (2 TW = 128 threads, one thread = one 4x4 block from classification to output):
 //   phase 1  work tile (int16, two samples per 32-bit word)
 //   phase 2  1-D Laplacians two samples per instruction (|2c - a - b| = max(2c - s, s - 2c) with VIADD.16x2 / VIADDMNMX.S16x2),
 //            summed per 2x2 cell; a task walks one word column over 12 rows with a rolling 3-row window
@@ -27,7 +27,7 @@ namespace ilf {
 namespace {
 
 // ---- band walking (ilf_ring.cuh): shared by the chroma kernel (and the luma kernel) ----
-constexpr int TW = RING_TILE_W;     // tile width in samples
+constexpr int TW = ALF_TILE;        // tile width in samples
 constexpr int BR = ALF_BAND_ROWS;   // rows of a band
 constexpr int WP = TW + 16;         // work-tile pitch in samples: [8: left halo slot][128][8: right halo slot], 288-byte rows
 constexpr int WX0 = 8;              // work-tile column of the tile's first sample
@@ -35,7 +35,7 @@ constexpr int WX0 = 8;              // work-tile column of the tile's first samp
 #define ALF_RING 4
 #endif
 #ifndef ALF_L_CTAS
-#define ALF_L_CTAS 3
+#define ALF_L_CTAS (ALF_TILE_W == 128 ? 3 : 5)
 #endif
 constexpr int RING_STAGES = ALF_RING;  // the tile being filtered + the tiles in flight
 constexpr int L_CTAS = ALF_L_CTAS;     // resident luma CTAs per SM the kernel is built for
@@ -77,11 +77,12 @@ constexpr int L_STAGE_STRIDE = (L_STAGE_BYTES + 127) & ~127;   // TMA destinatio
 constexpr int CELL_W = TW / 2 + 2, CELL_H = BR / 2 + 2;        // 66 x 18 cells of 2x2 samples, first cell at (x0-2, y0-2)
 constexpr int L_CELL_BYTES = CELL_H * CELL_W * 8;
 constexpr int L_SMEM_BYTES = RING_STAGES * L_STAGE_STRIDE + L_CELL_BYTES + RING_STAGES * 8;
-constexpr int NT = 256;
+constexpr int NT = 2 * TW;                                     // TW / 4 blocks across x 8 block rows
+constexpr int BPR = TW / 4;                                    // 4x4 blocks per tile row
 constexpr int LAP_ROWS = 6;                                    // sample rows a Laplacian task walks (3 cell rows)
 constexpr int LAP_COLS = CELL_W / 2;                           // a task covers two word columns (two cells per cell row)
 constexpr int LAP_TASKS = LAP_COLS * (CELL_H * 2 / LAP_ROWS);  // 33 column pairs x 6 row groups
-static_assert(CELL_W % 2 == 0 && (CELL_H * 2) % LAP_ROWS == 0 && LAP_TASKS <= 256, "Laplacian task grid");
+static_assert(CELL_W % 2 == 0 && (CELL_H * 2) % LAP_ROWS == 0 && LAP_TASKS <= 2 * TW, "Laplacian task grid");
 
 __constant__ uint8_t c_th[16] = {0, 1, 2, 2, 2, 2, 2, 3, 3, 3, 3, 3, 3, 3, 3, 4};
 __constant__ uint8_t c_transpose[8] = {0, 1, 0, 2, 2, 3, 1, 3};
@@ -147,8 +148,8 @@ __device__ __forceinline__ void alf_luma_cta(unsigned char* smem, const Geom& g,
   if (tid == 0)
     for (int t = walk.first; t <= walk.last && t < walk.first + RING_STAGES; t++) issue(t);
 
-  // this thread's 4x4 block of every tile: a warp = one row of 32 blocks
-  const int bj = tid & 31, bi = tid >> 5;
+  // this thread's 4x4 block of every tile: BPR blocks across, 8 block rows
+  const int bj = tid % BPR, bi = tid / BPR;
   const int by = y0 + 4 * bi;
   const uint8_t* __restrict__ en_row = sd.alf_ctu_enable + (size_t)((by + g.row0) >> g.ctu_log2) * g.ctus_w;
   const int max_val = (1 << g.bd_luma) - 1;
@@ -301,14 +302,14 @@ __device__ __forceinline__ void alf_luma_cta(unsigned char* smem, const Geom& g,
 
 // ---------------------------------------------------------------------------------------------------------
 // Chroma: 5x5 diamond, one filter per picture, no classification (filterBlk<ALF_FILTER_5>, AdaptiveLoopFilter.cpp:465-650).
-// Band walking over a TMA ring: box 128 x 36 (2 halo rows each side); a thread filters 8 samples x 2 rows from the work
+// Band walking over a TMA ring: box (TW + 16) x 36 (2 halo rows each side); a thread filters 8 samples x 2 rows from the work
 // tile: 6 window rows of 12 samples are unpacked once into registers and serve both output rows.
 // ---------------------------------------------------------------------------------------------------------
 constexpr int C_SR = BR + 2 * ALF_HALO_C;
 constexpr int C_STAGE_BYTES = WP * C_SR * 2;
 static_assert(C_STAGE_BYTES % 128 == 0, "TMA destinations are 128-byte aligned");
 constexpr int C_SMEM_BYTES = RING_STAGES * C_STAGE_BYTES + RING_STAGES * 8;
-constexpr int NTC = 256;
+constexpr int NTC = 2 * TW;   // TW / 8 eight-sample groups across x 16 row pairs
 
 // p points at sample x of a work-tile row; v[i] = sample x - 2 + i, i = 0..11
 __device__ __forceinline__ void load_row12(const int16_t* p, int v[12]) {
@@ -355,7 +356,7 @@ __device__ __forceinline__ void alf_chroma_cta(unsigned char* smem, const Geom& 
 #pragma unroll
   for (int i = 0; i < 7; i++) f[i] = sd.alf->chroma_coeff[i];
   const int max_val = (1 << g.bd_chroma) - 1;
-  const int k = tid & 15, rg = tid >> 4;  // 8 samples at column 8k, rows 2rg and 2rg + 1 of the band
+  const int k = tid % (TW / 8), rg = tid / (TW / 8);  // 8 samples at column 8k, rows 2rg and 2rg + 1 of the band
   const int y = by0 + 2 * rg;
   const uint8_t* __restrict__ en_row = sd.alf_ctu_enable + (size_t)plane * g.ctus_w * g.ctus_h + (size_t)((((y << 1) + g.row0) >> g.ctu_log2) * g.ctus_w);
 
@@ -436,7 +437,7 @@ static_assert(NT == NTC, "luma and chroma CTAs share one launch");
 
 static int alf_nseg(int bands_total, int ntx, bool luma) {
   if (luma) return pick_segments(bands_total, ntx, 148 * L_CTAS);
-  int nseg = (148 * 3 + bands_total - 1) / bands_total;
+  int nseg = (148 * L_CTAS + bands_total - 1) / bands_total;
   return nseg < 1 ? 1 : (nseg > ntx ? ntx : nseg);
 }
 
