@@ -10,8 +10,8 @@
 // One CTA per (CTU, component).  A warp owns a strip of 32 columns and walks it downwards with a rolling 3x3 window in
 // registers (three loads per sample row: the row below, L1 resident for the two neighbours); the eight signs of a sample give
 // its four edge classes.  Accumulation needs no atomics and no class-indexed registers: every (warp, type, class) has 32
-// words of shared memory, one per lane, and a sample adds (diff << 7) + 1 to the word of its class -- count (at most 64 per
-// lane and CTU) and sum of differences travel in one 32-bit word (19 + 7 bits), bank = lane, so the read-modify-write is
+// words of shared memory, one per lane, and a sample adds (diff << 8) + 1 to the word of its class -- count (at most 128 per
+// lane and CTU) and sum of differences travel in one 32-bit word (20 + 8 bits), bank = lane, so the read-modify-write is
 // conflict-free.  At the end every warp reduces its words (REDUX), one shared-memory atomic per class and warp builds the
 // CTA totals, and the CTA writes the 5 x 64 int64 words of SAOStatData.
 // Bound: HBM reads of two pictures (6 B per luma pixel); the output is 7.7 KB per CTU.
@@ -20,13 +20,17 @@
 namespace ilf {
 namespace {
 
-constexpr int NT = 256, NW = NT / 32;
+#ifndef SAO_STATS_THREADS
+#define SAO_STATS_THREADS 128
+#endif
+constexpr int NT = SAO_STATS_THREADS, NW = NT / 32;
+constexpr int CNT_BITS = 8;   // a lane sees at most 128 rows of a CTU: count < 2^8, |sum of differences| < 2^19 (12 bit) -> one 32-bit word
 constexpr int EO_WORDS = 4 * 5 * 32, BO_WORDS = 32 * 32, WARP_WORDS = EO_WORDS + BO_WORDS;  // per warp: [type][class][lane], [band][lane]
 constexpr int SMEM_BYTES = NW * WARP_WORDS * 4;
 
 __device__ __forceinline__ int sgn3(int a, int b) { return min(max(a - b, -1), 1); }
 
-__global__ void __launch_bounds__(NT, 4) sao_stats_kernel(Geom g, const SlotDev* __restrict__ slots, int first_slot, BatchCtl bc) {
+__global__ void __launch_bounds__(NT, 1024 / NT) sao_stats_kernel(Geom g, const SlotDev* __restrict__ slots, int first_slot, BatchCtl bc) {
   extern __shared__ __align__(16) int acc_all[];
   __shared__ int tot[5][64];
   pdl_launch_dependents();
@@ -57,7 +61,7 @@ __global__ void __launch_bounds__(NT, 4) sao_stats_kernel(Geom g, const SlotDev*
   __syncthreads();
   pdl_wait();  // the deblocking kernel has written the picture read from here on
 
-  // strips of 32 columns x row groups: 128-wide luma = 4 strips x 2 row groups, 64-wide chroma = 2 x 4
+  // strips of 32 columns x row groups (NW warps): 128-wide luma = 4 strips x 1 row group, 64-wide chroma = 2 x 2
   const int nstrips = (w + 31) >> 5, nrg = NW / nstrips;
   const int strip = warp % nstrips, rg = warp / nstrips;
   const int rh = (h + nrg - 1) / nrg;
@@ -95,7 +99,7 @@ __global__ void __launch_bounds__(NT, 4) sao_stats_kernel(Geom g, const SlotDev*
         const int y = yg + k;
         if (y < yb) {
           const int dl = D[k][0], d = D[k][1], dr = D[k][2];
-          const int v = ((O[k] - c) << 7) + 1;   // (diff << 7) + count
+          const int v = ((O[k] - c) << CNT_BITS) + 1;   // (diff << 8) + count
           const int c0 = sgn3(c, l) + sgn3(c, r), c1 = sgn3(c, u) + sgn3(c, d), c2 = sgn3(c, ul) + sgn3(c, dr), c3 = sgn3(c, ur) + sgn3(c, dl);
           const bool first = y == 0, yd = y < ey_d, y0r = y < ey_0;
           // the five words are distinct (different types): all loads first, then the stores
@@ -117,20 +121,21 @@ __global__ void __launch_bounds__(NT, 4) sao_stats_kernel(Geom g, const SlotDev*
   }
   __syncwarp();
   // Every warp folds its lanes.  Lane j sums the 32 words of row j (skewed, so that the lanes hit different banks):
-  // word = diff * 128 + count with count < 128, hence sum(diff) = (sum(word) - sum(count)) >> 7.
+  // word = diff * 256 + count with count < 256.
   for (int base = 0; base < 20 + 32; base += 32) {
     const int rowi = base + lane;
     if (rowi < 20 + 32) {
-      int sw = 0, sn = 0;
+      int sd = 0, sn = 0;
 #pragma unroll 8
       for (int k = 0; k < 32; k++) {
         const int wd = acc[rowi * 32 + ((k + lane) & 31)];
-        sw += wd; sn += wd & 127;
+        const int n = wd & ((1 << CNT_BITS) - 1);
+        sn += n; sd += (wd - n) >> CNT_BITS;
       }
       if (sn) {
         const int t = rowi < 20 ? rowi / 5 : 4, k = rowi < 20 ? rowi % 5 : rowi - 20;
         atomicAdd(&tot[t][32 + k], sn);
-        atomicAdd(&tot[t][k], (sw - sn) >> 7);
+        atomicAdd(&tot[t][k], sd);
       }
     }
   }
