@@ -321,7 +321,7 @@ int create_impl(ilf_ctx** out, const ilf_config* cfg, const ilf_band* band) {
       if (int rc = make_map3(ctx, &s.dev.tm_db[p], CU_TENSOR_MAP_DATA_TYPE_UINT16, plane_ptr(ctx, s, 0, p), pw, ph, 3, (size_t)pitch * 2, ctx->buf_elems * 2, p ? RING_TILE_W / 2 : RING_TILE_W,
                              p ? DB_BAND_ROWS / 2 : DB_BAND_ROWS))
         return rc;
-      if (int rc = make_map3(ctx, &s.dev.tm_sao[p], CU_TENSOR_MAP_DATA_TYPE_UINT16, plane_ptr(ctx, s, 0, p), pw, ph, 3, (size_t)pitch * 2, ctx->buf_elems * 2, RING_TILE_W,
+      if (int rc = make_map3(ctx, &s.dev.tm_sao[p], CU_TENSOR_MAP_DATA_TYPE_UINT16, plane_ptr(ctx, s, 0, p), pw, ph, 3, (size_t)pitch * 2, ctx->buf_elems * 2, SAO_TILE,
                              SAO_BAND_ROWS + 2))
         return rc;
       if (int rc = make_map3(ctx, &s.dev.tm_alf[p], CU_TENSOR_MAP_DATA_TYPE_UINT16, plane_ptr(ctx, s, 0, p), pw, ph, 3, (size_t)pitch * 2, ctx->buf_elems * 2, ALF_TILE + 16,

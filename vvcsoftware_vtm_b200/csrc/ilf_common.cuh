@@ -36,6 +36,10 @@ constexpr int RING_TILE_W = 128;   // samples per tile row, all planes (256-byte
 #define ALF_TILE_W 64
 #endif
 constexpr int ALF_TILE = ALF_TILE_W;
+#ifndef SAO_TILE_W
+#define SAO_TILE_W 128
+#endif
+constexpr int SAO_TILE = SAO_TILE_W;   // tile width of the SAO walk (its TMA boxes are SAO_TILE x 34)
 constexpr int DB_BAND_ROWS = 32;   // luma rows a deblocking CTA owns (shifted up by 4 rows; chroma: 16 rows shifted by 2)
 constexpr int SAO_BAND_ROWS = 32;  // rows a SAO CTA owns; the box adds one halo row above and below
 constexpr int ALF_BAND_ROWS = 32;  // rows an ALF CTA owns; the box adds 3 (luma, 7x7 + classification) or 2 (chroma, 5x5) halo rows on each side
@@ -46,7 +50,7 @@ struct alignas(64) SlotDev {
   CUtensorMap tm_db[3];     // box RING_TILE_W x DB_BAND_ROWS (luma), RING_TILE_W/2 x DB_BAND_ROWS/2 (chroma)
   CUtensorMap tm_info, tm_info_c;  // unit grids, tensor (unit x, unit y, 1) of uint32: box 32 x 8
   CUtensorMap tm_mv16, tm_mv32;    // motion vectors as uint32 words (2 / 4 per unit): box 64 x 8 / 128 x 8
-  CUtensorMap tm_sao[3];    // box RING_TILE_W x (SAO_BAND_ROWS + 2)
+  CUtensorMap tm_sao[3];    // box SAO_TILE x (SAO_BAND_ROWS + 2)
   CUtensorMap tm_alf[3];    // box (ALF_TILE + 16) x (ALF_BAND_ROWS + 2 * halo), loaded 8 samples left of the tile
   int16_t* buf[3][3];       // [buffer: 0 = input, 1, 2 = work][plane]
   const uint32_t* info;     // deblock grid, luma tree

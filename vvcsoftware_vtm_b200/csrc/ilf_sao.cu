@@ -29,12 +29,16 @@ namespace ilf {
 namespace {
 
 constexpr int R = 4;                       // rows per thread and tile
-constexpr int TW = RING_TILE_W;            // tile width (samples)
+constexpr int TW = SAO_TILE;               // tile width (samples)
 constexpr int BR = SAO_BAND_ROWS;          // rows of a band
 constexpr int SR = BR + 2;                 // staged rows: one halo row above and below
 constexpr int STAGES = 6;                  // ring depth: previous, current, next tile + 3 tiles in flight
 constexpr int STAGE_BYTES = TW * SR * 2;   // 8704
-constexpr int NTHREADS = 128;
+#ifndef SAO_CTAS
+#define SAO_CTAS (SAO_TILE_W == 128 ? 4 : 8)
+#endif
+constexpr int KPR = TW / 8;                // eight-sample strips per tile row
+constexpr int NTHREADS = KPR * (BR / R);   // one strip of R rows per thread
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGES * 8;
 
 struct Row { uint32_t v[4]; };  // 8 samples
@@ -116,7 +120,7 @@ __device__ __forceinline__ void eo_rows(const EoCtx& e, const Row (&v)[R + 2], c
 // nullptr at the picture border, where the availability flags already exclude the missing neighbour).
 __device__ __forceinline__ void sao_tile(const Geom& g, const SlotDev& sd, int plane, int16_t* __restrict__ dst, int tx, int by0, const int16_t* cur,
                                          const int16_t* prev, const int16_t* next) {
-  const int k = threadIdx.x & 15, rg = threadIdx.x >> 4;
+  const int k = threadIdx.x % KPR, rg = threadIdx.x / KPR;
   const int sh = plane ? 1 : 0;
   const int pw = g.width >> sh, ph_local = g.rows >> sh, ph_global = g.height >> sh;
   const int pitch = plane ? g.pitch_c : g.pitch_y;
@@ -170,7 +174,7 @@ __device__ __forceinline__ void sao_tile(const Geom& g, const SlotDev& sd, int p
   for (int i = 0; i < R + 2; i++) v[i] = ld_row(base + i * TW);
   if (type != ILF_SAO_EO_90) {
     const int16_t* lp = k > 0 ? base - 1 : (prev ? prev + (R * rg) * TW + TW - 1 : nullptr);
-    const int16_t* rp = k < 15 ? base + 8 : (next ? next + (R * rg) * TW : nullptr);
+    const int16_t* rp = k < KPR - 1 ? base + 8 : (next ? next + (R * rg) * TW : nullptr);
 #pragma unroll
     for (int i = 0; i < R + 2; i++) {
       const uint32_t lft = lp ? (uint16_t)lp[i * TW] : 0u, rgt = rp ? (uint16_t)rp[i * TW] : 0u;
@@ -198,7 +202,7 @@ __device__ __forceinline__ void sao_tile(const Geom& g, const SlotDev& sd, int p
   else eo_rows<-1, 1>(e, v, sft, out, pitch);
 }
 
-__global__ void __launch_bounds__(NTHREADS) sao_kernel(Geom g, const SlotDev* __restrict__ slots, int first_slot, BatchCtl bc, int bands_y, int bands_c, int nseg) {
+__global__ void __launch_bounds__(NTHREADS, SAO_CTAS) sao_kernel(Geom g, const SlotDev* __restrict__ slots, int first_slot, BatchCtl bc, int bands_y, int bands_c, int nseg) {
   extern __shared__ __align__(128) unsigned char smem[];
   pdl_launch_dependents();
   const unsigned ctl = bc.v[blockIdx.z];
@@ -260,7 +264,7 @@ void launch_sao(const Geom& g, const SlotDev* slots, int first_slot, int num_slo
   // enough CTAs to fill the machine when the batch is small: split bands into horizontal segments
   const int ntx = (g.width + TW - 1) / TW;
   const int bands = (bands_y + 2 * bands_c) * num_slots;
-  int nseg = (148 * 4 + bands - 1) / bands;
+  int nseg = (148 * SAO_CTAS + bands - 1) / bands;
   nseg = nseg < 1 ? 1 : (nseg > ntx ? ntx : nseg);
   dim3 grid(nseg, bands_y + 2 * bands_c, num_slots);
   launch_pdl(sao_kernel, grid, dim3(NTHREADS), SMEM_BYTES, st, g, slots, first_slot, ctl, bands_y, bands_c, nseg);
