@@ -453,7 +453,9 @@ static void launch_deblock_mv(const Geom& g, const SlotDev* slots, int first_slo
   static bool attr_set[64] = {};
   if (first_launch_on_device(attr_set)) { cudaFuncSetAttribute(deblock_kernel<MV>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); }
   const int bands = (g.rows + 4 + TH - 1) / TH, ntx = (g.width + TW - 1) / TW;
-  const int nseg = pick_segments(bands * num_slots, ntx, 148 * ILF_DB_MIN_CTAS, 1.5f);  // a segment that starts inside the picture runs one extra tile
+  int nseg = pick_segments(bands * num_slots, ntx, 148 * ILF_DB_MIN_CTAS, 1.5f);  // a segment that starts inside the picture runs one extra tile
+  static const int force = getenv("ILF_DB_NSEG") ? atoi(getenv("ILF_DB_NSEG")) : 0;  // experiment knob
+  if (force > 0) nseg = force < ntx ? force : ntx;
   dim3 grid(nseg, bands, num_slots);
   launch_pdl(deblock_kernel<MV>, grid, dim3(NTHREADS), smem, st, g, slots, first_slot, ctl, nseg);
 }
