@@ -46,7 +46,13 @@ constexpr int UW = TW / 4, UH = TH / 4;             // units per tile: 32 x 8, r
 #ifndef ILF_DB_SPLIT
 #define ILF_DB_SPLIT 0
 #endif
-constexpr int NTHREADS = ILF_DB_SPLIT ? 256 : 128;  // 128 tasks in each of the four phases
+// ILF_DB_WS=1: warp specialisation.  256 threads: the first 128 run the vertical pass of tile k + 1 while the second 128 run the
+// horizontal pass (and the stores) of tile k; an mbarrier per stage ("vertical pass done") orders the two groups, a named
+// barrier inside the horizontal group releases the stage of tile k - 1 to the ring.  No CTA-wide barrier in the loop.
+#ifndef ILF_DB_WS
+#define ILF_DB_WS 0
+#endif
+constexpr int NTHREADS = (ILF_DB_SPLIT || ILF_DB_WS) ? 256 : 128;  // 128 tasks in each of the four phases
 #ifndef ILF_DB_STAGES
 #define ILF_DB_STAGES 4
 #endif
@@ -257,6 +263,7 @@ __global__ void __launch_bounds__(NTHREADS, ILF_DB_MIN_CTAS) deblock_kernel(Geom
   const int tid = threadIdx.x;
   const int lt = tid & 127;  // task index within a phase
   const bool do_luma = !ILF_DB_SPLIT || tid < 128, do_chroma = !ILF_DB_SPLIT || tid >= 128;
+  const bool grp_v = !ILF_DB_WS || tid < 128, grp_h = !ILF_DB_WS || tid >= 128;  // vertical-pass / horizontal-pass group
   const int ty = blockIdx.y;
   const int y0 = ty * TH - 4, cy0 = ty * CTH - 2, uy0 = ty * UH - 1;  // band origin (local rows)
   const int rows = g.rows, crow = g.rows >> 1, cw = g.width >> 1;
@@ -268,31 +275,46 @@ __global__ void __launch_bounds__(NTHREADS, ILF_DB_MIN_CTAS) deblock_kernel(Geom
   const int first = max(ta - 1, 0), last = tb - 1;
   const int t_end = tb == ntx ? ntx : tb - 1;  // last step of the walk
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + stages * STRIDE);
-  DbShared& sh = *reinterpret_cast<DbShared*>(smem + stages * STRIDE + 8 * stages);
+  uint64_t* vdone = full + stages;   // ILF_DB_WS: the vertical pass of the stage's tile is complete (128 arrivals)
+  DbShared& sh = *reinterpret_cast<DbShared*>(smem + stages * STRIDE + 16 * stages);
   const bool has_ctree = sd.info_c != nullptr;
   const bool no_meta = (g.debug & 3) == 3;  // measurement aid: copy-only without the unit grids
   const uint32_t tx_bytes = no_meta ? (uint32_t)(TH * TW * 2 + 2 * CTH * CTW * 2) : (uint32_t)stage_tx_bytes<MV>(has_ctree);
-  auto issue = [&](int t, int si) {  // tile t into stage si
+  // The boxes of a tile are issued by the first lanes of the CTA's warps, one part each (ILF_DB_ISSUE_WARPS = 4), so that
+  // their descriptor fetches overlap: part 0 arms the barrier and loads luma, 1 both chroma planes, 2 the unit grids, 3 motion.
+  auto issue_part = [&](int t, int si, int part) {  // tile t into stage si
     Stage<MV>* st = reinterpret_cast<Stage<MV>*>(smem + si * STRIDE);
     uint64_t* bar = &full[si];
-    ring::mbar_expect_tx(bar, tx_bytes);
-    ring::tma_load_3d(&st->y[0][0], &sd.tm_db[0], bar, t * TW, y0, src_b);
-    ring::tma_load_3d(&st->c[0][0][0], &sd.tm_db[1], bar, t * CTW, cy0, src_b);
-    ring::tma_load_3d(&st->c[1][0][0], &sd.tm_db[2], bar, t * CTW, cy0, src_b);
-    if (no_meta) return;
-    ring::tma_load_3d(&st->info[0][0], &sd.tm_info, bar, t * UW, uy0, 0);
-    if (has_ctree) ring::tma_load_3d(&st->info_c[0][0], &sd.tm_info_c, bar, t * UW, uy0, 0);
-    if (MV == 1) ring::tma_load_3d(&st->mv[0][0], &sd.tm_mv16, bar, t * UW * 2, uy0, 0);
-    if (MV == 2) ring::tma_load_3d(&st->mv[0][0], &sd.tm_mv32, bar, t * UW * 4, uy0, 0);
+    if (part == 0) {
+      ring::mbar_expect_tx(bar, tx_bytes);
+      ring::tma_load_3d(&st->y[0][0], &sd.tm_db[0], bar, t * TW, y0, src_b);
+    } else if (part == 1) {
+      ring::tma_load_3d(&st->c[0][0][0], &sd.tm_db[1], bar, t * CTW, cy0, src_b);
+      ring::tma_load_3d(&st->c[1][0][0], &sd.tm_db[2], bar, t * CTW, cy0, src_b);
+    } else if (no_meta) {
+    } else if (part == 2) {
+      ring::tma_load_3d(&st->info[0][0], &sd.tm_info, bar, t * UW, uy0, 0);
+      if (has_ctree) ring::tma_load_3d(&st->info_c[0][0], &sd.tm_info_c, bar, t * UW, uy0, 0);
+    } else {
+      if (MV == 1) ring::tma_load_3d(&st->mv[0][0], &sd.tm_mv16, bar, t * UW * 2, uy0, 0);
+      if (MV == 2) ring::tma_load_3d(&st->mv[0][0], &sd.tm_mv32, bar, t * UW * 4, uy0, 0);
+    }
+  };
+#ifndef ILF_DB_ISSUE_WARPS
+#define ILF_DB_ISSUE_WARPS 4
+#endif
+  // every thread calls issue(); the lanes that own a part do the work
+  auto issue = [&](int t, int si) {
+    if (ILF_DB_ISSUE_WARPS == 4) { if ((tid & 31) == 0 && tid < 128) issue_part(t, si, tid >> 5); }
+    else if (tid == 0) { for (int part = 0; part < 4; part++) issue_part(t, si, part); }
   };
   if (tid == 0) {
-    for (int i = 0; i < stages; i++) ring::mbar_init(&full[i], 1);
+    for (int i = 0; i < stages; i++) { ring::mbar_init(&full[i], 1); ring::mbar_init(&vdone[i], 128); }
     ring::mbar_init_fence();
   }
   __syncthreads();
   pdl_wait();  // the previous chain's last stage has finished with the buffers this stage reads and writes
-  if (tid == 0)
-    for (int t = first; t <= last && t < first + stages; t++) issue(t, t - first);
+  for (int t = first; t <= last && t < first + stages; t++) issue(t, t - first);
   // picture parameters and tables -> shared memory (overlaps the first loads)
   for (int i = tid; i < (int)(sizeof(ilf_deblock_params) / 4); i += NTHREADS) reinterpret_cast<uint32_t*>(&sh.prm)[i] = __ldg(reinterpret_cast<const uint32_t*>(sd.db_params) + i);
   if (tid < 66) sh.tc[tid] = c_tc[tid];
@@ -316,14 +338,14 @@ __global__ void __launch_bounds__(NTHREADS, ILF_DB_MIN_CTAS) deblock_kernel(Geom
     t.st = reinterpret_cast<Stage<MV>*>(smem + si * STRIDE);
     t.prev = prev;
     t.ctree = has_ctree;
-    if (!flush) ring::mbar_wait(&full[si], phase);
+    if (!flush && grp_v) ring::mbar_wait(&full[si], phase);
     // tx < ta: the tile left of the walk.  Its last columns are stored by this walk's first step, so its vertical edges
     // are filtered here like any other tile's (all but edge 0, which does not reach those columns); nothing is stored.
     const bool pre = tx < ta;
     const int x0 = tx * TW, cx0 = tx * CTW;
 
     // ---- vertical edges, luma: task = 4 lines x 8 samples.  16 edge columns x 8 segment rows ----
-    if (do_luma && filt && !flush && ((lt & 15) > 0 || prev)) {
+    if (grp_v && do_luma && filt && !flush && ((lt & 15) > 0 || prev)) {
       const int e = lt & 15, sg = lt >> 4;
       const EdgeParams ep = luma_edge_params<MV>(t, g, sh, sg, 2 * e, sg, 2 * e - 1, true, x0 + 8 * e, y0 + 4 * sg);
       if (ep.bs) {
@@ -345,7 +367,7 @@ __global__ void __launch_bounds__(NTHREADS, ILF_DB_MIN_CTAS) deblock_kernel(Geom
       }
     }
     // ---- vertical edges, chroma: task = one unit = 2 lines x 4 samples.  2 planes x 8 edge columns x 8 unit rows ----
-    if (do_chroma && filt && !flush && (((lt >> 3) & 7) > 0 || prev)) {
+    if (grp_v && do_chroma && filt && !flush && (((lt >> 3) & 7) > 0 || prev)) {
       const int pl = lt >> 6, k = (lt >> 3) & 7, sg = lt & 7;
       bool no_p, no_q;
       const int tc = chroma_tc(t.cinfo(sg, 4 * k), t.cinfo(sg, 4 * k - 1), g, sh, true, pl, 2 * (cx0 + 8 * k), 2 * (cy0 + 2 * sg), no_p, no_q);
@@ -361,23 +383,28 @@ __global__ void __launch_bounds__(NTHREADS, ILF_DB_MIN_CTAS) deblock_kernel(Geom
         }
       }
     }
+    if (ILF_DB_WS && grp_v && tid < 128 && !flush) ring::mbar_arrive(&vdone[si]);
     if (pre) {
       prev = t.st;
       if (++si == stages) { si = 0; phase ^= 1u; }
       continue;
     }
-    __syncthreads();
-    // every thread is past the previous step's horizontal pass: the stage before the previous one is free
-    if (tid == 0) {
-      const int tf = tx - 2;  // tile whose stage is refilled
-      if (tf >= first && tf + stages <= last) issue(tf + stages, (si + stages - 2) % stages);
+    if (ILF_DB_WS) {
+      if (tid >= 128 && !flush) ring::mbar_wait(&vdone[si], phase);
+    } else {
+      __syncthreads();
+      // every thread is past the previous step's horizontal pass: the stage before the previous one is free
+      {
+        const int tf = tx - 2;  // tile whose stage is refilled
+        if (tf >= first && tf + stages <= last) issue(tf + stages, (si + stages - 2) % stages);
+      }
     }
 
     // ---- horizontal edges, luma: task = 4 columns x 8 rows, filtered and stored.  4 edge rows x unit columns -LAG_Y .. 31 - LAG_Y
     //      (a warp = one edge row: 256 contiguous bytes per stored row) ----
     {
       const int u = (lt & 31) - LAG_Y, h = lt >> 5;
-      if (do_luma && (u < 0 ? prev != nullptr : !flush)) {
+      if (grp_h && do_luma && (u < 0 ? prev != nullptr : !flush)) {
         const int16_t* sp = t.y(8 * h, 4 * u);
         uint2 raw[8];
 #pragma unroll
@@ -409,7 +436,7 @@ __global__ void __launch_bounds__(NTHREADS, ILF_DB_MIN_CTAS) deblock_kernel(Geom
     //      2 planes x 2 row groups x unit columns -LAG_C .. 31 - LAG_C ----
     {
       const int pl = lt >> 6, h = (lt >> 5) & 1, u = (lt & 31) - LAG_C;
-      if (do_chroma && (u < 0 ? prev != nullptr : !flush)) {
+      if (grp_h && do_chroma && (u < 0 ? prev != nullptr : !flush)) {
         const int16_t* sp = t.ch(pl, 8 * h, 2 * u);
         uint32_t raw[8];
 #pragma unroll
@@ -438,6 +465,15 @@ __global__ void __launch_bounds__(NTHREADS, ILF_DB_MIN_CTAS) deblock_kernel(Geom
         }
       }
     }
+    if (ILF_DB_WS && tid >= 128) {
+      // the horizontal group is done with the previous tile's stage: it goes back to the ring (the vertical group is at
+      // least one tile ahead and touches this tile's and the next tile's stages only)
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (tid == 128) {
+        const int tf = tx - 1;
+        if (tf >= first && tf + stages <= last) for (int part = 0; part < 4; part++) issue_part(tf + stages, (si + stages - 1) % stages, part);
+      }
+    }
     // no barrier here: the next step's vertical pass touches the next stage and the last four columns of this one, the
     // horizontal pass above reads neither
     prev = t.st;
@@ -449,7 +485,7 @@ __global__ void __launch_bounds__(NTHREADS, ILF_DB_MIN_CTAS) deblock_kernel(Geom
 
 template <int MV>
 static void launch_deblock_mv(const Geom& g, const SlotDev* slots, int first_slot, int num_slots, const BatchCtl& ctl, cudaStream_t st) {
-  const int smem = DB_STAGES * stage_stride<MV>() + DB_STAGES * 8 + (int)sizeof(DbShared);
+  const int smem = DB_STAGES * stage_stride<MV>() + DB_STAGES * 16 + (int)sizeof(DbShared);
   static bool attr_set[64] = {};
   if (first_launch_on_device(attr_set)) { cudaFuncSetAttribute(deblock_kernel<MV>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); }
   const int bands = (g.rows + 4 + TH - 1) / TH, ntx = (g.width + TW - 1) / TW;
