@@ -32,7 +32,10 @@ constexpr int R = 4;                       // rows per thread and tile
 constexpr int TW = SAO_TILE;               // tile width (samples)
 constexpr int BR = SAO_BAND_ROWS;          // rows of a band
 constexpr int SR = BR + 2;                 // staged rows: one halo row above and below
-constexpr int STAGES = 6;                  // ring depth: previous, current, next tile + 3 tiles in flight
+#ifndef SAO_STAGES
+#define SAO_STAGES 6
+#endif
+constexpr int STAGES = SAO_STAGES;                  // ring depth: previous, current, next tile + 3 tiles in flight
 constexpr int STAGE_BYTES = TW * SR * 2;   // 8704
 #ifndef SAO_CTAS
 #define SAO_CTAS (SAO_TILE_W == 128 ? 4 : 8)
