@@ -52,6 +52,10 @@ constexpr int UW = TW / 4, UH = TH / 4;             // units per tile: 32 x 8, r
 #ifndef ILF_DB_WS
 #define ILF_DB_WS 0
 #endif
+// ILF_DB_STCS=1: results leave with st.global.cs (streaming, evict-first) stores.
+#ifndef ILF_DB_STCS
+#define ILF_DB_STCS 0
+#endif
 constexpr int NTHREADS = (ILF_DB_SPLIT || ILF_DB_WS) ? 256 : 128;  // 128 tasks in each of the four phases
 #ifndef ILF_DB_STAGES
 #define ILF_DB_STAGES 4
@@ -427,7 +431,13 @@ __global__ void __launch_bounds__(NTHREADS, ILF_DB_MIN_CTAS) deblock_kernel(Geom
 #pragma unroll
           for (int i = 0; i < 8; i++) {
             const int y = y0 + 8 * h + i;
-            if (y >= 0 && y < rows) *reinterpret_cast<uint2*>(op + (size_t)i * g.pitch_y) = raw[i];
+            if (y >= 0 && y < rows) {
+#if ILF_DB_STCS
+              __stcs(reinterpret_cast<uint2*>(op + (size_t)i * g.pitch_y), raw[i]);
+#else
+              *reinterpret_cast<uint2*>(op + (size_t)i * g.pitch_y) = raw[i];
+#endif
+            }
           }
         }
       }
@@ -460,7 +470,13 @@ __global__ void __launch_bounds__(NTHREADS, ILF_DB_MIN_CTAS) deblock_kernel(Geom
 #pragma unroll
           for (int i = 0; i < 8; i++) {
             const int y = cy0 + 8 * h + i;
-            if (y >= 0 && y < crow) *reinterpret_cast<uint32_t*>(op + (size_t)i * g.pitch_c) = raw[i];
+            if (y >= 0 && y < crow) {
+#if ILF_DB_STCS
+              __stcs(reinterpret_cast<uint32_t*>(op + (size_t)i * g.pitch_c), raw[i]);
+#else
+              *reinterpret_cast<uint32_t*>(op + (size_t)i * g.pitch_c) = raw[i];
+#endif
+            }
           }
         }
       }

@@ -41,10 +41,22 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   } while (!done);
 }
 // box of a 3-D tensor (x, y, z) -> shared memory; completion is signalled on `bar` with the box's byte count
+// ILF_TMA_EVICT_FIRST=1: picture data is streamed once per stage, so the loads carry an evict-first L2 policy.
+#ifndef ILF_TMA_EVICT_FIRST
+#define ILF_TMA_EVICT_FIRST 0
+#endif
 __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int x, int y, int z) {
+#if ILF_TMA_EVICT_FIRST
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5}], [%2], %6;" ::"r"(smem_u32(dst)),
+               "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z), "l"(pol)
+               : "memory");
+#else
   asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(dst)), "l"(map),
                "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z)
                : "memory");
+#endif
 }
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int x, int y) {
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)), "l"(map),
