@@ -406,8 +406,7 @@ def run_bands(args, wl):
     stream = torch.cuda.ExternalStream(f.stream(), device=torch.device("cuda", local))
 
     def step():
-        for s in range(B):
-            f.band_exchange(s)
+        f.band_exchange(0, B)
         f.run(0, B, 7)
 
     def measure(side_set, steps):

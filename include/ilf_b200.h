@@ -278,8 +278,8 @@ void* ilf_stream(ilf_ctx* ctx); /* cudaStream_t of the context */
  *   ilf_band_connect    opens a neighbour's planes: direct pointer in the same process (peer access is enabled
  *                       when the devices differ), CUDA IPC mapping from another process (one process per GPU)
  *   ilf_band_exchange   copies the halo rows of the slot's input picture out of the connected neighbours'
- *                       input buffers, device to device (NVLink P2P between GPUs), on the context's upload
- *                       stream; the slot's next ilf_run is ordered after it.  The CALLER makes sure that the
+ *                       input buffers with one kernel that reads the peer memory directly (NVLink P2P between
+ *                       GPUs), on the context's upload stream; the slot's next ilf_run is ordered after it.  The CALLER makes sure that the
  *                       neighbours' uploads have completed (ilf_sync on them; a barrier between processes)
  *                       and that a neighbour does not upload its next picture before this exchange is done.
  *   ilf_download_band   the band's own rows of the filtered picture
@@ -304,6 +304,7 @@ int ilf_download_band(ilf_ctx* ctx, int slot, int16_t* y, ptrdiff_t stride_y, in
 int ilf_band_export(ilf_ctx* ctx, int slot, ilf_band_handle* out);
 int ilf_band_connect(ilf_ctx* ctx, int slot, int side, const ilf_band_handle* neighbour);
 int ilf_band_exchange(ilf_ctx* ctx, int slot);
+int ilf_band_exchange_batch(ilf_ctx* ctx, int first_slot, int num_slots); /* the same for several slots with one launch */
 
 #ifdef __cplusplus
 }

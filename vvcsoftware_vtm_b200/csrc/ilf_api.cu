@@ -558,31 +558,74 @@ int ilf_band_connect(ilf_ctx* ctx, int slot, int side, const ilf_band_handle* ne
   return ILF_OK;
 }
 
-int ilf_band_exchange(ilf_ctx* ctx, int slot) {
-  if (int rc = check_slot(ctx, slot)) return rc;
+// Halo rows come over NVLink with ONE kernel per call: every CTA row copies one (slot, side, plane) strip out of the
+// neighbour's input buffer (a peer or IPC-mapped pointer) with 8-byte loads and stores.  A strip is a few rows of a plane, so
+// a copy-engine transfer per strip (six per slot) costs more in launch latency than in bytes.
+namespace {
+struct HaloCopy { const int16_t* src; int16_t* dst; int src_pitch, dst_pitch, words, rows; };  // pitches in samples, words of 8 bytes per row
+constexpr int HALO_MAX = 96;
+struct HaloBatch { HaloCopy c[HALO_MAX]; };
+__global__ void __launch_bounds__(256) band_halo_kernel(HaloBatch hb) {
+  const HaloCopy& h = hb.c[blockIdx.y];
+  const int total = h.words * h.rows;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int r = i / h.words, x = i - r * h.words;
+    reinterpret_cast<uint2*>(h.dst + (size_t)r * h.dst_pitch)[x] = reinterpret_cast<const uint2*>(h.src + (size_t)r * h.src_pitch)[x];
+  }
+}
+}  // namespace
+
+int ilf_band_exchange_batch(ilf_ctx* ctx, int first_slot, int num_slots) {
+  if (!ctx) return ILF_ERR_ARG;
+  if (first_slot < 0 || num_slots < 1 || first_slot + num_slots > (int)ctx->slots.size()) return fail(ctx, ILF_ERR_ARG, "slot range [%d,+%d) out of range", first_slot, num_slots);
   if (!ctx->is_band) return fail(ctx, ILF_ERR_STATE, "not a band context");
-  Slot& s = ctx->slots[slot];
   const Geom& g = ctx->g;
   CU(ctx, cudaSetDevice(ctx->cfg.device));
-  CU(ctx, cudaStreamWaitEvent(ctx->s_up, s.ev_run, 0));  // kernels of the slot's previous run may still read the halo rows
-  for (int side = 0; side < 2; side++) {
-    // picture rows of the halo on this side
-    const int h0 = side == ILF_BAND_ABOVE ? g.row0 : g.out_row0 + g.out_rows;
-    const int h1 = side == ILF_BAND_ABOVE ? g.out_row0 : g.row0 + g.rows;
-    if (h1 <= h0) continue;  // picture border
-    const Slot::Neighbour& nb = s.nb[side];
-    if (!nb.planes) return fail(ctx, ILF_ERR_STATE, "slot %d: no neighbour connected %s the band", slot, side == ILF_BAND_ABOVE ? "above" : "below");
-    if (h0 < nb.row0 || h1 > nb.row0 + nb.rows) return fail(ctx, ILF_ERR_ARG, "neighbour band does not hold picture rows [%d,%d)", h0, h1);
-    for (int p = 0; p < 3; p++) {
-      const int sh = p ? 1 : 0, w = g.width >> sh, pitch = p ? g.pitch_c : g.pitch_y, npitch = p ? nb.pitch_c : nb.pitch_y;
-      const int16_t* src = nb.planes + (p >= 1 ? nb.plane_y : 0) + (p == 2 ? nb.plane_c : 0) + (size_t)((h0 - nb.row0) >> sh) * npitch;  // neighbour's input buffer (buffer 0)
-      int16_t* dst = plane_ptr(ctx, s, 0, p) + (size_t)((h0 - g.row0) >> sh) * pitch;
-      CU(ctx, cudaMemcpy2DAsync(dst, (size_t)pitch * 2, src, (size_t)npitch * 2, (size_t)w * 2, (h1 - h0) >> sh, cudaMemcpyDefault, ctx->s_up));
+  HaloBatch hb;
+  int n = 0;
+  auto flush = [&]() -> int {
+    if (!n) return ILF_OK;
+    band_halo_kernel<<<dim3(8, n), 256, 0, ctx->s_up>>>(hb);
+    CU(ctx, cudaGetLastError());
+    ctx->launches++;
+    n = 0;
+    return ILF_OK;
+  };
+  for (int slot = first_slot; slot < first_slot + num_slots; slot++) {
+    Slot& s = ctx->slots[slot];
+    CU(ctx, cudaStreamWaitEvent(ctx->s_up, s.ev_run, 0));  // kernels of the slot's previous run may still read the halo rows
+    for (int side = 0; side < 2; side++) {
+      // picture rows of the halo on this side
+      const int h0 = side == ILF_BAND_ABOVE ? g.row0 : g.out_row0 + g.out_rows;
+      const int h1 = side == ILF_BAND_ABOVE ? g.out_row0 : g.row0 + g.rows;
+      if (h1 <= h0) continue;  // picture border
+      const Slot::Neighbour& nb = s.nb[side];
+      if (!nb.planes) return fail(ctx, ILF_ERR_STATE, "slot %d: no neighbour connected %s the band", slot, side == ILF_BAND_ABOVE ? "above" : "below");
+      if (h0 < nb.row0 || h1 > nb.row0 + nb.rows) return fail(ctx, ILF_ERR_ARG, "neighbour band does not hold picture rows [%d,%d)", h0, h1);
+      for (int p = 0; p < 3; p++) {
+        const int sh = p ? 1 : 0, w = g.width >> sh, pitch = p ? g.pitch_c : g.pitch_y, npitch = p ? nb.pitch_c : nb.pitch_y;
+        if (n == HALO_MAX) if (int rc = flush()) return rc;
+        HaloCopy& c = hb.c[n++];
+        c.src = nb.planes + (p >= 1 ? nb.plane_y : 0) + (p == 2 ? nb.plane_c : 0) + (size_t)((h0 - nb.row0) >> sh) * npitch;  // neighbour's input buffer (buffer 0)
+        c.dst = plane_ptr(ctx, s, 0, p) + (size_t)((h0 - g.row0) >> sh) * pitch;
+        c.src_pitch = npitch; c.dst_pitch = pitch;
+        c.words = (w * 2) / 8;   // widths are multiples of 8 luma / 4 chroma samples
+        c.rows = (h1 - h0) >> sh;
+      }
     }
   }
-  CU(ctx, cudaEventRecord(s.ev_up, ctx->s_up));
-  s.h2d_pending = true;
+  if (int rc = flush()) return rc;
+  for (int slot = first_slot; slot < first_slot + num_slots; slot++) {
+    Slot& s = ctx->slots[slot];
+    CU(ctx, cudaEventRecord(s.ev_up, ctx->s_up));
+    s.h2d_pending = true;
+  }
   return ILF_OK;
+}
+
+int ilf_band_exchange(ilf_ctx* ctx, int slot) {
+  if (int rc = check_slot(ctx, slot)) return rc;
+  return ilf_band_exchange_batch(ctx, slot, 1);
 }
 
 int ilf_wait(ilf_ctx* ctx, int slot) {

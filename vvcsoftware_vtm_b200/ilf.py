@@ -62,6 +62,7 @@ def load_library():
     lib.ilf_band_export.argtypes = [vp, i, C.c_char_p]
     lib.ilf_band_connect.argtypes = [vp, i, i, C.c_char_p]
     lib.ilf_band_exchange.argtypes = [vp, i]
+    lib.ilf_band_exchange_batch.argtypes = [vp, i, i]
     lib.ilf_upload.argtypes = [vp, i, vp, pd, vp, pd, vp, pd]
     lib.ilf_download.argtypes = [vp, i, vp, pd, vp, pd, vp, pd]
     lib.ilf_sync.argtypes = [vp]
@@ -212,8 +213,9 @@ class InLoopFilter:
         assert len(handle) == BAND_HANDLE_BYTES
         self._ck(self._lib.ilf_band_connect(self._h, slot, side, handle))
 
-    def band_exchange(self, slot=0):
-        self._ck(self._lib.ilf_band_exchange(self._h, slot))
+    def band_exchange(self, slot=0, num_slots=1):
+        """Pull the halo rows of slots [slot, slot + num_slots) from the connected neighbours (one kernel over NVLink P2P)."""
+        self._ck(self._lib.ilf_band_exchange_batch(self._h, slot, num_slots))
 
     # ---- side information ------------------------------------------------------------------------
     def set_deblock_info(self, slot, params_bytes, info, info_chroma=None, mv16=None, mv32=None, ctu_slice=None):
