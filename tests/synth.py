@@ -49,16 +49,28 @@ def sao_params(rng, ctus_w, ctus_h, bd=10, p_off=0.25, all_avail=False):
     return a.view(np.uint8).reshape(n, 32)
 
 
-def alf_params(rng, ctus_w, ctus_h, is7=True, p_on=0.8, big=False):
+def alf_params(rng, ctus_w, ctus_h, is7=True, p_on=0.8, big=False, dot=False):
+    """big: every coefficient anywhere in +-511 (general arithmetic path).  dot: the limits of the dot-product path -- outer
+    coefficients over the whole int8 range with both extremes present, the four neighbours of the centre up to +-1500, the
+    centre whatever the normalisation leaves (negative and > 8000 occur)."""
     a = np.zeros(1, ALF_DT)
     lim = 511 if big else 40
-    lc = rng.integers(-lim, lim + 1, (25, 13))
-    lc[:, 12] = 512 - 2 * lc[:, :12].sum(axis=1) if is7 else 0
-    if not is7:
-        lc[:, 7:] = 0
-        lc[:, 6] = 512 - 2 * lc[:, :6].sum(axis=1)
-    a["luma_coeff"][0] = np.clip(lc, -32768, 32767)
+    n = 13 if is7 else 7
+    lc = np.zeros((25, 13), np.int64)
+    lc[:, :n - 1] = rng.integers(-lim, lim + 1, (25, n - 1))
     cc = rng.integers(-lim, lim + 1, 7)
+    if dot:
+        lc[:, :n - 1] = rng.integers(-128, 128, (25, n - 1))
+        lc[rng.integers(0, 25, 8), rng.integers(0, n - 1, 8)] = -128
+        lc[rng.integers(0, 25, 8), rng.integers(0, n - 1, 8)] = 127
+        inner = (6, 11) if is7 else (2, 5)      # (0, +-1) and (+-1, 0)
+        for k in inner:
+            lc[:, k] = rng.integers(-1500, 1501, 25)
+        cc[:6] = rng.integers(-128, 128, 6)
+        cc[0], cc[3] = -128, 127
+        cc[2], cc[5] = rng.integers(-1500, 1501, 2)
+    lc[:, n - 1] = 512 - 2 * lc[:, :n - 1].sum(axis=1)
+    a["luma_coeff"][0] = np.clip(lc, -32768, 32767)
     cc[6] = 512 - 2 * cc[:6].sum()
     a["chroma_coeff"][0] = cc
     a["luma_filter_7x7"][0] = 1 if is7 else 0

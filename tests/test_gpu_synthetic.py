@@ -53,18 +53,20 @@ def test_sao_component_off_for_whole_picture_is_skipped(ilf_lib, oracle):
 def test_alf_random_coefficients(w, h, bd, is7, seed, ilf_lib, oracle):
     rng = np.random.default_rng(seed)
     cw, ch = (w + 127) // 128, (h + 127) // 128
-    for kind, big in (("mix", False), ("noise", True)):
+    # small coefficients and the limits of the dot-product path (IDP.2A, ilf_alf_tab.cuh); anything in +-511: general path
+    for kind, big, dot, path in (("mix", False, False, 3), ("noise", False, True, 3), ("noise", True, False, 0), ("mix", False, True, 3)):
         pic = synth.picture(rng, w, h, bd, kind)
-        pb, en = synth.alf_params(rng, cw, ch, is7, big=big)
+        pb, en = synth.alf_params(rng, cw, ch, is7, big=big, dot=dot)
         want = oracle.alf(pic, bd, bd, 7, pb, en)
         with ilf_lib.InLoopFilter(w, h, bd, bd, 7) as f:
             f.upload(0, *(pic[k] for k in K))
             f.set_alf_params(0, pb, en)
+            assert f.alf_path(0) == path, "the arithmetic path the host chose is not the one this case is meant to cover"
             f.alf_process(0)
             got = f.download(0)
             cls = f.alf_classify(0)
         d = _diff(got, want)
-        assert not any(d.values()), f"{kind}: mismatching samples {d}"
+        assert not any(d.values()), f"{kind} big={big} dot={dot}: mismatching samples {d}"
 
 
 @pytest.mark.parametrize("w,h,bd,ctu_log2,mv32,seed", [(416, 240, 10, 7, False, 31), (200, 136, 8, 5, True, 32), (264, 200, 12, 6, False, 33), (1920, 1080, 10, 7, True, 34)])

@@ -13,15 +13,19 @@
 //
 // Luma, per tile (2 TW = 128 threads, one thread = one 4x4 block from classification to output):
 //   phase 1  work tile (int16, two samples per 32-bit word)
-//   phase 2  1-D Laplacians two samples per instruction (|2c - a - b| = max(2c - s, s - 2c) with VIADD.16x2 / VIADDMNMX.S16x2),
-//            summed per 2x2 cell; a task walks one word column over 12 rows with a rolling 3-row window
-//   phase 3  each thread sums the 4x4 cells of its block's 8x8 window and derives class + transpose (kept in a register)
-//   phase 4  each thread filters its block with the (class, transpose) coefficient row of the per-picture table that
-//            ilf_set_alf_params precomputed (SlotDev::alf_coef): the 10 window rows are read once from shared memory
-//            (3 x 8 bytes each), unpacked once into registers and shared by the block's four output rows
+//   phase 2  1-D Laplacians two samples per instruction on biased 16-bit lanes, summed per "quad" = 4x4 samples at offset
+//            (-2, -2) from the block grid (a task = one quad: two word columns x 4 rows with a rolling 3-row window; the
+//            lanes of a quad are folded with IDP.2A against 0x0101)
+//   phase 3  a block's 8x8 classification window is exactly 2x2 quads: four 16-byte loads, class + transpose in a register
+//   phase 4  each thread filters its block with the (class, transpose) entry of the per-picture table that
+//            ilf_set_alf_params precomputed.  Two arithmetic paths, chosen per picture by the host (SlotDev::alf_mode):
+//              dot-product path (ilf_alf_tab.cuh): IDP.2A on the packed words of the window, two taps per instruction,
+//                nothing unpacked -- 20 instead of ~33 instructions per sample; needs the outer coefficients in int8
+//              general path: 32-bit IMAD on unpacked samples with point-symmetric pair sums, any int16 coefficients
 // Tiles whose blocks are all in CTUs with ALF off are copied through without classification.
 #include "ilf_common.cuh"
 #include "ilf_ring.cuh"
+#include "ilf_alf_tab.cuh"
 
 namespace ilf {
 namespace {
@@ -74,15 +78,12 @@ __device__ __forceinline__ void pad_borders(int16_t* __restrict__ W, bool left, 
 constexpr int L_SR = BR + 2 * ALF_HALO_Y;                      // 38 staged rows
 constexpr int L_STAGE_BYTES = WP * L_SR * 2;                   // 10944 bytes per box
 constexpr int L_STAGE_STRIDE = (L_STAGE_BYTES + 127) & ~127;   // TMA destinations are 128-byte aligned
-constexpr int CELL_W = TW / 2 + 2, CELL_H = BR / 2 + 2;        // 66 x 18 cells of 2x2 samples, first cell at (x0-2, y0-2)
-constexpr int L_CELL_BYTES = CELL_H * CELL_W * 8;
-constexpr int L_SMEM_BYTES = RING_STAGES * L_STAGE_STRIDE + L_CELL_BYTES + RING_STAGES * 8;
+constexpr int QW = TW / 4 + 1, QH = BR / 4 + 1;                // 17 x 9 quads of 4x4 samples, first quad at (x0-2, y0-2)
+constexpr int L_CELL_BYTES = 2 * QH * QW * 16;                 // {V, H, D0, D1} sums as 32-bit words, two tiles
+constexpr int L_EN_BYTES = 528;                                // ALF flags of the CTU columns a walk touches (16384 / 32, padded)
+constexpr int L_SMEM_BYTES = RING_STAGES * L_STAGE_STRIDE + L_CELL_BYTES + RING_STAGES * 8 + L_EN_BYTES;
 constexpr int NT = 2 * TW;                                     // TW / 4 blocks across x 8 block rows
 constexpr int BPR = TW / 4;                                    // 4x4 blocks per tile row
-constexpr int LAP_ROWS = 6;                                    // sample rows a Laplacian task walks (3 cell rows)
-constexpr int LAP_COLS = CELL_W / 2;                           // a task covers two word columns (two cells per cell row)
-constexpr int LAP_TASKS = LAP_COLS * (CELL_H * 2 / LAP_ROWS);  // 33 column pairs x 6 row groups
-static_assert(CELL_W % 2 == 0 && (CELL_H * 2) % LAP_ROWS == 0 && LAP_TASKS <= 2 * TW, "Laplacian task grid");
 
 __constant__ uint8_t c_th[16] = {0, 1, 2, 2, 2, 2, 2, 3, 3, 3, 3, 3, 3, 3, 3, 4};
 __constant__ uint8_t c_transpose[8] = {0, 1, 0, 2, 2, 3, 1, 3};
@@ -116,6 +117,67 @@ __device__ __forceinline__ void load_win12(const int16_t* p, int v[12]) {
   v[8] = c.x & 0xFFFF; v[9] = c.x >> 16; v[10] = c.y & 0xFFFF; v[11] = c.y >> 16;
 }
 
+// IDP.2A: c + a.lo16 * b.byte[0 | 2] + a.hi16 * b.byte[1 | 3]; samples unsigned, coefficients signed
+__device__ __forceinline__ int dp2a_lo(uint32_t a, uint32_t b, int c) { int d; asm("dp2a.lo.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
+__device__ __forceinline__ int dp2a_hi(uint32_t a, uint32_t b, int c) { int d; asm("dp2a.hi.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
+__device__ __forceinline__ uint32_t dp2a_uu(uint32_t a, uint32_t b, uint32_t c) { uint32_t d; asm("dp2a.lo.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
+
+// Dot-product filter of ONE output sample (ilf_alf_tab.cuh).  R = radius of the slot layout the coefficient words `cw` are in,
+// RT = radius of the filter (RT < R: a 5x5 luma filter in the 7x7 layout; its empty slots are skipped at compile time).
+// row(dy) gives the packed words of window row y + dy; word m of a row holds the samples at x offsets 2m - XOFF, 2m - XOFF + 1
+// from output sample 0 of the thread, j = index of this output sample.  Everything folds at compile time once unrolled.
+template <int R, int RT, int XOFF, typename RowFn>
+__device__ __forceinline__ int dp_filter_sample(RowFn row, const uint32_t* cw, int j) {
+  const int p = j & 1;
+  constexpr int NR = alftab::num_regs<R>();
+  int acc = 256, hi = 0;
+#pragma unroll
+  for (int dy = -RT; dy <= RT; dy++)
+#pragma unroll
+    for (int q = 0; q <= R; q++) {
+      if (!alftab::holds<R, RT>(p, dy, q)) continue;
+      const int s = alftab::slot<R>(p, dy, q);
+      const uint32_t ww = row(dy)[(j + alftab::dx0<R>(p, q) + XOFF) / 2];
+      acc = (s & 1) ? dp2a_hi(ww, cw[p * NR + (s >> 1)], acc) : dp2a_lo(ww, cw[p * NR + (s >> 1)], acc);
+    }
+#pragma unroll
+  for (int dy = -1; dy <= 1; dy++)
+#pragma unroll
+    for (int q = 0; q <= 1; q++) {
+      if (!alftab::holds<1, 1>(p, dy, q)) continue;
+      const int s = alftab::slot<1>(p, dy, q);
+      const uint32_t ww = row(dy)[(j + alftab::dx0<1>(p, q) + XOFF) / 2];
+      hi = (s & 1) ? dp2a_hi(ww, cw[2 * NR + p * 2 + (s >> 1)], hi) : dp2a_lo(ww, cw[2 * NR + p * 2 + (s >> 1)], hi);
+    }
+  return (acc + (hi << alftab::HI_SHIFT)) >> 9;
+}
+
+// Luma block, dot-product path: wp = window row 0 (block row 0 minus 3), sample x - 4; tab = the block's table entry.
+template <int RT>
+__device__ __forceinline__ void filter_block_dp(const int16_t* wp, const uint32_t* __restrict__ tab, int16_t* __restrict__ out, int pitch, int max_val) {
+  uint32_t cw[alftab::LUMA_WORDS];
+  {
+    const uint4* tp = reinterpret_cast<const uint4*>(tab);
+#pragma unroll
+    for (int i = 0; i < alftab::LUMA_WORDS / 4; i++) { const uint4 v = __ldg(tp + i); cw[4 * i] = v.x; cw[4 * i + 1] = v.y; cw[4 * i + 2] = v.z; cw[4 * i + 3] = v.w; }
+  }
+  uint32_t w[10][6];  // w[s][m] = samples (x - 4 + 2m, x - 3 + 2m) of window row s
+  auto load = [&](int s) {
+    const uint2 a = *reinterpret_cast<const uint2*>(wp + s * WP), b = *reinterpret_cast<const uint2*>(wp + s * WP + 4), c = *reinterpret_cast<const uint2*>(wp + s * WP + 8);
+    w[s][0] = a.x; w[s][1] = a.y; w[s][2] = b.x; w[s][3] = b.y; w[s][4] = c.x; w[s][5] = c.y;
+  };
+#pragma unroll
+  for (int s = 3 - RT; s < 3 + RT; s++) load(s);
+#pragma unroll
+  for (int o = 0; o < 4; o++) {
+    load(o + 3 + RT);
+    int r[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) r[j] = __vimin_s32_relu(dp_filter_sample<3, RT, 4>([&](int dy) { return w[o + 3 + dy]; }, cw, j), max_val);
+    *reinterpret_cast<uint2*>(out + (size_t)o * pitch) = make_uint2(__byte_perm(r[0], r[1], 0x5410), __byte_perm(r[2], r[3], 0x5410));
+  }
+}
+
 // Luma CTA: band blockIdx.y, horizontal segment blockIdx.x of nseg.
 template <bool CLASSIFY_ONLY>
 __device__ __forceinline__ void alf_luma_cta(unsigned char* smem, const Geom& g, const SlotDev& sd, unsigned ctl, int nseg) {
@@ -127,11 +189,12 @@ __device__ __forceinline__ void alf_luma_cta(unsigned char* smem, const Geom& g,
   if (ta >= tb) return;
   ring::Walk<RING_STAGES> walk;
   walk.first = ta; walk.last = tb - 1;
-  uint2(*cell)[CELL_W] = reinterpret_cast<uint2(*)[CELL_W]>(smem + RING_STAGES * L_STAGE_STRIDE);  // {V | H << 16, D0 | D1 << 16} per 2x2 cell
+  // {V, H, D0, D1} per quad, double-buffered: tile t + 1 fills the other half while slower threads still read tile t's
+  uint4(*quad_buf)[QH][QW] = reinterpret_cast<uint4(*)[QH][QW]>(smem + RING_STAGES * L_STAGE_STRIDE);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + RING_STAGES * L_STAGE_STRIDE + L_CELL_BYTES);
+  uint8_t* en_s = smem + RING_STAGES * L_STAGE_STRIDE + L_CELL_BYTES + RING_STAGES * 8;  // ALF flag of the CTUs of this band's CTU row, from column c0
   const int y0 = (int)blockIdx.y * BR;  // local rows
   const int src_buf = ctl_src(ctl, 0);
-  int16_t* __restrict__ dst = sd.buf[ctl_dst(ctl, 0)][0];
   const CUtensorMap* map = &sd.tm_alf[0];
   auto stage_ptr = [&](int t) { return reinterpret_cast<int16_t*>(smem + walk.stage(t) * L_STAGE_STRIDE); };
   auto issue = [&](int t) {
@@ -142,46 +205,62 @@ __device__ __forceinline__ void alf_luma_cta(unsigned char* smem, const Geom& g,
   if (tid == 0) {
     for (int i = 0; i < RING_STAGES; i++) ring::mbar_init(&full[i], 1);
     ring::mbar_init_fence();
-  }
-  __syncthreads();
-  pdl_wait();  // the stage before this one has written the planes read from here on
-  if (tid == 0)
+    pdl_wait();  // the stage before this one has written the planes read from here on
     for (int t = walk.first; t <= walk.last && t < walk.first + RING_STAGES; t++) issue(t);
-
+  }
   // this thread's 4x4 block of every tile: BPR blocks across, 8 block rows
   const int bj = tid % BPR, bi = tid / BPR;
   const int by = y0 + 4 * bi;
-  const uint8_t* __restrict__ en_row = sd.alf_ctu_enable + (size_t)((by + g.row0) >> g.ctu_log2) * g.ctus_w;
+  const int c0 = (ta * TW) >> g.ctu_log2, c1 = min(g.ctus_w - 1, (tb * TW - 1) >> g.ctu_log2);  // CTU columns this walk touches
+  if (!CLASSIFY_ONLY) {
+    const uint8_t* __restrict__ en_row = sd.alf_ctu_enable + (size_t)((y0 + g.row0) >> g.ctu_log2) * g.ctus_w;  // a band lies in one CTU row
+    for (int c = c0 + tid; c <= c1; c += NT) en_s[c - c0] = en_row[c];
+  }
+  int16_t* __restrict__ dst = sd.buf[ctl_dst(ctl, 0)][0];
   const int max_val = (1 << g.bd_luma) - 1;
-  const bool is7 = CLASSIFY_ONLY ? true : sd.alf->luma_filter_7x7 != 0;
+  const bool is7 = CLASSIFY_ONLY ? true : (ctl & CTL_ALF_7X7) != 0;
+  const bool dot = CLASSIFY_ONLY ? false : (ctl & CTL_ALF_DOT_Y) != 0;  // dot-product path (ilf_alf_tab.cuh), else the general path
   const int shift = g.bd_luma + 4;
-  const uint32_t lap_k = 0x10001u << (g.bd_luma + 1), lap_k2 = lap_k << 1, lap_k4 = lap_k << 2;  // Laplacian lane bias K, 2K, 4K
+  const uint32_t lap_k = 0x10001u << (g.bd_luma + 1), lap_k2 = lap_k << 1;  // Laplacian lane bias K, 2K
+  const uint32_t quad_bias = 0u - (16u << (g.bd_luma + 1));                       // a quad collects K sixteen times
+  __syncthreads();  // barriers initialised, flags staged
+  pdl_wait();  // every thread: this kernel's stores must not overtake the previous stage's reads either
 
+  // One CTA barrier per tile: it publishes the tile's quads, and -- because every thread has then finished the previous
+  // tile -- it also frees the previous tile's stage, which thread 0 refills right after it.
   for (int tx = ta; tx < tb; tx++) {
     ring::mbar_wait(&full[walk.stage(tx)], walk.parity(tx));
     const int x0 = tx * TW, bx = x0 + 4 * bj;
     const bool blk_in = bx < g.width && by < rows;
-    const bool en = blk_in && (CLASSIFY_ONLY || en_row[bx >> g.ctu_log2] != 0);
+    bool any_en = CLASSIFY_ONLY, en = CLASSIFY_ONLY && blk_in;
+    if (!CLASSIFY_ONLY) {
+      // CTA-uniform: is ALF on in any CTU under this tile?
+      for (int c = x0 >> g.ctu_log2; c <= min(c1, (x0 + TW - 1) >> g.ctu_log2); c++) any_en |= en_s[c - c0] != 0;
+      en = blk_in && en_s[min(c1, bx >> g.ctu_log2) - c0] != 0;
+    }
     int16_t* W = stage_ptr(tx);
     int16_t* out = dst + (size_t)by * g.pitch_y + bx;
-    if (!__syncthreads_or(en)) {
+    uint4(*quad)[QW] = quad_buf[(tx - ta) & 1];
+    if (!any_en) {
       // every CTU under this tile has ALF off: copy through
       if (blk_in) {
 #pragma unroll
         for (int o = 0; o < 4; o++) *reinterpret_cast<uint2*>(out + (size_t)o * g.pitch_y) = *reinterpret_cast<const uint2*>(W + (ALF_HALO_Y + 4 * bi + o) * WP + WX0 + 4 * bj);
       }
+      __syncthreads();
+      if (tid == 0 && tx > ta && tx - 1 + RING_STAGES <= walk.last) issue(tx - 1 + RING_STAGES);
     } else {
       // ---- phase 1: the stage is the work tile; border tiles get their padding ----
       pad_borders<L_SR, ALF_HALO_Y, NT>(W, tx == 0, tx == ntx - 1, min(TW, g.width - x0), y0 - ALF_HALO_Y, rows);
 
-      // ---- phase 2: Laplacians per 2x2 cell, two samples per instruction.  Task = two word columns (cells 2q, 2q + 1: samples
-      //      x0-2+4q .. x0+1+4q) over the 6 sample rows of 3 cell rows: work-tile rows 6 rgp + 1 .. 6 rgp + 6, words 3 + 2q, 4 + 2q.
-      //      Everything is plain 32-bit arithmetic on biased lanes (no lane ever borrows or carries): with K = 2^(bd+1),
-      //      t' = 2c + K - a - b lies in (0, 2K), and max(t', 2K - t') = K + |2c - a - b|; the 4K a cell collects is taken off
-      //      when its two columns are combined.  (__vsub2 / __vneg2 are multi-instruction emulations on sm_100a.) ----
-      if (tid < LAP_TASKS) {
-        const int q = tid % LAP_COLS, rgp = tid / LAP_COLS;
-        const uint32_t* wp = reinterpret_cast<const uint32_t*>(W) + (LAP_ROWS * rgp) * (WP / 2) + 2 + 2 * q;
+      // ---- phase 2: Laplacians per quad (4x4 samples at (x0 - 2 + 4 qj, y0 - 2 + 4 qi)), two samples per instruction.  A task loads
+      //      work-tile rows 4 qi .. 4 qi + 5, words 2 + 2 qj .. 5 + 2 qj.  Everything is plain 32-bit arithmetic on biased lanes
+      //      (no lane ever borrows or carries): with K = 2^(bd+1), t' = 2c + K - a - b lies in (0, 2K), and
+      //      max(t', 2K - t') = K + |2c - a - b|; four rows of a lane stay below 2^16 up to 12 bit.  (__vsub2 / __vneg2 and the
+      //      packed abs-diffs are multi-instruction emulations on sm_100a.) ----
+      for (int t = tid; t < QW * QH; t += NT) {
+        const int qj = t % QW, qi = t / QW;
+        const uint32_t* wp = reinterpret_cast<const uint32_t*>(W) + (4 * qi) * (WP / 2) + 2 + 2 * qj;
         // per column j: centre / left-shifted / right-shifted word of the rows above (u), at (m) and below (d)
         uint32_t cu[2], lu[2], ru[2], cm[2], lm[2], rm[2], cd[2], ld[2], rd[2];
         auto load_row = [&](int r, uint32_t (&c)[2], uint32_t (&l)[2], uint32_t (&rr)[2]) {
@@ -193,44 +272,36 @@ __device__ __forceinline__ void alf_luma_cta(unsigned char* smem, const Geom& g,
         load_row(1, cm, lm, rm);
         uint32_t av[2], ah[2], ad0[2], ad1[2];
 #pragma unroll
-        for (int i = 0; i < LAP_ROWS; i++) {
+        for (int i = 0; i < 4; i++) {
           load_row(i + 2, cd, ld, rd);
 #pragma unroll
           for (int j = 0; j < 2; j++) {
             const uint32_t c2k = cm[j] + cm[j] + lap_k;
-            uint32_t t;
-            t = c2k - cu[j] - cd[j]; const uint32_t v = __vmaxu2(t, lap_k2 - t);     // K + |2c - up - down|
-            t = c2k - lm[j] - rm[j]; const uint32_t h = __vmaxu2(t, lap_k2 - t);     // K + |2c - left - right|
-            t = c2k - lu[j] - rd[j]; const uint32_t d0 = __vmaxu2(t, lap_k2 - t);    // K + |2c - up-left - down-right|
-            t = c2k - ru[j] - ld[j]; const uint32_t d1 = __vmaxu2(t, lap_k2 - t);    // K + |2c - up-right - down-left|
-            if ((i & 1) == 0) { av[j] = v; ah[j] = h; ad0[j] = d0; ad1[j] = d1; }
+            uint32_t u;
+            u = c2k - cu[j] - cd[j]; const uint32_t v = __vmaxu2(u, lap_k2 - u);     // K + |2c - up - down|
+            u = c2k - lm[j] - rm[j]; const uint32_t h = __vmaxu2(u, lap_k2 - u);     // K + |2c - left - right|
+            u = c2k - lu[j] - rd[j]; const uint32_t d0 = __vmaxu2(u, lap_k2 - u);    // K + |2c - up-left - down-right|
+            u = c2k - ru[j] - ld[j]; const uint32_t d1 = __vmaxu2(u, lap_k2 - u);    // K + |2c - up-right - down-left|
+            if (i == 0) { av[j] = v; ah[j] = h; ad0[j] = d0; ad1[j] = d1; }
             else { av[j] += v; ah[j] += h; ad0[j] += d0; ad1[j] += d1; }
             cu[j] = cm[j]; lu[j] = lm[j]; ru[j] = rm[j]; cm[j] = cd[j]; lm[j] = ld[j]; rm[j] = rd[j];
           }
-          if (i & 1) {
-            // both columns of each cell: {V, H} and {D0, D1} as 16-bit halves (a cell sum is < 2^15 up to 12 bit)
-            uint4 o;
-            o.x = __byte_perm(av[0], ah[0], 0x5410) + __byte_perm(av[0], ah[0], 0x7632) - lap_k4;
-            o.y = __byte_perm(ad0[0], ad1[0], 0x5410) + __byte_perm(ad0[0], ad1[0], 0x7632) - lap_k4;
-            o.z = __byte_perm(av[1], ah[1], 0x5410) + __byte_perm(av[1], ah[1], 0x7632) - lap_k4;
-            o.w = __byte_perm(ad0[1], ad1[1], 0x5410) + __byte_perm(ad0[1], ad1[1], 0x7632) - lap_k4;
-            *reinterpret_cast<uint4*>(&cell[(LAP_ROWS / 2) * rgp + (i >> 1)][2 * q]) = o;
-          }
         }
+        // fold the four lanes of each direction: IDP.2A against {1, 1} adds both halves of a word in 32 bits
+        uint4 o;
+        o.x = dp2a_uu(av[0], 0x0101u, dp2a_uu(av[1], 0x0101u, quad_bias));
+        o.y = dp2a_uu(ah[0], 0x0101u, dp2a_uu(ah[1], 0x0101u, quad_bias));
+        o.z = dp2a_uu(ad0[0], 0x0101u, dp2a_uu(ad0[1], 0x0101u, quad_bias));
+        o.w = dp2a_uu(ad1[0], 0x0101u, dp2a_uu(ad1[1], 0x0101u, quad_bias));
+        quad[qi][qj] = o;
       }
       __syncthreads();
+      if (tid == 0 && tx > ta && tx - 1 + RING_STAGES <= walk.last) issue(tx - 1 + RING_STAGES);
 
-      // ---- phase 3: 4x4 cells of the block's 8x8 window -> class.  Two cells add without a carry between the 16-bit halves
-      //      (12-bit safe); wider sums are taken in 32 bits ----
-      int sv = 0, sh = 0, sd0 = 0, sd1 = 0;
-#pragma unroll
-      for (int r = 0; r < 4; r++) {
-        const uint4 c01 = *reinterpret_cast<const uint4*>(&cell[2 * bi + r][2 * bj]);      // cells 0, 1: {vh0, d0, vh1, d1}
-        const uint4 c23 = *reinterpret_cast<const uint4*>(&cell[2 * bi + r][2 * bj + 2]);
-        const uint32_t a0 = c01.x + c01.z, a1 = c23.x + c23.z, b0 = c01.y + c01.w, b1 = c23.y + c23.w;
-        sv += (a0 & 0xFFFF) + (a1 & 0xFFFF); sh += (a0 >> 16) + (a1 >> 16);
-        sd0 += (b0 & 0xFFFF) + (b1 & 0xFFFF); sd1 += (b0 >> 16) + (b1 >> 16);
-      }
+      // ---- phase 3: the block's 8x8 window = quads (bi, bj) .. (bi + 1, bj + 1) -> class ----
+      const uint4 q00 = quad[bi][bj], q01 = quad[bi][bj + 1], q10 = quad[bi + 1][bj], q11 = quad[bi + 1][bj + 1];
+      const int sv = (int)(q00.x + q01.x + q10.x + q11.x), sh = (int)(q00.y + q01.y + q10.y + q11.y);
+      const int sd0 = (int)(q00.z + q01.z + q10.z + q11.z), sd1 = (int)(q00.w + q01.w + q10.w + q11.w);
       const int cl = classify(sv, sh, sd0, sd1, shift);
       if (CLASSIFY_ONLY) {
         const int ux = bx >> 2, uy = by >> 2;
@@ -241,6 +312,10 @@ __device__ __forceinline__ void alf_luma_cta(unsigned char* smem, const Geom& g,
         if (!en) {
 #pragma unroll
           for (int o = 0; o < 4; o++) *reinterpret_cast<uint2*>(out + (size_t)o * g.pitch_y) = *reinterpret_cast<const uint2*>(wp + (3 + o) * WP + 4);
+        } else if (dot) {
+          const uint32_t* tab = sd.alf_coef_dp + ((cl & 31) * 4 + (cl >> 5)) * alftab::LUMA_WORDS;
+          if (is7) filter_block_dp<3>(wp, tab, out, g.pitch_y, max_val);
+          else filter_block_dp<2>(wp, tab, out, g.pitch_y, max_val);
         } else {
           int f[16];
           {
@@ -295,8 +370,6 @@ __device__ __forceinline__ void alf_luma_cta(unsigned char* smem, const Geom& g,
         }
       }
     }
-    __syncthreads();  // the stage and the cells are free
-    if (tid == 0 && tx + RING_STAGES <= walk.last) issue(tx + RING_STAGES);
   }
 }
 
@@ -355,6 +428,13 @@ __device__ __forceinline__ void alf_chroma_cta(unsigned char* smem, const Geom& 
   int f[7];
 #pragma unroll
   for (int i = 0; i < 7; i++) f[i] = sd.alf->chroma_coeff[i];
+  const bool dot = (ctl & CTL_ALF_DOT_C) != 0;  // dot-product path (ilf_alf_tab.cuh), else the general path
+  uint32_t ccw[alftab::CHROMA_WORDS];
+  {
+    const uint4* tp = reinterpret_cast<const uint4*>(sd.alf_coef_dp + 25 * 4 * alftab::LUMA_WORDS);
+#pragma unroll
+    for (int i = 0; i < alftab::CHROMA_WORDS / 4; i++) { const uint4 v = __ldg(tp + i); ccw[4 * i] = v.x; ccw[4 * i + 1] = v.y; ccw[4 * i + 2] = v.z; ccw[4 * i + 3] = v.w; }
+  }
   const int max_val = (1 << g.bd_chroma) - 1;
   const int k = tid % (TW / 8), rg = tid / (TW / 8);  // 8 samples at column 8k, rows 2rg and 2rg + 1 of the band
   const int y = by0 + 2 * rg;
@@ -383,6 +463,23 @@ __device__ __forceinline__ void alf_chroma_cta(unsigned char* smem, const Geom& 
 #pragma unroll
           for (int o = 0; o < 2; o++)
             if (o < nrows) *reinterpret_cast<uint4*>(out + (size_t)o * g.pitch_c) = *reinterpret_cast<const uint4*>(wp + (2 + o) * WP);
+        } else if (dot) {
+          uint32_t w[6][6];  // w[r][m] = samples (x - 2 + 2m, x - 1 + 2m) of window row r
+#pragma unroll
+          for (int r = 0; r < 6; r++) {
+            const uint4 b = *reinterpret_cast<const uint4*>(wp + r * WP);
+            w[r][0] = *reinterpret_cast<const uint32_t*>(wp + r * WP - 2); w[r][1] = b.x; w[r][2] = b.y; w[r][3] = b.z; w[r][4] = b.w;
+            w[r][5] = *reinterpret_cast<const uint32_t*>(wp + r * WP + 8);
+          }
+#pragma unroll
+          for (int o = 0; o < 2; o++) {
+            if (o >= nrows) break;
+            int r[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) r[j] = __vimin_s32_relu(dp_filter_sample<2, 2, 2>([&](int dy) { return w[o + 2 + dy]; }, ccw, j), max_val);
+            *reinterpret_cast<uint4*>(out + (size_t)o * g.pitch_c) =
+                make_uint4(__byte_perm(r[0], r[1], 0x5410), __byte_perm(r[2], r[3], 0x5410), __byte_perm(r[4], r[5], 0x5410), __byte_perm(r[6], r[7], 0x5410));
+          }
         } else {
           int w[6][12];
 #pragma unroll

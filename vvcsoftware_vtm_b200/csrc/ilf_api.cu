@@ -11,12 +11,15 @@
 #include <unistd.h>
 
 #include "ilf_common.cuh"
+#include "ilf_alf_tab.cuh"
 
 using namespace ilf;
 
 namespace {
 
 thread_local std::string g_create_error;
+
+constexpr int ALF_DP_WORDS = 25 * 4 * alftab::LUMA_WORDS + alftab::CHROMA_WORDS;
 
 struct Slot {
   int16_t* planes = nullptr;   // one allocation: 3 buffers x (Y, Cb, Cr)
@@ -28,6 +31,7 @@ struct Slot {
   ilf_sao_ctu* sao = nullptr;
   ilf_alf_params* alf = nullptr;
   int* alf_coef = nullptr;     // [25][4][16] transposed luma coefficient table
+  uint32_t* alf_coef_dp = nullptr;  // [25][4][20] + [16]: dot-product layout of the luma filters and of the chroma filter (ilf_alf_tab.cuh)
   uint8_t* alf_ctu_enable = nullptr;
   uint8_t* alf_class = nullptr;
   int16_t* org = nullptr;      // source picture of the encoder (3 planes, same layout as one buffer of `planes`); allocated by ilf_set_original
@@ -45,6 +49,7 @@ struct Slot {
   int result_buf[3] = {0, 0, 0};  // buffer holding the current picture, per plane
   bool sao_on[3] = {false, false, false};  // any CTU with SAO enabled, per component
   bool alf_on[3] = {false, false, false};
+  bool alf_is7 = false;            // luma filter shape of the slot's ALF parameters
   // Transfer pipeline: H2D copies run on the context's upload stream, kernels on the compute stream, D2H copies on the
   // download stream; the three are ordered per slot with these events, so upload of picture n+1, filtering of picture n
   // and download of picture n-1 overlap when the caller cycles through several slots.
@@ -219,6 +224,7 @@ int create_impl(ilf_ctx** out, const ilf_config* cfg, const ilf_band* band) {
   *out = nullptr;
   if (cfg->width <= 0 || cfg->height <= 0 || (cfg->width & 7) || (cfg->height & 7))
     return fail(nullptr, ILF_ERR_ARG, "picture size %dx%d must be positive multiples of 8", cfg->width, cfg->height);
+  if (cfg->width > 16384 || cfg->height > 16384) return fail(nullptr, ILF_ERR_UNSUPPORTED, "picture size %dx%d above 16384", cfg->width, cfg->height);
   if (cfg->bit_depth_luma < 8 || cfg->bit_depth_luma > 12 || cfg->bit_depth_chroma < 8 || cfg->bit_depth_chroma > 12)
     return fail(nullptr, ILF_ERR_ARG, "bit depth must be in 8..12");
   if (cfg->ctu_log2 < 5 || cfg->ctu_log2 > 7) return fail(nullptr, ILF_ERR_ARG, "ctu_log2 must be 5, 6 or 7");
@@ -292,13 +298,14 @@ int create_impl(ilf_ctx** out, const ilf_config* cfg, const ilf_band* band) {
     CU(ctx, cudaMalloc(&s.sao, sizeof(ilf_sao_ctu) * ctx->num_ctus));
     CU(ctx, cudaMalloc(&s.alf, sizeof(ilf_alf_params)));
     CU(ctx, cudaMalloc(&s.alf_coef, 25 * 4 * 16 * sizeof(int)));
+    CU(ctx, cudaMalloc(&s.alf_coef_dp, ALF_DP_WORDS * sizeof(uint32_t)));
     CU(ctx, cudaMalloc(&s.alf_ctu_enable, 3 * (size_t)ctx->num_ctus));
     CU(ctx, cudaMalloc(&s.alf_class, units));
     auto up256 = [](size_t v) { return (v + 255) & ~size_t(255); };
     s.side_off[0] = 0;
     s.side_off[1] = up256(sizeof(ilf_deblock_params)) + 2 * up256(units * 4) + up256(units * 16) + up256(ctx->num_ctus);
     s.side_off[2] = s.side_off[1] + up256(sizeof(ilf_sao_ctu) * ctx->num_ctus);
-    s.side_off[3] = s.side_off[2] + up256(sizeof(ilf_alf_params)) + up256(3 * (size_t)ctx->num_ctus) + up256(25 * 4 * 16 * sizeof(int));
+    s.side_off[3] = s.side_off[2] + up256(sizeof(ilf_alf_params)) + up256(3 * (size_t)ctx->num_ctus) + up256(25 * 4 * 16 * sizeof(int)) + up256(ALF_DP_WORDS * sizeof(uint32_t));
     s.pinned_side_bytes = s.side_off[3];
     CU(ctx, cudaMallocHost(&s.pinned_side, s.pinned_side_bytes));
     CU(ctx, cudaEventCreateWithFlags(&s.ev_up, cudaEventDisableTiming));
@@ -368,7 +375,7 @@ int ilf_destroy(ilf_ctx* ctx) {
   for (Slot& s : ctx->slots) {
     for (auto& nb : s.nb) if (nb.ipc_base) cudaIpcCloseMemHandle(nb.ipc_base);
     cudaFree(s.planes); cudaFree(s.info); cudaFree(s.info_c); cudaFree(s.mv); cudaFree(s.ctu_slice); cudaFree(s.db_params);
-    cudaFree(s.sao); cudaFree(s.alf); cudaFree(s.alf_coef); cudaFree(s.alf_ctu_enable); cudaFree(s.alf_class);
+    cudaFree(s.sao); cudaFree(s.alf); cudaFree(s.alf_coef); cudaFree(s.alf_coef_dp); cudaFree(s.alf_ctu_enable); cudaFree(s.alf_class);
     cudaFree(s.org); cudaFree(s.stats_avail); cudaFree(s.stats);
     if (s.pinned) cudaFreeHost(s.pinned);
     if (s.pinned_side) cudaFreeHost(s.pinned_side);
@@ -743,9 +750,26 @@ int ilf_set_alf_params(ilf_ctx* ctx, int slot, const ilf_alf_params* params, con
         for (int k = 0; k < 16; k++)
           tab[cl][tr][k] = is7 ? (k < 13 ? params->luma_coeff[cl][perm7[tr][k]] : 0) : (k < 7 ? params->luma_coeff[cl][perm5[tr][k]] : 0);
     if (int rc = stage_side(ctx, s, s.alf_coef, tab, sizeof(tab), cur, lim)) return rc;
+    // The same filters in the dot-product layout (ilf_alf_tab.cuh); a picture whose outer coefficients do not fit int8 keeps
+    // the general path.  ILF_ALF_GENERAL=1 forces the general path (measurement / parity aid).
+    static const bool force_general = getenv("ILF_ALF_GENERAL") && atoi(getenv("ILF_ALF_GENERAL")) != 0;
+    uint32_t dp[ALF_DP_WORDS];
+    bool luma_ok = !force_general, chroma_ok = !force_general;
+    for (int cl = 0; cl < 25 && luma_ok; cl++)
+      for (int tr = 0; tr < 4; tr++) {
+        uint32_t* e = dp + (cl * 4 + tr) * alftab::LUMA_WORDS;
+        luma_ok &= is7 ? alftab::build_entry<3, 3>(tab[cl][tr], e, alftab::LUMA_WORDS) : alftab::build_entry<3, 2>(tab[cl][tr], e, alftab::LUMA_WORDS);
+      }
+    int fc[7];
+    for (int k = 0; k < 7; k++) fc[k] = params->chroma_coeff[k];
+    chroma_ok = chroma_ok && alftab::build_entry<2, 2>(fc, dp + 25 * 4 * alftab::LUMA_WORDS, alftab::CHROMA_WORDS);
+    s.dev.alf_mode = (luma_ok ? 1 : 0) | (chroma_ok ? 2 : 0);
+    s.alf_is7 = is7;
+    if (int rc = stage_side(ctx, s, s.alf_coef_dp, dp, sizeof(dp), cur, lim)) return rc;
   }
   CU(ctx, cudaEventRecord(s.ev_side[2], ctx->s_up));
   s.dev.alf_coef = s.alf_coef;
+  s.dev.alf_coef_dp = s.alf_coef_dp;
   s.dev.alf = s.alf;
   s.dev.alf_ctu_enable = s.alf_ctu_enable;
   s.has_alf = true;
@@ -816,6 +840,7 @@ static int run_stage(ilf_ctx* ctx, int first, int n, int stage) {
         if (!on[i][p]) { v |= 1u << (6 + p); continue; }
         s.result_buf[p] = s.result_buf[p] == 1 ? 2 : 1;
       }
+      if (stage == 2) v |= ((s.dev.alf_mode & 1) ? CTL_ALF_DOT_Y : 0) | ((s.dev.alf_mode & 2) ? CTL_ALF_DOT_C : 0) | (s.alf_is7 ? CTL_ALF_7X7 : 0);
       word[i] = (uint16_t)v;
     }
     auto compact = [&](bool use_y, bool use_c, BatchCtl& ctl, double& bytes) {
@@ -1011,6 +1036,11 @@ int ilf_kernel_times(ilf_ctx* ctx, double ms_sum[ILF_NUM_KERNELS], long long lau
   return ILF_OK;
 }
 long long ilf_launch_count(const ilf_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int ilf_alf_path(ilf_ctx* ctx, int slot) {
+  if (int rc = check_slot(ctx, slot)) return rc;
+  if (!ctx->slots[slot].has_alf) return fail(ctx, ILF_ERR_STATE, "slot %d: ALF parameters not set", slot);
+  return ctx->slots[slot].dev.alf_mode;
+}
 
 int ilf_slot_input_planes(ilf_ctx* ctx, int slot, void* planes[3], int32_t pitch[3]) {
   if (int rc = check_slot(ctx, slot)) return rc;

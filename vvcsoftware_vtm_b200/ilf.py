@@ -85,6 +85,7 @@ def load_library():
     lib.ilf_get_sao_stats.argtypes = [vp, i, vp]
     lib.ilf_kernel_times.argtypes = [vp, C.POINTER(C.c_double * NUM_KERNELS), C.POINTER(C.c_longlong * NUM_KERNELS), C.POINTER(C.c_double * NUM_KERNELS)]
     lib.ilf_set_timing.argtypes = [vp, i]
+    lib.ilf_alf_path.argtypes = [vp, i]
     lib.ilf_launch_count.argtypes = [vp]
     lib.ilf_launch_count.restype = C.c_longlong
     lib.ilf_slot_input_planes.argtypes = [vp, i, C.POINTER(vp * 3), C.POINTER(C.c_int32 * 3)]
@@ -283,6 +284,13 @@ class InLoopFilter:
         ms = (C.c_double * NUM_KERNELS)(); n = (C.c_longlong * NUM_KERNELS)(); nb = (C.c_double * NUM_KERNELS)()
         self._ck(self._lib.ilf_kernel_times(self._h, C.byref(ms), C.byref(n), C.byref(nb)))
         return {k: (ms[i], n[i], nb[i]) for i, k in enumerate(self.KERNELS)}
+
+    def alf_path(self, slot=0):
+        """Bits ILF_ALF_PATH_LUMA_DOT (1) / ILF_ALF_PATH_CHROMA_DOT (2): which arithmetic path the slot's ALF filters take."""
+        r = self._lib.ilf_alf_path(self._h, slot)
+        if r < 0:
+            self._ck(r)
+        return r
 
     def launch_count(self):
         return int(self._lib.ilf_launch_count(self._h))
