@@ -35,7 +35,7 @@ static int run(std::mt19937& rng, int nwords, int cases) {
     for (int k = 0; k < n - 1; k++) sum += f[k];
     f[n - 1] = it % 3 == 0 ? 512 - 2 * sum : (int)(rng() % 32001) - 16000;
     uint32_t e[32];
-    if (!build_entry<R, RT>(f, e, nwords)) { printf("entry rejected unexpectedly\n"); bad++; continue; }
+    if (!build_entry<R, RT>(f, e, nwords, nullptr)) { printf("entry rejected unexpectedly\n"); bad++; continue; }
     // window of 16 x 16 samples, outputs at (8, 8) and (9, 8)
     int smp[16][16];
     for (auto& row : smp) for (int& v : row) v = rng() % 4096;
@@ -89,9 +89,9 @@ int main() {
     for (int i = 0; i < 16; i++) if (seen[i] != 1) { printf("7x7 slot %d used %d times\n", i, seen[i]); bad++; }
   }
   // out-of-range coefficients are rejected
-  { int f[16] = {0}; f[0] = 128; f[12] = 512; uint32_t e[32]; if (build_entry<3, 3>(f, e, LUMA_WORDS)) { printf("128 accepted\n"); bad++; } }
-  { int f[16] = {0}; f[0] = -129; f[12] = 512; uint32_t e[32]; if (build_entry<3, 3>(f, e, LUMA_WORDS)) { printf("-129 accepted\n"); bad++; } }
-  { int f[16] = {0}; f[12] = 16400; uint32_t e[32]; if (build_entry<3, 3>(f, e, LUMA_WORDS)) { printf("centre 16400 accepted\n"); bad++; } }
+  { int f[16] = {0}; f[0] = 128; f[12] = 512; uint32_t e[32]; if (build_entry<3, 3>(f, e, LUMA_WORDS, nullptr)) { printf("128 accepted\n"); bad++; } }
+  { int f[16] = {0}; f[0] = -129; f[12] = 512; uint32_t e[32]; if (build_entry<3, 3>(f, e, LUMA_WORDS, nullptr)) { printf("-129 accepted\n"); bad++; } }
+  { int f[16] = {0}; f[12] = 16400; uint32_t e[32]; if (build_entry<3, 3>(f, e, LUMA_WORDS, nullptr)) { printf("centre 16400 accepted\n"); bad++; } }
   printf(bad ? "FAILED: %d\n" : "ok\n", bad);
   return bad != 0;
 }

@@ -1,8 +1,10 @@
 #!/bin/bash
-# Round-2 ALF A/B: GPU parity tests of the ALF paths, then the device-resident bench with variants.
+# Round-2 ALF A/B: (optional) GPU parity tests of the ALF paths, then the device-resident bench with variants.
 mkdir -p gpurun_out
+if [ -z "$NOTEST" ]; then
 python -m pytest tests -m gpu -x -q -k "alf or capture or fullsize or smoke" > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/pytest_gpu.log
 tail -5 gpurun_out/pytest_gpu.log
+fi
 run() {
   local label=$1; shift
   env "$@" python bench.py --steps 30 --warmup 3 --e2e-steps 1 --no-cpu-baseline > gpurun_out/b_$label.json 2>gpurun_out/b_$label.err || { echo "$label FAILED"; tail -3 gpurun_out/b_$label.err; return; }
@@ -15,7 +17,7 @@ PY
 }
 run dot X=1
 run dot_split ILF_ALF_SPLIT=1
-run general_split ILF_ALF_GENERAL=1 ILF_ALF_SPLIT=1
+[ -z "$NOGEN" ] && run general_split ILF_ALF_GENERAL=1 ILF_ALF_SPLIT=1
 for v in "$@"; do
 run ${v} ILF_B200_LIB=$PWD/variants/libilf_$v.so
 run ${v}_split ILF_B200_LIB=$PWD/variants/libilf_$v.so ILF_ALF_SPLIT=1

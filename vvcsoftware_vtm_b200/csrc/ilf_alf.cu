@@ -81,17 +81,16 @@ constexpr int L_STAGE_STRIDE = (L_STAGE_BYTES + 127) & ~127;   // TMA destinatio
 constexpr int QW = TW / 4 + 1, QH = BR / 4 + 1;                // 17 x 9 quads of 4x4 samples, first quad at (x0-2, y0-2)
 constexpr int L_CELL_BYTES = 2 * QH * QW * 16;                 // {V, H, D0, D1} sums as 32-bit words, two tiles
 constexpr int L_EN_BYTES = 528;                                // ALF flags of the CTU columns a walk touches (16384 / 32, padded)
-constexpr int L_SMEM_BYTES = RING_STAGES * L_STAGE_STRIDE + L_CELL_BYTES + RING_STAGES * 8 + L_EN_BYTES;
+constexpr int L_ON_BYTES = 256;                                // per tile of a walk (16384 / 64): ALF on anywhere under it
+constexpr int L_SMEM_BYTES = RING_STAGES * L_STAGE_STRIDE + L_CELL_BYTES + RING_STAGES * 8 + L_EN_BYTES + L_ON_BYTES;
 constexpr int NT = 2 * TW;                                     // TW / 4 blocks across x 8 block rows
 constexpr int BPR = TW / 4;                                    // 4x4 blocks per tile row
 
-__constant__ uint8_t c_th[16] = {0, 1, 2, 2, 2, 2, 2, 3, 3, 3, 3, 3, 3, 3, 3, 4};
-__constant__ uint8_t c_transpose[8] = {0, 1, 0, 2, 2, 3, 1, 3};
-
-// Class of one 4x4 block from its four window sums (AdaptiveLoopFilter.cpp:390-451).
+// Class of one 4x4 block from its four window sums (AdaptiveLoopFilter.cpp:390-451); the two small tables live in immediates.
 __device__ __forceinline__ int classify(int sum_v, int sum_h, int sum_d0, int sum_d1, int shift) {
-  const int activity = clip3i(0, 15, ((sum_v + sum_h) * 32) >> shift);
-  int class_idx = c_th[activity];
+  const int activity = min(15, (sum_v + sum_h) >> (shift - 5));           // Clip3(0, 15, (tempAct * 32) >> shift), sums are >= 0
+  // th[16] = {0, 1, 2, 2, 2, 2, 2, 3, 3, 3, 3, 3, 3, 3, 3, 4} (:294), one nibble per entry
+  int class_idx = (int)(((activity & 8) ? 0x43333333u : 0x32222210u) >> (4 * (activity & 7))) & 7;
   int hv1, hv0, d1, d0, dir_hv, dir_d;
   if (sum_v > sum_h) { hv1 = sum_v; hv0 = sum_h; dir_hv = 1; } else { hv1 = sum_h; hv0 = sum_v; dir_hv = 3; }
   if (sum_d0 > sum_d1) { d1 = sum_d0; d0 = sum_d1; dir_d = 0; } else { d1 = sum_d1; d0 = sum_d0; dir_d = 2; }
@@ -106,7 +105,8 @@ __device__ __forceinline__ int classify(int sum_v, int sum_h, int sum_d0, int su
   if (hvd1 > 2 * hvd0) strength = 1;
   if (hvd1 * 2 > 9 * hvd0) strength = 2;
   if (strength) class_idx += (((main_dir & 1) << 1) + strength) * 5;
-  return class_idx | (c_transpose[main_dir * 2 + (sec_dir >> 1)] << 5);
+  // transposeTable[8] = {0, 1, 0, 2, 2, 3, 1, 3} (:450)
+  return class_idx | (int)((0x31322010u >> (4 * (main_dir * 2 + (sec_dir >> 1)))) & 3) << 5;
 }
 
 // One work-tile row of a block's window: p = sample x - 4 (8-byte aligned); v[i] = sample x - 4 + i
@@ -124,9 +124,10 @@ __device__ __forceinline__ uint32_t dp2a_uu(uint32_t a, uint32_t b, uint32_t c) 
 
 // Dot-product filter of ONE output sample (ilf_alf_tab.cuh).  R = radius of the slot layout the coefficient words `cw` are in,
 // RT = radius of the filter (RT < R: a 5x5 luma filter in the 7x7 layout; its empty slots are skipped at compile time).
+// HI_CENTRE: only the centre coefficient has a high part (the usual case: its four neighbours fit int8) -- one IDP instead of four.
 // row(dy) gives the packed words of window row y + dy; word m of a row holds the samples at x offsets 2m - XOFF, 2m - XOFF + 1
 // from output sample 0 of the thread, j = index of this output sample.  Everything folds at compile time once unrolled.
-template <int R, int RT, int XOFF, typename RowFn>
+template <int R, int RT, int XOFF, bool HI_CENTRE, typename RowFn>
 __device__ __forceinline__ int dp_filter_sample(RowFn row, const uint32_t* cw, int j) {
   const int p = j & 1;
   constexpr int NR = alftab::num_regs<R>();
@@ -145,6 +146,7 @@ __device__ __forceinline__ int dp_filter_sample(RowFn row, const uint32_t* cw, i
 #pragma unroll
     for (int q = 0; q <= 1; q++) {
       if (!alftab::holds<1, 1>(p, dy, q)) continue;
+      if (HI_CENTRE && !(dy == 0 && alftab::dx0<1>(p, q) <= 0 && alftab::dx0<1>(p, q) + 1 >= 0)) continue;
       const int s = alftab::slot<1>(p, dy, q);
       const uint32_t ww = row(dy)[(j + alftab::dx0<1>(p, q) + XOFF) / 2];
       hi = (s & 1) ? dp2a_hi(ww, cw[2 * NR + p * 2 + (s >> 1)], hi) : dp2a_lo(ww, cw[2 * NR + p * 2 + (s >> 1)], hi);
@@ -152,8 +154,69 @@ __device__ __forceinline__ int dp_filter_sample(RowFn row, const uint32_t* cw, i
   return (acc + (hi << alftab::HI_SHIFT)) >> 9;
 }
 
+// Laplacian work of one thread: a column of quads (4x4 samples at (x0 - 2 + 4 qj, y0 - 2 + 4 qi) of a work tile), two samples per
+// instruction.  Quad qi reads work-tile rows 4 qi .. 4 qi + 5, words 2 + 2 qj .. 5 + 2 qj with a rolling 3-row window that carries
+// on into the quad below.  Everything is plain 32-bit arithmetic on biased lanes (no lane ever borrows or carries): with
+// K = 2^(bd+1), t' = 2c + K - a - b lies in (0, 2K), and max(t', 2K - t') = K + |2c - a - b|; four rows of a lane stay below 2^16 up
+// to 12 bit.  (__vsub2 / __vneg2 and the packed abs-diffs are multi-instruction emulations on sm_100a.)  A row comes in four parts
+// so that the caller can spread it between other instructions: these run on the ALU pipe, the dot-product filter on the FMA
+// pipe, and one warp can keep both busy.
+struct LapTask {
+  const uint32_t* wp;
+  uint32_t lap_k, lap_k2;
+  // per column j: centre / left-shifted / right-shifted word of the row above (u), of the current row (m) and of the row below (d)
+  uint32_t cu[2], lu[2], ru[2], cm[2], lm[2], rm[2], cd[2], ld[2], rd[2];
+  uint32_t av[2], ah[2], ad0[2], ad1[2];
+  __device__ __forceinline__ void load_row(int r, uint32_t (&c)[2], uint32_t (&l)[2], uint32_t (&rr)[2]) const {
+    const uint2 a = *reinterpret_cast<const uint2*>(wp + r * (WP / 2)), b = *reinterpret_cast<const uint2*>(wp + r * (WP / 2) + 2);
+    const uint32_t f12 = __funnelshift_r(a.y, b.x, 16);
+    c[0] = a.y; c[1] = b.x; l[0] = __funnelshift_r(a.x, a.y, 16); rr[0] = f12; l[1] = f12; rr[1] = __funnelshift_r(b.x, b.y, 16);
+  }
+  __device__ __forceinline__ void begin(const int16_t* W, int qi, int qj, uint32_t k) {
+    wp = reinterpret_cast<const uint32_t*>(W) + (4 * qi) * (WP / 2) + 2 + 2 * qj;
+    lap_k = k; lap_k2 = k << 1;
+    load_row(0, cu, lu, ru);
+    load_row(1, cm, lm, rm);
+    wp += 2 * (WP / 2);
+    av[0] = av[1] = ah[0] = ah[1] = ad0[0] = ad0[1] = ad1[0] = ad1[1] = 0;
+  }
+  // The next row of the column (rows 4n .. 4n + 3 make quad n) in four parts k = 0..3 (in order)
+  __device__ __forceinline__ void part(int k) {
+    if (k == 0) { load_row(0, cd, ld, rd); wp += WP / 2; }
+    const int j = k >> 1;
+    const uint32_t c2k = cm[j] + cm[j] + lap_k;
+    uint32_t u;
+    if ((k & 1) == 0) {
+      u = c2k - cu[j] - cd[j]; const uint32_t v = __vmaxu2(u, lap_k2 - u);     // K + |2c - up - down|
+      u = c2k - lm[j] - rm[j]; const uint32_t h = __vmaxu2(u, lap_k2 - u);     // K + |2c - left - right|
+      av[j] += v; ah[j] += h;
+    } else {
+      u = c2k - lu[j] - rd[j]; const uint32_t d0 = __vmaxu2(u, lap_k2 - u);    // K + |2c - up-left - down-right|
+      u = c2k - ru[j] - ld[j]; const uint32_t d1 = __vmaxu2(u, lap_k2 - u);    // K + |2c - up-right - down-left|
+      ad0[j] += d0; ad1[j] += d1;
+      cu[j] = cm[j]; lu[j] = lm[j]; ru[j] = rm[j]; cm[j] = cd[j]; lm[j] = ld[j]; rm[j] = rd[j];
+    }
+  }
+  __device__ __forceinline__ void row() {
+#pragma unroll
+    for (int k = 0; k < 4; k++) part(k);
+  }
+  // {V, H, D0, D1} of the quad just finished (and the sums start again for the quad below): IDP.2A against {1, 1} adds both halves
+  // of a word in 32 bits; a quad collected K sixteen times
+  __device__ __forceinline__ uint4 fold() {
+    const uint32_t quad_bias = 0u - ((lap_k & 0xFFFFu) << 4);
+    uint4 o;
+    o.x = dp2a_uu(av[0], 0x0101u, dp2a_uu(av[1], 0x0101u, quad_bias));
+    o.y = dp2a_uu(ah[0], 0x0101u, dp2a_uu(ah[1], 0x0101u, quad_bias));
+    o.z = dp2a_uu(ad0[0], 0x0101u, dp2a_uu(ad0[1], 0x0101u, quad_bias));
+    o.w = dp2a_uu(ad1[0], 0x0101u, dp2a_uu(ad1[1], 0x0101u, quad_bias));
+    av[0] = av[1] = ah[0] = ah[1] = ad0[0] = ad0[1] = ad1[0] = ad1[1] = 0;
+    return o;
+  }
+};
+
 // Luma block, dot-product path: wp = window row 0 (block row 0 minus 3), sample x - 4; tab = the block's table entry.
-template <int RT>
+template <int RT, bool HI_CENTRE>
 __device__ __forceinline__ void filter_block_dp(const int16_t* wp, const uint32_t* __restrict__ tab, int16_t* __restrict__ out, int pitch, int max_val) {
   uint32_t cw[alftab::LUMA_WORDS];
   {
@@ -173,12 +236,65 @@ __device__ __forceinline__ void filter_block_dp(const int16_t* wp, const uint32_
     load(o + 3 + RT);
     int r[4];
 #pragma unroll
-    for (int j = 0; j < 4; j++) r[j] = __vimin_s32_relu(dp_filter_sample<3, RT, 4>([&](int dy) { return w[o + 3 + dy]; }, cw, j), max_val);
+    for (int j = 0; j < 4; j++) r[j] = __vimin_s32_relu(dp_filter_sample<3, RT, 4, HI_CENTRE>([&](int dy) { return w[o + 3 + dy]; }, cw, j), max_val);
     *reinterpret_cast<uint2*>(out + (size_t)o * pitch) = make_uint2(__byte_perm(r[0], r[1], 0x5410), __byte_perm(r[2], r[3], 0x5410));
   }
 }
 
+// The hot path: 7x7 dot-product filter of a block interleaved with the thread's quads of the NEXT tile (lap.begin was called).
+// The SM's instruction caches decide how this is written: a straight-line block (16 samples x 20 IDP + a quad = 600 instructions,
+// 10 KB) next to the rest of the tile loop does not fit the per-sub-partition L0 cache, every instruction is then fetched from
+// the SM's instruction cache and THAT becomes the limiter (ncu: sm__icc_requests at 70 % of peak, issue slots 65 % used, no
+// pipe above 55 %).  So the block is a LOOP over pairs of output rows (8 window rows are re-read per pair: 24 instead of 15
+// bytes of shared memory per sample, which the LSU pipe has to spare), 2 output rows + 2 Laplacian rows per trip.  Threads that
+// own a second quad (the tile's bottom quad row) take two more trips without the filter part (nquads = 2).
+template <bool HI_CENTRE>
+__device__ __forceinline__ void filter_block_fused(const int16_t* wp, const uint32_t* __restrict__ tab, int16_t* __restrict__ out, int pitch, int max_val, LapTask& lap, int nquads,
+                                                   uint4* q0, uint4* q1) {
+  uint32_t cw[alftab::LUMA_WORDS];
+  {
+    const uint4* tp = reinterpret_cast<const uint4*>(tab);
+#pragma unroll
+    for (int i = 0; i < alftab::LUMA_WORDS / 4; i++) { const uint4 v = __ldg(tp + i); cw[4 * i] = v.x; cw[4 * i + 1] = v.y; cw[4 * i + 2] = v.z; cw[4 * i + 3] = v.w; }
+  }
+#pragma unroll 1
+  for (int it = 0; it < 2 * nquads; it++) {
+    if (it < 2) {
+      uint32_t w[8][6];  // w[s][m] = samples (x - 4 + 2m, x - 3 + 2m) of window row 2 it + s
+#pragma unroll
+      for (int s = 0; s < 8; s++) {
+        const uint2 a = *reinterpret_cast<const uint2*>(wp + s * WP), b = *reinterpret_cast<const uint2*>(wp + s * WP + 4), c = *reinterpret_cast<const uint2*>(wp + s * WP + 8);
+        w[s][0] = a.x; w[s][1] = a.y; w[s][2] = b.x; w[s][3] = b.y; w[s][4] = c.x; w[s][5] = c.y;
+      }
+#pragma unroll
+      for (int o = 0; o < 2; o++) {
+        int r[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          lap.part(j);
+          r[j] = __vimin_s32_relu(dp_filter_sample<3, 3, 4, HI_CENTRE>([&](int dy) { return w[o + 3 + dy]; }, cw, j), max_val);
+        }
+        *reinterpret_cast<uint2*>(out + (size_t)o * pitch) = make_uint2(__byte_perm(r[0], r[1], 0x5410), __byte_perm(r[2], r[3], 0x5410));
+      }
+      wp += 2 * WP;
+      out += 2 * (size_t)pitch;
+    } else {
+      lap.row();
+      lap.row();
+    }
+    if (it & 1) {
+      const uint4 q = lap.fold();
+      if (it == 1) *q0 = q; else if (q1) *q1 = q;
+    }
+  }
+}
+
 // Luma CTA: band blockIdx.y, horizontal segment blockIdx.x of nseg.
+//
+// Software pipeline over the tiles of the walk: while a thread filters its block of tile t (phase 4) it computes its quads of
+// tile t + 1 (phase 2).  Thread (bi, bj) owns quad (bi, bj + 1); the threads of the last block row also own the tile's bottom quad
+// row (8, bj + 1); quad column 0 of a tile is column 16 of the tile before it and is copied, not computed.  One CTA barrier per
+// tile publishes the quads of tile t + 1 and frees the stage of tile t, which thread 0 refills right after it.
 template <bool CLASSIFY_ONLY>
 __device__ __forceinline__ void alf_luma_cta(unsigned char* smem, const Geom& g, const SlotDev& sd, unsigned ctl, int nseg) {
   if (ctl_skip(ctl, 0) || (int)blockIdx.x >= nseg) return;
@@ -187,125 +303,110 @@ __device__ __forceinline__ void alf_luma_cta(unsigned char* smem, const Geom& g,
   const int ntx = (g.width + TW - 1) / TW;
   const int ta = (int)blockIdx.x * ntx / nseg, tb = ((int)blockIdx.x + 1) * ntx / nseg;
   if (ta >= tb) return;
-  ring::Walk<RING_STAGES> walk;
-  walk.first = ta; walk.last = tb - 1;
-  // {V, H, D0, D1} per quad, double-buffered: tile t + 1 fills the other half while slower threads still read tile t's
-  uint4(*quad_buf)[QH][QW] = reinterpret_cast<uint4(*)[QH][QW]>(smem + RING_STAGES * L_STAGE_STRIDE);
+  uint4(*quad_buf)[QH][QW] = reinterpret_cast<uint4(*)[QH][QW]>(smem + RING_STAGES * L_STAGE_STRIDE);  // {V, H, D0, D1} per quad, two tiles
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + RING_STAGES * L_STAGE_STRIDE + L_CELL_BYTES);
   uint8_t* en_s = smem + RING_STAGES * L_STAGE_STRIDE + L_CELL_BYTES + RING_STAGES * 8;  // ALF flag of the CTUs of this band's CTU row, from column c0
+  uint8_t* on_s = en_s + L_EN_BYTES;                                                      // per tile of the walk: ALF on in any CTU under it
   const int y0 = (int)blockIdx.y * BR;  // local rows
   const int src_buf = ctl_src(ctl, 0);
   const CUtensorMap* map = &sd.tm_alf[0];
-  auto stage_ptr = [&](int t) { return reinterpret_cast<int16_t*>(smem + walk.stage(t) * L_STAGE_STRIDE); };
-  auto issue = [&](int t) {
-    uint64_t* bar = &full[walk.stage(t)];
-    ring::mbar_expect_tx(bar, L_STAGE_BYTES);
-    ring::tma_load_3d(stage_ptr(t), map, bar, t * TW - WX0, y0 - ALF_HALO_Y, src_buf);
+  auto issue = [&](int t, int stage) {
+    ring::mbar_expect_tx(&full[stage], L_STAGE_BYTES);
+    ring::tma_load_3d(smem + stage * L_STAGE_STRIDE, map, &full[stage], t * TW - WX0, y0 - ALF_HALO_Y, src_buf);
   };
   if (tid == 0) {
     for (int i = 0; i < RING_STAGES; i++) ring::mbar_init(&full[i], 1);
     ring::mbar_init_fence();
     pdl_wait();  // the stage before this one has written the planes read from here on
-    for (int t = walk.first; t <= walk.last && t < walk.first + RING_STAGES; t++) issue(t);
+    for (int i = 0; i < RING_STAGES && ta + i < tb; i++) issue(ta + i, i);
   }
   // this thread's 4x4 block of every tile: BPR blocks across, 8 block rows
   const int bj = tid % BPR, bi = tid / BPR;
   const int by = y0 + 4 * bi;
   const int c0 = (ta * TW) >> g.ctu_log2, c1 = min(g.ctus_w - 1, (tb * TW - 1) >> g.ctu_log2);  // CTU columns this walk touches
+  const uint8_t* __restrict__ en_row = sd.alf_ctu_enable + (size_t)((y0 + g.row0) >> g.ctu_log2) * g.ctus_w;  // a band lies in one CTU row
   if (!CLASSIFY_ONLY) {
-    const uint8_t* __restrict__ en_row = sd.alf_ctu_enable + (size_t)((y0 + g.row0) >> g.ctu_log2) * g.ctus_w;  // a band lies in one CTU row
     for (int c = c0 + tid; c <= c1; c += NT) en_s[c - c0] = en_row[c];
+    for (int t = ta + tid; t < tb; t += NT) {
+      bool any = false;
+      for (int c = (t * TW) >> g.ctu_log2; c <= min(c1, (t * TW + TW - 1) >> g.ctu_log2); c++) any |= en_row[c] != 0;
+      on_s[t - ta] = any;
+    }
   }
   int16_t* __restrict__ dst = sd.buf[ctl_dst(ctl, 0)][0];
   const int max_val = (1 << g.bd_luma) - 1;
   const bool is7 = CLASSIFY_ONLY ? true : (ctl & CTL_ALF_7X7) != 0;
   const bool dot = CLASSIFY_ONLY ? false : (ctl & CTL_ALF_DOT_Y) != 0;  // dot-product path (ilf_alf_tab.cuh), else the general path
+  const bool hi_centre = (ctl & CTL_ALF_HIC_Y) != 0;                    // only the centre coefficient has a high part
   const int shift = g.bd_luma + 4;
-  const uint32_t lap_k = 0x10001u << (g.bd_luma + 1), lap_k2 = lap_k << 1;  // Laplacian lane bias K, 2K
-  const uint32_t quad_bias = 0u - (16u << (g.bd_luma + 1));                       // a quad collects K sixteen times
+  const uint32_t lap_k = 0x10001u << (g.bd_luma + 1);  // Laplacian lane bias K in both lanes
+  const bool vborder = y0 - ALF_HALO_Y < 0 || y0 - ALF_HALO_Y + L_SR > rows;
+  const bool bottom_row = bi == BR / 4 - 1;   // this thread also owns quad (8, bj + 1)
+  const bool long_warp = tid >= NT - 32;      // the warp that holds the last block row runs two quads per thread
   __syncthreads();  // barriers initialised, flags staged
   pdl_wait();  // every thread: this kernel's stores must not overtake the previous stage's reads either
 
-  // One CTA barrier per tile: it publishes the tile's quads, and -- because every thread has then finished the previous
-  // tile -- it also frees the previous tile's stage, which thread 0 refills right after it.
-  for (int tx = ta; tx < tb; tx++) {
-    ring::mbar_wait(&full[walk.stage(tx)], walk.parity(tx));
-    const int x0 = tx * TW, bx = x0 + 4 * bj;
+  // tile t has landed in `stage`: border padding (phase 1), CTA-uniform; returns whether ALF is on anywhere under the tile
+  auto prepare = [&](int t, int stage, uint32_t parity) {
+    ring::mbar_wait(&full[stage], parity);
+    const bool on = CLASSIFY_ONLY || on_s[t - ta] != 0;
+    if (on && (vborder || t == 0 || t == ntx - 1))
+      pad_borders<L_SR, ALF_HALO_Y, NT>(reinterpret_cast<int16_t*>(smem + stage * L_STAGE_STRIDE), t == 0, t == ntx - 1, min(TW, g.width - t * TW), y0 - ALF_HALO_Y, rows);
+    return on;
+  };
+  auto lap_quad = [&](const int16_t* W, int qi, int qj, uint4(*quad)[QW]) {
+    LapTask lap;
+    lap.begin(W, qi, qj, lap_k);
+#pragma unroll
+    for (int i = 0; i < 4; i++) lap.row();
+    quad[qi][qj] = lap.fold();
+  };
+  // the quads of this thread, not interleaved with anything
+  auto lap_own = [&](const int16_t* W, uint4(*quad)[QW]) {
+    lap_quad(W, bi, bj + 1, quad);
+    if (bottom_row) lap_quad(W, bi + 1, bj + 1, quad);
+  };
+
+  int stage = 0;
+  uint32_t parity = 0;
+  bool on = prepare(ta, 0, 0);
+  if (on) {
+    lap_own(reinterpret_cast<const int16_t*>(smem), quad_buf[0]);
+    if (tid < QH) lap_quad(reinterpret_cast<const int16_t*>(smem), tid, 0, quad_buf[0]);
+  }
+  __syncthreads();
+  int16_t* out = dst + (size_t)by * g.pitch_y + ta * TW + 4 * bj;
+  for (int tx = ta; tx < tb; tx++, out += TW) {
+    const int bx = tx * TW + 4 * bj;
     const bool blk_in = bx < g.width && by < rows;
-    bool any_en = CLASSIFY_ONLY, en = CLASSIFY_ONLY && blk_in;
-    if (!CLASSIFY_ONLY) {
-      // CTA-uniform: is ALF on in any CTU under this tile?
-      for (int c = x0 >> g.ctu_log2; c <= min(c1, (x0 + TW - 1) >> g.ctu_log2); c++) any_en |= en_s[c - c0] != 0;
-      en = blk_in && en_s[min(c1, bx >> g.ctu_log2) - c0] != 0;
-    }
-    int16_t* W = stage_ptr(tx);
-    int16_t* out = dst + (size_t)by * g.pitch_y + bx;
+    const bool en = on && blk_in && (CLASSIFY_ONLY || en_s[min(c1, bx >> g.ctu_log2) - c0] != 0);
+    const int16_t* W = reinterpret_cast<const int16_t*>(smem + stage * L_STAGE_STRIDE);
     uint4(*quad)[QW] = quad_buf[(tx - ta) & 1];
-    if (!any_en) {
+    uint4(*quad_next)[QW] = quad_buf[(tx + 1 - ta) & 1];
+    const int stage1 = stage + 1 == RING_STAGES ? 0 : stage + 1;
+    const uint32_t parity1 = stage1 == 0 ? parity ^ 1 : parity;
+    const bool on_next = tx + 1 < tb && prepare(tx + 1, stage1, parity1);
+    const int16_t* W1 = reinterpret_cast<const int16_t*>(smem + stage1 * L_STAGE_STRIDE);
+    if (on_next && tid < QH) {
+      if (on) quad_next[tid][0] = quad[tid][QW - 1];   // quad column 0 of the next tile = column 16 of this one
+      else lap_quad(W1, tid, 0, quad_next);
+    }
+    const bool fuse = on_next && en && dot && is7;   // this thread interleaves its quads of the next tile with its filter
+    if (on_next && !fuse) lap_own(W1, quad_next);
+    if (!on) {
       // every CTU under this tile has ALF off: copy through
       if (blk_in) {
 #pragma unroll
         for (int o = 0; o < 4; o++) *reinterpret_cast<uint2*>(out + (size_t)o * g.pitch_y) = *reinterpret_cast<const uint2*>(W + (ALF_HALO_Y + 4 * bi + o) * WP + WX0 + 4 * bj);
       }
-      __syncthreads();
-      if (tid == 0 && tx > ta && tx - 1 + RING_STAGES <= walk.last) issue(tx - 1 + RING_STAGES);
     } else {
-      // ---- phase 1: the stage is the work tile; border tiles get their padding ----
-      pad_borders<L_SR, ALF_HALO_Y, NT>(W, tx == 0, tx == ntx - 1, min(TW, g.width - x0), y0 - ALF_HALO_Y, rows);
-
-      // ---- phase 2: Laplacians per quad (4x4 samples at (x0 - 2 + 4 qj, y0 - 2 + 4 qi)), two samples per instruction.  A task loads
-      //      work-tile rows 4 qi .. 4 qi + 5, words 2 + 2 qj .. 5 + 2 qj.  Everything is plain 32-bit arithmetic on biased lanes
-      //      (no lane ever borrows or carries): with K = 2^(bd+1), t' = 2c + K - a - b lies in (0, 2K), and
-      //      max(t', 2K - t') = K + |2c - a - b|; four rows of a lane stay below 2^16 up to 12 bit.  (__vsub2 / __vneg2 and the
-      //      packed abs-diffs are multi-instruction emulations on sm_100a.) ----
-      for (int t = tid; t < QW * QH; t += NT) {
-        const int qj = t % QW, qi = t / QW;
-        const uint32_t* wp = reinterpret_cast<const uint32_t*>(W) + (4 * qi) * (WP / 2) + 2 + 2 * qj;
-        // per column j: centre / left-shifted / right-shifted word of the rows above (u), at (m) and below (d)
-        uint32_t cu[2], lu[2], ru[2], cm[2], lm[2], rm[2], cd[2], ld[2], rd[2];
-        auto load_row = [&](int r, uint32_t (&c)[2], uint32_t (&l)[2], uint32_t (&rr)[2]) {
-          const uint2 a = *reinterpret_cast<const uint2*>(wp + r * (WP / 2)), b = *reinterpret_cast<const uint2*>(wp + r * (WP / 2) + 2);
-          const uint32_t f12 = __funnelshift_r(a.y, b.x, 16);
-          c[0] = a.y; c[1] = b.x; l[0] = __funnelshift_r(a.x, a.y, 16); rr[0] = f12; l[1] = f12; rr[1] = __funnelshift_r(b.x, b.y, 16);
-        };
-        load_row(0, cu, lu, ru);
-        load_row(1, cm, lm, rm);
-        uint32_t av[2], ah[2], ad0[2], ad1[2];
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-          load_row(i + 2, cd, ld, rd);
-#pragma unroll
-          for (int j = 0; j < 2; j++) {
-            const uint32_t c2k = cm[j] + cm[j] + lap_k;
-            uint32_t u;
-            u = c2k - cu[j] - cd[j]; const uint32_t v = __vmaxu2(u, lap_k2 - u);     // K + |2c - up - down|
-            u = c2k - lm[j] - rm[j]; const uint32_t h = __vmaxu2(u, lap_k2 - u);     // K + |2c - left - right|
-            u = c2k - lu[j] - rd[j]; const uint32_t d0 = __vmaxu2(u, lap_k2 - u);    // K + |2c - up-left - down-right|
-            u = c2k - ru[j] - ld[j]; const uint32_t d1 = __vmaxu2(u, lap_k2 - u);    // K + |2c - up-right - down-left|
-            if (i == 0) { av[j] = v; ah[j] = h; ad0[j] = d0; ad1[j] = d1; }
-            else { av[j] += v; ah[j] += h; ad0[j] += d0; ad1[j] += d1; }
-            cu[j] = cm[j]; lu[j] = lm[j]; ru[j] = rm[j]; cm[j] = cd[j]; lm[j] = ld[j]; rm[j] = rd[j];
-          }
-        }
-        // fold the four lanes of each direction: IDP.2A against {1, 1} adds both halves of a word in 32 bits
-        uint4 o;
-        o.x = dp2a_uu(av[0], 0x0101u, dp2a_uu(av[1], 0x0101u, quad_bias));
-        o.y = dp2a_uu(ah[0], 0x0101u, dp2a_uu(ah[1], 0x0101u, quad_bias));
-        o.z = dp2a_uu(ad0[0], 0x0101u, dp2a_uu(ad0[1], 0x0101u, quad_bias));
-        o.w = dp2a_uu(ad1[0], 0x0101u, dp2a_uu(ad1[1], 0x0101u, quad_bias));
-        quad[qi][qj] = o;
-      }
-      __syncthreads();
-      if (tid == 0 && tx > ta && tx - 1 + RING_STAGES <= walk.last) issue(tx - 1 + RING_STAGES);
-
       // ---- phase 3: the block's 8x8 window = quads (bi, bj) .. (bi + 1, bj + 1) -> class ----
       const uint4 q00 = quad[bi][bj], q01 = quad[bi][bj + 1], q10 = quad[bi + 1][bj], q11 = quad[bi + 1][bj + 1];
       const int sv = (int)(q00.x + q01.x + q10.x + q11.x), sh = (int)(q00.y + q01.y + q10.y + q11.y);
       const int sd0 = (int)(q00.z + q01.z + q10.z + q11.z), sd1 = (int)(q00.w + q01.w + q10.w + q11.w);
       const int cl = classify(sv, sh, sd0, sd1, shift);
       if (CLASSIFY_ONLY) {
-        const int ux = bx >> 2, uy = by >> 2;
-        if (blk_in) sd.alf_class[(size_t)uy * g.units_w + ux] = (uint8_t)cl;
+        if (blk_in) sd.alf_class[(size_t)(by >> 2) * g.units_w + (bx >> 2)] = (uint8_t)cl;
       } else if (blk_in) {
         // ---- phase 4: filter the block ----
         const int16_t* wp = W + (4 * bi) * WP + WX0 + 4 * bj - 4;  // window row 0 (= block row 0 minus 3), sample x - 4
@@ -314,9 +415,24 @@ __device__ __forceinline__ void alf_luma_cta(unsigned char* smem, const Geom& g,
           for (int o = 0; o < 4; o++) *reinterpret_cast<uint2*>(out + (size_t)o * g.pitch_y) = *reinterpret_cast<const uint2*>(wp + (3 + o) * WP + 4);
         } else if (dot) {
           const uint32_t* tab = sd.alf_coef_dp + ((cl & 31) * 4 + (cl >> 5)) * alftab::LUMA_WORDS;
-          if (is7) filter_block_dp<3>(wp, tab, out, g.pitch_y, max_val);
-          else filter_block_dp<2>(wp, tab, out, g.pitch_y, max_val);
+          if (fuse) {
+            LapTask lap;
+            lap.begin(W1, bi, bj + 1, lap_k);
+            uint4* q0 = &quad_next[bi][bj + 1];
+            uint4* q1 = bottom_row ? &quad_next[bi + 1][bj + 1] : nullptr;
+            if (hi_centre) filter_block_fused<true>(wp, tab, out, g.pitch_y, max_val, lap, long_warp ? 2 : 1, q0, q1);
+            else filter_block_fused<false>(wp, tab, out, g.pitch_y, max_val, lap, long_warp ? 2 : 1, q0, q1);
+          } else if (is7) {
+            if (hi_centre) filter_block_dp<3, true>(wp, tab, out, g.pitch_y, max_val);
+            else filter_block_dp<3, false>(wp, tab, out, g.pitch_y, max_val);
+          } else {
+            if (hi_centre) filter_block_dp<2, true>(wp, tab, out, g.pitch_y, max_val);
+            else filter_block_dp<2, false>(wp, tab, out, g.pitch_y, max_val);
+          }
         } else {
+#ifdef ALF_DOT_ONLY  // diagnosis: how much does the size of the kernel (instruction cache) cost?
+          __trap();
+#else
           int f[16];
           {
             const int4* cp = reinterpret_cast<const int4*>(sd.alf_coef + ((cl & 31) * 4 + (cl >> 5)) * 16);
@@ -367,9 +483,14 @@ __device__ __forceinline__ void alf_luma_cta(unsigned char* smem, const Geom& g,
               *reinterpret_cast<uint2*>(out + (size_t)o * g.pitch_y) = make_uint2(p0, p1);
             }
           }
+#endif
         }
       }
     }
+    __syncthreads();  // quads of tile tx + 1 complete; nobody reads the stage of tile tx any more
+    if (tid == 0 && tx + RING_STAGES < tb) issue(tx + RING_STAGES, stage);
+    on = on_next;
+    stage = stage1; parity = parity1;
   }
 }
 
@@ -428,6 +549,7 @@ __device__ __forceinline__ void alf_chroma_cta(unsigned char* smem, const Geom& 
   int f[7];
 #pragma unroll
   for (int i = 0; i < 7; i++) f[i] = sd.alf->chroma_coeff[i];
+  const bool hi_centre = (ctl & CTL_ALF_HIC_C) != 0;
   const bool dot = (ctl & CTL_ALF_DOT_C) != 0;  // dot-product path (ilf_alf_tab.cuh), else the general path
   uint32_t ccw[alftab::CHROMA_WORDS];
   {
@@ -476,7 +598,8 @@ __device__ __forceinline__ void alf_chroma_cta(unsigned char* smem, const Geom& 
             if (o >= nrows) break;
             int r[8];
 #pragma unroll
-            for (int j = 0; j < 8; j++) r[j] = __vimin_s32_relu(dp_filter_sample<2, 2, 2>([&](int dy) { return w[o + 2 + dy]; }, ccw, j), max_val);
+            for (int j = 0; j < 8; j++)
+              r[j] = __vimin_s32_relu(hi_centre ? dp_filter_sample<2, 2, 2, true>([&](int dy) { return w[o + 2 + dy]; }, ccw, j) : dp_filter_sample<2, 2, 2, false>([&](int dy) { return w[o + 2 + dy]; }, ccw, j), max_val);
             *reinterpret_cast<uint4*>(out + (size_t)o * g.pitch_c) =
                 make_uint4(__byte_perm(r[0], r[1], 0x5410), __byte_perm(r[2], r[3], 0x5410), __byte_perm(r[4], r[5], 0x5410), __byte_perm(r[6], r[7], 0x5410));
           }

@@ -8,7 +8,7 @@
 // output parity.
 //
 // Coefficients are int16 in the bitstream; the ones next to the centre and the centre itself are often outside int8
-// (centre ~ 150..1000 of 512 = 1.0).  Every tap with |dx| + |dy| <= 1 is therefore split c = lo + 128 hi, lo in [-64, 63],
+// (centre ~ 150..1000 of 512 = 1.0).  A tap with |dx| + |dy| <= 1 outside int8 is therefore split c = lo + 128 hi, lo in [-64, 63],
 // and the high parts form a second, radius-1 diamond (4 slots per parity) whose sum is shifted left by 7.  All other taps
 // must fit int8 -- true for the filters real encoders produce at >= 1080p, not guaranteed; ilf_set_alf_params checks
 // the picture's filters and selects the general 32-bit multiply path when one does not fit (bit-exact either way).
@@ -61,24 +61,28 @@ constexpr int LUMA_WORDS = 20, CHROMA_WORDS = 16 /* 14 used */;
 constexpr int HI_SHIFT = 7;
 
 // Host side: builds one entry from the coefficients f[] (reference order of the radius-RT diamond) in a radius-R layout.
-// Returns false when a coefficient does not fit the layout (the caller then uses the general path).
+// Returns false when a coefficient does not fit the layout (the caller then uses the general path); *neigh_hi is set when one of
+// the four neighbours of the centre needed a high part (else only the centre has one and the kernels skip three of the four
+// high-part slots).
 template <int R, int RT>
-inline bool build_entry(const int* f, uint32_t* out, int nwords) {
+inline bool build_entry(const int* f, uint32_t* out, int nwords, bool* neigh_hi) {
   for (int i = 0; i < nwords; i++) out[i] = 0;
   bool ok = true;
+  auto hi_of = [](int c) { return c >= -128 && c <= 127 ? 0 : (c + 64) >> HI_SHIFT; };
   auto lo_part = [&](int dx, int dy) -> int {
     const int k = coef_index<RT>(dx, dy);
     if (k < 0) return 0;
     const int c = f[k];
-    if (iabs(dx) + iabs(dy) <= 1) return c - (((c + 64) >> HI_SHIFT) << HI_SHIFT);
+    if (iabs(dx) + iabs(dy) <= 1) return c - (hi_of(c) << HI_SHIFT);
     if (c < -128 || c > 127) ok = false;
     return c;
   };
   auto hi_part = [&](int dx, int dy) -> int {
     const int k = coef_index<RT>(dx, dy);
     if (k < 0 || iabs(dx) + iabs(dy) > 1) return 0;
-    const int h = (f[k] + 64) >> HI_SHIFT;
+    const int h = hi_of(f[k]);
     if (h < -128 || h > 127) ok = false;
+    if (h && (dx || dy) && neigh_hi) *neigh_hi = true;
     return h;
   };
   const int nr = num_regs<R>();

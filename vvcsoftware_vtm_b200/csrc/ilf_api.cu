@@ -754,16 +754,16 @@ int ilf_set_alf_params(ilf_ctx* ctx, int slot, const ilf_alf_params* params, con
     // the general path.  ILF_ALF_GENERAL=1 forces the general path (measurement / parity aid).
     static const bool force_general = getenv("ILF_ALF_GENERAL") && atoi(getenv("ILF_ALF_GENERAL")) != 0;
     uint32_t dp[ALF_DP_WORDS];
-    bool luma_ok = !force_general, chroma_ok = !force_general;
+    bool luma_ok = !force_general, chroma_ok = !force_general, luma_nhi = false, chroma_nhi = false;
     for (int cl = 0; cl < 25 && luma_ok; cl++)
       for (int tr = 0; tr < 4; tr++) {
         uint32_t* e = dp + (cl * 4 + tr) * alftab::LUMA_WORDS;
-        luma_ok &= is7 ? alftab::build_entry<3, 3>(tab[cl][tr], e, alftab::LUMA_WORDS) : alftab::build_entry<3, 2>(tab[cl][tr], e, alftab::LUMA_WORDS);
+        luma_ok &= is7 ? alftab::build_entry<3, 3>(tab[cl][tr], e, alftab::LUMA_WORDS, &luma_nhi) : alftab::build_entry<3, 2>(tab[cl][tr], e, alftab::LUMA_WORDS, &luma_nhi);
       }
     int fc[7];
     for (int k = 0; k < 7; k++) fc[k] = params->chroma_coeff[k];
-    chroma_ok = chroma_ok && alftab::build_entry<2, 2>(fc, dp + 25 * 4 * alftab::LUMA_WORDS, alftab::CHROMA_WORDS);
-    s.dev.alf_mode = (luma_ok ? 1 : 0) | (chroma_ok ? 2 : 0);
+    chroma_ok = chroma_ok && alftab::build_entry<2, 2>(fc, dp + 25 * 4 * alftab::LUMA_WORDS, alftab::CHROMA_WORDS, &chroma_nhi);
+    s.dev.alf_mode = (luma_ok ? 1 : 0) | (chroma_ok ? 2 : 0) | (luma_ok && !luma_nhi ? 4 : 0) | (chroma_ok && !chroma_nhi ? 8 : 0);
     s.alf_is7 = is7;
     if (int rc = stage_side(ctx, s, s.alf_coef_dp, dp, sizeof(dp), cur, lim)) return rc;
   }
@@ -840,7 +840,8 @@ static int run_stage(ilf_ctx* ctx, int first, int n, int stage) {
         if (!on[i][p]) { v |= 1u << (6 + p); continue; }
         s.result_buf[p] = s.result_buf[p] == 1 ? 2 : 1;
       }
-      if (stage == 2) v |= ((s.dev.alf_mode & 1) ? CTL_ALF_DOT_Y : 0) | ((s.dev.alf_mode & 2) ? CTL_ALF_DOT_C : 0) | (s.alf_is7 ? CTL_ALF_7X7 : 0);
+      if (stage == 2) v |= ((s.dev.alf_mode & 1) ? CTL_ALF_DOT_Y : 0) | ((s.dev.alf_mode & 2) ? CTL_ALF_DOT_C : 0) | (s.alf_is7 ? CTL_ALF_7X7 : 0) |
+                       ((s.dev.alf_mode & 4) ? CTL_ALF_HIC_Y : 0) | ((s.dev.alf_mode & 8) ? CTL_ALF_HIC_C : 0);
       word[i] = (uint16_t)v;
     }
     auto compact = [&](bool use_y, bool use_c, BatchCtl& ctl, double& bytes) {
@@ -1039,7 +1040,7 @@ long long ilf_launch_count(const ilf_ctx* ctx) { return ctx ? ctx->launches : 0;
 int ilf_alf_path(ilf_ctx* ctx, int slot) {
   if (int rc = check_slot(ctx, slot)) return rc;
   if (!ctx->slots[slot].has_alf) return fail(ctx, ILF_ERR_STATE, "slot %d: ALF parameters not set", slot);
-  return ctx->slots[slot].dev.alf_mode;
+  return ctx->slots[slot].dev.alf_mode & 3;
 }
 
 int ilf_slot_input_planes(ilf_ctx* ctx, int slot, void* planes[3], int32_t pitch[3]) {
