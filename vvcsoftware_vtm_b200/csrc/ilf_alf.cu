@@ -126,9 +126,11 @@ __device__ __forceinline__ uint32_t dp2a_uu(uint32_t a, uint32_t b, uint32_t c) 
 // RT = radius of the filter (RT < R: a 5x5 luma filter in the 7x7 layout; its empty slots are skipped at compile time).
 // HI_CENTRE: only the centre coefficient has a high part (the usual case: its four neighbours fit int8) -- one IDP instead of four.
 // row(dy) gives the packed words of window row y + dy; word m of a row holds the samples at x offsets 2m - XOFF, 2m - XOFF + 1
-// from output sample 0 of the thread, j = index of this output sample.  Everything folds at compile time once unrolled.
+// from output sample 0 of the thread, j = index of this output sample.  Rows -RT and +RT hold one tap each with the same
+// coefficient (point symmetry): top_bottom, when given, is the packed SUM of the two rows and one IDP serves both.
+// Everything folds at compile time once unrolled.
 template <int R, int RT, int XOFF, bool HI_CENTRE, typename RowFn>
-__device__ __forceinline__ int dp_filter_sample(RowFn row, const uint32_t* cw, int j) {
+__device__ __forceinline__ int dp_filter_sample(RowFn row, const uint32_t* top_bottom, const uint32_t* cw, int j) {
   const int p = j & 1;
   constexpr int NR = alftab::num_regs<R>();
   int acc = 256, hi = 0;
@@ -137,8 +139,9 @@ __device__ __forceinline__ int dp_filter_sample(RowFn row, const uint32_t* cw, i
 #pragma unroll
     for (int q = 0; q <= R; q++) {
       if (!alftab::holds<R, RT>(p, dy, q)) continue;
-      const int s = alftab::slot<R>(p, dy, q);
-      const uint32_t ww = row(dy)[(j + alftab::dx0<R>(p, q) + XOFF) / 2];
+      if (top_bottom && dy == -RT) continue;
+      const int s = alftab::slot<R>(p, dy, q), m = (j + alftab::dx0<R>(p, q) + XOFF) / 2;
+      const uint32_t ww = top_bottom && dy == RT ? top_bottom[m] : row(dy)[m];
       acc = (s & 1) ? dp2a_hi(ww, cw[p * NR + (s >> 1)], acc) : dp2a_lo(ww, cw[p * NR + (s >> 1)], acc);
     }
 #pragma unroll
@@ -154,66 +157,46 @@ __device__ __forceinline__ int dp_filter_sample(RowFn row, const uint32_t* cw, i
   return (acc + (hi << alftab::HI_SHIFT)) >> 9;
 }
 
-// Laplacian work of one thread: a column of quads (4x4 samples at (x0 - 2 + 4 qj, y0 - 2 + 4 qi) of a work tile), two samples per
-// instruction.  Quad qi reads work-tile rows 4 qi .. 4 qi + 5, words 2 + 2 qj .. 5 + 2 qj with a rolling 3-row window that carries
-// on into the quad below.  Everything is plain 32-bit arithmetic on biased lanes (no lane ever borrows or carries): with
-// K = 2^(bd+1), t' = 2c + K - a - b lies in (0, 2K), and max(t', 2K - t') = K + |2c - a - b|; four rows of a lane stay below 2^16 up
-// to 12 bit.  (__vsub2 / __vneg2 and the packed abs-diffs are multi-instruction emulations on sm_100a.)  A row comes in four parts
-// so that the caller can spread it between other instructions: these run on the ALU pipe, the dot-product filter on the FMA
-// pipe, and one warp can keep both busy.
-struct LapTask {
-  const uint32_t* wp;
-  uint32_t lap_k, lap_k2;
-  // per column j: centre / left-shifted / right-shifted word of the row above (u), of the current row (m) and of the row below (d)
-  uint32_t cu[2], lu[2], ru[2], cm[2], lm[2], rm[2], cd[2], ld[2], rd[2];
-  uint32_t av[2], ah[2], ad0[2], ad1[2];
-  __device__ __forceinline__ void load_row(int r, uint32_t (&c)[2], uint32_t (&l)[2], uint32_t (&rr)[2]) const {
+// Laplacians of one quad: 4x4 samples at (x0 - 2 + 4 qj, y0 - 2 + 4 qi) of a work tile, two samples per instruction.  Reads
+// work-tile rows 4 qi .. 4 qi + 5, words 2 + 2 qj .. 5 + 2 qj.  Everything is plain 32-bit arithmetic on biased lanes (no lane
+// ever borrows or carries): with K = 2^(bd+1), t' = 2c + K - a - b lies in (0, 2K), and max(t', 2K - t') = K + |2c - a - b|; four
+// rows of a lane stay below 2^16 up to 12 bit.  (__vsub2 / __vneg2 and the packed abs-diffs are multi-instruction emulations on
+// sm_100a.)  Returns {V, H, D0, D1}: IDP.2A against {1, 1} adds both halves of a word in 32 bits; a quad collected K sixteen times.
+__device__ __forceinline__ uint4 lap_quad(const int16_t* W, int qi, int qj, uint32_t lap_k) {
+  const uint32_t* wp = reinterpret_cast<const uint32_t*>(W) + (4 * qi) * (WP / 2) + 2 + 2 * qj;
+  const uint32_t lap_k2 = lap_k << 1;
+  // rows[r][j]: centre / left-shifted / right-shifted word of row r, column j
+  uint32_t c[6][2], l[6][2], rr[6][2];
+#pragma unroll
+  for (int r = 0; r < 6; r++) {
     const uint2 a = *reinterpret_cast<const uint2*>(wp + r * (WP / 2)), b = *reinterpret_cast<const uint2*>(wp + r * (WP / 2) + 2);
     const uint32_t f12 = __funnelshift_r(a.y, b.x, 16);
-    c[0] = a.y; c[1] = b.x; l[0] = __funnelshift_r(a.x, a.y, 16); rr[0] = f12; l[1] = f12; rr[1] = __funnelshift_r(b.x, b.y, 16);
+    c[r][0] = a.y; c[r][1] = b.x; l[r][0] = __funnelshift_r(a.x, a.y, 16); rr[r][0] = f12; l[r][1] = f12; rr[r][1] = __funnelshift_r(b.x, b.y, 16);
   }
-  __device__ __forceinline__ void begin(const int16_t* W, int qi, int qj, uint32_t k) {
-    wp = reinterpret_cast<const uint32_t*>(W) + (4 * qi) * (WP / 2) + 2 + 2 * qj;
-    lap_k = k; lap_k2 = k << 1;
-    load_row(0, cu, lu, ru);
-    load_row(1, cm, lm, rm);
-    wp += 2 * (WP / 2);
-    av[0] = av[1] = ah[0] = ah[1] = ad0[0] = ad0[1] = ad1[0] = ad1[1] = 0;
-  }
-  // The next row of the column (rows 4n .. 4n + 3 make quad n) in four parts k = 0..3 (in order)
-  __device__ __forceinline__ void part(int k) {
-    if (k == 0) { load_row(0, cd, ld, rd); wp += WP / 2; }
-    const int j = k >> 1;
-    const uint32_t c2k = cm[j] + cm[j] + lap_k;
-    uint32_t u;
-    if ((k & 1) == 0) {
-      u = c2k - cu[j] - cd[j]; const uint32_t v = __vmaxu2(u, lap_k2 - u);     // K + |2c - up - down|
-      u = c2k - lm[j] - rm[j]; const uint32_t h = __vmaxu2(u, lap_k2 - u);     // K + |2c - left - right|
-      av[j] += v; ah[j] += h;
-    } else {
-      u = c2k - lu[j] - rd[j]; const uint32_t d0 = __vmaxu2(u, lap_k2 - u);    // K + |2c - up-left - down-right|
-      u = c2k - ru[j] - ld[j]; const uint32_t d1 = __vmaxu2(u, lap_k2 - u);    // K + |2c - up-right - down-left|
-      ad0[j] += d0; ad1[j] += d1;
-      cu[j] = cm[j]; lu[j] = lm[j]; ru[j] = rm[j]; cm[j] = cd[j]; lm[j] = ld[j]; rm[j] = rd[j];
-    }
-  }
-  __device__ __forceinline__ void row() {
+  uint32_t acc[4][2];
 #pragma unroll
-    for (int k = 0; k < 4; k++) part(k);
+  for (int j = 0; j < 2; j++) {
+    uint32_t v[4][4];
+#pragma unroll
+    for (int r = 1; r <= 4; r++) {
+      const uint32_t c2k = c[r][j] + c[r][j] + lap_k;
+      uint32_t u;
+      u = c2k - c[r - 1][j] - c[r + 1][j]; v[0][r - 1] = __vmaxu2(u, lap_k2 - u);    // K + |2c - up - down|
+      u = c2k - l[r][j] - rr[r][j]; v[1][r - 1] = __vmaxu2(u, lap_k2 - u);           // K + |2c - left - right|
+      u = c2k - l[r - 1][j] - rr[r + 1][j]; v[2][r - 1] = __vmaxu2(u, lap_k2 - u);   // K + |2c - up-left - down-right|
+      u = c2k - rr[r - 1][j] - l[r + 1][j]; v[3][r - 1] = __vmaxu2(u, lap_k2 - u);   // K + |2c - up-right - down-left|
+    }
+#pragma unroll
+    for (int d = 0; d < 4; d++) acc[d][j] = (v[d][0] + v[d][1]) + v[d][2] + v[d][3];
   }
-  // {V, H, D0, D1} of the quad just finished (and the sums start again for the quad below): IDP.2A against {1, 1} adds both halves
-  // of a word in 32 bits; a quad collected K sixteen times
-  __device__ __forceinline__ uint4 fold() {
-    const uint32_t quad_bias = 0u - ((lap_k & 0xFFFFu) << 4);
-    uint4 o;
-    o.x = dp2a_uu(av[0], 0x0101u, dp2a_uu(av[1], 0x0101u, quad_bias));
-    o.y = dp2a_uu(ah[0], 0x0101u, dp2a_uu(ah[1], 0x0101u, quad_bias));
-    o.z = dp2a_uu(ad0[0], 0x0101u, dp2a_uu(ad0[1], 0x0101u, quad_bias));
-    o.w = dp2a_uu(ad1[0], 0x0101u, dp2a_uu(ad1[1], 0x0101u, quad_bias));
-    av[0] = av[1] = ah[0] = ah[1] = ad0[0] = ad0[1] = ad1[0] = ad1[1] = 0;
-    return o;
-  }
-};
+  const uint32_t quad_bias = 0u - ((lap_k & 0xFFFFu) << 4);
+  uint4 o;
+  o.x = dp2a_uu(acc[0][0], 0x0101u, dp2a_uu(acc[0][1], 0x0101u, quad_bias));
+  o.y = dp2a_uu(acc[1][0], 0x0101u, dp2a_uu(acc[1][1], 0x0101u, quad_bias));
+  o.z = dp2a_uu(acc[2][0], 0x0101u, dp2a_uu(acc[2][1], 0x0101u, quad_bias));
+  o.w = dp2a_uu(acc[3][0], 0x0101u, dp2a_uu(acc[3][1], 0x0101u, quad_bias));
+  return o;
+}
 
 // Luma block, dot-product path: wp = window row 0 (block row 0 minus 3), sample x - 4; tab = the block's table entry.
 template <int RT, bool HI_CENTRE>
@@ -234,67 +217,25 @@ __device__ __forceinline__ void filter_block_dp(const int16_t* wp, const uint32_
 #pragma unroll
   for (int o = 0; o < 4; o++) {
     load(o + 3 + RT);
+    uint32_t tbsum[6];  // rows -RT and +RT: one tap each (dx = 0, words 2 and 3), same coefficient
+    tbsum[2] = w[o + 3 - RT][2] + w[o + 3 + RT][2];
+    tbsum[3] = w[o + 3 - RT][3] + w[o + 3 + RT][3];
     int r[4];
 #pragma unroll
-    for (int j = 0; j < 4; j++) r[j] = __vimin_s32_relu(dp_filter_sample<3, RT, 4, HI_CENTRE>([&](int dy) { return w[o + 3 + dy]; }, cw, j), max_val);
+    for (int j = 0; j < 4; j++) r[j] = __vimin_s32_relu(dp_filter_sample<3, RT, 4, HI_CENTRE>([&](int dy) { return w[o + 3 + dy]; }, tbsum, cw, j), max_val);
     *reinterpret_cast<uint2*>(out + (size_t)o * pitch) = make_uint2(__byte_perm(r[0], r[1], 0x5410), __byte_perm(r[2], r[3], 0x5410));
   }
 }
 
-// The hot path: 7x7 dot-product filter of a block interleaved with the thread's quads of the NEXT tile (lap.begin was called).
-// The SM's instruction caches decide how this is written: a straight-line block (16 samples x 20 IDP + a quad = 600 instructions,
-// 10 KB) next to the rest of the tile loop does not fit the per-sub-partition L0 cache, every instruction is then fetched from
-// the SM's instruction cache and THAT becomes the limiter (ncu: sm__icc_requests at 70 % of peak, issue slots 65 % used, no
-// pipe above 55 %).  So the block is a LOOP over pairs of output rows (8 window rows are re-read per pair: 24 instead of 15
-// bytes of shared memory per sample, which the LSU pipe has to spare), 2 output rows + 2 Laplacian rows per trip.  Threads that
-// own a second quad (the tile's bottom quad row) take two more trips without the filter part (nquads = 2).
-template <bool HI_CENTRE>
-__device__ __forceinline__ void filter_block_fused(const int16_t* wp, const uint32_t* __restrict__ tab, int16_t* __restrict__ out, int pitch, int max_val, LapTask& lap, int nquads,
-                                                   uint4* q0, uint4* q1) {
-  uint32_t cw[alftab::LUMA_WORDS];
-  {
-    const uint4* tp = reinterpret_cast<const uint4*>(tab);
-#pragma unroll
-    for (int i = 0; i < alftab::LUMA_WORDS / 4; i++) { const uint4 v = __ldg(tp + i); cw[4 * i] = v.x; cw[4 * i + 1] = v.y; cw[4 * i + 2] = v.z; cw[4 * i + 3] = v.w; }
-  }
-#pragma unroll 1
-  for (int it = 0; it < 2 * nquads; it++) {
-    if (it < 2) {
-      uint32_t w[8][6];  // w[s][m] = samples (x - 4 + 2m, x - 3 + 2m) of window row 2 it + s
-#pragma unroll
-      for (int s = 0; s < 8; s++) {
-        const uint2 a = *reinterpret_cast<const uint2*>(wp + s * WP), b = *reinterpret_cast<const uint2*>(wp + s * WP + 4), c = *reinterpret_cast<const uint2*>(wp + s * WP + 8);
-        w[s][0] = a.x; w[s][1] = a.y; w[s][2] = b.x; w[s][3] = b.y; w[s][4] = c.x; w[s][5] = c.y;
-      }
-#pragma unroll
-      for (int o = 0; o < 2; o++) {
-        int r[4];
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-          lap.part(j);
-          r[j] = __vimin_s32_relu(dp_filter_sample<3, 3, 4, HI_CENTRE>([&](int dy) { return w[o + 3 + dy]; }, cw, j), max_val);
-        }
-        *reinterpret_cast<uint2*>(out + (size_t)o * pitch) = make_uint2(__byte_perm(r[0], r[1], 0x5410), __byte_perm(r[2], r[3], 0x5410));
-      }
-      wp += 2 * WP;
-      out += 2 * (size_t)pitch;
-    } else {
-      lap.row();
-      lap.row();
-    }
-    if (it & 1) {
-      const uint4 q = lap.fold();
-      if (it == 1) *q0 = q; else if (q1) *q1 = q;
-    }
-  }
-}
-
-// Luma CTA: band blockIdx.y, horizontal segment blockIdx.x of nseg.
+// Luma CTA: band blockIdx.y, horizontal segment blockIdx.x of nseg.  Per tile: Laplacians of the tile's 17 x 9 quads (phase 2), ONE CTA
+// barrier, then every thread classifies and filters its 4x4 block (phases 3, 4).  The quads are double-buffered, so the barrier of
+// tile t + 1 is also what tells thread 0 that the stage of tile t is free again.
 //
-// Software pipeline over the tiles of the walk: while a thread filters its block of tile t (phase 4) it computes its quads of
-// tile t + 1 (phase 2).  Thread (bi, bj) owns quad (bi, bj + 1); the threads of the last block row also own the tile's bottom quad
-// row (8, bj + 1); quad column 0 of a tile is column 16 of the tile before it and is copied, not computed.  One CTA barrier per
-// tile publishes the quads of tile t + 1 and frees the stage of tile t, which thread 0 refills right after it.
+// What bounds this kernel (tools/ubench/rf.cu, mix.cu; profiles/r02_alf_*): IDP.2A issues every second clock on the one heavy
+// FMA pipe, and an ALU-pipe instruction issued between two IDPs still costs 0.5 - 1 clock (a 1:1 mix of IDP and IADD3 / VIMNMX /
+// SHF / PRMT with register operands runs at 0.63 - 0.73 instructions per clock, not 1.0), so interleaving the phases buys
+// nothing: time = 2 x IDPs + ~0.8 x everything else, and the work is cut by instruction count: 16 IDP per sample (15 low parts
+// + the centre's high part), Laplacians two samples per instruction, per-tile bookkeeping kept out of the loop.
 template <bool CLASSIFY_ONLY>
 __device__ __forceinline__ void alf_luma_cta(unsigned char* smem, const Geom& g, const SlotDev& sd, unsigned ctl, int nseg) {
   if (ctl_skip(ctl, 0) || (int)blockIdx.x >= nseg) return;
@@ -341,58 +282,31 @@ __device__ __forceinline__ void alf_luma_cta(unsigned char* smem, const Geom& g,
   const int shift = g.bd_luma + 4;
   const uint32_t lap_k = 0x10001u << (g.bd_luma + 1);  // Laplacian lane bias K in both lanes
   const bool vborder = y0 - ALF_HALO_Y < 0 || y0 - ALF_HALO_Y + L_SR > rows;
-  const bool bottom_row = bi == BR / 4 - 1;   // this thread also owns quad (8, bj + 1)
-  const bool long_warp = tid >= NT - 32;      // the warp that holds the last block row runs two quads per thread
+  // the quads of this thread: one, and for 25 threads of the last warp a second one
+  const int qi0 = tid / QW, qj0 = tid % QW, qi1 = (tid - 96 + NT) / QW, qj1 = (tid - 96 + NT) % QW;
+  const bool two_quads = tid >= 96 && tid - 96 + NT < QW * QH;
   __syncthreads();  // barriers initialised, flags staged
   pdl_wait();  // every thread: this kernel's stores must not overtake the previous stage's reads either
 
-  // tile t has landed in `stage`: border padding (phase 1), CTA-uniform; returns whether ALF is on anywhere under the tile
-  auto prepare = [&](int t, int stage, uint32_t parity) {
-    ring::mbar_wait(&full[stage], parity);
-    const bool on = CLASSIFY_ONLY || on_s[t - ta] != 0;
-    if (on && (vborder || t == 0 || t == ntx - 1))
-      pad_borders<L_SR, ALF_HALO_Y, NT>(reinterpret_cast<int16_t*>(smem + stage * L_STAGE_STRIDE), t == 0, t == ntx - 1, min(TW, g.width - t * TW), y0 - ALF_HALO_Y, rows);
-    return on;
-  };
-  auto lap_quad = [&](const int16_t* W, int qi, int qj, uint4(*quad)[QW]) {
-    LapTask lap;
-    lap.begin(W, qi, qj, lap_k);
-#pragma unroll
-    for (int i = 0; i < 4; i++) lap.row();
-    quad[qi][qj] = lap.fold();
-  };
-  // the quads of this thread, not interleaved with anything
-  auto lap_own = [&](const int16_t* W, uint4(*quad)[QW]) {
-    lap_quad(W, bi, bj + 1, quad);
-    if (bottom_row) lap_quad(W, bi + 1, bj + 1, quad);
-  };
-
   int stage = 0;
   uint32_t parity = 0;
-  bool on = prepare(ta, 0, 0);
-  if (on) {
-    lap_own(reinterpret_cast<const int16_t*>(smem), quad_buf[0]);
-    if (tid < QH) lap_quad(reinterpret_cast<const int16_t*>(smem), tid, 0, quad_buf[0]);
-  }
-  __syncthreads();
   int16_t* out = dst + (size_t)by * g.pitch_y + ta * TW + 4 * bj;
   for (int tx = ta; tx < tb; tx++, out += TW) {
+    ring::mbar_wait(&full[stage], parity);
+    const bool on = CLASSIFY_ONLY || on_s[tx - ta] != 0;   // CTA-uniform: ALF on in some CTU under this tile
+    int16_t* W = reinterpret_cast<int16_t*>(smem + stage * L_STAGE_STRIDE);
+    uint4(*quad)[QW] = quad_buf[(tx - ta) & 1];
+    if (on) {
+      // ---- phase 1: the stage is the work tile; border tiles get their padding ----
+      if (vborder || tx == 0 || tx == ntx - 1) pad_borders<L_SR, ALF_HALO_Y, NT>(W, tx == 0, tx == ntx - 1, min(TW, g.width - tx * TW), y0 - ALF_HALO_Y, rows);
+      // ---- phase 2: Laplacians per quad ----
+      quad[qi0][qj0] = lap_quad(W, qi0, qj0, lap_k);
+      if (two_quads) quad[qi1][qj1] = lap_quad(W, qi1, qj1, lap_k);
+    }
+    __syncthreads();  // quads of this tile complete; every thread has finished the previous tile
+    if (tid == 0 && tx > ta && tx - 1 + RING_STAGES < tb) issue(tx - 1 + RING_STAGES, stage == 0 ? RING_STAGES - 1 : stage - 1);
     const int bx = tx * TW + 4 * bj;
     const bool blk_in = bx < g.width && by < rows;
-    const bool en = on && blk_in && (CLASSIFY_ONLY || en_s[min(c1, bx >> g.ctu_log2) - c0] != 0);
-    const int16_t* W = reinterpret_cast<const int16_t*>(smem + stage * L_STAGE_STRIDE);
-    uint4(*quad)[QW] = quad_buf[(tx - ta) & 1];
-    uint4(*quad_next)[QW] = quad_buf[(tx + 1 - ta) & 1];
-    const int stage1 = stage + 1 == RING_STAGES ? 0 : stage + 1;
-    const uint32_t parity1 = stage1 == 0 ? parity ^ 1 : parity;
-    const bool on_next = tx + 1 < tb && prepare(tx + 1, stage1, parity1);
-    const int16_t* W1 = reinterpret_cast<const int16_t*>(smem + stage1 * L_STAGE_STRIDE);
-    if (on_next && tid < QH) {
-      if (on) quad_next[tid][0] = quad[tid][QW - 1];   // quad column 0 of the next tile = column 16 of this one
-      else lap_quad(W1, tid, 0, quad_next);
-    }
-    const bool fuse = on_next && en && dot && is7;   // this thread interleaves its quads of the next tile with its filter
-    if (on_next && !fuse) lap_own(W1, quad_next);
     if (!on) {
       // every CTU under this tile has ALF off: copy through
       if (blk_in) {
@@ -410,19 +324,12 @@ __device__ __forceinline__ void alf_luma_cta(unsigned char* smem, const Geom& g,
       } else if (blk_in) {
         // ---- phase 4: filter the block ----
         const int16_t* wp = W + (4 * bi) * WP + WX0 + 4 * bj - 4;  // window row 0 (= block row 0 minus 3), sample x - 4
-        if (!en) {
+        if (en_s[(bx >> g.ctu_log2) - c0] == 0) {
 #pragma unroll
           for (int o = 0; o < 4; o++) *reinterpret_cast<uint2*>(out + (size_t)o * g.pitch_y) = *reinterpret_cast<const uint2*>(wp + (3 + o) * WP + 4);
         } else if (dot) {
           const uint32_t* tab = sd.alf_coef_dp + ((cl & 31) * 4 + (cl >> 5)) * alftab::LUMA_WORDS;
-          if (fuse) {
-            LapTask lap;
-            lap.begin(W1, bi, bj + 1, lap_k);
-            uint4* q0 = &quad_next[bi][bj + 1];
-            uint4* q1 = bottom_row ? &quad_next[bi + 1][bj + 1] : nullptr;
-            if (hi_centre) filter_block_fused<true>(wp, tab, out, g.pitch_y, max_val, lap, long_warp ? 2 : 1, q0, q1);
-            else filter_block_fused<false>(wp, tab, out, g.pitch_y, max_val, lap, long_warp ? 2 : 1, q0, q1);
-          } else if (is7) {
+          if (is7) {
             if (hi_centre) filter_block_dp<3, true>(wp, tab, out, g.pitch_y, max_val);
             else filter_block_dp<3, false>(wp, tab, out, g.pitch_y, max_val);
           } else {
@@ -430,9 +337,6 @@ __device__ __forceinline__ void alf_luma_cta(unsigned char* smem, const Geom& g,
             else filter_block_dp<2, false>(wp, tab, out, g.pitch_y, max_val);
           }
         } else {
-#ifdef ALF_DOT_ONLY  // diagnosis: how much does the size of the kernel (instruction cache) cost?
-          __trap();
-#else
           int f[16];
           {
             const int4* cp = reinterpret_cast<const int4*>(sd.alf_coef + ((cl & 31) * 4 + (cl >> 5)) * 16);
@@ -483,14 +387,10 @@ __device__ __forceinline__ void alf_luma_cta(unsigned char* smem, const Geom& g,
               *reinterpret_cast<uint2*>(out + (size_t)o * g.pitch_y) = make_uint2(p0, p1);
             }
           }
-#endif
         }
       }
     }
-    __syncthreads();  // quads of tile tx + 1 complete; nobody reads the stage of tile tx any more
-    if (tid == 0 && tx + RING_STAGES < tb) issue(tx + RING_STAGES, stage);
-    on = on_next;
-    stage = stage1; parity = parity1;
+    if (++stage == RING_STAGES) { stage = 0; parity ^= 1; }
   }
 }
 
@@ -549,14 +449,6 @@ __device__ __forceinline__ void alf_chroma_cta(unsigned char* smem, const Geom& 
   int f[7];
 #pragma unroll
   for (int i = 0; i < 7; i++) f[i] = sd.alf->chroma_coeff[i];
-  const bool hi_centre = (ctl & CTL_ALF_HIC_C) != 0;
-  const bool dot = (ctl & CTL_ALF_DOT_C) != 0;  // dot-product path (ilf_alf_tab.cuh), else the general path
-  uint32_t ccw[alftab::CHROMA_WORDS];
-  {
-    const uint4* tp = reinterpret_cast<const uint4*>(sd.alf_coef_dp + 25 * 4 * alftab::LUMA_WORDS);
-#pragma unroll
-    for (int i = 0; i < alftab::CHROMA_WORDS / 4; i++) { const uint4 v = __ldg(tp + i); ccw[4 * i] = v.x; ccw[4 * i + 1] = v.y; ccw[4 * i + 2] = v.z; ccw[4 * i + 3] = v.w; }
-  }
   const int max_val = (1 << g.bd_chroma) - 1;
   const int k = tid % (TW / 8), rg = tid / (TW / 8);  // 8 samples at column 8k, rows 2rg and 2rg + 1 of the band
   const int y = by0 + 2 * rg;
@@ -585,24 +477,6 @@ __device__ __forceinline__ void alf_chroma_cta(unsigned char* smem, const Geom& 
 #pragma unroll
           for (int o = 0; o < 2; o++)
             if (o < nrows) *reinterpret_cast<uint4*>(out + (size_t)o * g.pitch_c) = *reinterpret_cast<const uint4*>(wp + (2 + o) * WP);
-        } else if (dot) {
-          uint32_t w[6][6];  // w[r][m] = samples (x - 2 + 2m, x - 1 + 2m) of window row r
-#pragma unroll
-          for (int r = 0; r < 6; r++) {
-            const uint4 b = *reinterpret_cast<const uint4*>(wp + r * WP);
-            w[r][0] = *reinterpret_cast<const uint32_t*>(wp + r * WP - 2); w[r][1] = b.x; w[r][2] = b.y; w[r][3] = b.z; w[r][4] = b.w;
-            w[r][5] = *reinterpret_cast<const uint32_t*>(wp + r * WP + 8);
-          }
-#pragma unroll
-          for (int o = 0; o < 2; o++) {
-            if (o >= nrows) break;
-            int r[8];
-#pragma unroll
-            for (int j = 0; j < 8; j++)
-              r[j] = __vimin_s32_relu(hi_centre ? dp_filter_sample<2, 2, 2, true>([&](int dy) { return w[o + 2 + dy]; }, ccw, j) : dp_filter_sample<2, 2, 2, false>([&](int dy) { return w[o + 2 + dy]; }, ccw, j), max_val);
-            *reinterpret_cast<uint4*>(out + (size_t)o * g.pitch_c) =
-                make_uint4(__byte_perm(r[0], r[1], 0x5410), __byte_perm(r[2], r[3], 0x5410), __byte_perm(r[4], r[5], 0x5410), __byte_perm(r[6], r[7], 0x5410));
-          }
         } else {
           int w[6][12];
 #pragma unroll
