@@ -4,8 +4,13 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include <unistd.h>
@@ -20,6 +25,61 @@ namespace {
 thread_local std::string g_create_error;
 
 constexpr int ALF_DP_WORDS = 25 * 4 * alftab::LUMA_WORDS;
+
+// Pageable host planes (the reference's PelStorage) go through page-locked staging buffers.  A single memcpy thread moves about
+// 8 GB/s, a 4K picture is 25 MB each way, so the staging copies are cut into row chunks that a few helper threads copy while the
+// DMA engine already moves the chunks that are done (upload), or as soon as the DMA engine has delivered them (download).
+// Page-locking the caller's planes instead (cudaHostRegister) costs 20 - 300 ms per plane set on the boxes measured and goes stale
+// when the owner frees or recycles the memory, so the library never does that on its own.  ILF_COPY_THREADS (default 4; 1 = inline).
+class CopyPool {
+ public:
+  ~CopyPool() {
+    { std::lock_guard<std::mutex> l(m_); stop_ = true; }
+    cv_.notify_all();
+    for (auto& t : th_) t.join();
+  }
+  int threads() {
+    static const int n = getenv("ILF_COPY_THREADS") ? std::max(1, atoi(getenv("ILF_COPY_THREADS"))) : 4;
+    return n;
+  }
+  // runs fn(0 .. ntasks-1) on the helper threads; returns at once.  One batch at a time (wait() before the next).
+  void start(int ntasks, std::function<void(int)> fn) {
+    if (th_.empty()) for (int i = 0; i < threads(); i++) th_.emplace_back([this] { loop(); });
+    { std::lock_guard<std::mutex> l(m_); fn_ = std::move(fn); ntasks_ = ntasks; next_ = 0; done_ = 0; gen_++; }
+    cv_.notify_all();
+  }
+  void wait() {
+    std::unique_lock<std::mutex> l(m_);
+    cv_done_.wait(l, [this] { return done_ == ntasks_; });
+  }
+ private:
+  void loop() {
+    unsigned long long seen = 0;
+    for (;;) {
+      std::unique_lock<std::mutex> l(m_);
+      cv_.wait(l, [&] { return stop_ || (gen_ != seen && next_ < ntasks_); });
+      if (stop_) return;
+      const unsigned long long g = gen_;
+      while (gen_ == g && next_ < ntasks_) {
+        const int i = next_++;
+        l.unlock();
+        fn_(i);
+        l.lock();
+        if (++done_ == ntasks_) cv_done_.notify_all();
+      }
+      seen = g;
+    }
+  }
+  std::vector<std::thread> th_;
+  std::mutex m_;
+  std::condition_variable cv_, cv_done_;
+  std::function<void(int)> fn_;
+  int ntasks_ = 0, next_ = 0, done_ = 0;
+  unsigned long long gen_ = 0;
+  bool stop_ = false;
+};
+constexpr int COPY_CHUNKS_MAX = 24;
+struct CopyChunk { int plane, row0, rows; size_t stage_off; };  // rows of one plane; offset into the staging buffer in samples
 
 struct Slot {
   int16_t* planes = nullptr;   // one allocation: 3 buffers x (Y, Cb, Cr)
@@ -38,7 +98,8 @@ struct Slot {
   uint8_t* stats_avail = nullptr;
   long long* stats = nullptr;  // [num_ctus][3][5][64]
   bool has_org = false;
-  int16_t* pinned = nullptr;   // host staging for pageable planes, one picture; allocated on first use
+  int16_t* pinned = nullptr;   // host staging for pageable planes on the way up, one picture; allocated on first use
+  int16_t* pinned_down = nullptr;  // ... and on the way down
   uint8_t* pinned_side = nullptr;  // host staging for side information
   size_t pinned_side_bytes = 0;
   SlotDev dev;                 // host copy of the device descriptor
@@ -93,6 +154,8 @@ struct ilf_ctx {
   double kernel_bytes[ILF_NUM_KERNELS] = {0, 0, 0, 0, 0};
   long long kernel_launches[ILF_NUM_KERNELS] = {0, 0, 0, 0, 0};
   int num_ctus = 0;
+  CopyPool copy_pool;
+  cudaEvent_t chunk_ev[COPY_CHUNKS_MAX] = {};   // download: chunk i has reached the staging buffer
 };
 
 namespace {
@@ -378,10 +441,12 @@ int ilf_destroy(ilf_ctx* ctx) {
     cudaFree(s.sao); cudaFree(s.alf); cudaFree(s.alf_coef); cudaFree(s.alf_coef_dp); cudaFree(s.alf_ctu_enable); cudaFree(s.alf_class);
     cudaFree(s.org); cudaFree(s.stats_avail); cudaFree(s.stats);
     if (s.pinned) cudaFreeHost(s.pinned);
+    if (s.pinned_down) cudaFreeHost(s.pinned_down);
     if (s.pinned_side) cudaFreeHost(s.pinned_side);
     for (cudaEvent_t e : {s.ev_up, s.ev_down, s.ev_side[0], s.ev_side[1], s.ev_side[2]}) if (e) cudaEventDestroy(e);
   }
   for (cudaEvent_t e : ctx->run_ring) if (e) cudaEventDestroy(e);
+  for (cudaEvent_t e : ctx->chunk_ev) if (e) cudaEventDestroy(e);
   cudaFree(ctx->slots_dev);
   for (auto& t : ctx->timed) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
   for (cudaEvent_t e : ctx->free_events) cudaEventDestroy(e);
@@ -406,6 +471,23 @@ int ilf_get_band(const ilf_ctx* ctx, ilf_band* out, int32_t* first_row, int32_t*
   return ILF_OK;
 }
 
+// Row chunks of a staged transfer of LOCAL luma rows [first, first + n): luma in up to 8 pieces, each chroma plane in up to 2
+// (about 2 MB each for a 4K picture).
+static int make_chunks(const Geom& g, int first, int n, CopyChunk* out) {
+  int k = 0;
+  size_t off = 0;
+  for (int p = 0; p < 3; p++) {
+    const int w = p ? g.width / 2 : g.width, h = p ? n / 2 : n, r0 = p ? first / 2 : first;
+    const int pieces = std::max(1, std::min(p ? 2 : 8, h / 64));
+    for (int i = 0; i < pieces; i++) {
+      const int a = (int)((long long)h * i / pieces), b = (int)((long long)h * (i + 1) / pieces);
+      out[k++] = {p, r0 + a, b - a, off + (size_t)a * w};
+    }
+    off += (size_t)w * h;
+  }
+  return k;
+}
+
 // Copies host rows [first, first + n) (LOCAL luma rows of the held region; chroma rows first/2 ..) into the slot's input buffer.
 static int upload_rows(ilf_ctx* ctx, int slot, const int16_t* y, ptrdiff_t sy, const int16_t* cb, ptrdiff_t scb, const int16_t* cr, ptrdiff_t scr, int first, int n) {
   if (int rc = check_slot(ctx, slot)) return rc;
@@ -421,20 +503,43 @@ static int upload_rows(ilf_ctx* ctx, int slot, const int16_t* y, ptrdiff_t sy, c
   const bool direct = is_pinned(y) && is_pinned(cb) && is_pinned(cr);
   if (!direct) {
     if (!s.pinned) CU(ctx, cudaMallocHost(&s.pinned, ctx->buf_elems * sizeof(int16_t)));
-    CU(ctx, cudaEventSynchronize(s.ev_up));    // staging buffer: previous staged upload consumed ...
-    CU(ctx, cudaEventSynchronize(s.ev_down));  // ... and no staged download in flight
+    CU(ctx, cudaEventSynchronize(s.ev_up));    // staging buffer: the previous staged upload has been consumed
   }
-  int16_t* stage = s.pinned;
-  for (int p = 0; p < 3; p++) {
-    const int w = p ? g.width / 2 : g.width, h = p ? n / 2 : n, r0 = p ? first / 2 : first, pitch = p ? g.pitch_c : g.pitch_y;
-    int16_t* dst = plane_ptr(ctx, s, 0, p) + (size_t)r0 * pitch;
-    if (direct) {
-      CU(ctx, cudaMemcpy2DAsync(dst, (size_t)pitch * 2, srcs[p], (size_t)strides[p] * 2, (size_t)w * 2, h, cudaMemcpyHostToDevice, ctx->s_up));
-    } else {
-      for (int r = 0; r < h; r++) memcpy(stage + (size_t)r * w, srcs[p] + (ptrdiff_t)r * strides[p], (size_t)w * 2);
-      CU(ctx, cudaMemcpy2DAsync(dst, (size_t)pitch * 2, stage, (size_t)w * 2, (size_t)w * 2, h, cudaMemcpyHostToDevice, ctx->s_up));
-      stage += (size_t)w * h;
+  if (direct) {
+    for (int p = 0; p < 3; p++) {
+      const int w = p ? g.width / 2 : g.width, h = p ? n / 2 : n, r0 = p ? first / 2 : first, pitch = p ? g.pitch_c : g.pitch_y;
+      CU(ctx, cudaMemcpy2DAsync(plane_ptr(ctx, s, 0, p) + (size_t)r0 * pitch, (size_t)pitch * 2, srcs[p], (size_t)strides[p] * 2, (size_t)w * 2, h, cudaMemcpyHostToDevice, ctx->s_up));
     }
+  } else {
+    // helper threads fill the staging buffer chunk by chunk; this thread hands every finished chunk to the DMA engine, in order
+    CopyChunk ch[COPY_CHUNKS_MAX];
+    const int nch = make_chunks(g, first, n, ch);
+    const int first_l = first;
+    std::atomic<int> ready[COPY_CHUNKS_MAX];
+    for (int i = 0; i < nch; i++) ready[i].store(0, std::memory_order_relaxed);
+    int16_t* stage = s.pinned;
+    auto copy = [&, stage](int i) {
+      const CopyChunk& c = ch[i];
+      const int w = c.plane ? g.width / 2 : g.width, base = c.plane ? first_l / 2 : first_l;
+      const int16_t* src = srcs[c.plane] + (ptrdiff_t)(c.row0 - base) * strides[c.plane];
+      int16_t* d = stage + c.stage_off;
+      for (int r = 0; r < c.rows; r++) memcpy(d + (size_t)r * w, src + (ptrdiff_t)r * strides[c.plane], (size_t)w * 2);
+      ready[i].store(1, std::memory_order_release);
+    };
+    const bool par = ctx->copy_pool.threads() > 1 && nch > 1;
+    if (par) ctx->copy_pool.start(nch, copy);
+    cudaError_t err = cudaSuccess;
+    for (int i = 0; i < nch; i++) {
+      if (par) while (!ready[i].load(std::memory_order_acquire)) std::this_thread::yield();
+      else copy(i);
+      const CopyChunk& c = ch[i];
+      const int w = c.plane ? g.width / 2 : g.width, pitch = c.plane ? g.pitch_c : g.pitch_y;
+      const cudaError_t e = cudaMemcpy2DAsync(plane_ptr(ctx, s, 0, c.plane) + (size_t)c.row0 * pitch, (size_t)pitch * 2, stage + c.stage_off, (size_t)w * 2, (size_t)w * 2, c.rows,
+                                              cudaMemcpyHostToDevice, ctx->s_up);
+      if (e != cudaSuccess && err == cudaSuccess) err = e;
+    }
+    if (par) ctx->copy_pool.wait();
+    CU(ctx, err);
   }
   CU(ctx, cudaEventRecord(s.ev_up, ctx->s_up));
   s.h2d_pending = true;
@@ -480,23 +585,36 @@ static int download_rows(ilf_ctx* ctx, int slot, int16_t* y, ptrdiff_t sy, int16
     s.d2h_pending = true;
     return ILF_OK;
   }
-  if (!s.pinned) CU(ctx, cudaMallocHost(&s.pinned, ctx->buf_elems * sizeof(int16_t)));
-  CU(ctx, cudaEventSynchronize(s.ev_up));  // the staging buffer may hold a staged upload that is still being copied
-  int16_t* stage = s.pinned;
-  for (int p = 0; p < 3; p++) {
-    const int w = p ? g.width / 2 : g.width, h = p ? n / 2 : n, r0 = p ? first / 2 : first, pitch = p ? g.pitch_c : g.pitch_y;
-    CU(ctx, cudaMemcpy2DAsync(stage, (size_t)w * 2, plane_ptr(ctx, s, s.result_buf[p], p) + (size_t)r0 * pitch, (size_t)pitch * 2, (size_t)w * 2, h, cudaMemcpyDeviceToHost, ctx->s_down));
-    stage += (size_t)w * h;
+  // staged: the DMA engine delivers row chunks into the page-locked buffer, helper threads (and this one) copy every chunk on to
+  // the caller's planes as soon as its event has fired
+  if (!s.pinned_down) CU(ctx, cudaMallocHost(&s.pinned_down, ctx->buf_elems * sizeof(int16_t)));
+  CopyChunk ch[COPY_CHUNKS_MAX];
+  const int nch = make_chunks(g, first, n, ch);
+  int16_t* stage = s.pinned_down;
+  for (int i = 0; i < nch; i++) {
+    const CopyChunk& c = ch[i];
+    const int w = c.plane ? g.width / 2 : g.width, pitch = c.plane ? g.pitch_c : g.pitch_y;
+    if (!ctx->chunk_ev[i]) CU(ctx, cudaEventCreateWithFlags(&ctx->chunk_ev[i], cudaEventDisableTiming));
+    CU(ctx, cudaMemcpy2DAsync(stage + c.stage_off, (size_t)w * 2, plane_ptr(ctx, s, s.result_buf[c.plane], c.plane) + (size_t)c.row0 * pitch, (size_t)pitch * 2, (size_t)w * 2, c.rows,
+                              cudaMemcpyDeviceToHost, ctx->s_down));
+    CU(ctx, cudaEventRecord(ctx->chunk_ev[i], ctx->s_down));
   }
   CU(ctx, cudaEventRecord(s.ev_down, ctx->s_down));
-  CU(ctx, cudaEventSynchronize(s.ev_down));  // synchronous: nothing left pending
-  stage = s.pinned;
-  for (int p = 0; p < 3; p++) {
-    const int w = p ? g.width / 2 : g.width, h = p ? n / 2 : n;
-    for (int r = 0; r < h; r++) memcpy(dsts[p] + (ptrdiff_t)r * strides[p], stage + (size_t)r * w, (size_t)w * 2);
-    stage += (size_t)w * h;
-  }
-  return ILF_OK;
+  std::atomic<int> failed(0);
+  const int device = ctx->cfg.device;
+  auto copy = [&, stage, device](int i) {
+    const CopyChunk& c = ch[i];
+    cudaSetDevice(device);
+    if (cudaEventSynchronize(ctx->chunk_ev[i]) != cudaSuccess) { failed.store(1); return; }
+    const int w = c.plane ? g.width / 2 : g.width, base = c.plane ? first / 2 : first;
+    int16_t* d = dsts[c.plane] + (ptrdiff_t)(c.row0 - base) * strides[c.plane];
+    const int16_t* src = stage + c.stage_off;
+    for (int r = 0; r < c.rows; r++) memcpy(d + (ptrdiff_t)r * strides[c.plane], src + (size_t)r * w, (size_t)w * 2);
+  };
+  if (ctx->copy_pool.threads() > 1 && nch > 1) { ctx->copy_pool.start(nch, copy); ctx->copy_pool.wait(); }
+  else for (int i = 0; i < nch; i++) copy(i);
+  if (failed.load()) return fail(ctx, ILF_ERR_CUDA, "device -> host copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+  return ILF_OK;  // synchronous: nothing left pending
 }
 
 int ilf_download_async(ilf_ctx* ctx, int slot, int16_t* y, ptrdiff_t sy, int16_t* cb, ptrdiff_t scb, int16_t* cr, ptrdiff_t scr) {

@@ -15,6 +15,9 @@
 #include "CommonLib/Unit.h"
 #include "CommonLib/UnitTools.h"
 
+void* ( *IlfPackMemory::alloc )( size_t ) = malloc;
+void ( *IlfPackMemory::release )( void* )  = free;
+
 namespace
 {
 // Per-picture scratch that plays the role of the reference's per-CTU arrays m_aapbEdgeFilter / m_aapucBS
@@ -86,7 +89,7 @@ struct PackCtx  // one per worker
 void packCU( PackCtx& pc, const CodingUnit& cu, int layer )
 {
   const PreCalcValues& pcv = *cu.cs->pcv;
-  std::vector<uint32_t>& info = layer == 0 ? pc.out->info : pc.out->infoChroma;
+  auto& info = layer == 0 ? pc.out->info : pc.out->infoChroma;
   EdgeScratch&          es   = pc.scratch[layer];
   const int             unitsW = pc.out->unitsW, unitsH = pc.out->unitsH;
   const bool            lumaValid = cu.Y().valid();

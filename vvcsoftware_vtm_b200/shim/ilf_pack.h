@@ -17,6 +17,7 @@
 
 #include <cstddef>
 #include <cstdint>
+#include <new>
 #include <vector>
 
 #include "ilf_b200.h"
@@ -25,15 +26,41 @@ class CodingStructure;
 struct SAOBlkParam;
 struct AlfSliceParam;
 
+// Where the big side-information arrays live.  The packer itself is plain C++ (it is also linked into tools that have no CUDA
+// library); the host shim points these at ilf_host_alloc / ilf_host_free before the first picture, so that the arrays sit in
+// page-locked memory the packer owns for its whole life: the library then copies them to the device straight from there
+// (ilf_b200.h "transfer pipeline"), nothing is registered or unregistered per picture, and a vector that grows simply gets a
+// new page-locked block.  Set once, before the first ilfPackDeblock call.
+struct IlfPackMemory
+{
+  static void* ( *alloc )( size_t );
+  static void ( *release )( void* );
+};
+template<class T> struct IlfPackAlloc
+{
+  typedef T value_type;
+  IlfPackAlloc() {}
+  template<class U> IlfPackAlloc( const IlfPackAlloc<U>& ) {}
+  T* allocate( size_t n )
+  {
+    void* p = IlfPackMemory::alloc( n * sizeof( T ) );
+    if( !p ) throw std::bad_alloc();
+    return static_cast<T*>( p );
+  }
+  void deallocate( T* p, size_t ) { IlfPackMemory::release( p ); }
+  template<class U> bool operator==( const IlfPackAlloc<U>& ) const { return true; }
+  template<class U> bool operator!=( const IlfPackAlloc<U>& ) const { return false; }
+};
+
 struct IlfPackedDeblock
 {
   int                   unitsW = 0, unitsH = 0, ctusW = 0, ctusH = 0;
   ilf_deblock_params    params;
-  std::vector<uint32_t> info;        // luma-tree layer
-  std::vector<uint32_t> infoChroma;  // chroma-tree layer, empty when the picture has no dual-tree slice
+  std::vector<uint32_t, IlfPackAlloc<uint32_t> > info;        // luma-tree layer
+  std::vector<uint32_t, IlfPackAlloc<uint32_t> > infoChroma;  // chroma-tree layer, empty when the picture has no dual-tree slice
   bool                  wantMv32 = true;  // in: also fill mv32 (the shim asks for it only after a picture did not fit 16 bits)
-  std::vector<int32_t>  mv32;        // 4 per unit (when wantMv32)
-  std::vector<int16_t>  mv16;        // same values as int16, valid while mvFits16
+  std::vector<int32_t, IlfPackAlloc<int32_t> >  mv32;        // 4 per unit (when wantMv32)
+  std::vector<int16_t, IlfPackAlloc<int16_t> >  mv16;        // same values as int16, valid while mvFits16
   bool                  mvFits16 = true;
   bool                  anyInter = false;
   std::vector<uint8_t>  ctuSlice;

@@ -21,6 +21,7 @@
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <thread>
 #include <utility>
 #include <vector>
 
@@ -45,8 +46,6 @@ struct ShimState
   const Picture* mirrored = nullptr;  // picture whose host reco buffer equals the slot's current device state (just downloaded) ...
   int            mirroredPoc = -1;    // ... and its POC (Picture objects are recycled)
   bool           timing   = false;
-  bool           pin      = true;     // page-lock the reference's picture planes on first sight (ILF_SHIM_PIN=0: stage through the library)
-  std::vector<std::pair<const char*, size_t>> pinned, unpinnable, seenOnce;
   long long      usDeblock = 0, usSao = 0, usAlf = 0;
   int            picCount = 0;
   ~ShimState()
@@ -63,7 +62,8 @@ ShimState& state()
   {
     init     = true;
     s.timing = getenv( "ILF_TIMING" ) && atoi( getenv( "ILF_TIMING" ) ) != 0;
-    s.pin    = !( getenv( "ILF_SHIM_PIN" ) && atoi( getenv( "ILF_SHIM_PIN" ) ) == 0 );
+    IlfPackMemory::alloc   = ilf_host_alloc;   // the packer's arrays in page-locked memory (ilf_pack.h)
+    IlfPackMemory::release = ilf_host_free;
   }
   return s;
 }
@@ -106,44 +106,13 @@ ShimState& contextFor( const CodingStructure& cs )
   return s;
 }
 
-// The decoded-picture buffer is allocated once and recycled (Picture::create).  Page-locking a plane costs about as much as
-// five staged copies of it (cudaHostRegister runs at ~1 GB/s), so a plane is registered when it comes around the THIRD time:
-// from then on the library copies straight from / into it (ilf_b200.h "transfer pipeline") instead of staging 25 MB per 4K
-// picture through its own pinned buffer.  A range that cannot be registered stays pageable.
-void pinPlane( ShimState& s, const Pel* buf, int stride, int w, int h )
-{
-  if( !s.pin ) return;
-  const char*  lo    = reinterpret_cast<const char*>( buf );
-  const size_t bytes = ( size_t( h - 1 ) * stride + w ) * sizeof( Pel );
-  for( auto& r : s.pinned ) if( lo >= r.first && lo + bytes <= r.first + r.second ) return;
-  for( auto& r : s.unpinnable ) if( lo == r.first && bytes == r.second ) return;
-  int seen = 0;
-  for( auto& r : s.seenOnce ) seen += lo == r.first && bytes == r.second;
-  if( seen < 2 ) { s.seenOnce.emplace_back( lo, bytes ); return; }   // third appearance: the buffer is clearly being recycled
-  if( ilf_host_register( const_cast<char*>( lo ), bytes ) == ILF_OK ) s.pinned.emplace_back( lo, bytes );
-  else s.unpinnable.emplace_back( lo, bytes );
-}
-void pinPlanes( ShimState& s, const CPelUnitBuf& u )
-{
-  for( int c = 0; c < 3; c++ ) { const CPelBuf b = u.get( ComponentID( c ) ); pinPlane( s, b.buf, b.stride, b.width, b.height ); }
-}
-
-// The packer's arrays live between pictures (static in loopFilterPic); once their storage is page-locked the library copies
-// them to the device without staging (2 MB + 4 MB per 4K picture).  Re-registered when a vector moved (geometry change).
-void pinArray( ShimState& s, std::pair<const char*, size_t>& slot, const void* p, size_t bytes )
-{
-  if( !s.pin || !p || !bytes ) return;
-  const char* lo = reinterpret_cast<const char*>( p );
-  if( slot.first == lo && slot.second >= bytes ) return;
-  if( slot.first ) ilf_host_unregister( const_cast<char*>( slot.first ) );
-  slot = { nullptr, 0 };
-  if( ilf_host_register( const_cast<char*>( lo ), bytes ) == ILF_OK ) slot = { lo, bytes };
-}
-
+// The reference's picture planes are pageable and are handed to the library as they are: ilf_upload / ilf_download stage them
+// through the library's own page-locked buffers with a few copy threads (ilf_api.cu CopyPool).  Page-locking the planes of the
+// decoded-picture buffer instead (cudaHostRegister) was tried: 20 - 300 ms per plane set on the boxes measured, and a
+// registration outlives the Picture it was made for (Picture::destroy, a new CVS), so the shim registers nothing.
 void upload( ShimState& s, CodingStructure& cs )
 {
   const CPelUnitBuf reco = cs.getRecoBuf();
-  pinPlanes( s, reco );
   const CPelBuf     y = reco.get( COMPONENT_Y ), cb = reco.get( COMPONENT_Cb ), cr = reco.get( COMPONENT_Cr );
   ck( s, ilf_upload( s.ctx, 0, y.buf, y.stride, cb.buf, cb.stride, cr.buf, cr.stride ), "ilf_upload" );
   s.resident = cs.picture;
@@ -178,7 +147,15 @@ void LoopFilter::loopFilterPic( CodingStructure& cs )
   const auto t0 = clk::now();
   ShimState& s  = contextFor( cs );
   const auto tc = clk::now();
-  static IlfPackedDeblock db;  // kept between pictures: the arrays keep their pages
+  // the picture goes up on a helper thread while this one packs (the library is not entered by anybody else meanwhile)
+  int        upRc = ILF_OK;
+  struct Joiner { std::thread t; ~Joiner() { if( t.joinable() ) t.join(); } } up;   // (the packer may THROW)
+  up.t = std::thread( [&] {
+    const CPelUnitBuf reco = cs.getRecoBuf();
+    const CPelBuf     y = reco.get( COMPONENT_Y ), cb = reco.get( COMPONENT_Cb ), cr = reco.get( COMPONENT_Cr );
+    upRc = ilf_upload( s.ctx, 0, y.buf, y.stride, cb.buf, cb.stride, cr.buf, cr.stride );
+  } );
+  static IlfPackedDeblock db;  // kept between pictures: the arrays keep their (page-locked) storage
   db.wantMv32 = false;
   ilfPackDeblock( cs, db );  // the walk over CUs/TUs/motion of LoopFilter.cpp:167-222, 243-541, flattened
   if( db.anyInter && !db.mvFits16 )
@@ -186,12 +163,11 @@ void LoopFilter::loopFilterPic( CodingStructure& cs )
     db.wantMv32 = true;  // a motion vector beyond 16 bits: walk again for the 32-bit array
     ilfPackDeblock( cs, db );
   }
-  static std::pair<const char*, size_t> pinInfo, pinInfoC, pinMv;
-  pinArray( s, pinInfo, db.info.data(), db.info.capacity() * sizeof( uint32_t ) );
-  pinArray( s, pinInfoC, db.infoChroma.data(), db.infoChroma.capacity() * sizeof( uint32_t ) );
-  pinArray( s, pinMv, db.mv16.data(), db.mv16.capacity() * sizeof( int16_t ) );
   const auto tp = clk::now();
-  upload( s, cs );
+  up.t.join();
+  ck( s, upRc, "ilf_upload" );
+  s.resident = cs.picture;
+  s.mirrored = nullptr;
   const auto tu = clk::now();
   ck( s, ilf_set_deblock_info( s.ctx, 0, &db.params, db.info.data(), db.infoChroma.empty() ? nullptr : db.infoChroma.data(),
                                ( db.anyInter && db.mvFits16 ) ? db.mv16.data() : nullptr, ( db.anyInter && !db.mvFits16 ) ? db.mv32.data() : nullptr, db.ctuSlice.data() ),
