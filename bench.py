@@ -200,7 +200,7 @@ class ClockSampler(threading.Thread):
 # ------------------------------------------------------------------------------------------------------------------
 # reference arm / cpu_baseline: the unmodified reference decoder with the timing hook, one process per core
 # ------------------------------------------------------------------------------------------------------------------
-def reference_chain_run(stream, width, height, procs, max_pics=None):
+def reference_chain_run(stream, width, height, procs, max_pics=None, simd=None):
     """Run `procs` reference decoders concurrently on the stream; return (pictures per proc, [chain seconds per proc],
     per-stage seconds of proc 0)."""
     exe = os.path.join(ROOT, "oracle", "_ref", "vtm_capture")
@@ -213,7 +213,7 @@ def reference_chain_run(stream, width, height, procs, max_pics=None):
         env["ILF_EXIT_AFTER"] = str(max_pics)
     ps = []
     for i in range(procs):
-        cmd = [exe, "-b", path, "-d", "10", "-o", "/dev/null"]
+        cmd = [exe, "-b", path, "-d", "10", "-o", "/dev/null"] + ([f"--SIMD={simd}"] if simd else [])
         if hasattr(os, "sched_setaffinity"):
             cmd = ["taskset", "-c", str(sorted(os.sched_getaffinity(0))[i % len(os.sched_getaffinity(0))])] + cmd
         ps.append(subprocess.Popen(cmd, env=env, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True))
@@ -248,6 +248,13 @@ def oracle_port_run(width, height, pics, planes):
     return n, dt
 
 
+def shared_config(wl, workload, world):
+    """The part of `config` both arms print verbatim (the driver compares the arms' configs): which pictures a step covers."""
+    n = len(load_sideinfo(workload))
+    return {"workload": wl["desc"], "stream": f"tests/golden/streams/{wl['stream']}.bin", "pictures_per_step_per_gpu": n,
+            "chain": "deblock -> SAO -> ALF with the stream's own per-CTU decisions", "gpus": world}
+
+
 def cpu_baseline(wl, cores, pics=None, planes=None):
     w, h = wl["width"], wl["height"]
     mpx = w * h / 1e6
@@ -256,14 +263,52 @@ def cpu_baseline(wl, cores, pics=None, planes=None):
         n, chain, stages = r
         value = sum(n * mpx / c for c in chain)
         single = reference_chain_run(wl["stream"], w, h, 1)
-        return {"value": round(value, 1), "unit": "Mpixel/s", "cores": cores, "kind": "reference",
-                "sample": f"{n} pictures of tests/golden/streams/{wl['stream']}.bin decoded by {cores} concurrent unmodified VTM 2.1 decoders (--SIMD default = best available); "
-                          f"filter-chain time only (steady_clock around loopFilterPic/SAOProcess/ALFProcess)",
-                "single_thread_value": round(single[0] * mpx / single[1][0], 1),
-                "stage_share": [round(s / sum(stages), 3) for s in stages]}
+        out = {"value": round(value, 1), "unit": "Mpixel/s", "cores": cores, "kind": "reference",
+               "sample": f"all {n} pictures of tests/golden/streams/{wl['stream']}.bin decoded by {cores} concurrent unmodified VTM 2.1 decoders (--SIMD default = best available, "
+                         f"AVX2 on this box); filter-chain time only (steady_clock around loopFilterPic/SAOProcess/ALFProcess)",
+               "single_thread_value": round(single[0] * mpx / single[1][0], 1),
+               "stage_share": [round(s / sum(stages), 3) for s in stages]}
+        try:   # the same with --SIMD=SCALAR (only ALF has a SIMD path in this reference)
+            ns, cs, _ = reference_chain_run(wl["stream"], w, h, cores, simd="SCALAR")
+            s1 = reference_chain_run(wl["stream"], w, h, 1, simd="SCALAR")
+            out["simd_scalar"] = {"value": round(sum(ns * mpx / c for c in cs), 1), "single_thread_value": round(s1[0] * mpx / s1[1][0], 1)}
+        except Exception as e:  # pragma: no cover
+            out["simd_scalar"] = {"error": str(e)[:200]}
+        return out
     n, dt = oracle_port_run(w, h, pics, planes)
     return {"value": round(n * mpx / dt, 1), "unit": "Mpixel/s", "cores": 1, "kind": "port",
             "sample": f"{n} synthetic pictures through oracle/liboracle.so (scalar C restatement), oracle/_ref absent"}
+
+
+def dropin_leg():
+    """The reference-API path, measured in the reference's own decoder: per-picture time of the three filter calls in DecoderApp with
+    the host shim + libilf_b200.so (pack + upload + kernels + download, pageable PelStorage planes) against the stock CPU filters, on
+    the committed 1080p and 4K random-access streams; average over ALL pictures after the first (which carries the CUDA context)."""
+    shim, stock = os.path.join(ROOT, "oracle", "_ref", "DecoderApp_ilf_b200"), os.path.join(ROOT, "oracle", "_ref", "vtm_capture")
+    if not (os.path.exists(shim) and os.path.exists(stock)):
+        return {"unavailable": "oracle/_ref binaries did not travel"}
+    out = {}
+    for name in ("ra_1080p", "ra_4k"):
+        bit = os.path.join(ROOT, "tests", "golden", "streams", name + ".bin")
+        if not os.path.exists(bit):
+            continue
+        res = {}
+        for label, exe in (("cpu", stock), ("gpu", shim)):
+            env = dict(os.environ, ILF_TIMING="1")
+            env.pop("ILF_CAPTURE_DIR", None)
+            r = subprocess.run([exe, "-b", bit, "-d", "10", "-o", "/dev/null"], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+            us = [tuple(int(v) for v in m) for m in re.findall(r"\[ILFTIME\].*deblock_us=(\d+) sao_us=(\d+) alf_us=(\d+)", r.stderr)]
+            if r.returncode != 0 or len(us) < 2:
+                res[label] = {"error": (r.stderr or r.stdout)[-200:]}
+                continue
+            us = us[1:]
+            res[label] = {"ms_per_picture": round(sum(sum(u) for u in us) / len(us) / 1e3, 3), "pictures": len(us),
+                          "stage_ms": [round(sum(u[k] for u in us) / len(us) / 1e3, 3) for k in range(3)], "hash_sei_ok": r.stdout.count("(OK)")}
+        if "ms_per_picture" in res.get("cpu", {}) and "ms_per_picture" in res.get("gpu", {}):
+            res["gpu_over_cpu_time"] = round(res["gpu"]["ms_per_picture"] / res["cpu"]["ms_per_picture"], 3)
+        out[name] = res
+    out["what"] = "filter ms per picture inside DecoderApp: gpu = host shim (ilf_pack + ilf_upload + kernels + ilf_download through the C ABI), cpu = the reference's own filters, one thread"
+    return out
 
 
 def run_reference(args, wl):
@@ -273,9 +318,7 @@ def run_reference(args, wl):
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count()
     w, h = wl["width"], wl["height"]
     mpx = w * h / 1e6
-    # bounded sample per step: the first pictures of the stream in decoding order (I + B pictures of one RA GOP) on every core;
-    # fewer of them when many steps are asked for, so that the whole run stays within a few minutes (a step costs a decode)
-    sample_pics = 5 if args.steps <= 20 else (3 if args.steps <= 50 else 2)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if reference_chain_run(wl["stream"], w, h, 1, 1) is None:
         # the reference binary did not travel: time the C restatement instead
         pics = load_sideinfo(args.workload)
@@ -283,21 +326,22 @@ def run_reference(args, wl):
         n, dt = oracle_port_run(w, h, pics, planes)
         val, ms, kind, c, smp = n * mpx / dt, dt / n * 1e3, "port", 1, "oracle/liboracle.so, synthetic planes"
     else:
+        # a step = the whole stream (the same pictures the B200 arm filters per step) on every core at once
         for _ in range(args.warmup):
-            reference_chain_run(wl["stream"], w, h, cores, sample_pics)
-        tot_px, tot_t = 0.0, 0.0
+            reference_chain_run(wl["stream"], w, h, cores)
+        tot_t = 0.0
         vals = []
         for _ in range(args.steps):
-            n, chain, _st = reference_chain_run(wl["stream"], w, h, cores, sample_pics)
+            n, chain, _st = reference_chain_run(wl["stream"], w, h, cores)
             vals.append(sum(n * mpx / c for c in chain))
             tot_t += max(chain)
         val = float(np.mean(vals))
         ms = tot_t / args.steps * 1e3
         kind, c = "reference", cores
-        smp = f"each step: first {sample_pics} pictures of {wl['stream']}.bin on each of {cores} concurrent VTM 2.1 decoders, filter-chain time only"
+        smp = f"each step: all {n} pictures of {wl['stream']}.bin on each of {cores} concurrent unmodified VTM 2.1 decoders (one per host core), filter-chain time only"
     line = {"impl": "reference", "metric": "deblock+SAO+ALF Mpixel/s", "value": round(val, 1), "unit": "Mpixel/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(ms, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int16",
-            "data": "synthetic", "config": {"workload": wl["desc"]},
+            "data": "synthetic", "config": shared_config(wl, args.workload, world),
             "cpu_baseline": {"value": round(val, 1), "unit": "Mpixel/s", "cores": c, "kind": kind, "sample": smp},
             "e2e": {"value": round(val, 1), "unit": "Mpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     emit(line)
@@ -348,91 +392,96 @@ def chain_table(kt, ms_region, steps, pixels_per_step, peak):
     return {"algo_mb_per_step": round(nbytes / steps / 1e6, 1), "bytes_per_pixel": round(nbytes / (steps * pixels_per_step), 2), "gbs": round(gbs, 1), "frac": round(gbs / peak, 4)}
 
 
-def run_bands(args, wl):
-    """BASELINE config 4: every rank owns a band of CTU rows of ONE picture (vvcsoftware_vtm_b200.bands), uploads its own rows,
-    pulls 16 halo rows per side from its neighbours' input planes (CUDA IPC mapping, device-to-device over NVLink P2P) and runs the
-    chain on its band.  A step = halo exchange + chain for `--batch` (default 4) resident pictures; strong scaling."""
-    import torch
-    import torch.distributed as dist
-    import vvcsoftware_vtm_b200 as v
-    from vvcsoftware_vtm_b200 import bands
+def plane_crcs(planes):
+    import zlib
+    return [zlib.crc32(np.ascontiguousarray(p).tobytes()) for p in planes]
 
-    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    torch.cuda.set_device(local)
-    if world > 1:
-        bind_to_gpu_numa(local)
-    v.load_library()
+
+def bands_record(args, wl, rank, world, local, dist, torch, v):
+    """BASELINE config 4: every rank owns a band of CTU rows of ONE picture (vvcsoftware_vtm_b200.bands), uploads its own rows,
+    pulls 16 halo rows per side from its neighbours' input planes (CUDA IPC mapping, device-to-device over NVLink P2P, one copy
+    kernel) and runs the chain on its band.  A step = halo exchange + chain for B resident pictures; strong scaling.  The record
+    carries a PARITY check -- every rank's own rows after the chain, CRC-32 per plane, against the same rows of the whole picture
+    filtered by one context on rank 0 -- and the whole-picture time of rank 0 (the N = 1 figure of the same run).  Returns the
+    record on rank 0, None elsewhere; raises on a parity mismatch."""
+    from vvcsoftware_vtm_b200 import bands
     w, h = wl["width"], wl["height"]
     mpx = w * h / 1e6
-    side = load_sideinfo(args.workload)
-    B = args.batch or 4
+    side = load_sideinfo("intra_8k_bands")
+    side_on = all_on_sideinfo(side)
+    B = args.bands_batch
+    steps = max(3, min(args.steps, 20))
     f = bands.make_band_context(w, h, 10, 10, 7, rank, world, local, num_slots=B)
     y0, y1 = f.own_row0, f.own_row0 + f.own_rows
     # synthetic planes: a 4K texture tiled 2 x 2 (every rank builds the picture and keeps its own rows)
     q = synth_planes(w // 2, h // 2, 1, seed=8000)[0]
     pic = [np.tile(p, (2, 2)) for p in q]
     own = [np.ascontiguousarray(pic[0][y0:y1]), np.ascontiguousarray(pic[1][y0 // 2:y1 // 2]), np.ascontiguousarray(pic[2][y0 // 2:y1 // 2])]
-    del pic
+    if rank != 0:
+        del pic
     pins = [torch.from_numpy(a).pin_memory() for a in own]
     own = [t.numpy() for t in pins]
 
-    def set_side(slot, si):
-        s = bands.slice_side_info(si, f.row0, f.rows)
-        f.set_deblock_info(slot, s["db_params"].tobytes(), s["db_info"], s.get("db_info_c"), s.get("db_mv16"), None, s["ctu_slice"])
-        f.set_sao_params(slot, s["sao_ctus"])
-        f.set_alf_params(slot, s["alf_params"].tobytes(), s["alf_ctu_enable"])
+    def set_side(ctx, slot, si, sliced=True):
+        s_ = bands.slice_side_info(si, ctx.row0, ctx.rows) if sliced else si
+        ctx.set_deblock_info(slot, s_["db_params"].tobytes(), s_["db_info"], s_.get("db_info_c"), s_.get("db_mv16"), None, s_["ctu_slice"])
+        ctx.set_sao_params(slot, s_["sao_ctus"])
+        ctx.set_alf_params(slot, s_["alf_params"].tobytes(), s_["alf_ctu_enable"])
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for s in range(B):
-        f.upload_band(s, *own)
+    for s_ in range(B):
+        f.upload_band(s_, *own)
     f.sync()
     handles = [None] * world
-    for s in range(B):
-        mine = f.band_export(s)
+    for s_ in range(B):
+        mine = f.band_export(s_)
         if world > 1:
             dist.all_gather_object(handles, mine)
         else:
             handles = [mine]
-        bands.connect_bands(f, s, rank, world, handles)
+        bands.connect_bands(f, s_, rank, world, handles)
     barrier()   # every rank's input planes are resident before anybody pulls halos
     halo_rows = (f.own_row0 - f.row0) + (f.row0 + f.rows - (f.own_row0 + f.own_rows))
     stream = torch.cuda.ExternalStream(f.stream(), device=torch.device("cuda", local))
+
+    def timed(ctx, step_fn, n_steps, strm, sync_ranks=True):
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if sync_ranks:
+            barrier()
+        else:
+            torch.cuda.synchronize()
+        with torch.cuda.stream(strm):
+            ev0.record(strm)
+            for _ in range(n_steps):
+                step_fn()
+            ev1.record(strm)
+        if sync_ranks:
+            barrier()
+        else:
+            torch.cuda.synchronize()
+        return ev0.elapsed_time(ev1)
 
     def step():
         f.band_exchange(0, B)
         f.run(0, B, 7)
 
-    def measure(side_set, steps):
-        for s in range(B):
-            set_side(s, side_set[0])
+    def measure(side_set):
+        for s_ in range(B):
+            set_side(f, s_, side_set[0])
         f.sync()
         for _ in range(max(args.warmup, 3)):
             step()
         f.sync()
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-
-        def region():
-            barrier()
-            with torch.cuda.stream(stream):
-                ev0.record(stream)
-                for _ in range(steps):
-                    step()
-                ev1.record(stream)
-            barrier()
-            return ev0.elapsed_time(ev1)
-        f.set_timing(False)          # pass 1: the timed region proper
+        f.set_timing(False)
         l0 = f.launch_count()
-        ms = region()
+        ms = timed(f, step, steps, stream)
         n_launch = f.launch_count() - l0
-        f.set_timing(True)           # pass 2: the same steps with an event pair around every launch (per-kernel durations)
-        region()
+        f.set_timing(True)
+        timed(f, step, steps, stream)
         kt = f.kernel_times()
         f.set_timing(False)
         t = torch.tensor([ms], dtype=torch.float64, device="cuda")
@@ -440,22 +489,61 @@ def run_bands(args, wl):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item()), kt, n_launch
 
-    clocks = ClockSampler(local, period=0.01)
-    clocks.start()
-    ms_on, kt_on, _ = measure(all_on_sideinfo(side), args.steps)
-    ms_total, ktimes, launches = measure(side, args.steps)
-    clk = clocks.finish()
-    value = B * args.steps * mpx / (ms_total * 1e-3)       # the picture is shared: whole-job pixels = B pictures per step
-    value_on = B * args.steps * mpx / (ms_on * 1e-3)
+    ms_total, ktimes, launches = measure(side)
+    ms_on, kt_on, _ = measure(side_on)          # leaves the all-on side information and its result in the slots
+    value = B * steps * mpx / (ms_total * 1e-3)       # the picture is shared: whole-job pixels = B pictures per step
+    value_on = B * steps * mpx / (ms_on * 1e-3)
+
+    # ---- parity: own rows of slot 0 (all CTUs on) against the whole picture filtered by ONE context on rank 0 ----
+    got = f.download_band(0)
+    crcs = plane_crcs([got["y"], got["cb"], got["cr"]])
+    all_crcs = [None] * world
+    if world > 1:
+        dist.all_gather_object(all_crcs, (y0, y1, crcs))
+    else:
+        all_crcs = [(y0, y1, crcs)]
+    whole = None
+    if rank == 0:
+        g = v.InLoopFilter(w, h, 10, 10, 7, device=local, num_slots=B)
+        pin_full = [torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in pic]
+        for s_ in range(B):
+            g.upload(s_, *(t.numpy() for t in pin_full))
+            set_side(g, s_, side_on[0], sliced=False)
+        g.run(0, 1, 7)
+        ref = g.download(0)
+        bad = []
+        for r_, (a0, a1, c) in enumerate(all_crcs):
+            want = plane_crcs([ref["y"][a0:a1], ref["cb"][a0 // 2:a1 // 2], ref["cr"][a0 // 2:a1 // 2]])
+            if want != c:
+                bad.append(r_)
+        if bad:
+            raise SystemExit(f"bench.py: band parity FAILED on ranks {bad}: the rows a band context produced differ from the whole-picture result")
+        # the N = 1 figure of the same run: the whole picture, B resident copies, on rank 0's GPU alone
+        gstream = torch.cuda.ExternalStream(g.stream(), device=torch.device("cuda", local))
+        for _ in range(3):
+            g.run(0, B, 7)
+        g.sync()
+        ms1_on = timed(g, lambda: g.run(0, B, 7), steps, gstream, sync_ranks=False)
+        for s_ in range(B):
+            set_side(g, s_, side[0], sliced=False)
+        for _ in range(3):
+            g.run(0, B, 7)
+        g.sync()
+        ms1 = timed(g, lambda: g.run(0, B, 7), steps, gstream, sync_ranks=False)
+        whole = {"value": round(B * steps * mpx / (ms1 * 1e-3), 1), "ms_per_step": round(ms1 / steps, 4),
+                 "all_on_value": round(B * steps * mpx / (ms1_on * 1e-3), 1), "all_on_ms_per_step": round(ms1_on / steps, 4)}
+        g.close()
+        del pic
+    barrier()
 
     # end to end: own rows up from page-locked memory, halos from the neighbours, chain, own rows down; one picture at a time,
     # the ranks meet once per picture (uploads done -> halos may be pulled)
-    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    e2e_steps = max(1, min(steps, args.e2e_steps))
     nbytes_own = sum(a.nbytes for a in own)
 
     def e2e_pic():
         f.upload_band(0, *own)
-        set_side(0, side[0])
+        set_side(f, 0, side[0])
         f.sync()
         if world > 1:
             dist.barrier()
@@ -477,30 +565,116 @@ def run_bands(args, wl):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = e2e_steps * mpx / float(t.item())
+    rec = None
+    if rank == 0:
+        peak, _src = hbm_peak()
+        own_px = f.rows * w   # pixels rank 0 really filters per picture (own rows + redundant halo rows)
+        rec = {"what": "BASELINE config 4: ONE 7680x4320 picture in CTU-row bands, one band per GPU; a step = halo exchange + chain for the resident pictures (strong scaling)",
+               "value": round(value, 1), "unit": "Mpixel/s", "ms_per_step": round(ms_total / steps, 4), "steps": steps, "pictures_per_step": B,
+               "bands": bands.band_partition((h + 127) // 128, world), "halo_rows_per_side": 16, "halo_bytes_per_picture_rank0": halo_rows * w * 3,
+               "exchange": "one copy kernel per step reads the neighbours' input planes over NVLink P2P (CUDA IPC mapping between the per-GPU processes), no collective",
+               "bands_parity": "ok", "parity_how": "CRC-32 per plane of every rank's own rows (all CTUs on) == the same rows of the whole picture filtered by one context on rank 0",
+               "per_kernel": kernel_table(ktimes, peak), "chain": chain_table(ktimes, ms_total, steps, B * own_px, peak),
+               "all_on": {"value": round(value_on, 1), "ms_per_step": round(ms_on / steps, 4), "per_kernel": kernel_table(kt_on, peak), "chain": chain_table(kt_on, ms_on, steps, B * own_px, peak)},
+               "n1_whole_picture_same_run": whole,
+               "strong_scaling_efficiency": {"stream_decisions": round(value / (world * whole["value"]), 3), "all_on": round(value_on / (world * whole["all_on_value"]), 3),
+                                             "formula": "value / (n_gpus x whole-picture value of rank 0 in this run)"},
+               "e2e": {"value": round(e2e_value, 1), "unit": "Mpixel/s", "h2d_bytes_per_step": nbytes_own, "d2h_bytes_per_step": nbytes_own, "steps": e2e_steps,
+                       "path": "per picture and rank: upload_band (own rows, page-locked) + side information + barrier + band_exchange + run + download_band"},
+               "gpu_launches": launches}
+    f.close()
+    return rec
 
+
+def streams_record(args, rank, world, local, dist, torch, v):
+    """BASELINE config 5: 64 independent 1080p low-delay streams dealt round-robin to the GPUs, every picture of every stream resident,
+    a step = the chain over all of them (strong scaling: the 64 streams are the fixed job)."""
+    from vvcsoftware_vtm_b200 import bands
+    wl = WORKLOADS["ld_1080p_x64"]
+    w, h = wl["width"], wl["height"]
+    mpx = w * h / 1e6
+    sets = [load_sideinfo(n) for n in wl["npz"]]
+    mine = bands.deal_streams(wl["streams"], world)[rank]
+    side = [pic for st in mine for pic in sets[st % len(sets)]]
+    B = len(side)
+    total_pics = sum(len(sets[st % len(sets)]) for st in range(wl["streams"]))
+    steps = max(3, min(args.steps, 20))
+    planes = synth_planes(w, h, 4, seed=3000 + rank)
+    f = v.InLoopFilter(w, h, 10, 10, 7, device=local, num_slots=B)
+    pins = [[torch.from_numpy(np.ascontiguousarray(p)).pin_memory() for p in trip] for trip in planes]
+
+    def set_side(slot, si):
+        f.set_deblock_info(slot, si["db_params"].tobytes(), si["db_info"], si.get("db_info_c"), si.get("db_mv16"), None, si["ctu_slice"])
+        f.set_sao_params(slot, si["sao_ctus"])
+        f.set_alf_params(slot, si["alf_params"].tobytes(), si["alf_ctu_enable"])
+
+    for s_ in range(B):
+        f.upload(s_, *(t.numpy() for t in pins[s_ % len(pins)]))
+    stream = torch.cuda.ExternalStream(f.stream(), device=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    out = {}
+    for label, side_set in (("stream_decisions", side), ("all_on", all_on_sideinfo(side))):
+        for s_ in range(B):
+            set_side(s_, side_set[s_])
+        f.sync()
+        for _ in range(3):
+            f.run(0, B, 7)
+        f.sync()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        with torch.cuda.stream(stream):
+            ev0.record(stream)
+            for _ in range(steps):
+                f.run(0, B, 7)
+            ev1.record(stream)
+        barrier()
+        t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        out[label] = {"value": round(total_pics * steps * mpx / (ms * 1e-3), 1), "ms_per_step": round(ms / steps, 4)}
+    f.close()
+    if rank != 0:
+        return None
+    return {"what": "BASELINE config 5: 64 independent 1920x1080 low-delay streams (9 pictures each, two encoded streams replicated) dealt round-robin to the GPUs, no collective; "
+                    "a step = the chain over every resident picture of every stream (strong scaling over the fixed 64 streams)",
+            "unit": "Mpixel/s", "streams": wl["streams"], "pictures_total": total_pics, "pictures_on_rank0": B, "steps": steps,
+            "value": out["stream_decisions"]["value"], "ms_per_step": out["stream_decisions"]["ms_per_step"], "all_on": out["all_on"]}
+
+
+def run_bands(args, wl):
+    """`--workload intra_8k_bands`: the band record as the line of its own."""
+    import torch
+    import torch.distributed as dist
+    import vvcsoftware_vtm_b200 as v
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    if world > 1:
+        bind_to_gpu_numa(local)
+    v.load_library()
+    clocks = ClockSampler(local, period=0.01)
+    clocks.start()
+    rec = bands_record(args, wl, rank, world, local, dist, torch, v)
+    clk = clocks.finish()
     if rank == 0:
         peak, peak_src = hbm_peak()
-        own_px = f.rows * w   # pixels rank 0 really filters per picture (own rows + redundant halo rows)
-        per_kernel = kernel_table(ktimes, peak)
-        dom = max(per_kernel, key=lambda k: per_kernel[k]["avg_ms"])
-        pk_on = kernel_table(kt_on, peak)
-        line = {"metric": "deblock+SAO+ALF Mpixel/s", "value": round(value, 1), "unit": "Mpixel/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-                "ms_per_step": round(ms_total / args.steps, 4), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int16", "data": "synthetic",
-                "config": {"workload": wl["desc"], "pictures_per_step": B, "bands": bands.band_partition((h + 127) // 128, world), "halo_rows_per_side": 16,
-                           "halo_bytes_per_picture_rank0": halo_rows * w * 3, "exchange": "cudaMemcpy2DAsync device-to-device out of the neighbour's planes (CUDA IPC mapping, NVLink P2P), no collective",
-                           "side_info": f"real, bench_data/{wl['npz'][0]}.npz", "planes": "synthetic texture + 8x8 blockiness",
-                           "l2": "per rank working set of a stage: %d MB" % (B * 2 * own_px * 3 // 10 ** 6)},
-                "roofline": {"bound": "hbm", "kernel": dom, "achieved": per_kernel[dom]["algo_gbs"], "peak": peak, "unit": "GB/s", "frac": per_kernel[dom]["frac"], "traffic": None,
-                             "peak_source": peak_src, "note": "per-kernel numbers of rank 0 (its band incl. halo rows)",
-                             "chain": chain_table(ktimes, ms_total, args.steps, B * own_px, peak), "per_kernel": per_kernel,
-                             "all_on": {"value": round(value_on, 1), "unit": "Mpixel/s", "ms_per_step": round(ms_on / args.steps, 4),
-                                        "chain": chain_table(kt_on, ms_on, args.steps, B * own_px, peak), "per_kernel": pk_on}},
-                "cpu_baseline": None,
-                "e2e": {"value": round(e2e_value, 1), "unit": "Mpixel/s", "h2d_bytes_per_step": nbytes_own, "d2h_bytes_per_step": nbytes_own, "steps": e2e_steps,
-                        "path": "per picture and rank: upload_band (own rows, page-locked) + side information + barrier + band_exchange + run + download_band"},
-                "gpu_launches": launches, "clocks": clk}
+        pk = rec["per_kernel"]
+        dom = max(pk, key=lambda k: pk[k]["avg_ms"])
+        line = {"metric": "deblock+SAO+ALF Mpixel/s", "value": rec["value"], "unit": "Mpixel/s", "n_gpus": world, "steps": rec["steps"], "warmup": max(args.warmup, 3),
+                "ms_per_step": rec["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int16", "data": "synthetic",
+                "config": {"workload": wl["desc"], "pictures_per_step": rec["pictures_per_step"], "bands": rec["bands"]},
+                "roofline": {"bound": "hbm", "kernel": dom, "achieved": pk[dom]["algo_gbs"], "peak": peak, "unit": "GB/s", "frac": pk[dom]["frac"], "traffic": None, "peak_source": peak_src,
+                             "note": "per-kernel numbers of rank 0 (its band incl. halo rows)"},
+                "bands_8k": rec, "cpu_baseline": None, "e2e": rec["e2e"], "gpu_launches": rec["gpu_launches"], "clocks": clk}
         emit(line)
-    f.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -680,6 +854,13 @@ def run_b200(args, wl):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * Be * e2e_steps * mpx / float(t.item())
 
+    f.close()
+    # ---- the other sharded configurations of BASELINE.json, in the same line (the driver's scaling run launches only this command) ----
+    sub = {}
+    if not args.quick and "streams" not in wl:
+        torch.cuda.empty_cache()
+        sub["bands_8k"] = bands_record(args, WORKLOADS["intra_8k_bands"], rank, world, local, dist, torch, v)
+        sub["streams_64"] = streams_record(args, rank, world, local, dist, torch, v)
     if rank == 0:
         peak, peak_src = hbm_peak()
         per_kernel = kernel_table(ktimes, peak)
@@ -688,13 +869,15 @@ def run_b200(args, wl):
         pk_on = kernel_table(kt_on, peak)
         dom_on = max(pk_on, key=lambda k: pk_on[k]["avg_ms"])
         cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count()
-        cpu = cpu_baseline(wl, cores, side, planes) if (world == 1 and not args.no_cpu_baseline) else None
+        cpu = cpu_baseline(wl, cores, side, planes) if (world == 1 and not args.no_cpu_baseline and not args.quick) else None
+        dropin = dropin_leg() if (world == 1 and not args.quick) else None
         line = {"metric": "deblock+SAO+ALF Mpixel/s", "value": round(value, 1), "unit": "Mpixel/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": round(ms_total / args.steps, 4), "higher_is_better": True, "scaling": wl.get("scaling", "weak"),
                 "vs_baseline": None, "dtype": "int16", "data": "synthetic",
-                "config": {"workload": wl["desc"], "batch_pictures_per_gpu": B, "side_info": f"real, bench_data/{','.join(wl.get('npz', [args.workload]))}.npz ({len(side)} pictures per GPU)",
-                           "planes": "synthetic texture + 8x8 blockiness", "l2": f"working set {B * 2 * h2d / 1e6:.0f} MB per stage > 126 MB L2 (inputs larger than L2, no flush)",
-                           "parallelism": f"independent pictures, {world} GPU(s), no collective"},
+                "config": shared_config(wl, args.workload, world),
+                "config_detail": {"batch_pictures_per_gpu": B, "side_info": f"real, bench_data/{','.join(wl.get('npz', [args.workload]))}.npz ({len(side)} pictures per GPU)",
+                                  "planes": "synthetic texture + 8x8 blockiness", "l2": f"working set {B * 2 * h2d / 1e6:.0f} MB per stage > 126 MB L2 (inputs larger than L2, no flush)",
+                                  "parallelism": f"independent pictures, {world} GPU(s), no collective"},
                 "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4),
                              "traffic": (ncu_traffic(dom, B) or {}).get("bytes_per_launch"), "traffic_detail": ncu_traffic(dom, B),
                              "peak_source": peak_src, "chain": chain_table(ktimes, ms_total, args.steps, B * mpx * 1e6, peak), "per_kernel": per_kernel,
@@ -710,8 +893,10 @@ def run_b200(args, wl):
                 "e2e": {"value": round(e2e_value, 1), "unit": "Mpixel/s", "h2d_bytes_per_step": Be * h2d + side_b, "d2h_bytes_per_step": Be * d2h, "pictures_per_step": Be,
                         "steps": e2e_steps, "path": "per picture InLoopFilter.upload + set_deblock_info/set_sao_params/set_alf_params + run + download_async (C ABI ilf_upload / ilf_set_* / ilf_run / ilf_download_async / ilf_wait), page-locked host buffers, slots cycled"},
                 "gpu_launches": launches, "clocks": clk}
+        if dropin is not None:
+            line["dropin"] = dropin
+        line.update({k: r for k, r in sub.items() if r is not None})
         emit(line)
-    f.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -726,6 +911,8 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="pictures resident per GPU and filtered per step (default: every picture of the workload's side information once, e.g. the 17 pictures of one 4K random-access GOP)")
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="kernel A/B runs: no CPU baseline, no drop-in leg, no bands_8k / streams_64 sub-records")
+    ap.add_argument("--bands-batch", type=int, default=16, help="resident 8K pictures per step of the band configuration")
     args = ap.parse_args()
     args.workload = args.workload or default_workload()
     wl = WORKLOADS[args.workload]

@@ -13,7 +13,9 @@ SHIM_DEC = os.path.join(ROOT, "oracle", "_ref", "DecoderApp_ilf_b200")
 STOCK_DEC = os.path.join(ROOT, "oracle", "_ref", "DecoderApp")
 pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not os.path.exists(SHIM_DEC), reason="oracle/_ref/DecoderApp_ilf_b200 not built (needs /root/reference at build time)")]
 
-STREAMS = {"intra_416x240": 8, "ra_416x240": 17, "ldp_416x240": 6, "ldb_416x240": 6, "ra_1080p": 32, "ld_1080p_s3001": 9}
+# every committed stream: BASELINE configs 1 (416x240), 2 (1080p RA), 3 (4K RA), 4 (the 8K intra picture) and 5 (1080p low delay)
+STREAMS = {"intra_416x240": 8, "ra_416x240": 17, "ldp_416x240": 6, "ldb_416x240": 6, "ra_1080p": 32, "ld_1080p_s3001": 9, "ld_1080p_s3002": 9,
+           "ra_4k": 17, "intra_8k": 1}
 
 
 def _md5(path):

@@ -2,7 +2,7 @@
 # A/B the library variants under variants/ on the device-resident bench (run on the GPU box): tools/ab.sh [name...]
 run() {
   local label=$1; shift
-  env "$@" python bench.py --steps 30 --warmup 3 --e2e-steps 1 --no-cpu-baseline > /tmp/b.json 2>/tmp/b.err || { echo "$label FAILED"; tail -3 /tmp/b.err; return; }
+  env "$@" python bench.py --steps 30 --warmup 3 --e2e-steps 1 --quick > /tmp/b.json 2>/tmp/b.err || { echo "$label FAILED"; tail -3 /tmp/b.err; return; }
   python - "$label" <<'PY'
 import json,sys
 d=json.load(open('/tmp/b.json'))

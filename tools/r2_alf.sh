@@ -7,7 +7,7 @@ tail -5 gpurun_out/pytest_gpu.log
 fi
 run() {
   local label=$1; shift
-  env "$@" python bench.py --steps 30 --warmup 3 --e2e-steps 1 --no-cpu-baseline > gpurun_out/b_$label.json 2>gpurun_out/b_$label.err || { echo "$label FAILED"; tail -3 gpurun_out/b_$label.err; return; }
+  env "$@" python bench.py --steps 30 --warmup 3 --e2e-steps 1 --quick > gpurun_out/b_$label.json 2>gpurun_out/b_$label.err || { echo "$label FAILED"; tail -3 gpurun_out/b_$label.err; return; }
   python - "$label" <<'PY'
 import json,sys
 d=json.load(open('gpurun_out/b_%s.json'%sys.argv[1]))
