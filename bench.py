@@ -375,6 +375,19 @@ def ncu_traffic(kernel, batch):
     return None
 
 
+def host_ceiling(world, h2d_bytes_per_picture, mpx):
+    """What the box's host side allows for the end-to-end leg with `world` GPUs copying at once (profiles/r02_pcie_probe_mg.json,
+    tools/pcie_probe_mg.py on an 8-GPU box of this pool): both-directions GB/s and the Mpixel/s that bounds."""
+    try:
+        rows = json.load(open(os.path.join(ROOT, "profiles", "r02_pcie_probe_mg.json")))["rows"]
+        row = max((r for r in rows if r["gpus_copying"] <= world), key=lambda r: r["gpus_copying"])
+        gbs = row["both_each_dir"]["aggregate_gbs"]
+        return {"both_directions_gbs_each_way": gbs, "gpus_copying": row["gpus_copying"], "mpixel_per_s": round(gbs * 1e9 / h2d_bytes_per_picture * mpx, 1),
+                "source": "profiles/r02_pcie_probe_mg.json (measured on an 8-GPU box of this pool; a smaller lease may sit on a different host)"}
+    except Exception:
+        return None
+
+
 def kernel_table(kt, peak):
     tab = {}
     for k, (ms, n, nbytes) in kt.items():
@@ -891,6 +904,7 @@ def run_b200(args, wl):
                                                 mpixel_per_s=round(B * mpx / (kt_stats[0] / max(kt_stats[1], 1) * 1e-3), 1))},
                 "cpu_baseline": cpu,
                 "e2e": {"value": round(e2e_value, 1), "unit": "Mpixel/s", "h2d_bytes_per_step": Be * h2d + side_b, "d2h_bytes_per_step": Be * d2h, "pictures_per_step": Be,
+                        "host_ceiling": host_ceiling(world, (Be * h2d + side_b) / Be, mpx),
                         "steps": e2e_steps, "path": "per picture InLoopFilter.upload + set_deblock_info/set_sao_params/set_alf_params + run + download_async (C ABI ilf_upload / ilf_set_* / ilf_run / ilf_download_async / ilf_wait), page-locked host buffers, slots cycled"},
                 "gpu_launches": launches, "clocks": clk}
         if dropin is not None:
