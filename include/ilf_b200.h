@@ -243,6 +243,24 @@ int ilf_sao_stats(ilf_ctx* ctx, int first_slot, int num_slots);
 int ilf_get_sao_stats(ilf_ctx* ctx, int slot, int64_t* out);
 
 /* ---------------------------------------------------------------------------------------------
+ * Post-filter consumers on the device-resident picture: what the decoder does with a picture right after the
+ * in-loop filters.
+ *   ilf_picture_hash       the two decoded-picture-hash methods that are not inherently serial, calcCRC and calcChecksum
+ *                          (source/Lib/CommonLib/PicYuvMD5.cpp:91-175), of the slot's CURRENT picture: out[Y, Cb, Cr] = the 16-bit CRC
+ *                          / 32-bit checksum the reference puts into the digest, big-endian, before comparing it with the SEI
+ *                          (DecLib.cpp:579-588).  12 bytes come down instead of the picture.  MD5 stays on the host.
+ *   ilf_download_extended  ilf_download into planes that have `margin` luma (margin / 2 chroma) samples of room on every side (a
+ *                          PelStorage of Picture::create, Picture.cpp:791-…), and the margins filled by replication as
+ *                          Picture::extendPicBorder does (Picture.cpp:996-1040) -- the caller marks the picture as extended.
+ * Not available on band contexts.
+ * ------------------------------------------------------------------------------------------- */
+#define ILF_HASH_CRC 1
+#define ILF_HASH_CHECKSUM 2
+int ilf_picture_hash(ilf_ctx* ctx, int slot, int kind, uint32_t out[3]);
+int ilf_download_extended(ilf_ctx* ctx, int slot, int16_t* y, ptrdiff_t stride_y, int16_t* cb, ptrdiff_t stride_cb, int16_t* cr, ptrdiff_t stride_cr,
+                          int margin);
+
+/* ---------------------------------------------------------------------------------------------
  * Measurement helpers (bench.py).  Accumulated device time per kernel in milliseconds since
  * ilf_set_timing(ctx, 1) (CUDA event pairs around every launch on the context's stream, collected
  * without synchronising inside ilf_run), number of kernel launches issued since ilf_create, and

@@ -536,3 +536,52 @@ int ilf_oracle_sao_stats_block(const int16_t* src, ptrdiff_t ss, const int16_t* 
                   (avail6 >> 4) & 1, (avail6 >> 5) & 1, out);
   return 0;
 }
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Post-filter consumers: decoded-picture hash CRC / checksum and reference border extension.
+ * --------------------------------------------------------------------------------------------------------- */
+/* compCRC, PicYuvMD5.cpp:91-128: CRC-16 (poly 0x1021, register starts at 0xffff) over the low byte then -- above 8 bit -- the high
+ * byte of every sample in raster order, message bits shifted in at the bottom, 16 zero bits appended. */
+unsigned ilf_oracle_crc(const int16_t* plane, ptrdiff_t stride, int width, int height, int bit_depth) {
+  unsigned crc = 0xffff;
+  for (int y = 0; y < height; y++)
+    for (int x = 0; x < width; x++) {
+      const unsigned v = (uint16_t)plane[y * stride + x];
+      for (int b = 0; b < (bit_depth > 8 ? 16 : 8); b++) {
+        const unsigned msb = (crc >> 15) & 1, bit = b < 8 ? (v >> (7 - b)) & 1 : (v >> (23 - b)) & 1;
+        crc = (((crc << 1) + bit) & 0xffff) ^ (msb * 0x1021);
+      }
+    }
+  for (int b = 0; b < 16; b++) {
+    const unsigned msb = (crc >> 15) & 1;
+    crc = ((crc << 1) & 0xffff) ^ (msb * 0x1021);
+  }
+  return crc;
+}
+
+/* compChecksum, PicYuvMD5.cpp:144-163 */
+unsigned ilf_oracle_checksum(const int16_t* plane, ptrdiff_t stride, int width, int height, int bit_depth) {
+  uint32_t sum = 0;
+  for (int y = 0; y < height; y++)
+    for (int x = 0; x < width; x++) {
+      const unsigned mask = ((x & 0xff) ^ (y & 0xff) ^ (x >> 8) ^ (y >> 8)) & 0xff;
+      const unsigned v = (uint16_t)plane[y * stride + x];
+      sum += (v & 0xff) ^ mask;
+      if (bit_depth > 8) sum += (v >> 8) ^ mask;
+    }
+  return sum;
+}
+
+/* Picture::extendPicBorder, Picture.cpp:996-1040, one plane: `plane` points at sample (0, 0) of a buffer that has xmargin columns
+ * and ymargin rows of room on every side. */
+void ilf_oracle_extend_border(int16_t* plane, ptrdiff_t stride, int width, int height, int xmargin, int ymargin) {
+  for (int y = 0; y < height; y++)
+    for (int x = 0; x < xmargin; x++) {
+      plane[y * stride - xmargin + x] = plane[y * stride];
+      plane[y * stride + width + x] = plane[y * stride + width - 1];
+    }
+  for (int y = 0; y < ymargin; y++) {
+    memcpy(plane + (height + y) * stride - xmargin, plane + (height - 1) * stride - xmargin, sizeof(int16_t) * (size_t)(width + 2 * xmargin));
+    memcpy(plane - (y + 1) * stride - xmargin, plane - xmargin, sizeof(int16_t) * (size_t)(width + 2 * xmargin));
+  }
+}

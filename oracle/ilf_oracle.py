@@ -133,3 +133,28 @@ def sao_stats_block(src, org, x0, y0, w, h, bd, is_chroma, avail6):
     gp = org.ctypes.data + 2 * (y0 * org.shape[1] + x0)
     assert f(sp, src.shape[1], gp, org.shape[1], w, h, bd, int(is_chroma), avail6, _p(out)) == 0
     return out
+
+
+def picture_hash(pic, bd_luma, bd_chroma, kind):
+    """calcCRC / calcChecksum (PicYuvMD5.cpp:130-175): [Y, Cb, Cr] values; kind = "crc" or "checksum"."""
+    f = lib().ilf_oracle_crc if kind == "crc" else lib().ilf_oracle_checksum
+    f.restype = C.c_uint
+    f.argtypes = [C.c_void_p, C.c_ssize_t, C.c_int, C.c_int, C.c_int]
+    out = []
+    for k, bd in (("y", bd_luma), ("cb", bd_chroma), ("cr", bd_chroma)):
+        a = np.ascontiguousarray(pic[k], dtype=np.int16)
+        out.append(int(f(_p(a), a.shape[1], a.shape[1], a.shape[0], bd)))
+    return out
+
+
+def extend_border(plane, xmargin, ymargin):
+    """Picture::extendPicBorder of one plane: returns the (h + 2 ymargin, w + 2 xmargin) array with replicated borders."""
+    plane = np.ascontiguousarray(plane, dtype=np.int16)
+    h, w = plane.shape
+    big = np.full((h + 2 * ymargin, w + 2 * xmargin), -1, np.int16)
+    big[ymargin:ymargin + h, xmargin:xmargin + w] = plane
+    f = lib().ilf_oracle_extend_border
+    f.restype = None
+    f.argtypes = [C.c_void_p, C.c_ssize_t, C.c_int, C.c_int, C.c_int, C.c_int]
+    f(big.ctypes.data + 2 * (ymargin * big.shape[1] + xmargin), big.shape[1], w, h, xmargin, ymargin)
+    return big

@@ -11,6 +11,9 @@
 
 #include "CommonLib/AdaptiveLoopFilter.h"
 #include "CommonLib/SampleAdaptiveOffset.h"
+#include "CommonLib/CodingStructure.h"
+#include "CommonLib/Picture.h"
+#include "CommonLib/SEI.h"
 #include "EncoderLib/CABACWriter.h"
 // getBlkStats and the skip-line tables are private members of the reference class: open them for this test door only
 // (every header the class needs is already included above, so nothing else is parsed under the define)
@@ -121,6 +124,55 @@ int ref_sao_blk_stats( int is_chroma, int bit_depth, const int16_t* src, const i
     memcpy( out + t * 64, stats[t].diff, sizeof( int64_t ) * 32 );
     memcpy( out + t * 64 + 32, stats[t].count, sizeof( int64_t ) * 32 );
   }
+  return 0;
+}
+}
+
+// The decoded-picture hashes the reference compares with the SEI (PicYuvMD5.cpp:91-175; the component functions have external linkage
+// but no header) and Picture::extendPicBorder (Picture.cpp:996-1040) on a real Picture object.
+uint32_t compCRC( int bitdepth, const Pel* plane, uint32_t width, uint32_t height, uint32_t stride, PictureHash& digest );
+uint32_t compChecksum( int bitdepth, const Pel* plane, uint32_t width, uint32_t height, uint32_t stride, PictureHash& digest, const BitDepths& bitDepths );
+extern "C" {
+unsigned ref_plane_crc( const int16_t* plane, int stride, int w, int h, int bit_depth )
+{
+  PictureHash d;
+  compCRC( bit_depth, plane, w, h, stride, d );
+  return ( unsigned( d.hash[0] ) << 8 ) | d.hash[1];
+}
+unsigned ref_plane_checksum( const int16_t* plane, int stride, int w, int h, int bit_depth )
+{
+  PictureHash d;
+  BitDepths   bd;
+  bd.recon[0] = bd.recon[1] = bit_depth;
+  compChecksum( bit_depth, plane, w, h, stride, d, bd );
+  return ( unsigned( d.hash[0] ) << 24 ) | ( unsigned( d.hash[1] ) << 16 ) | ( unsigned( d.hash[2] ) << 8 ) | d.hash[3];
+}
+// in: three dense planes (4:2:0); out: the three planes WITH their margins (luma margin `margin`, chroma margin / 2), dense
+int ref_extend_pic_border( const int16_t* y, const int16_t* cb, const int16_t* cr, int w, int h, int margin, int16_t* oy, int16_t* ocb, int16_t* ocr )
+{
+  Picture pic;
+  pic.create( CHROMA_420, Size( w, h ), 128, margin, true );
+  CodingStructure cs( g_globalUnitCache.cuCache, g_globalUnitCache.puCache, g_globalUnitCache.tuCache );
+  cs.area = UnitArea( CHROMA_420, Area( 0, 0, w, h ) );
+  pic.cs  = &cs;
+  const int16_t* in[3]  = { y, cb, cr };
+  int16_t*       out[3] = { oy, ocb, ocr };
+  for( int c = 0; c < 3; c++ )
+  {
+    PelBuf b = pic.getRecoBuf().get( ComponentID( c ) );
+    for( unsigned r = 0; r < b.height; r++ ) memcpy( b.buf + ptrdiff_t( r ) * b.stride, in[c] + size_t( r ) * b.width, b.width * sizeof( Pel ) );
+  }
+  pic.m_bIsBorderExtended = false;
+  pic.extendPicBorder();
+  for( int c = 0; c < 3; c++ )
+  {
+    PelBuf    b  = pic.getRecoBuf().get( ComponentID( c ) );
+    const int mx = margin >> ( c ? 1 : 0 ), my = mx;
+    const int ow = int( b.width ) + 2 * mx;
+    for( int r = -my; r < int( b.height ) + my; r++ ) memcpy( out[c] + size_t( r + my ) * ow, b.buf + ptrdiff_t( r ) * b.stride - mx, ow * sizeof( Pel ) );
+  }
+  pic.cs = nullptr;
+  pic.destroy();
   return 0;
 }
 }

@@ -129,3 +129,26 @@ def test_sao_statistics_block_vs_reference(units, oracle, bd, is_chroma, w, h, s
             assert units.ref_sao_blk_stats(is_chroma, bd, sp, gp, W, W, w, h, avail6, want.ctypes.data) == 0
             got = oracle.sao_stats_block(src, org, 8, 8, w, h, bd, is_chroma, avail6)
             assert np.array_equal(got, want), f"{kind} avail6={avail6:06b}: types differing {np.nonzero((got != want).any(axis=1))[0]}"
+
+
+# ---- post-filter consumers: decoded-picture hash and reference border extension ----
+@pytest.mark.skipif(not os.path.exists(UNITS), reason="oracle/_ref/libvtm_units.so not built (needs /root/reference)")
+@pytest.mark.parametrize("bd,w,h", [(10, 416, 240), (8, 264, 72), (12, 136, 264), (10, 200, 136), (10, 8, 8)])
+def test_oracle_hash_and_border_match_reference(bd, w, h, oracle):
+    """oracle CRC / checksum == the reference's compCRC / compChecksum (PicYuvMD5.cpp:91-163); oracle border extension ==
+    Picture::extendPicBorder run on a real Picture (Picture.cpp:996-1040)."""
+    ref = C.CDLL(UNITS)
+    rng = np.random.default_rng(bd * 1000 + w)
+    pic = {"y": rng.integers(0, 1 << bd, (h, w)).astype(np.int16), "cb": rng.integers(0, 1 << bd, (h // 2, w // 2)).astype(np.int16),
+           "cr": rng.integers(0, 1 << bd, (h // 2, w // 2)).astype(np.int16)}
+    for kind, fn in (("crc", ref.ref_plane_crc), ("checksum", ref.ref_plane_checksum)):
+        fn.restype = C.c_uint
+        fn.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
+        want = [fn(pic[k].ctypes.data, pic[k].shape[1], pic[k].shape[1], pic[k].shape[0], bd) for k in ("y", "cb", "cr")]
+        assert oracle.picture_hash(pic, bd, bd, kind) == want, kind
+    m = 16
+    outs = [np.zeros((a.shape[0] + 2 * (m >> s), a.shape[1] + 2 * (m >> s)), np.int16) for a, s in ((pic["y"], 0), (pic["cb"], 1), (pic["cr"], 1))]
+    ref.ref_extend_pic_border.argtypes = [C.c_void_p] * 3 + [C.c_int] * 3 + [C.c_void_p] * 3
+    assert ref.ref_extend_pic_border(pic["y"].ctypes.data, pic["cb"].ctypes.data, pic["cr"].ctypes.data, w, h, m, *(o.ctypes.data for o in outs)) == 0
+    for o, (k, s) in zip(outs, (("y", 0), ("cb", 1), ("cr", 1))):
+        assert np.array_equal(o, oracle.extend_border(pic[k], m >> s, m >> s)), k

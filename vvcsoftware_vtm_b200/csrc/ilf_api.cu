@@ -155,6 +155,7 @@ struct ilf_ctx {
   long long kernel_launches[ILF_NUM_KERNELS] = {0, 0, 0, 0, 0};
   int num_ctus = 0;
   CopyPool copy_pool;
+  uint32_t* hash_scratch = nullptr;   // ilf_picture_hash
   cudaEvent_t chunk_ev[COPY_CHUNKS_MAX] = {};   // download: chunk i has reached the staging buffer
 };
 
@@ -448,6 +449,7 @@ int ilf_destroy(ilf_ctx* ctx) {
   for (cudaEvent_t e : ctx->run_ring) if (e) cudaEventDestroy(e);
   for (cudaEvent_t e : ctx->chunk_ev) if (e) cudaEventDestroy(e);
   cudaFree(ctx->slots_dev);
+  cudaFree(ctx->hash_scratch);
   for (auto& t : ctx->timed) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
   for (cudaEvent_t e : ctx->free_events) cudaEventDestroy(e);
   for (cudaStream_t st : {ctx->s_up, ctx->stream, ctx->s_down}) if (st) cudaStreamDestroy(st);
@@ -751,6 +753,66 @@ int ilf_band_exchange_batch(ilf_ctx* ctx, int first_slot, int num_slots) {
 int ilf_band_exchange(ilf_ctx* ctx, int slot) {
   if (int rc = check_slot(ctx, slot)) return rc;
   return ilf_band_exchange_batch(ctx, slot, 1);
+}
+
+// Decoded-picture hash of the slot's current picture, computed where the picture is (ilf_hash.cu).
+int ilf_picture_hash(ilf_ctx* ctx, int slot, int kind, uint32_t out[3]) {
+  if (int rc = check_slot(ctx, slot)) return rc;
+  if (!out || (kind != ILF_HASH_CRC && kind != ILF_HASH_CHECKSUM)) return fail(ctx, ILF_ERR_ARG, "bad hash kind or null output");
+  if (ctx->is_band) return fail(ctx, ILF_ERR_STATE, "a band context holds a part of the picture only");
+  Slot& s = ctx->slots[slot];
+  if (!s.uploaded) return fail(ctx, ILF_ERR_STATE, "slot %d: hash before upload", slot);
+  CU(ctx, cudaSetDevice(ctx->cfg.device));
+  if (!ctx->hash_scratch) CU(ctx, cudaMalloc(&ctx->hash_scratch, (6 * 16384 + 8) * sizeof(uint32_t)));
+  if (s.h2d_pending) CU(ctx, cudaStreamWaitEvent(ctx->stream, s.ev_up, 0));   // a picture no stage has touched yet
+  const int16_t* planes[3];
+  for (int p = 0; p < 3; p++) planes[p] = plane_ptr(ctx, s, s.result_buf[p], p);
+  uint32_t crc[3], sum[3];
+  CU(ctx, picture_hash(ctx->g, planes, ctx->hash_scratch, ctx->stream, crc, sum));
+  ctx->launches += 2;
+  for (int p = 0; p < 3; p++) out[p] = kind == ILF_HASH_CRC ? crc[p] : sum[p];
+  return ILF_OK;
+}
+
+// Reference border extension on the way down (Picture::extendPicBorder, Picture.cpp:996-1040): the planes are downloaded into buffers
+// that have `margin` luma (margin / 2 chroma) samples of room on every side, and the margins are filled by replication -- rows by
+// the copy threads, so the decoder's own extendPicBorder pass over the picture is not needed any more.
+int ilf_download_extended(ilf_ctx* ctx, int slot, int16_t* y, ptrdiff_t sy, int16_t* cb, ptrdiff_t scb, int16_t* cr, ptrdiff_t scr, int margin) {
+  if (margin < 0 || (margin & 1)) return fail(ctx, ILF_ERR_ARG, "margin must be even and >= 0");
+  if (ctx && ctx->is_band) return fail(ctx, ILF_ERR_STATE, "not available on band contexts");
+  if (int rc = ilf_download(ctx, slot, y, sy, cb, scb, cr, scr)) return rc;
+  const Geom& g = ctx->g;
+  int16_t* planes[3] = {y, cb, cr};
+  const ptrdiff_t strides[3] = {sy, scb, scr};
+  // left / right margins of every row, in row chunks on the copy threads; then the top / bottom rows (which include the corners)
+  struct Job { int plane, row0, rows; };
+  Job jobs[COPY_CHUNKS_MAX];
+  int nj = 0;
+  for (int p = 0; p < 3; p++) {
+    const int h = p ? g.height / 2 : g.height, pieces = std::max(1, std::min(p ? 2 : 8, h / 64));
+    for (int i = 0; i < pieces; i++) jobs[nj++] = {p, (int)((long long)h * i / pieces), (int)((long long)h * (i + 1) / pieces) - (int)((long long)h * i / pieces)};
+  }
+  auto sides = [&](int i) {
+    const Job& j = jobs[i];
+    const int w = j.plane ? g.width / 2 : g.width, m = j.plane ? margin / 2 : margin;
+    for (int r = j.row0; r < j.row0 + j.rows; r++) {
+      int16_t* row = planes[j.plane] + (ptrdiff_t)r * strides[j.plane];
+      const int16_t a = row[0], b = row[w - 1];
+      for (int x = 0; x < m; x++) { row[-m + x] = a; row[w + x] = b; }
+    }
+  };
+  if (ctx->copy_pool.threads() > 1) { ctx->copy_pool.start(nj, sides); ctx->copy_pool.wait(); }
+  else for (int i = 0; i < nj; i++) sides(i);
+  for (int p = 0; p < 3; p++) {
+    const int w = p ? g.width / 2 : g.width, h = p ? g.height / 2 : g.height, m = p ? margin / 2 : margin;
+    int16_t* top = planes[p] - m;
+    int16_t* bot = planes[p] + (ptrdiff_t)(h - 1) * strides[p] - m;
+    for (int r = 1; r <= m; r++) {
+      memcpy(top - (ptrdiff_t)r * strides[p], top, sizeof(int16_t) * (size_t)(w + 2 * m));
+      memcpy(bot + (ptrdiff_t)r * strides[p], bot, sizeof(int16_t) * (size_t)(w + 2 * m));
+    }
+  }
+  return ILF_OK;
 }
 
 int ilf_wait(ilf_ctx* ctx, int slot) {

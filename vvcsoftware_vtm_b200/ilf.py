@@ -86,6 +86,8 @@ def load_library():
     lib.ilf_kernel_times.argtypes = [vp, C.POINTER(C.c_double * NUM_KERNELS), C.POINTER(C.c_longlong * NUM_KERNELS), C.POINTER(C.c_double * NUM_KERNELS)]
     lib.ilf_set_timing.argtypes = [vp, i]
     lib.ilf_alf_path.argtypes = [vp, i]
+    lib.ilf_picture_hash.argtypes = [vp, i, i, C.POINTER(C.c_uint32 * 3)]
+    lib.ilf_download_extended.argtypes = [vp, i, vp, pd, vp, pd, vp, pd, i]
     lib.ilf_launch_count.argtypes = [vp]
     lib.ilf_launch_count.restype = C.c_longlong
     lib.ilf_slot_input_planes.argtypes = [vp, i, C.POINTER(vp * 3), C.POINTER(C.c_int32 * 3)]
@@ -284,6 +286,24 @@ class InLoopFilter:
         ms = (C.c_double * NUM_KERNELS)(); n = (C.c_longlong * NUM_KERNELS)(); nb = (C.c_double * NUM_KERNELS)()
         self._ck(self._lib.ilf_kernel_times(self._h, C.byref(ms), C.byref(n), C.byref(nb)))
         return {k: (ms[i], n[i], nb[i]) for i, k in enumerate(self.KERNELS)}
+
+    def picture_hash(self, slot=0, kind="crc"):
+        """calcCRC / calcChecksum of the slot's current picture on the device: [Y, Cb, Cr]."""
+        out = (C.c_uint32 * 3)()
+        self._ck(self._lib.ilf_picture_hash(self._h, slot, 1 if kind == "crc" else 2, C.byref(out)))
+        return [int(v) for v in out]
+
+    def download_extended(self, slot, margin):
+        """The slot's picture with Picture::extendPicBorder applied: dict of planes of size (h + 2 m, w + 2 m), m = margin (luma) or margin / 2."""
+        out = {}
+        ptrs = []
+        for k, sh in (("y", 0), ("cb", 1), ("cr", 1)):
+            m = margin >> sh
+            a = np.full(((self.height >> sh) + 2 * m, (self.width >> sh) + 2 * m), -1, np.int16)
+            out[k] = a
+            ptrs += [C.c_void_p(a.ctypes.data + 2 * (m * a.shape[1] + m)), a.shape[1]]
+        self._ck(self._lib.ilf_download_extended(self._h, slot, *ptrs, margin))
+        return out
 
     def alf_path(self, slot=0):
         """ILF_ALF_PATH_LUMA_DOT (1) when the slot's luma filters take the IDP.2A dot-product path, 0 for the general path."""

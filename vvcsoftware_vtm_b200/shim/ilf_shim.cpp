@@ -119,11 +119,21 @@ void upload( ShimState& s, CodingStructure& cs )
   s.mirrored = nullptr;
 }
 
+// In the decoder the filtered picture is final, and its next use is as a reference picture with replicated borders
+// (Slice.cpp:389-413 call Picture::extendPicBorder): the download writes the margins too and marks the picture as extended, so
+// that the reference's own pass over the picture is skipped.  The encoder keeps modifying / re-filtering the picture: plain download.
 void download( ShimState& s, CodingStructure& cs )
 {
-  PelUnitBuf reco = cs.getRecoBuf();  // (page-locked or not as upload() left it)
+  PelUnitBuf reco = cs.getRecoBuf();
   PelBuf     y = reco.get( COMPONENT_Y ), cb = reco.get( COMPONENT_Cb ), cr = reco.get( COMPONENT_Cr );
-  ck( s, ilf_download( s.ctx, 0, y.buf, y.stride, cb.buf, cb.stride, cr.buf, cr.stride ), "ilf_download" );
+  static const bool extend = !( getenv( "ILF_SHIM_EXTEND" ) && atoi( getenv( "ILF_SHIM_EXTEND" ) ) == 0 );
+  if( extend && !cs.pcv->isEncoder && ( cs.picture->margin & 1 ) == 0 )
+  {
+    ck( s, ilf_download_extended( s.ctx, 0, y.buf, y.stride, cb.buf, cb.stride, cr.buf, cr.stride, int( cs.picture->margin ) ), "ilf_download_extended" );
+    cs.picture->m_bIsBorderExtended = true;
+  }
+  else
+    ck( s, ilf_download( s.ctx, 0, y.buf, y.stride, cb.buf, cb.stride, cr.buf, cr.stride ), "ilf_download" );
   s.resident    = nullptr;
   s.mirrored    = cs.picture;
   s.mirroredPoc = cs.slice->getPOC();
