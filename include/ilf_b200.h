@@ -243,6 +243,21 @@ int ilf_sao_stats(ilf_ctx* ctx, int first_slot, int num_slots);
 int ilf_get_sao_stats(ilf_ctx* ctx, int slot, int64_t* out);
 
 /* ---------------------------------------------------------------------------------------------
+ * Encoder ALF statistics on the device-resident picture: replaces EncAdaptiveLoopFilter::deriveStatsForFiltering /
+ * getBlkStats / calcCovariance (EncoderLib/EncAdaptiveLoopFilter.cpp:1317-1514), including the block classification of the picture
+ * it measures (deriveClassification, :257).  ilf_alf_stats works on the CURRENT state of the slots' pictures (after ilf_sao: the
+ * picture the encoder's ALF search sees) and on the source pictures given with ilf_set_original; ilf_get_alf_stats copies a slot's
+ * result to the host: out[num_ctus][ILF_ALF_STATS_WORDS] int64 -- exactly the integers the reference's doubles hold.  Per CTU:
+ *   luma  [25 classes][105]   7x7 shape: E[k][l] for k <= l row-major (91), y[k] (13), pixAcc (1)
+ *   Cb    [36], Cr [36]       5x5 shape: E (28), y (7), pixAcc
+ * The luma statistics of the 5x5 shape (m_filterShapes[CHANNEL_TYPE_LUMA][0]) are rows / columns {2, 5, 6, 7, 10, 11, 12} of the 7x7
+ * record: under every transposition the 5x5 taps are those taps of the 7x7 diamond.  Not available on band contexts.
+ * ------------------------------------------------------------------------------------------- */
+#define ILF_ALF_STATS_WORDS (25 * 105 + 36 + 36)
+int ilf_alf_stats(ilf_ctx* ctx, int first_slot, int num_slots);
+int ilf_get_alf_stats(ilf_ctx* ctx, int slot, int64_t* out);
+
+/* ---------------------------------------------------------------------------------------------
  * Post-filter consumers on the device-resident picture: what the decoder does with a picture right after the
  * in-loop filters.
  *   ilf_picture_hash       the two decoded-picture-hash methods that are not inherently serial, calcCRC and calcChecksum
@@ -272,7 +287,8 @@ int ilf_download_extended(ilf_ctx* ctx, int slot, int16_t* y, ptrdiff_t stride_y
 #define ILF_KERNEL_ALF_LUMA 2   /* the whole ALF stage: luma and chroma bands are CTAs of ONE launch (luma only when ILF_ALF_SPLIT=1) */
 #define ILF_KERNEL_ALF_CHROMA 3 /* the separate chroma launch of ILF_ALF_SPLIT=1 (measurement aid); otherwise unused */
 #define ILF_KERNEL_SAO_STATS 4  /* ilf_sao_stats */
-#define ILF_NUM_KERNELS 5
+#define ILF_KERNEL_ALF_STATS 5  /* ilf_alf_stats: classification + the three statistics launches */
+#define ILF_NUM_KERNELS 6
 int ilf_set_timing(ilf_ctx* ctx, int enable); /* enable != 0: clear the accumulators and time every launch */
 /* algo_bytes: bytes the launches had to move = 2 bytes x (read + write) x samples of the planes they processed
  * (planes whose stage is off for the whole picture are skipped and not counted).  Synchronises the stream. */

@@ -585,3 +585,66 @@ void ilf_oracle_extend_border(int16_t* plane, ptrdiff_t stride, int width, int h
     memcpy(plane - (y + 1) * stride - xmargin, plane - xmargin, sizeof(int16_t) * (size_t)(width + 2 * xmargin));
   }
 }
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Encoder ALF statistics: EncAdaptiveLoopFilter::deriveStatsForFiltering / getBlkStats / calcCovariance
+ * (EncoderLib/EncAdaptiveLoopFilter.cpp:1317-1514).  Per CTU and class the covariance of the 13 (7) symmetric tap sums of the
+ * reconstruction around every sample, their correlation with (original - reconstruction) and its energy.  The reference keeps
+ * doubles that hold exact integers (< 2^53); here int64.  Layout per CTU (ILF_ALF_STATS_WORDS): luma [25 classes][105] with the
+ * 7x7 shape (the 5x5 shape's statistics are the rows / columns {2, 5, 6, 7, 10, 11, 12} of it), then Cb [36], Cr [36] with the
+ * 5x5 shape; one record = E upper triangle row-major (k <= l), then y[k], then pixAcc.
+ * --------------------------------------------------------------------------------------------------------- */
+/* tap k of the canonical (transposeIdx 0) enumeration of calcCovariance :1442-1461: rows -half..-1 left to right, then the left
+ * half of the centre row; transposeIdx t maps the offset (a, b) to 0: (a, b), 1: (b, a), 2: (-a, b), 3: (b, -a) (:1463-1510) */
+static void alf_stats_taps(int half, int t, int dx[12], int dy[12]) {
+  int k = 0;
+  for (int b = -half; b <= 0; b++)
+    for (int a = -(half + b); a <= (b < 0 ? half + b : -1); a++, k++) {
+      dx[k] = t == 0 ? a : (t == 1 ? b : (t == 2 ? -a : b));
+      dy[k] = t == 0 ? b : (t == 1 ? a : (t == 2 ? b : -a));
+    }
+}
+
+/* rec: picture padded by replication (clamped reads); cls: classIdx | transposeIdx << 5 per 4x4 block (NULL: class 0, no transpose) */
+static void alf_stats_plane(const Pel* rec, ptrdiff_t rs, const Pel* org, ptrdiff_t os, int w, int h, int half, const uint8_t* cls, int units_w, int ctu_log2_c,
+                            int ctus_w, long long* out, size_t ctu_words, size_t plane_off, int rec_words) {
+  const int n = half == 3 ? 13 : 7;
+  for (int y = 0; y < h; y++)
+    for (int x = 0; x < w; x++) {
+      const int c = cls ? cls[(y >> 2) * units_w + (x >> 2)] : 0;
+      int dx[12], dy[12], e[13];
+      alf_stats_taps(half, c >> 5, dx, dy);
+      for (int k = 0; k < n - 1; k++) e[k] = px(rec, rs, w, h, x + dx[k], y + dy[k]) + px(rec, rs, w, h, x - dx[k], y - dy[k]);
+      e[n - 1] = rec[y * rs + x];
+      const int yl = org[y * os + x] - rec[y * rs + x];
+      long long* o = out + (size_t)((y >> ctu_log2_c) * ctus_w + (x >> ctu_log2_c)) * ctu_words + plane_off + (size_t)(c & 31) * rec_words;
+      int i = 0;
+      for (int k = 0; k < n; k++)
+        for (int l = k; l < n; l++) o[i++] += (long long)e[k] * e[l];
+      for (int k = 0; k < n; k++) o[i++] += (long long)e[k] * yl;
+      o[i] += (long long)yl * yl;
+    }
+}
+
+int ilf_oracle_alf_stats(const int16_t* const rec[3], const ptrdiff_t rec_stride[3], const int16_t* const org[3], const ptrdiff_t org_stride[3], int width, int height,
+                         int bd_luma, int ctu_log2, long long* out) {
+  const int uw = width / 4, uh = height / 4, ctus_w = (width + (1 << ctu_log2) - 1) >> ctu_log2, ctus_h = (height + (1 << ctu_log2) - 1) >> ctu_log2;
+  const size_t words = 25 * 105 + 36 + 36;
+  uint8_t* cls = (uint8_t*)malloc((size_t)uw * uh);
+  if (!cls) return -1;
+  ilf_oracle_alf_classify(rec[0], rec_stride[0], width, height, bd_luma, cls);
+  memset(out, 0, sizeof(long long) * words * ctus_w * ctus_h);
+  alf_stats_plane(rec[0], rec_stride[0], org[0], org_stride[0], width, height, 3, cls, uw, ctu_log2, ctus_w, out, words, 0, 105);
+  alf_stats_plane(rec[1], rec_stride[1], org[1], org_stride[1], width / 2, height / 2, 2, NULL, 0, ctu_log2 - 1, ctus_w, out, words, 25 * 105, 36);
+  alf_stats_plane(rec[2], rec_stride[2], org[2], org_stride[2], width / 2, height / 2, 2, NULL, 0, ctu_log2 - 1, ctus_w, out, words, 25 * 105 + 36, 36);
+  free(cls);
+  return 0;
+}
+
+/* one plane as ONE block with explicit classes (unit test against the reference's getBlkStats): out[classes][n (n + 1) / 2 + n + 1] */
+int ilf_oracle_alf_stats_block(const int16_t* rec, ptrdiff_t rs, const int16_t* org, ptrdiff_t os, int w, int h, int shape7, const uint8_t* cls_per_unit, long long* out) {
+  const int n = shape7 ? 13 : 7, words = n * (n + 1) / 2 + n + 1;
+  memset(out, 0, sizeof(long long) * (size_t)words * (cls_per_unit ? 25 : 1));
+  alf_stats_plane(rec, rs, org, os, w, h, shape7 ? 3 : 2, cls_per_unit, (w + 3) / 4, 30, 1, out, 0, 0, words);
+  return 0;
+}

@@ -158,3 +158,34 @@ def extend_border(plane, xmargin, ymargin):
     f.argtypes = [C.c_void_p, C.c_ssize_t, C.c_int, C.c_int, C.c_int, C.c_int]
     f(big.ctypes.data + 2 * (ymargin * big.shape[1] + xmargin), big.shape[1], w, h, xmargin, ymargin)
     return big
+
+
+ALF_STATS_WORDS = 25 * 105 + 36 + 36
+ALF_5X5_IN_7X7 = (2, 5, 6, 7, 10, 11, 12)   # coefficient k of the 5x5 shape sits at this index of the 7x7 shape
+
+
+def alf_stats(rec, org, bd_luma, ctu_log2):
+    """EncAdaptiveLoopFilter::deriveStatsForFiltering: int64 [num_ctus, ALF_STATS_WORDS] (luma [25][105] 7x7, Cb [36], Cr [36] 5x5;
+    a record = E upper triangle row-major, y, pixAcc)."""
+    r, rp, rs = _planes3(rec)
+    o, op, os_ = _planes3(org)
+    h, w = r[0].shape
+    ctu = 1 << ctu_log2
+    n = ((w + ctu - 1) // ctu) * ((h + ctu - 1) // ctu)
+    out = np.zeros((n, ALF_STATS_WORDS), dtype=np.int64)
+    f = lib().ilf_oracle_alf_stats
+    f.restype = C.c_int
+    f.argtypes = [C.c_void_p] * 4 + [C.c_int] * 4 + [C.c_void_p]
+    assert f(rp, rs, op, os_, w, h, bd_luma, ctu_log2, _p(out)) == 0
+    return out
+
+
+def alf_stats_unpack(rec_words, n):
+    """(E [n, n] symmetric, y [n], pixAcc) from one record of n (n + 1) / 2 + n + 1 words."""
+    E = np.zeros((n, n), np.int64)
+    i = 0
+    for k in range(n):
+        for l in range(k, n):
+            E[k, l] = E[l, k] = rec_words[i]
+            i += 1
+    return E, np.array(rec_words[i:i + n]), int(rec_words[i + n])

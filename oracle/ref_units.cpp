@@ -19,6 +19,7 @@
 // (every header the class needs is already included above, so nothing else is parsed under the define)
 #define private public
 #include "EncoderLib/EncSampleAdaptiveOffset.h"
+#include "EncoderLib/EncAdaptiveLoopFilter.h"
 #undef private
 
 namespace
@@ -175,4 +176,44 @@ int ref_extend_pic_border( const int16_t* y, const int16_t* cb, const int16_t* c
   pic.destroy();
   return 0;
 }
+}
+
+// EncAdaptiveLoopFilter::getBlkStats (EncAdaptiveLoopFilter.cpp:1394-1440) of one block of a plane: rec / org point at sample (0, 0)
+// of planes that have at least 3 samples of margin; cls = classIdx | transposeIdx << 5 per SAMPLE row-major over (w, h), or NULL
+// (chroma: one class).  shape7 = 1: 7x7 (13 coefficients), 0: 5x5 (7).  out[classes][n n + n + 1] doubles as the reference holds them:
+// E row-major (full symmetric matrix), y, pixAcc.
+extern "C" int ref_alf_blk_stats( int shape7, const int16_t* org, int org_stride, const int16_t* rec, int rec_stride, int x0, int y0, int w, int h, const uint8_t* cls, int cls_stride,
+                                  double* out )
+{
+  static EncAdaptiveLoopFilter* enc = new EncAdaptiveLoopFilter;
+  const AlfFilterShape shape( shape7 ? 7 : 5 );
+  const int            n       = shape.numCoeff;
+  const int            classes = cls ? MAX_NUM_ALF_CLASSES : 1;
+  std::vector<AlfCovariance> cov( classes );
+  for( auto& c : cov ) { c.create( n ); c.reset(); }
+  std::vector<std::vector<AlfClassifier>> rows;
+  std::vector<AlfClassifier*>             ptrs;
+  if( cls )
+  {
+    rows.resize( y0 + h );
+    for( int y = 0; y < y0 + h; y++ )
+    {
+      rows[y].resize( x0 + w );
+      for( int x = 0; x < x0 + w; x++ ) rows[y][x] = AlfClassifier( cls[y * cls_stride + x] & 31, cls[y * cls_stride + x] >> 5 );
+      ptrs.push_back( rows[y].data() );
+    }
+  }
+  const CompArea area( COMPONENT_Y, CHROMA_420, Area( x0, y0, w, h ) );
+  enc->getBlkStats( cov.data(), shape, cls ? ptrs.data() : nullptr, const_cast<Pel*>( org ) + y0 * org_stride + x0, org_stride, const_cast<Pel*>( rec ) + y0 * rec_stride + x0,
+                    rec_stride, area );
+  for( int c = 0; c < classes; c++ )
+  {
+    double* o = out + size_t( c ) * ( n * n + n + 1 );
+    for( int k = 0; k < n; k++ )
+      for( int l = 0; l < n; l++ ) *o++ = cov[c].E[k][l];
+    for( int k = 0; k < n; k++ ) *o++ = cov[c].y[k];
+    *o = cov[c].pixAcc;
+    cov[c].destroy();
+  }
+  return 0;
 }

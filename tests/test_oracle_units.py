@@ -152,3 +152,37 @@ def test_oracle_hash_and_border_match_reference(bd, w, h, oracle):
     assert ref.ref_extend_pic_border(pic["y"].ctypes.data, pic["cb"].ctypes.data, pic["cr"].ctypes.data, w, h, m, *(o.ctypes.data for o in outs)) == 0
     for o, (k, s) in zip(outs, (("y", 0), ("cb", 1), ("cr", 1))):
         assert np.array_equal(o, oracle.extend_border(pic[k], m >> s, m >> s)), k
+
+
+# ---- encoder ALF statistics ----
+@pytest.mark.parametrize("shape7,w,h,bd,classes", [(1, 32, 24, 10, True), (0, 32, 24, 10, True), (0, 24, 16, 10, False), (1, 16, 16, 8, True), (1, 40, 8, 12, True)])
+def test_oracle_alf_stats_match_reference_getblkstats(shape7, w, h, bd, classes, oracle):
+    """oracle == EncAdaptiveLoopFilter::getBlkStats / calcCovariance (EncAdaptiveLoopFilter.cpp:1394-1514) for both filter shapes, all four
+    transposes and 25 classes: E, y and pixAcc (the reference's doubles hold exact integers)."""
+    ref = C.CDLL(UNITS)
+    rng = np.random.default_rng(shape7 * 100 + w + bd)
+    rec = rng.integers(0, 1 << bd, (h, w)).astype(np.int16)
+    org = np.clip(rec.astype(np.int32) + rng.integers(-40, 41, (h, w)), 0, (1 << bd) - 1).astype(np.int16)
+    m = 4
+    rec_pad = np.pad(rec, m, mode="edge")
+    n = 13 if shape7 else 7
+    words = n * (n + 1) // 2 + n + 1
+    if classes:
+        cls_u = (rng.integers(0, 25, (h // 4, w // 4)) | (rng.integers(0, 4, (h // 4, w // 4)) << 5)).astype(np.uint8)
+        cls_s = np.ascontiguousarray(np.kron(cls_u, np.ones((4, 4), np.uint8)))
+    ncl = 25 if classes else 1
+    out = np.zeros((ncl, n * n + n + 1), np.float64)
+    f = ref.ref_alf_blk_stats
+    f.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+    rp = rec_pad.ctypes.data + 2 * (m * rec_pad.shape[1] + m)
+    assert f(shape7, org.ctypes.data, w, rp, rec_pad.shape[1], 0, 0, w, h, cls_s.ctypes.data if classes else None, w, out.ctypes.data) == 0
+    got = np.zeros((ncl, words), np.int64)
+    g = oracle.lib().ilf_oracle_alf_stats_block
+    g.argtypes = [C.c_void_p, C.c_ssize_t, C.c_void_p, C.c_ssize_t, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    assert g(rec.ctypes.data, w, org.ctypes.data, w, w, h, shape7, cls_u.ctypes.data if classes else None, got.ctypes.data) == 0
+    assert out.any()
+    for c in range(ncl):
+        E, y, pa = oracle.alf_stats_unpack(got[c], n)
+        assert np.array_equal(E, out[c, :n * n].reshape(n, n).astype(np.int64)), f"class {c}: E"
+        assert np.array_equal(y, out[c, n * n:n * n + n].astype(np.int64)), f"class {c}: y"
+        assert pa == int(out[c, n * n + n]), f"class {c}: pixAcc"

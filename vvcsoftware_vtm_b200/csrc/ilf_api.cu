@@ -97,6 +97,7 @@ struct Slot {
   int16_t* org = nullptr;      // source picture of the encoder (3 planes, same layout as one buffer of `planes`); allocated by ilf_set_original
   uint8_t* stats_avail = nullptr;
   long long* stats = nullptr;  // [num_ctus][3][5][64]
+  long long* alf_stats = nullptr;  // [num_ctus][ILF_ALF_STATS_WORDS]
   bool has_org = false;
   int16_t* pinned = nullptr;   // host staging for pageable planes on the way up, one picture; allocated on first use
   int16_t* pinned_down = nullptr;  // ... and on the way down
@@ -150,9 +151,9 @@ struct ilf_ctx {
   static constexpr int RUN_RING = 64;
   cudaEvent_t run_ring[RUN_RING] = {};
   unsigned run_pos = 0;
-  double kernel_ms[ILF_NUM_KERNELS] = {0, 0, 0, 0, 0};
-  double kernel_bytes[ILF_NUM_KERNELS] = {0, 0, 0, 0, 0};
-  long long kernel_launches[ILF_NUM_KERNELS] = {0, 0, 0, 0, 0};
+  double kernel_ms[ILF_NUM_KERNELS] = {};
+  double kernel_bytes[ILF_NUM_KERNELS] = {};
+  long long kernel_launches[ILF_NUM_KERNELS] = {};
   int num_ctus = 0;
   CopyPool copy_pool;
   uint32_t* hash_scratch = nullptr;   // ilf_picture_hash
@@ -440,7 +441,7 @@ int ilf_destroy(ilf_ctx* ctx) {
     for (auto& nb : s.nb) if (nb.ipc_base) cudaIpcCloseMemHandle(nb.ipc_base);
     cudaFree(s.planes); cudaFree(s.info); cudaFree(s.info_c); cudaFree(s.mv); cudaFree(s.ctu_slice); cudaFree(s.db_params);
     cudaFree(s.sao); cudaFree(s.alf); cudaFree(s.alf_coef); cudaFree(s.alf_coef_dp); cudaFree(s.alf_ctu_enable); cudaFree(s.alf_class);
-    cudaFree(s.org); cudaFree(s.stats_avail); cudaFree(s.stats);
+    cudaFree(s.org); cudaFree(s.stats_avail); cudaFree(s.stats); cudaFree(s.alf_stats);
     if (s.pinned) cudaFreeHost(s.pinned);
     if (s.pinned_down) cudaFreeHost(s.pinned_down);
     if (s.pinned_side) cudaFreeHost(s.pinned_side);
@@ -1193,6 +1194,58 @@ int ilf_get_sao_stats(ilf_ctx* ctx, int slot, int64_t* out) {
   if (!s.stats) return fail(ctx, ILF_ERR_STATE, "slot %d: no statistics (ilf_set_original / ilf_sao_stats first)", slot);
   CU(ctx, cudaSetDevice(ctx->cfg.device));
   CU(ctx, cudaMemcpyAsync(out, s.stats, (size_t)ctx->num_ctus * 3 * ILF_SAO_STATS_WORDS * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  return ILF_OK;
+}
+
+// Encoder ALF statistics: block classification of the slots' current pictures, then the covariance launches (ilf_alf_stats.cu).
+int ilf_alf_stats(ilf_ctx* ctx, int first_slot, int num_slots) {
+  if (!ctx) return ILF_ERR_ARG;
+  if (first_slot < 0 || num_slots < 1 || first_slot + num_slots > (int)ctx->slots.size()) return fail(ctx, ILF_ERR_ARG, "slot range [%d,+%d) out of range", first_slot, num_slots);
+  if (ctx->is_band) return fail(ctx, ILF_ERR_STATE, "not available on band contexts");
+  CU(ctx, cudaSetDevice(ctx->cfg.device));
+  const Geom& g = ctx->g;
+  const size_t bytes = (size_t)ctx->num_ctus * ILF_ALF_STATS_WORDS * sizeof(long long);
+  for (int i = first_slot; i < first_slot + num_slots; i++) {
+    Slot& s = ctx->slots[i];
+    if (!s.uploaded || !s.has_org) return fail(ctx, ILF_ERR_STATE, "slot %d: statistics need ilf_upload and ilf_set_original", i);
+    if (!s.alf_stats) {
+      CU(ctx, cudaMalloc(&s.alf_stats, bytes));
+      s.dev.alf_stats = s.alf_stats;
+      if (int rc = push_desc(ctx, i)) return rc;
+    }
+    if (s.h2d_pending) { CU(ctx, cudaStreamWaitEvent(ctx->stream, s.ev_up, 0)); s.h2d_pending = false; }
+    CU(ctx, cudaMemsetAsync(s.alf_stats, 0, bytes, ctx->stream));
+  }
+  for (int c0 = first_slot; c0 < first_slot + num_slots; c0 += MAX_BATCH) {
+    const int cn = std::min(MAX_BATCH, first_slot + num_slots - c0);
+    BatchCtl ctl;
+    for (int i = 0; i < cn; i++) {
+      const Slot& s = ctx->slots[c0 + i];
+      ctl.v[i] = (uint16_t)(s.result_buf[0] | (s.result_buf[1] << 2) | (s.result_buf[2] << 4));
+      ctl.slot[i] = (uint8_t)i;
+    }
+    // algorithmic bytes: the reconstructed and the original picture are read once (2 B x 1.5 samples x 2 pictures per luma pixel)
+    if (int rc = timed_begin(ctx, ILF_KERNEL_ALF_STATS, 6.0 * g.width * g.height * cn)) return rc;
+    launch_alf_classify(g, ctx->slots_dev, c0, cn, ctl, ctx->stream);
+    launch_alf_stats(g, ctx->slots_dev, c0, cn, ctl, ctx->stream);
+    if (int rc = timed_end(ctx)) return rc;
+    ctx->launches += 4;
+    CU(ctx, cudaGetLastError());
+  }
+  cudaEvent_t done = ctx->run_ring[ctx->run_pos++ % ilf_ctx::RUN_RING];
+  CU(ctx, cudaEventRecord(done, ctx->stream));
+  for (int i = first_slot; i < first_slot + num_slots; i++) ctx->slots[i].ev_run = done;
+  return ILF_OK;
+}
+
+int ilf_get_alf_stats(ilf_ctx* ctx, int slot, int64_t* out) {
+  if (int rc = check_slot(ctx, slot)) return rc;
+  if (!out) return fail(ctx, ILF_ERR_ARG, "null output");
+  Slot& s = ctx->slots[slot];
+  if (!s.alf_stats) return fail(ctx, ILF_ERR_STATE, "slot %d: no statistics (ilf_set_original / ilf_alf_stats first)", slot);
+  CU(ctx, cudaSetDevice(ctx->cfg.device));
+  CU(ctx, cudaMemcpyAsync(out, s.alf_stats, (size_t)ctx->num_ctus * ILF_ALF_STATS_WORDS * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
   CU(ctx, cudaStreamSynchronize(ctx->stream));
   return ILF_OK;
 }

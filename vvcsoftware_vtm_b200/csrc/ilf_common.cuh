@@ -70,6 +70,7 @@ struct alignas(64) SlotDev {
   const int16_t* org[3];          // source picture of the encoder (ilf_set_original), plane pitches as buf
   const uint8_t* stats_avail;     // [num_ctus] ILF_AVAIL_* of the statistics pass
   long long* stats;               // [num_ctus][3][5][64] SAO statistics (ilf_sao_stats)
+  long long* alf_stats;           // [num_ctus][ILF_ALF_STATS_WORDS] ALF statistics (ilf_alf_stats)
 };
 
 // Per-launch control word of every slot of a batch (kernel parameter, indexed with blockIdx.z).  Each plane of a
@@ -145,6 +146,7 @@ void launch_sao(const Geom& g, const SlotDev* slots, int first_slot, int num_slo
 void launch_alf(const Geom& g, const SlotDev* slots, int first_slot, int num_slots, const BatchCtl& ctl, int planes /* bit 0 luma, bit 1 chroma */, cudaStream_t st);
 void launch_sao_stats(const Geom& g, const SlotDev* slots, int first_slot, int num_slots, const BatchCtl& ctl, cudaStream_t st);
 cudaError_t picture_hash(const Geom& g, const int16_t* const planes[3], uint32_t* scratch, cudaStream_t st, uint32_t out_crc[3], uint32_t out_sum[3]);
+void launch_alf_stats(const Geom& g, const SlotDev* slots, int first_slot, int num_slots, const BatchCtl& ctl, cudaStream_t st);
 void launch_alf_classify(const Geom& g, const SlotDev* slots, int first_slot, int num_slots, const BatchCtl& ctl, cudaStream_t st);
 
 }  // namespace ilf

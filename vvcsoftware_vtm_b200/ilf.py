@@ -35,7 +35,8 @@ def lib_path():
 
 
 _LIB = None
-NUM_KERNELS = 5   # ILF_NUM_KERNELS
+NUM_KERNELS = 6   # ILF_NUM_KERNELS
+ALF_STATS_WORDS = 25 * 105 + 36 + 36   # ILF_ALF_STATS_WORDS
 
 
 def load_library():
@@ -86,6 +87,8 @@ def load_library():
     lib.ilf_kernel_times.argtypes = [vp, C.POINTER(C.c_double * NUM_KERNELS), C.POINTER(C.c_longlong * NUM_KERNELS), C.POINTER(C.c_double * NUM_KERNELS)]
     lib.ilf_set_timing.argtypes = [vp, i]
     lib.ilf_alf_path.argtypes = [vp, i]
+    lib.ilf_alf_stats.argtypes = [vp, i, i]
+    lib.ilf_get_alf_stats.argtypes = [vp, i, vp]
     lib.ilf_picture_hash.argtypes = [vp, i, i, C.POINTER(C.c_uint32 * 3)]
     lib.ilf_download_extended.argtypes = [vp, i, vp, pd, vp, pd, vp, pd, i]
     lib.ilf_launch_count.argtypes = [vp]
@@ -279,13 +282,24 @@ class InLoopFilter:
     def set_timing(self, on):
         self._ck(self._lib.ilf_set_timing(self._h, int(on)))
 
-    KERNELS = ("deblock", "sao", "alf", "alf_chroma", "sao_stats")   # "alf" = the whole ALF stage (one launch); with ILF_ALF_SPLIT=1: luma only, "alf_chroma" the second launch
+    KERNELS = ("deblock", "sao", "alf", "alf_chroma", "sao_stats", "alf_stats")   # "alf" = the whole ALF stage (one launch); with ILF_ALF_SPLIT=1: luma only, "alf_chroma" the second launch
 
     def kernel_times(self):
         """{kernel: (total ms, launches, algorithmic bytes)} since set_timing(True); synchronises the context's stream."""
         ms = (C.c_double * NUM_KERNELS)(); n = (C.c_longlong * NUM_KERNELS)(); nb = (C.c_double * NUM_KERNELS)()
         self._ck(self._lib.ilf_kernel_times(self._h, C.byref(ms), C.byref(n), C.byref(nb)))
         return {k: (ms[i], n[i], nb[i]) for i, k in enumerate(self.KERNELS)}
+
+    def alf_stats(self, first_slot=0, num_slots=1):
+        """Encoder ALF statistics (EncAdaptiveLoopFilter::deriveStatsForFiltering) of the slots' current pictures against their originals."""
+        self._ck(self._lib.ilf_alf_stats(self._h, first_slot, num_slots))
+
+    def get_alf_stats(self, slot=0):
+        ctu = 1 << self.cfg.ctu_log2
+        n = ((self.width + ctu - 1) // ctu) * ((self.height + ctu - 1) // ctu)
+        out = np.zeros((n, ALF_STATS_WORDS), np.int64)
+        self._ck(self._lib.ilf_get_alf_stats(self._h, slot, _ptr(out)))
+        return out
 
     def picture_hash(self, slot=0, kind="crc"):
         """calcCRC / calcChecksum of the slot's current picture on the device: [Y, Cb, Cr]."""
