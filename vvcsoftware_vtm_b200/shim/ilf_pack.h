@@ -96,5 +96,8 @@ void ilfPackAlf( CodingStructure& cs, AlfSliceParam& alfSliceParam, IlfPackedAlf
 // ctuAvail the ILF_AVAIL_L/_A/_AL flags per CTU; out[numCtus][3][5][64] in SAOStatData layout (diff[32], count[32]).
 struct ilfPlanes { const int16_t* p[3]; ptrdiff_t stride[3]; };
 void ilfShimSaoStatistics( CodingStructure& cs, const ilfPlanes& org, const ilfPlanes& src, const uint8_t* ctuAvail, int64_t* out );
+// Encoder ALF statistics and block classification of `rec` (the SAO'd picture) against `org`: out[numCtus][ILF_ALF_STATS_WORDS],
+// classMap[unitsH][unitsW] = classIdx | transposeIdx << 5.
+void ilfShimAlfStatistics( CodingStructure& cs, const ilfPlanes& org, const ilfPlanes& rec, int64_t* out, uint8_t* classMap );
 
 #endif

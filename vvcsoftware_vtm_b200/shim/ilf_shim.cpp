@@ -255,3 +255,20 @@ void ilfShimSaoStatistics( CodingStructure& cs, const ilfPlanes& org, const ilfP
   ck( s, ilf_get_sao_stats( s.ctx, 0, out ), "ilf_get_sao_stats" );
   if( s.timing ) fprintf( stderr, "[ILFTIME] poc=%d sao_stats_us=%lld impl=b200\n", cs.slice->getPOC(), usSince( t0 ) );
 }
+
+// Encoder ALF statistics (called by EncAdaptiveLoopFilter::ALFProcess in ilf_shim_enc.cpp): the SAO'd picture and the source
+// picture go up, 21 KB of integers per CTU and one byte per 4x4 block come back.
+void ilfShimAlfStatistics( CodingStructure& cs, const ilfPlanes& org, const ilfPlanes& rec, int64_t* out, uint8_t* classMap )
+{
+  const auto t0 = clk::now();
+  ShimState& s  = contextFor( cs );
+  ck( s, ilf_upload( s.ctx, 0, rec.p[0], rec.stride[0], rec.p[1], rec.stride[1], rec.p[2], rec.stride[2] ), "ilf_upload" );
+  s.resident = nullptr;
+  s.mirrored = nullptr;
+  std::vector<uint8_t> avail( cs.pcv->sizeInCtus, 0 );
+  ck( s, ilf_set_original( s.ctx, 0, org.p[0], org.stride[0], org.p[1], org.stride[1], org.p[2], org.stride[2], avail.data() ), "ilf_set_original" );
+  ck( s, ilf_alf_stats( s.ctx, 0, 1 ), "ilf_alf_stats" );
+  ck( s, ilf_alf_classify( s.ctx, 0, classMap ), "ilf_alf_classify" );
+  ck( s, ilf_get_alf_stats( s.ctx, 0, out ), "ilf_get_alf_stats" );
+  if( s.timing ) fprintf( stderr, "[ILFTIME] poc=%d alf_stats_us=%lld impl=b200\n", cs.slice->getPOC(), usSince( t0 ) );
+}

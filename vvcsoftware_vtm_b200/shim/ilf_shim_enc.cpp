@@ -1,4 +1,9 @@
-// ilf_shim_enc.cpp -- host shim, encoder side: EncSampleAdaptiveOffset::SAOProcess with its statistics pass on the GPU.
+// ilf_shim_enc.cpp -- host shim, encoder side: the statistics passes of the encoder's SAO and ALF searches on the GPU.
+//
+//   EncAdaptiveLoopFilter::ALFProcess       replaces source/Lib/EncoderLib/EncAdaptiveLoopFilter.cpp:220-268
+//     its deriveClassification (:257) and deriveStatsForFiltering (:260, :1317-1514) become ilf_upload / ilf_set_original /
+//     ilf_alf_stats / ilf_alf_classify / ilf_get_alf_stats on the SAO'd picture; the filter derivation (alfEncoder) stays the
+//     reference's own code and reads the class map and the covariances exactly as its own passes would have left them.
 //
 //   EncSampleAdaptiveOffset::SAOProcess     replaces source/Lib/EncoderLib/EncSampleAdaptiveOffset.cpp:213-253
 //     its call of getStatistics (:227, :278-331, getBlkStats :1122-1487) becomes ilf_set_original / ilf_sao_stats /
@@ -14,6 +19,7 @@
 
 #include "CommonLib/CodingStructure.h"
 #include "CommonLib/Picture.h"
+#include "EncoderLib/EncAdaptiveLoopFilter.h"
 #include "EncoderLib/EncSampleAdaptiveOffset.h"
 #include "ilf_b200.h"
 #include "ilf_pack.h"
@@ -73,4 +79,92 @@ void EncSampleAdaptiveOffset::SAOProcess( CodingStructure& cs, bool* sliceEnable
   decideBlkParams( cs, sliceEnabled, m_statData, src, res, &reconParams[0], cs.picture->getSAO(), bTestSAODisableAtPictureLevel, saoEncodingRate, saoEncodingRateChroma );
 #endif
   xPCMLFDisableProcess( cs );
+}
+
+// ------------------------------------------------------------------------------------------------------------
+void EncAdaptiveLoopFilter::ALFProcess( CodingStructure& cs, const double* lambdas, AlfSliceParam& alfSliceParam )
+{
+  CHECK( cs.pcv->chrFormat != CHROMA_420, "libilf_b200 supports 4:2:0 only" );
+  // ---- set-up: as the reference (:222-252) ----
+  alfSliceParam.filterShapes = m_filterShapes;
+  m_clpRngs                  = cs.slice->getClpRngs();
+  for( int compIdx = 0; compIdx < MAX_NUM_COMPONENT; compIdx++ ) m_ctuEnableFlag[compIdx] = cs.picture->getAlfCtuEnableFlag( compIdx );
+  alfSliceParam.reset();
+#if DISTORTION_LAMBDA_BUGFIX
+  const int shiftLuma   = 2 * DISTORTION_PRECISION_ADJUSTMENT( m_inputBitDepth[CHANNEL_TYPE_LUMA] );
+  const int shiftChroma = 2 * DISTORTION_PRECISION_ADJUSTMENT( m_inputBitDepth[CHANNEL_TYPE_CHROMA] );
+#else
+  const int shiftLuma   = 2 * DISTORTION_PRECISION_ADJUSTMENT( m_inputBitDepth[CHANNEL_TYPE_LUMA] - 8 );
+  const int shiftChroma = 2 * DISTORTION_PRECISION_ADJUSTMENT( m_inputBitDepth[CHANNEL_TYPE_CHROMA] - 8 );
+#endif
+  m_lambda[COMPONENT_Y]  = lambdas[COMPONENT_Y] * double( 1 << shiftLuma );
+  m_lambda[COMPONENT_Cb] = lambdas[COMPONENT_Cb] * double( 1 << shiftChroma );
+  m_lambda[COMPONENT_Cr] = lambdas[COMPONENT_Cr] * double( 1 << shiftChroma );
+  PelUnitBuf orgYuv = cs.getOrgBuf();
+  m_tempBuf.copyFrom( cs.getRecoBuf() );
+  PelUnitBuf recYuv = m_tempBuf.getBuf( cs.area );
+  recYuv.extendBorderPel( MAX_ALF_FILTER_LENGTH >> 1 );
+
+  // ---- classification + statistics on the device ----
+  const PreCalcValues& pcv = *cs.pcv;
+  ilfPlanes po, pr;
+  for( int c = 0; c < 3; c++ )
+  {
+    po.p[c] = orgYuv.get( ComponentID( c ) ).buf; po.stride[c] = orgYuv.get( ComponentID( c ) ).stride;
+    pr.p[c] = recYuv.get( ComponentID( c ) ).buf; pr.stride[c] = recYuv.get( ComponentID( c ) ).stride;
+  }
+  const int            unitsW = int( pcv.lumaWidth ) / 4, unitsH = int( pcv.lumaHeight ) / 4;
+  std::vector<int64_t> words( size_t( pcv.sizeInCtus ) * ILF_ALF_STATS_WORDS );
+  std::vector<uint8_t> cls( size_t( unitsW ) * unitsH );
+  ilfShimAlfStatistics( cs, po, pr, words.data(), cls.data() );
+  for( int by = 0; by < unitsH; by++ )
+    for( int bx = 0; bx < unitsW; bx++ )
+    {
+      const AlfClassifier c( cls[size_t( by ) * unitsW + bx] & 31, cls[size_t( by ) * unitsW + bx] >> 5 );
+      for( int y = 0; y < 4; y++ )
+        for( int x = 0; x < 4; x++ ) m_classifier[4 * by + y][4 * bx + x] = c;
+    }
+  // a record = E upper triangle row-major, y, pixAcc of the 7x7 (luma) / 5x5 (chroma) shape; the luma 5x5 shape is a slice of it
+  static const int in7[7] = { 2, 5, 6, 7, 10, 11, 12 };
+  auto fill = [&]( AlfCovariance& cov, const int64_t* rec, int nRec, const int* map )
+  {
+    const int n = cov.numCoeff;
+    for( int k = 0; k < n; k++ )
+    {
+      const int rk = map ? map[k] : k;
+      for( int l = k; l < n; l++ )
+      {
+        const int rl = map ? map[l] : l;
+        const int a = std::min( rk, rl ), b = std::max( rk, rl );
+        cov.E[k][l] = cov.E[l][k] = double( rec[a * nRec - a * ( a - 1 ) / 2 + ( b - a )] );
+      }
+      cov.y[k] = double( rec[nRec * ( nRec + 1 ) / 2 + rk] );
+    }
+    cov.pixAcc = double( rec[nRec * ( nRec + 1 ) / 2 + nRec] );
+  };
+  for( int ch = 0; ch < 2; ch++ )
+    for( size_t shape = 0; shape < m_filterShapes[ch].size(); shape++ )
+      for( int classIdx = 0; classIdx < ( ch == 0 ? MAX_NUM_ALF_CLASSES : 1 ); classIdx++ ) m_alfCovarianceFrame[ch][shape][classIdx].reset();
+  for( int ctu = 0; ctu < m_numCTUsInPic; ctu++ )
+  {
+    const int64_t* w = &words[size_t( ctu ) * ILF_ALF_STATS_WORDS];
+    for( size_t shape = 0; shape < m_filterShapes[CHANNEL_TYPE_LUMA].size(); shape++ )
+      for( int classIdx = 0; classIdx < MAX_NUM_ALF_CLASSES; classIdx++ )
+      {
+        AlfCovariance& cov = m_alfCovariance[COMPONENT_Y][shape][ctu][classIdx];
+        fill( cov, w + classIdx * 105, 13, m_filterShapes[CHANNEL_TYPE_LUMA][shape].filterLength == 7 ? nullptr : in7 );
+        m_alfCovarianceFrame[CHANNEL_TYPE_LUMA][shape][classIdx] += cov;
+      }
+    for( int c = 1; c < 3; c++ )
+      for( size_t shape = 0; shape < m_filterShapes[CHANNEL_TYPE_CHROMA].size(); shape++ )
+      {
+        AlfCovariance& cov = m_alfCovariance[c][shape][ctu][0];
+        fill( cov, w + 25 * 105 + ( c - 1 ) * 36, 7, nullptr );
+        m_alfCovarianceFrame[CHANNEL_TYPE_CHROMA][shape][0] += cov;
+      }
+  }
+
+  // ---- filter derivation: the reference's own search (:262-268) ----
+  alfEncoder( cs, alfSliceParam, orgYuv, recYuv, cs.getRecoBuf(), CHANNEL_TYPE_LUMA );
+  if( alfSliceParam.enabledFlag[COMPONENT_Y] ) alfEncoder( cs, alfSliceParam, orgYuv, recYuv, cs.getRecoBuf(), CHANNEL_TYPE_CHROMA );
 }
