@@ -805,6 +805,21 @@ def run_b200(args, wl):
         f.sao_stats(0, B)
     kt_stats = f.kernel_times()["sao_stats"]
     f.set_timing(False)
+    # encoder ALF statistics (classification + covariances) on the SAO'd pictures, and the decoded-picture hash of a resident picture
+    f.run(0, B, 3)
+    for _ in range(2):
+        f.alf_stats(0, B)
+    f.sync()
+    f.set_timing(True)
+    for _ in range(max(3, args.steps // 4)):
+        f.alf_stats(0, B)
+    kt_alf_stats = f.kernel_times()["alf_stats"]
+    f.set_timing(False)
+    f.picture_hash(0, "crc")
+    t_h = time.perf_counter()
+    for _ in range(10):
+        f.picture_hash(0, "crc")
+    hash_ms = (time.perf_counter() - t_h) / 10 * 1e3
 
     # ---- end to end through the public API: host planes + side information in, filtered host planes out ----
     # Host buffers are page-locked (what a host integration does with its picture buffers: ilf_host_alloc /
@@ -901,7 +916,11 @@ def run_b200(args, wl):
                                         "chain": chain_table(kt_on, ms_on, args.steps, B * mpx * 1e6, peak), "per_kernel": pk_on}},
                 "next_rows": {"sao_stats": dict(kernel_table({"sao_stats": kt_stats}, peak)["sao_stats"],
                                                 what="encoder SAO statistics (EncSampleAdaptiveOffset::getStatistics) of the resident deblocked pictures, one launch per step; algorithmic bytes = deblocked + original picture read once (6 B/pixel)",
-                                                mpixel_per_s=round(B * mpx / (kt_stats[0] / max(kt_stats[1], 1) * 1e-3), 1))},
+                                                mpixel_per_s=round(B * mpx / (kt_stats[0] / max(kt_stats[1], 1) * 1e-3), 1)),
+                              "alf_stats": dict(kernel_table({"alf_stats": kt_alf_stats}, peak)["alf_stats"],
+                                                what="encoder ALF statistics (EncAdaptiveLoopFilter::deriveClassification + deriveStatsForFiltering) of the resident SAO'd pictures: classification + three covariance launches per step; multiply-bound (105 IMAD per luma sample), algorithmic bytes = reconstructed + original picture read once (6 B/pixel)",
+                                                mpixel_per_s=round(B * mpx / (kt_alf_stats[0] / max(kt_alf_stats[1], 1) * 1e-3), 1)),
+                              "picture_hash": {"ms_per_picture": round(hash_ms, 3), "what": "ilf_picture_hash (CRC of the three planes of one resident picture, host call to host result: two launches + 24 bytes down)"}},
                 "cpu_baseline": cpu,
                 "e2e": {"value": round(e2e_value, 1), "unit": "Mpixel/s", "h2d_bytes_per_step": Be * h2d + side_b, "d2h_bytes_per_step": Be * d2h, "pictures_per_step": Be,
                         "host_ceiling": host_ceiling(world, (Be * h2d + side_b) / Be, mpx),

@@ -212,6 +212,8 @@ int ilf_set_alf_params(ilf_ctx* ctx, int slot, const ilf_alf_params* params,
  * as one batched launch per stage (pictures of a batch are independent).  A stage in the mask
  * whose side information was not set since the last upload is an error.  The result of a slot is
  * what ilf_download returns; the uploaded input is preserved, so ilf_run can be repeated.
+ * Every requested stage of every slot is validated before anything is launched.  The slots of a batch may mix the motion-vector
+ * representations (none / mv16 / mv32): the deblocking stage then takes one launch per representation present.
  * ilf_deblock / ilf_sao / ilf_alf are the per-class entry points of the shim (one stage, one slot;
  * each consumes the previous stage's output).
  * ------------------------------------------------------------------------------------------- */

@@ -95,3 +95,43 @@ def test_batched_slots(ilf_lib):
         for i, c in enumerate(caps):
             assert not any(_diff(f.download(i), {k: c[f"alf_{k}"] for k in K}).values()), f"slot {i}"
         assert 1 <= f.launch_count() <= 4    # planes whose stage is off in every picture of the batch are not launched
+
+
+def test_batch_with_mixed_motion_vector_representations(ilf_lib):
+    """One ilf_run over an intra picture given without motion vectors, a picture with int16 and one with int32 vectors: the library
+    launches the deblocking kernel once per representation present in the batch."""
+    caps = [G.load_golden(p) for p in G.golden_files() if any(t in p for t in ("ra_416x240_00", "ra_416x240_01", "ra_416x240_05"))]
+    assert len(caps) == 3
+    with _ctx(ilf_lib, caps[0], num_slots=3) as f:
+        for i, c in enumerate(caps):
+            f.upload(i, *(c[f"pre_{k}"] for k in K))
+            mv = c["db_mv32"]
+            mv16, mv32 = (None, None) if i == 0 else ((mv.astype(np.int16), None) if i == 1 else (None, mv))
+            if i == 0:
+                assert not mv.any()          # the intra picture really has no motion
+            f.set_deblock_info(i, c["db_params"].tobytes(), c["db_info"], c.get("db_info_c"), mv16, mv32, c["ctu_slice"])
+            f.set_sao_params(i, c["sao_ctus"])
+            f.set_alf_params(i, c["alf_params"].tobytes(), c["alf_ctu_enable"])
+        f.run(0, 3, 7)
+        for i, c in enumerate(caps):
+            assert not any(_diff(f.download(i), {k: c[f"alf_{k}"] for k in K}).values()), f"slot {i}"
+
+
+def test_run_with_missing_side_information_launches_nothing(ilf_lib):
+    """ilf_run validates every stage of every slot first: a slot without SAO parameters fails the call before any kernel runs, and the
+    slots' state is untouched (the next complete run gives the reference result)."""
+    c = G.load_golden([p for p in G.golden_files() if "ra_416x240_01" in p][0])
+    with _ctx(ilf_lib, c, num_slots=2) as f:
+        for i in range(2):
+            f.upload(i, *(c[f"pre_{k}"] for k in K))
+            f.set_deblock_info(i, c["db_params"].tobytes(), c["db_info"], c.get("db_info_c"), c["db_mv32"].astype(np.int16), None, c["ctu_slice"])
+            f.set_alf_params(i, c["alf_params"].tobytes(), c["alf_ctu_enable"])
+        f.set_sao_params(0, c["sao_ctus"])
+        n0 = f.launch_count()
+        with pytest.raises(ilf_lib.IlfError):
+            f.run(0, 2, 7)
+        assert f.launch_count() == n0
+        f.set_sao_params(1, c["sao_ctus"])
+        f.run(0, 2, 7)
+        for i in range(2):
+            assert not any(_diff(f.download(i), {k: c[f"alf_{k}"] for k in K}).values())

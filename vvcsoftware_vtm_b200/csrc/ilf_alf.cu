@@ -538,11 +538,11 @@ static int alf_nseg(int bands_total, int ntx, bool luma) {
 // planes: bit 0 = luma, bit 1 = chroma (the slots' control words say which planes of which slot really run)
 void launch_alf(const Geom& g, const SlotDev* slots, int first_slot, int num_slots, const BatchCtl& ctl, int planes, cudaStream_t st) {
   static bool attr_set[64] = {};
-  if (first_launch_on_device(attr_set)) {
+  once_per_device(attr_set, [] {
     cudaFuncSetAttribute(alf_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, L_SMEM_BYTES);
     cudaFuncSetAttribute(alf_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, C_SMEM_BYTES);
     cudaFuncSetAttribute(alf_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, L_SMEM_BYTES > C_SMEM_BYTES ? L_SMEM_BYTES : C_SMEM_BYTES);
-  }
+  });
   const int bands_y = (g.rows + BR - 1) / BR, bands_c = (g.rows / 2 + BR - 1) / BR;
   const int nseg_y = alf_nseg(bands_y * num_slots, (g.width + TW - 1) / TW, true);
   const int nseg_c = alf_nseg(2 * bands_c * num_slots, (g.width / 2 + TW - 1) / TW, false);
@@ -554,7 +554,7 @@ void launch_alf(const Geom& g, const SlotDev* slots, int first_slot, int num_slo
 
 void launch_alf_classify(const Geom& g, const SlotDev* slots, int first_slot, int num_slots, const BatchCtl& ctl, cudaStream_t st) {
   static bool attr_set[64] = {};
-  if (first_launch_on_device(attr_set)) { cudaFuncSetAttribute(alf_classify_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L_SMEM_BYTES); }
+  once_per_device(attr_set, [&] { cudaFuncSetAttribute(alf_classify_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L_SMEM_BYTES); });
   const int bands_y = (g.rows + BR - 1) / BR;
   const int nseg = alf_nseg(bands_y * num_slots, (g.width + TW - 1) / TW, true);
   launch_pdl(alf_classify_kernel, dim3(nseg, bands_y, num_slots), dim3(NT), L_SMEM_BYTES, st, g, slots, first_slot, ctl, nseg);

@@ -672,7 +672,10 @@ int ilf_band_connect(ilf_ctx* ctx, int slot, int side, const ilf_band_handle* ne
         cudaError_t e = cudaDeviceEnablePeerAccess(h.device, 0);
         if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(ctx, ILF_ERR_CUDA, "cudaDeviceEnablePeerAccess(%d) failed: %s", h.device, cudaGetErrorString(e));
         cudaGetLastError();
-      }  // without peer access the copies below are staged through the host by the driver (cudaMemcpyPeer semantics)
+      } else {
+        // the halo kernel dereferences the neighbour's pointer: without a peer mapping that is an illegal address, not a slow path
+        return fail(ctx, ILF_ERR_UNSUPPORTED, "no peer access from device %d to device %d: band mode needs NVLink / PCIe P2P between neighbouring bands", ctx->cfg.device, h.device);
+      }
     }
     nb.planes = (const int16_t*)(uintptr_t)h.ptr;
   } else {
@@ -991,17 +994,6 @@ static int timed_collect(ilf_ctx* ctx) {
 // the other work buffer (1 or 2), never buffer 0, so the uploaded input survives and ilf_run can be repeated.  Planes
 // for which the stage is off in the whole picture are skipped and keep their buffer.
 static int run_stage(ilf_ctx* ctx, int first, int n, int stage) {
-  int mv_mode = 0;
-  for (int i = first; i < first + n; i++) {
-    Slot& s = ctx->slots[i];
-    if (!s.uploaded) return fail(ctx, ILF_ERR_STATE, "slot %d: run before upload", i);
-    const bool have = stage == 0 ? s.has_db : (stage == 1 ? s.has_sao : s.has_alf);
-    if (!have) return fail(ctx, ILF_ERR_STATE, "slot %d: side information of stage %d not set since the last upload", i, stage);
-    if (stage == 0) mv_mode = std::max(mv_mode, s.mv_mode);
-  }
-  if (stage == 0)
-    for (int i = first; i < first + n; i++)
-      if (ctx->slots[i].mv_mode != mv_mode) return fail(ctx, ILF_ERR_ARG, "slots of one batch must use the same MV representation (none / mv16 / mv32)");
   const Geom& g = ctx->g;
   const double plane_bytes[3] = {2.0 * g.width * g.rows * 2, 2.0 * (g.width / 2) * (g.rows / 2) * 2, 2.0 * (g.width / 2) * (g.rows / 2) * 2};  // read + write
   for (int c0 = first; c0 < first + n; c0 += MAX_BATCH) {
@@ -1021,12 +1013,13 @@ static int run_stage(ilf_ctx* ctx, int first, int n, int stage) {
       if (stage == 2) v |= ((s.dev.alf_mode & 1) ? CTL_ALF_DOT_Y : 0) | (s.alf_is7 ? CTL_ALF_7X7 : 0) | ((s.dev.alf_mode & 4) ? CTL_ALF_HIC_Y : 0);
       word[i] = (uint16_t)v;
     }
-    auto compact = [&](bool use_y, bool use_c, BatchCtl& ctl, double& bytes) {
+    auto compact = [&](bool use_y, bool use_c, BatchCtl& ctl, double& bytes, int mv_mode = -1) {
       int m = 0;
       bytes = 0;
       for (int i = 0; i < cn; i++) {
         const bool y = use_y && on[i][0], c = use_c && (on[i][1] || on[i][2]);
         if (!y && !c) continue;
+        if (mv_mode >= 0 && ctx->slots[c0 + i].mv_mode != mv_mode) continue;
         ctl.v[m] = word[i];
         ctl.slot[m] = (uint8_t)i;
         m++;
@@ -1038,12 +1031,21 @@ static int run_stage(ilf_ctx* ctx, int first, int n, int stage) {
     if (ctx->timed.size() >= 4096) if (int rc = timed_collect(ctx)) return rc;
     BatchCtl ctl;
     double bytes = 0;
-    if (stage == 0 || stage == 1) {
+    if (stage == 0) {
+      // one launch per motion-vector representation present in the batch (none / int16 / int32 are different kernels)
+      for (int mode = 0; mode < 3; mode++) {
+        const int m = compact(true, true, ctl, bytes, mode);
+        if (!m) continue;
+        if (int rc = timed_begin(ctx, stage, bytes)) return rc;
+        launch_deblock(g, ctx->slots_dev, c0, m, ctl, mode, ctx->stream);
+        if (int rc = timed_end(ctx)) return rc;
+        ctx->launches++;
+      }
+    } else if (stage == 1) {
       const int m = compact(true, true, ctl, bytes);
       if (m) {
         if (int rc = timed_begin(ctx, stage, bytes)) return rc;
-        if (stage == 0) launch_deblock(g, ctx->slots_dev, c0, m, ctl, mv_mode, ctx->stream);
-        else launch_sao(g, ctx->slots_dev, c0, m, ctl, ctx->stream);
+        launch_sao(g, ctx->slots_dev, c0, m, ctl, ctx->stream);
         if (int rc = timed_end(ctx)) return rc;
         ctx->launches++;
       }
@@ -1085,6 +1087,16 @@ int ilf_run(ilf_ctx* ctx, int first_slot, int num_slots, unsigned stages) {
   if (!ctx) return ILF_ERR_ARG;
   if (first_slot < 0 || num_slots < 1 || first_slot + num_slots > (int)ctx->slots.size()) return fail(ctx, ILF_ERR_ARG, "slot range [%d,+%d) out of range", first_slot, num_slots);
   if (!(stages & ILF_STAGE_ALL)) return fail(ctx, ILF_ERR_ARG, "empty stage mask");
+  // validate every requested stage of every slot before anything is launched or any buffer rotation is recorded
+  for (int i = first_slot; i < first_slot + num_slots; i++) {
+    const Slot& s = ctx->slots[i];
+    if (!s.uploaded) return fail(ctx, ILF_ERR_STATE, "slot %d: run before upload", i);
+    for (int st = 0; st < 3; st++) {
+      if (!(stages & (1u << st))) continue;
+      const bool have = st == 0 ? s.has_db : (st == 1 ? s.has_sao : s.has_alf);
+      if (!have) return fail(ctx, ILF_ERR_STATE, "slot %d: side information of stage %d not set since the last upload", i, st);
+    }
+  }
   CU(ctx, cudaSetDevice(ctx->cfg.device));
   // A full run always restarts from the uploaded input.
   if (stages & ILF_STAGE_DEBLOCK)
@@ -1094,12 +1106,14 @@ int ilf_run(ilf_ctx* ctx, int first_slot, int num_slots, unsigned stages) {
     if (s.h2d_pending) { CU(ctx, cudaStreamWaitEvent(ctx->stream, s.ev_up, 0)); s.h2d_pending = false; }
     if (s.d2h_pending) { CU(ctx, cudaStreamWaitEvent(ctx->stream, s.ev_down, 0)); s.d2h_pending = false; }  // a download may still read the buffer this run overwrites
   }
-  for (int st = 0; st < 3; st++)
-    if (stages & (1u << st)) if (int rc = run_stage(ctx, first_slot, num_slots, st)) return rc;
+  int rc = ILF_OK;
+  for (int st = 0; st < 3 && rc == ILF_OK; st++)
+    if (stages & (1u << st)) rc = run_stage(ctx, first_slot, num_slots, st);
+  // whatever was launched is fenced by the run event, also on an error path: later uploads / downloads of these slots wait for it
   cudaEvent_t done = ctx->run_ring[ctx->run_pos++ % ilf_ctx::RUN_RING];
   CU(ctx, cudaEventRecord(done, ctx->stream));
   for (int i = first_slot; i < first_slot + num_slots; i++) ctx->slots[i].ev_run = done;
-  return ILF_OK;
+  return rc;
 }
 
 int ilf_deblock(ilf_ctx* ctx, int slot) { if (int rc = check_slot(ctx, slot)) return rc; return ilf_run(ctx, slot, 1, ILF_STAGE_DEBLOCK); }

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
+#include <mutex>
 
 #include "ilf_b200.h"
 
@@ -113,13 +114,18 @@ inline int pick_segments(int bands_total, int ntx, int resident, float startup_t
   return best;
 }
 
-// cudaFuncSetAttribute is per device: a process may hold contexts on several GPUs, so "already raised" is tracked per device.
-inline bool first_launch_on_device(bool (&seen)[64]) {
+// cudaFuncSetAttribute is per device: a process may hold contexts on several GPUs (and threads), so "already raised" is tracked
+// per device under a lock, and the caller raises the attributes while it holds it (set_attrs runs once per device).
+template <typename F>
+inline void once_per_device(bool (&seen)[64], F set_attrs) {
+  static std::mutex mu;
   int dev = 0;
   cudaGetDevice(&dev);
-  if (dev < 0 || dev >= 64 || seen[dev]) return false;
+  if (dev < 0 || dev >= 64) return;
+  std::lock_guard<std::mutex> lock(mu);
+  if (seen[dev]) return;
+  set_attrs();
   seen[dev] = true;
-  return true;
 }
 
 // Programmatic dependent launch: the stages of a chain are consecutive kernels on one stream.  Every kernel lets its

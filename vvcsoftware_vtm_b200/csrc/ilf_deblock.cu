@@ -503,7 +503,7 @@ template <int MV>
 static void launch_deblock_mv(const Geom& g, const SlotDev* slots, int first_slot, int num_slots, const BatchCtl& ctl, cudaStream_t st) {
   const int smem = DB_STAGES * stage_stride<MV>() + DB_STAGES * 16 + (int)sizeof(DbShared);
   static bool attr_set[64] = {};
-  if (first_launch_on_device(attr_set)) { cudaFuncSetAttribute(deblock_kernel<MV>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); }
+  once_per_device(attr_set, [&] { cudaFuncSetAttribute(deblock_kernel<MV>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); });
   const int bands = (g.rows + 4 + TH - 1) / TH, ntx = (g.width + TW - 1) / TW;
   int nseg = pick_segments(bands * num_slots, ntx, 148 * ILF_DB_MIN_CTAS, 1.5f);  // a segment that starts inside the picture runs one extra tile
   static const int force = getenv("ILF_DB_NSEG") ? atoi(getenv("ILF_DB_NSEG")) : 0;  // experiment knob

@@ -18,7 +18,7 @@ namespace {
 
 __constant__ uint16_t c_crc_tab[256];            // register (v << 8) after 8 zero bits
 
-__device__ __forceinline__ uint32_t crc_byte(uint32_t s, uint32_t b) { return (((s << 8) | b) & 0xffffu) ^ c_crc_tab[s >> 8]; }
+__device__ __forceinline__ uint32_t crc_byte(const uint16_t* tab, uint32_t s, uint32_t b) { return (((s << 8) | b) & 0xffffu) ^ tab[s >> 8]; }
 __device__ __forceinline__ uint32_t mat_apply(const uint16_t* col, uint32_t s) {
   uint32_t r = 0;
 #pragma unroll
@@ -35,7 +35,10 @@ struct HashArgs {
 };
 
 // one thread per row: zero-register CRC and checksum of the row
-__global__ void __launch_bounds__(128) hash_rows_kernel(HashArgs a) {
+__global__ void __launch_bounds__(32) hash_rows_kernel(HashArgs a) {
+  __shared__ uint16_t tab[256];   // the lanes index it with different values: shared memory, not the constant cache
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) tab[i] = c_crc_tab[i];
+  __syncthreads();
   const int p = blockIdx.y, r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= a.height[p]) return;
   const int w = a.width[p];
@@ -45,9 +48,9 @@ __global__ void __launch_bounds__(128) hash_rows_kernel(HashArgs a) {
   const uint32_t my = (r & 0xff) ^ (r >> 8);
   auto sample = [&](uint32_t smp, int x) {
     const uint32_t mask = (my ^ (x & 0xff) ^ (x >> 8)) & 0xff;
-    s = crc_byte(s, smp & 0xff);
+    s = crc_byte(tab, s, smp & 0xff);
     sum += (smp & 0xff) ^ mask;
-    if (two) { s = crc_byte(s, smp >> 8); sum += (smp >> 8) ^ mask; }
+    if (two) { s = crc_byte(tab, s, smp >> 8); sum += (smp >> 8) ^ mask; }
   };
   for (int x8 = 0; x8 < w / 8; x8++) {
     const uint4 v = __ldg(row + x8);
@@ -141,7 +144,7 @@ cudaError_t picture_hash(const Geom& g, const int16_t* const planes[3], uint32_t
     tab_set[dev] = true;
   }
   const int maxh = a.height[0];
-  hash_rows_kernel<<<dim3((maxh + 127) / 128, 3), 128, 0, st>>>(a);
+  hash_rows_kernel<<<dim3((maxh + 31) / 32, 3), 32, 0, st>>>(a);   // one warp per CTA: the 4320 row walks of a 4K picture spread over all SMs
   hash_reduce_kernel<<<3, 1024, 0, st>>>(a, out);
   uint32_t h[6];
   cudaError_t e = cudaMemcpyAsync(h, out, sizeof(h), cudaMemcpyDeviceToHost, st);

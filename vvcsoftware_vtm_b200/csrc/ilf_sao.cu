@@ -262,7 +262,7 @@ __global__ void __launch_bounds__(NTHREADS, SAO_CTAS) sao_kernel(Geom g, const S
 
 void launch_sao(const Geom& g, const SlotDev* slots, int first_slot, int num_slots, const BatchCtl& ctl, cudaStream_t st) {
   static bool attr_set[64] = {};
-  if (first_launch_on_device(attr_set)) { cudaFuncSetAttribute(sao_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES); }
+  once_per_device(attr_set, [&] { cudaFuncSetAttribute(sao_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES); });
   const int bands_y = (g.rows + BR - 1) / BR, bands_c = (g.rows / 2 + BR - 1) / BR;
   // enough CTAs to fill the machine when the batch is small: split bands into horizontal segments
   const int ntx = (g.width + TW - 1) / TW;

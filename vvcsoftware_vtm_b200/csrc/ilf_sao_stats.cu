@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) sao_stats_kernel(Geom g, const 
 
 void launch_sao_stats(const Geom& g, const SlotDev* slots, int first_slot, int num_slots, const BatchCtl& ctl, cudaStream_t st) {
   static bool attr_set[64] = {};
-  if (first_launch_on_device(attr_set)) cudaFuncSetAttribute(sao_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  once_per_device(attr_set, [&] { cudaFuncSetAttribute(sao_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES); });
   launch_pdl(sao_stats_kernel, dim3(g.ctus_w * g.ctus_h, 3, num_slots), dim3(NT), SMEM_BYTES, st, g, slots, first_slot, ctl);
 }
 
