@@ -100,7 +100,7 @@ def test_batched_slots(ilf_lib):
 def test_batch_with_mixed_motion_vector_representations(ilf_lib):
     """One ilf_run over an intra picture given without motion vectors, a picture with int16 and one with int32 vectors: the library
     launches the deblocking kernel once per representation present in the batch."""
-    caps = [G.load_golden(p) for p in G.golden_files() if any(t in p for t in ("ra_416x240_00", "ra_416x240_01", "ra_416x240_05"))]
+    caps = [G.load_golden(p) for p in G.golden_files() if os.path.basename(p) in ("ra_416x240_00.npz", "ra_416x240_01.npz", "ra_416x240_05.npz")]
     assert len(caps) == 3
     with _ctx(ilf_lib, caps[0], num_slots=3) as f:
         for i, c in enumerate(caps):
@@ -108,7 +108,7 @@ def test_batch_with_mixed_motion_vector_representations(ilf_lib):
             mv = c["db_mv32"]
             mv16, mv32 = (None, None) if i == 0 else ((mv.astype(np.int16), None) if i == 1 else (None, mv))
             if i == 0:
-                assert not mv.any()          # the intra picture really has no motion
+                assert (c["db_info"] & 1).all()          # every unit of the I picture is intra: its motion arrays are never read
             f.set_deblock_info(i, c["db_params"].tobytes(), c["db_info"], c.get("db_info_c"), mv16, mv32, c["ctu_slice"])
             f.set_sao_params(i, c["sao_ctus"])
             f.set_alf_params(i, c["alf_params"].tobytes(), c["alf_ctu_enable"])

@@ -80,7 +80,7 @@ constexpr int L_STAGE_BYTES = WP * L_SR * 2;                   // 10944 bytes pe
 constexpr int L_STAGE_STRIDE = (L_STAGE_BYTES + 127) & ~127;   // TMA destinations are 128-byte aligned
 constexpr int QW = TW / 4 + 1, QH = BR / 4 + 1;                // 17 x 9 quads of 4x4 samples, first quad at (x0-2, y0-2)
 constexpr int L_CELL_BYTES = 2 * QH * QW * 16;                 // {V, H, D0, D1} sums as 32-bit words, two tiles
-constexpr int L_EN_BYTES = 528;                                // ALF flags of the CTU columns a walk touches (16384 / 32, padded)
+constexpr int L_EN_BYTES = 2 * 528;                            // ALF flags of the CTU columns a walk touches (16384 / 32, padded), two CTU rows
 constexpr int L_ON_BYTES = 256;                                // per tile of a walk (16384 / 64): ALF on anywhere under it
 constexpr int L_SMEM_BYTES = RING_STAGES * L_STAGE_STRIDE + L_CELL_BYTES + RING_STAGES * 8 + L_EN_BYTES + L_ON_BYTES;
 constexpr int NT = 2 * TW;                                     // TW / 4 blocks across x 8 block rows
@@ -265,15 +265,20 @@ __device__ __forceinline__ void alf_luma_cta(unsigned char* smem, const Geom& g,
   const int bj = tid % BPR, bi = tid / BPR;
   const int by = y0 + 4 * bi;
   const int c0 = (ta * TW) >> g.ctu_log2, c1 = min(g.ctus_w - 1, (tb * TW - 1) >> g.ctu_log2);  // CTU columns this walk touches
-  const uint8_t* __restrict__ en_row = sd.alf_ctu_enable + (size_t)((y0 + g.row0) >> g.ctu_log2) * g.ctus_w;  // a band lies in one CTU row
+  // A band of 32 rows lies in one CTU row of a whole picture; in a band context the held rows start 16 rows above a CTU row, so
+  // it can straddle two.  en_s[r][c]: flags of CTU row r0 + r, columns from c0.
+  const int r0 = (y0 + g.row0) >> g.ctu_log2, r1 = min(g.ctus_h - 1, (min(y0 + BR, rows) - 1 + g.row0) >> g.ctu_log2);
+  const int ncol = c1 - c0 + 1;
   if (!CLASSIFY_ONLY) {
-    for (int c = c0 + tid; c <= c1; c += NT) en_s[c - c0] = en_row[c];
+    for (int i = tid; i < (r1 - r0 + 1) * ncol; i += NT) en_s[i] = sd.alf_ctu_enable[(size_t)(r0 + i / ncol) * g.ctus_w + c0 + i % ncol];
     for (int t = ta + tid; t < tb; t += NT) {
       bool any = false;
-      for (int c = (t * TW) >> g.ctu_log2; c <= min(c1, (t * TW + TW - 1) >> g.ctu_log2); c++) any |= en_row[c] != 0;
+      for (int r = r0; r <= r1; r++)
+        for (int c = (t * TW) >> g.ctu_log2; c <= min(c1, (t * TW + TW - 1) >> g.ctu_log2); c++) any |= sd.alf_ctu_enable[(size_t)r * g.ctus_w + c] != 0;
       on_s[t - ta] = any;
     }
   }
+  const int en_off = (min(r1, (by + g.row0) >> g.ctu_log2) - r0) * ncol - c0;   // this thread's row of en_s
   int16_t* __restrict__ dst = sd.buf[ctl_dst(ctl, 0)][0];
   const int max_val = (1 << g.bd_luma) - 1;
   const bool is7 = CLASSIFY_ONLY ? true : (ctl & CTL_ALF_7X7) != 0;
@@ -324,7 +329,7 @@ __device__ __forceinline__ void alf_luma_cta(unsigned char* smem, const Geom& g,
       } else if (blk_in) {
         // ---- phase 4: filter the block ----
         const int16_t* wp = W + (4 * bi) * WP + WX0 + 4 * bj - 4;  // window row 0 (= block row 0 minus 3), sample x - 4
-        if (en_s[(bx >> g.ctu_log2) - c0] == 0) {
+        if (en_s[en_off + (bx >> g.ctu_log2)] == 0) {
 #pragma unroll
           for (int o = 0; o < 4; o++) *reinterpret_cast<uint2*>(out + (size_t)o * g.pitch_y) = *reinterpret_cast<const uint2*>(wp + (3 + o) * WP + 4);
         } else if (dot) {
