@@ -297,10 +297,11 @@ int ilf_set_timing(ilf_ctx* ctx, int enable); /* enable != 0: clear the accumula
 int ilf_kernel_times(ilf_ctx* ctx, double ms_sum[ILF_NUM_KERNELS], long long launches[ILF_NUM_KERNELS],
                      double algo_bytes[ILF_NUM_KERNELS]);
 long long ilf_launch_count(const ilf_ctx* ctx);
-/* Which arithmetic path the slot's luma ALF filters take (chosen by ilf_set_alf_params from the coefficient ranges; results are
- * bit-exact either way): ILF_ALF_PATH_LUMA_DOT = the IDP.2A dot-product path (every coefficient outside the centre and its four
- * neighbours fits int8), 0 = the general 32-bit multiply path.  Chroma always takes the general path.  Negative = ilf_status. */
+/* Which arithmetic path the slot's ALF filters take (chosen by ilf_set_alf_params from the coefficient ranges; results are
+ * bit-exact either way): bit 0 = luma, bit 1 = chroma on the IDP.2A dot-product path (every coefficient outside the centre and its
+ * four neighbours fits int8), else the general 32-bit multiply path.  Negative = ilf_status. */
 #define ILF_ALF_PATH_LUMA_DOT 1
+#define ILF_ALF_PATH_CHROMA_DOT 2
 int ilf_alf_path(ilf_ctx* ctx, int slot);
 int ilf_slot_input_planes(ilf_ctx* ctx, int slot, void* planes[3], int32_t pitch[3]);
 int ilf_slot_output_planes(ilf_ctx* ctx, int slot, void* planes[3], int32_t pitch[3]);

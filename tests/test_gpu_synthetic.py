@@ -54,7 +54,7 @@ def test_alf_random_coefficients(w, h, bd, is7, seed, ilf_lib, oracle):
     rng = np.random.default_rng(seed)
     cw, ch = (w + 127) // 128, (h + 127) // 128
     # small coefficients and the limits of the dot-product path (IDP.2A, ilf_alf_tab.cuh); anything in +-511: general path
-    for kind, big, dot, path in (("mix", False, False, 1), ("noise", False, True, 1), ("noise", True, False, 0), ("mix", False, True, 1)):
+    for kind, big, dot, path in (("mix", False, False, 3), ("noise", False, True, 3), ("noise", True, False, 0), ("mix", False, True, 3)):
         pic = synth.picture(rng, w, h, bd, kind)
         pb, en = synth.alf_params(rng, cw, ch, is7, big=big, dot=dot)
         want = oracle.alf(pic, bd, bd, 7, pb, en)

@@ -420,6 +420,32 @@ __device__ __forceinline__ void load_row12(const int16_t* p, int v[12]) {
   v[10] = c & 0xFFFF; v[11] = c >> 16;
 }
 
+// Chroma, dot-product path: 8 samples x 2 rows per thread from the packed words of a 6-row window (w[r][m] = samples (x - 2 + 2m, x - 1 + 2m)
+// of window row r); cw = the picture's chroma filter in the radius-2 layout (ilf_alf_tab.cuh).  9 IDP per sample (8 low parts -- the
+// top and bottom rows share one -- and the centre's high part) against 7 IMAD + 6 adds + 4.5 unpacks of the general path.
+template <bool HI_CENTRE>
+__device__ __forceinline__ void filter_chroma_dp(const int16_t* wp, const uint32_t (&cw)[alftab::CHROMA_WORDS], int16_t* __restrict__ out, int pitch, int nrows, int max_val) {
+  uint32_t w[6][6];
+#pragma unroll
+  for (int r = 0; r < 6; r++) {
+    const uint4 b = *reinterpret_cast<const uint4*>(wp + r * WP);
+    w[r][0] = *reinterpret_cast<const uint32_t*>(wp + r * WP - 2); w[r][1] = b.x; w[r][2] = b.y; w[r][3] = b.z; w[r][4] = b.w;
+    w[r][5] = *reinterpret_cast<const uint32_t*>(wp + r * WP + 8);
+  }
+#pragma unroll
+  for (int o = 0; o < 2; o++) {
+    if (o >= nrows) break;
+    uint32_t tbsum[6];
+#pragma unroll
+    for (int m = 1; m <= 4; m++) tbsum[m] = w[o][m] + w[o + 4][m];   // rows -2 and +2: one tap each (dx = 0), same coefficient
+    int r[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) r[j] = __vimin_s32_relu(dp_filter_sample<2, 2, 2, HI_CENTRE>([&](int dy) { return w[o + 2 + dy]; }, tbsum, cw, j), max_val);
+    *reinterpret_cast<uint4*>(out + (size_t)o * pitch) =
+        make_uint4(__byte_perm(r[0], r[1], 0x5410), __byte_perm(r[2], r[3], 0x5410), __byte_perm(r[4], r[5], 0x5410), __byte_perm(r[6], r[7], 0x5410));
+  }
+}
+
 // Chroma CTA: band `cband` (0 .. 2 bands_c - 1: Cb bands, then Cr bands), horizontal segment blockIdx.x of nseg.
 __device__ __forceinline__ void alf_chroma_cta(unsigned char* smem, const Geom& g, const SlotDev& sd, unsigned ctl, int cband, int bands_c, int nseg) {
   const int plane = 1 + (cband >= bands_c), band = cband - (plane - 1) * bands_c;
@@ -454,6 +480,13 @@ __device__ __forceinline__ void alf_chroma_cta(unsigned char* smem, const Geom& 
   int f[7];
 #pragma unroll
   for (int i = 0; i < 7; i++) f[i] = sd.alf->chroma_coeff[i];
+  const bool dot = (ctl & CTL_ALF_DOT_C) != 0, hi_centre = (ctl & CTL_ALF_HIC_C) != 0;   // dot-product path (ilf_alf_tab.cuh), else the general path
+  uint32_t ccw[alftab::CHROMA_WORDS];
+  if (dot) {
+    const uint4* tp = reinterpret_cast<const uint4*>(sd.alf_coef_dp + 25 * 4 * alftab::LUMA_WORDS);
+#pragma unroll
+    for (int i = 0; i < alftab::CHROMA_WORDS / 4; i++) { const uint4 v = __ldg(tp + i); ccw[4 * i] = v.x; ccw[4 * i + 1] = v.y; ccw[4 * i + 2] = v.z; ccw[4 * i + 3] = v.w; }
+  }
   const int max_val = (1 << g.bd_chroma) - 1;
   const int k = tid % (TW / 8), rg = tid / (TW / 8);  // 8 samples at column 8k, rows 2rg and 2rg + 1 of the band
   const int y = by0 + 2 * rg;
@@ -482,6 +515,9 @@ __device__ __forceinline__ void alf_chroma_cta(unsigned char* smem, const Geom& 
 #pragma unroll
           for (int o = 0; o < 2; o++)
             if (o < nrows) *reinterpret_cast<uint4*>(out + (size_t)o * g.pitch_c) = *reinterpret_cast<const uint4*>(wp + (2 + o) * WP);
+        } else if (dot) {
+          if (hi_centre) filter_chroma_dp<true>(wp, ccw, out, g.pitch_c, nrows, max_val);
+          else filter_chroma_dp<false>(wp, ccw, out, g.pitch_c, nrows, max_val);
         } else {
           int w[6][12];
 #pragma unroll

@@ -56,9 +56,8 @@ static_assert(coef_index<3>(0, 0) == 12 && coef_index<3>(1, 0) == 11 && coef_ind
               coef_index<3>(2, -1) == 8 && coef_index<3>(1, 2) == 1 && coef_index<3>(0, -3) == 0 && coef_index<2>(0, 0) == 6 && coef_index<2>(-1, 1) == 3, "coefficient order");
 
 // Words of one table entry.  Luma: radius-3 layout (a 5x5 luma filter sits in it at the same sample positions):
-// [0, 8) even-x slots, [8, 16) odd-x slots, [16, 18) / [18, 20) high parts.  (A radius-2 layout would take 14 words: the chroma
-// filter was tried on this path and is no faster than its 32-bit form -- 7 IMAD against 10 IDP -- so chroma does not use it.)
-constexpr int LUMA_WORDS = 20, CHROMA_WORDS = 16 /* host test of the radius-2 layout only */;
+// [0, 8) even-x slots, [8, 16) odd-x slots, [16, 18) / [18, 20) high parts.  Chroma: radius-2 layout: [0, 5), [5, 10), [10, 12), [12, 14).
+constexpr int LUMA_WORDS = 20, CHROMA_WORDS = 16 /* 14 used */;
 constexpr int HI_SHIFT = 7;
 
 // Host side: builds one entry from the coefficients f[] (reference order of the radius-RT diamond) in a radius-R layout.

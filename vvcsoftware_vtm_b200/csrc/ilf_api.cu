@@ -24,7 +24,7 @@ namespace {
 
 thread_local std::string g_create_error;
 
-constexpr int ALF_DP_WORDS = 25 * 4 * alftab::LUMA_WORDS;
+constexpr int ALF_DP_WORDS = 25 * 4 * alftab::LUMA_WORDS + alftab::CHROMA_WORDS;
 
 // Pageable host planes (the reference's PelStorage) go through page-locked staging buffers.  A single memcpy thread moves about
 // 8 GB/s, a 4K picture is 25 MB each way, so the staging copies are cut into row chunks that a few helper threads copy while the
@@ -91,7 +91,7 @@ struct Slot {
   ilf_sao_ctu* sao = nullptr;
   ilf_alf_params* alf = nullptr;
   int* alf_coef = nullptr;     // [25][4][16] transposed luma coefficient table
-  uint32_t* alf_coef_dp = nullptr;  // [25][4][20]: dot-product layout of the luma filters (ilf_alf_tab.cuh)
+  uint32_t* alf_coef_dp = nullptr;  // [25][4][20] + [16]: dot-product layout of the luma filters and of the chroma filter (ilf_alf_tab.cuh)
   uint8_t* alf_ctu_enable = nullptr;
   uint8_t* alf_class = nullptr;
   int16_t* org = nullptr;      // source picture of the encoder (3 planes, same layout as one buffer of `planes`); allocated by ilf_set_original
@@ -944,7 +944,13 @@ int ilf_set_alf_params(ilf_ctx* ctx, int slot, const ilf_alf_params* params, con
         uint32_t* e = dp + (cl * 4 + tr) * alftab::LUMA_WORDS;
         luma_ok &= is7 ? alftab::build_entry<3, 3>(tab[cl][tr], e, alftab::LUMA_WORDS, &luma_nhi) : alftab::build_entry<3, 2>(tab[cl][tr], e, alftab::LUMA_WORDS, &luma_nhi);
       }
-    s.dev.alf_mode = (luma_ok ? 1 : 0) | (luma_ok && !luma_nhi ? 4 : 0);
+    // the chroma filter (meaningful only when chroma ALF is on: a slice without it leaves the array unset)
+    static const bool chroma_general = getenv("ILF_ALF_CHROMA_GENERAL") && atoi(getenv("ILF_ALF_CHROMA_GENERAL")) != 0;
+    bool chroma_nhi = false;
+    int fc[7];
+    for (int k = 0; k < 7; k++) fc[k] = params->chroma_coeff[k];
+    const bool chroma_ok = !force_general && !chroma_general && alftab::build_entry<2, 2>(fc, dp + 25 * 4 * alftab::LUMA_WORDS, alftab::CHROMA_WORDS, &chroma_nhi);
+    s.dev.alf_mode = (luma_ok ? 1 : 0) | (chroma_ok ? 2 : 0) | (luma_ok && !luma_nhi ? 4 : 0) | (chroma_ok && !chroma_nhi ? 8 : 0);
     s.alf_is7 = is7;
     if (int rc = stage_side(ctx, s, s.alf_coef_dp, dp, sizeof(dp), cur, lim)) return rc;
   }
@@ -1010,7 +1016,8 @@ static int run_stage(ilf_ctx* ctx, int first, int n, int stage) {
         if (!on[i][p]) { v |= 1u << (6 + p); continue; }
         s.result_buf[p] = s.result_buf[p] == 1 ? 2 : 1;
       }
-      if (stage == 2) v |= ((s.dev.alf_mode & 1) ? CTL_ALF_DOT_Y : 0) | (s.alf_is7 ? CTL_ALF_7X7 : 0) | ((s.dev.alf_mode & 4) ? CTL_ALF_HIC_Y : 0);
+      if (stage == 2) v |= ((s.dev.alf_mode & 1) ? CTL_ALF_DOT_Y : 0) | (s.alf_is7 ? CTL_ALF_7X7 : 0) | ((s.dev.alf_mode & 4) ? CTL_ALF_HIC_Y : 0) |
+                       ((s.dev.alf_mode & 2) ? CTL_ALF_DOT_C : 0) | ((s.dev.alf_mode & 8) ? CTL_ALF_HIC_C : 0);
       word[i] = (uint16_t)v;
     }
     auto compact = [&](bool use_y, bool use_c, BatchCtl& ctl, double& bytes, int mv_mode = -1) {
@@ -1283,7 +1290,7 @@ long long ilf_launch_count(const ilf_ctx* ctx) { return ctx ? ctx->launches : 0;
 int ilf_alf_path(ilf_ctx* ctx, int slot) {
   if (int rc = check_slot(ctx, slot)) return rc;
   if (!ctx->slots[slot].has_alf) return fail(ctx, ILF_ERR_STATE, "slot %d: ALF parameters not set", slot);
-  return ctx->slots[slot].dev.alf_mode & 1;
+  return ctx->slots[slot].dev.alf_mode & 3;
 }
 
 int ilf_slot_input_planes(ilf_ctx* ctx, int slot, void* planes[3], int32_t pitch[3]) {

@@ -63,9 +63,9 @@ struct alignas(64) SlotDev {
   const ilf_sao_ctu* sao;
   const ilf_alf_params* alf;
   const int* alf_coef;            // [25 classes][4 transposes][16] luma coefficients, transposition applied (set by ilf_set_alf_params)
-  const uint32_t* alf_coef_dp;    // [25][4][20] the same filters in the dot-product layout (ilf_alf_tab.cuh)
-  int alf_mode;                   // bit 0: the luma filters fit the dot-product path (else the general path); bit 2: only their centre
-                                  // coefficient has a high part
+  const uint32_t* alf_coef_dp;    // [25][4][20] the same filters in the dot-product layout (ilf_alf_tab.cuh), then [16] words of the chroma filter
+  int alf_mode;                   // bit 0 / 1: the luma filters / the chroma filter fit the dot-product path (else the general path);
+                                  // bit 2 / 3: only their centre coefficient has a high part
   const uint8_t* alf_ctu_enable;  // [3][num_ctus]
   uint8_t* alf_class;             // [units_h][units_w] scratch / output of ilf_alf_classify
   const int16_t* org[3];          // source picture of the encoder (ilf_set_original), plane pitches as buf
@@ -81,11 +81,11 @@ struct alignas(64) SlotDev {
 // no CTA touches it and its result stays where it was.
 constexpr int MAX_BATCH = 128;
 struct BatchCtl {
-  uint16_t v[MAX_BATCH];     // bits 2p..2p+1: source buffer of plane p; bit 6+p: skip plane p; bits 9..11: CTL_ALF_*
+  uint16_t v[MAX_BATCH];     // bits 2p..2p+1: source buffer of plane p; bit 6+p: skip plane p; bits 9..13: CTL_ALF_*
   uint8_t slot[MAX_BATCH];   // slot (relative to first_slot) that grid layer blockIdx.z works on: launches cover active slots only
 };
 // ALF launches: arithmetic path and luma filter shape of the slot (ilf_set_alf_params), so that a CTA knows them without a load
-constexpr unsigned CTL_ALF_DOT_Y = 1u << 9, CTL_ALF_7X7 = 1u << 10, CTL_ALF_HIC_Y = 1u << 11;
+constexpr unsigned CTL_ALF_DOT_Y = 1u << 9, CTL_ALF_7X7 = 1u << 10, CTL_ALF_HIC_Y = 1u << 11, CTL_ALF_DOT_C = 1u << 12, CTL_ALF_HIC_C = 1u << 13;
 __host__ __device__ __forceinline__ int ctl_src(unsigned c, int plane) { return (c >> (2 * plane)) & 3; }
 __host__ __device__ __forceinline__ int ctl_dst(unsigned c, int plane) { return ctl_src(c, plane) == 1 ? 2 : 1; }
 __host__ __device__ __forceinline__ bool ctl_skip(unsigned c, int plane) { return (c >> (6 + plane)) & 1; }

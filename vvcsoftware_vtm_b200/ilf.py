@@ -320,7 +320,7 @@ class InLoopFilter:
         return out
 
     def alf_path(self, slot=0):
-        """ILF_ALF_PATH_LUMA_DOT (1) when the slot's luma filters take the IDP.2A dot-product path, 0 for the general path."""
+        """Bits ILF_ALF_PATH_LUMA_DOT (1) / ILF_ALF_PATH_CHROMA_DOT (2): which arithmetic path the slot's ALF filters take."""
         r = self._lib.ilf_alf_path(self._h, slot)
         if r < 0:
             self._ck(r)
