@@ -905,7 +905,9 @@ def run_b200(args, wl):
                 "config": shared_config(wl, args.workload, world),
                 "config_detail": {"batch_pictures_per_gpu": B, "side_info": f"real, bench_data/{','.join(wl.get('npz', [args.workload]))}.npz ({len(side)} pictures per GPU)",
                                   "planes": "synthetic texture + 8x8 blockiness", "l2": f"working set {B * 2 * h2d / 1e6:.0f} MB per stage > 126 MB L2 (inputs larger than L2, no flush)",
-                                  "parallelism": f"independent pictures, {world} GPU(s), no collective"},
+                                  "parallelism": f"independent pictures, {world} GPU(s), no collective",
+                                  "run_lanes": f.run_lanes(),
+                                  "run_lanes_what": "ilf_run deals the chain over the resident batch to this many compute streams (groups of pictures of similar cost): value / ms_per_step are measured that way, the per-kernel durations with one kernel at a time on one stream"},
                 "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4),
                              "traffic": (ncu_traffic(dom, B) or {}).get("bytes_per_launch"), "traffic_detail": ncu_traffic(dom, B),
                              "peak_source": peak_src, "chain": chain_table(ktimes, ms_total, args.steps, B * mpx * 1e6, peak), "per_kernel": per_kernel,

@@ -297,6 +297,13 @@ int ilf_set_timing(ilf_ctx* ctx, int enable); /* enable != 0: clear the accumula
 int ilf_kernel_times(ilf_ctx* ctx, double ms_sum[ILF_NUM_KERNELS], long long launches[ILF_NUM_KERNELS],
                      double algo_bytes[ILF_NUM_KERNELS]);
 long long ilf_launch_count(const ilf_ctx* ctx);
+/* Lanes.  ilf_run deals a CHAIN (two or more stages) over a batch of at least ILF_RUN_LANE_MIN slots (default 8) to this many
+ * extra compute streams (environment ILF_RUN_LANES at ilf_create, default 2, 1 = off): the slots of a batch are independent
+ * pictures, so one lane's kernel fills the SMs that another lane's draining kernel leaves idle, and the instruction-bound ALF
+ * CTAs of one lane share SMs with the memory-bound deblocking / SAO CTAs of another.  Every slot still sees its stages in
+ * order; the context's stream (ilf_stream) joins the lanes after every run, uploads / downloads / later runs are ordered per
+ * slot by events.  Per-kernel timing (ilf_set_timing) keeps a run on the context's stream.  Returns the lane count (1 = off). */
+int ilf_run_lanes(const ilf_ctx* ctx);
 /* Which arithmetic path the slot's ALF filters take (chosen by ilf_set_alf_params from the coefficient ranges; results are
  * bit-exact either way): bit 0 = luma, bit 1 = chroma on the IDP.2A dot-product path (every coefficient outside the centre and its
  * four neighbours fits int8), else the general 32-bit multiply path.  Negative = ilf_status. */

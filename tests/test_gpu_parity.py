@@ -97,6 +97,38 @@ def test_batched_slots(ilf_lib):
         assert 1 <= f.launch_count() <= 4    # planes whose stage is off in every picture of the batch are not launched
 
 
+@pytest.mark.parametrize("policy", [0, 1])
+def test_chain_dealt_to_lanes(policy, ilf_lib, monkeypatch):
+    """A chain over a batch at or above the lane threshold is dealt to several compute streams (ilf_run, ILF_RUN_LANES): every
+    slot still gets the reference result, also when the grouping changes between runs (a slot moves to another lane), when a
+    single-stage run on the compute stream follows, and for the picture hash taken on the compute stream afterwards."""
+    monkeypatch.setenv("ILF_RUN_LANES", "3")
+    monkeypatch.setenv("ILF_RUN_LANE_MIN", "4")
+    monkeypatch.setenv("ILF_RUN_LANE_POLICY", str(policy))
+    caps = [G.load_golden(p) for p in G.golden_files() if "ra_416x240" in p]
+    n = 7
+    with _ctx(ilf_lib, caps[0], num_slots=n) as f:
+        for i in range(n):
+            c = caps[i % len(caps)]
+            f.upload(i, *(c[f"pre_{k}"] for k in K))
+            _set_all(f, i, c)
+        for first, cnt in ((0, n), (1, 6), (0, 5), (2, 4)):     # different groupings: slots change lanes between runs
+            f.run(first, cnt, 7)
+        f.run(0, n, 1)          # single stage: compute stream only, ordered after the lanes
+        f.run(0, n, 6)          # SAO + ALF as a chain on the lanes again
+        for i in range(n):
+            c = caps[i % len(caps)]
+            assert not any(_diff(f.download(i), {k: c[f"alf_{k}"] for k in K}).values()), f"slot {i}"
+        f.run(0, n, 7)
+        crc = f.picture_hash(n - 1, "crc")
+        c = caps[(n - 1) % len(caps)]
+        with _ctx(ilf_lib, c) as g1:
+            g1.upload(0, *(c[f"pre_{k}"] for k in K))
+            _set_all(g1, 0, c)
+            g1.run(0, 1, 7)
+            assert list(crc) == list(g1.picture_hash(0, "crc"))
+
+
 def test_batch_with_mixed_motion_vector_representations(ilf_lib):
     """One ilf_run over an intra picture given without motion vectors, a picture with int16 and one with int32 vectors: the library
     launches the deblocking kernel once per representation present in the batch."""

@@ -579,17 +579,19 @@ static int alf_nseg(int bands_total, int ntx, bool luma) {
 // planes: bit 0 = luma, bit 1 = chroma (the slots' control words say which planes of which slot really run)
 void launch_alf(const Geom& g, const SlotDev* slots, int first_slot, int num_slots, const BatchCtl& ctl, int planes, cudaStream_t st) {
   static bool attr_set[64] = {};
-  once_per_device(attr_set, [] {
-    cudaFuncSetAttribute(alf_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, L_SMEM_BYTES);
-    cudaFuncSetAttribute(alf_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, C_SMEM_BYTES);
-    cudaFuncSetAttribute(alf_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, L_SMEM_BYTES > C_SMEM_BYTES ? L_SMEM_BYTES : C_SMEM_BYTES);
+  static const int pad = env_int("ILF_ALF_SMEM_PAD");
+  const int smem_l = L_SMEM_BYTES + pad, smem_c = C_SMEM_BYTES + pad, smem_lc = smem_l > smem_c ? smem_l : smem_c;
+  once_per_device(attr_set, [&] {
+    cudaFuncSetAttribute(alf_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_l);
+    cudaFuncSetAttribute(alf_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_c);
+    cudaFuncSetAttribute(alf_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_lc);
   });
   const int bands_y = (g.rows + BR - 1) / BR, bands_c = (g.rows / 2 + BR - 1) / BR;
   const int nseg_y = alf_nseg(bands_y * num_slots, (g.width + TW - 1) / TW, true);
   const int nseg_c = alf_nseg(2 * bands_c * num_slots, (g.width / 2 + TW - 1) / TW, false);
-  if (planes == 1) launch_pdl(alf_kernel<1>, dim3(nseg_y, bands_y, num_slots), dim3(NT), L_SMEM_BYTES, st, g, slots, first_slot, ctl, bands_y, bands_c, nseg_y, nseg_c);
-  else if (planes == 2) launch_pdl(alf_kernel<2>, dim3(nseg_c, 2 * bands_c, num_slots), dim3(NT), C_SMEM_BYTES, st, g, slots, first_slot, ctl, bands_y, bands_c, nseg_y, nseg_c);
-  else launch_pdl(alf_kernel<3>, dim3(nseg_y > nseg_c ? nseg_y : nseg_c, bands_y + 2 * bands_c, num_slots), dim3(NT), L_SMEM_BYTES > C_SMEM_BYTES ? L_SMEM_BYTES : C_SMEM_BYTES, st, g,
+  if (planes == 1) launch_pdl(alf_kernel<1>, dim3(nseg_y, bands_y, num_slots), dim3(NT), smem_l, st, g, slots, first_slot, ctl, bands_y, bands_c, nseg_y, nseg_c);
+  else if (planes == 2) launch_pdl(alf_kernel<2>, dim3(nseg_c, 2 * bands_c, num_slots), dim3(NT), smem_c, st, g, slots, first_slot, ctl, bands_y, bands_c, nseg_y, nseg_c);
+  else launch_pdl(alf_kernel<3>, dim3(nseg_y > nseg_c ? nseg_y : nseg_c, bands_y + 2 * bands_c, num_slots), dim3(NT), smem_lc, st, g,
                   slots, first_slot, ctl, bands_y, bands_c, nseg_y, nseg_c);
 }
 

@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <atomic>
 #include <condition_variable>
 #include <functional>
@@ -117,6 +118,7 @@ struct Slot {
   // and download of picture n-1 overlap when the caller cycles through several slots.
   cudaEvent_t ev_up = nullptr;     // all H2D copies of the slot (planes + side information) issued so far are done
   cudaEvent_t ev_run = nullptr;    // all kernels issued so far on the slot are done (an event of the context's run ring, shared by the slots of a run)
+  cudaStream_t run_stream = nullptr;  // stream ev_run was recorded on: the compute stream or one of its lanes (nullptr: no kernel yet)
   cudaEvent_t ev_down = nullptr;   // the last D2H copy of the slot is done
   cudaEvent_t ev_side[3] = {nullptr, nullptr, nullptr};  // the pinned side-information region of stage k is free again
   size_t side_off[4] = {0, 0, 0, 0};                       // regions of pinned_side per stage
@@ -136,6 +138,13 @@ struct ilf_ctx {
   cudaStream_t stream = nullptr;   // compute stream (kernels)
   cudaStream_t s_up = nullptr;     // host -> device copies
   cudaStream_t s_down = nullptr;   // device -> host copies
+  // Lanes: a chain over a large batch is dealt to `num_lanes` extra compute streams (ilf_run), so that the drain of one lane's
+  // kernel overlaps another lane's kernels; the compute stream joins them (waits for their run events) without holding them up.
+  static constexpr int MAX_LANES = 4;
+  cudaStream_t lane[MAX_LANES] = {};
+  int num_lanes = 1;
+  int lane_min_slots = 8;          // batches smaller than this run on the compute stream alone
+  int lane_policy = 1;             // how ilf_run deals slots to lanes (see there)
   std::vector<Slot> slots;
   SlotDev* slots_dev = nullptr;
   size_t plane_y = 0, plane_c = 0, buf_elems = 0;  // elements per plane / per 3-plane buffer
@@ -146,11 +155,12 @@ struct ilf_ctx {
   struct TimedLaunch { int kernel; cudaEvent_t a, b; };
   std::vector<TimedLaunch> timed;
   std::vector<cudaEvent_t> free_events;
-  // one event per ilf_run marks the end of its kernels for every slot of the run; a ring is enough because waiting on a
-  // re-recorded event only waits longer (same stream)
+  // one event per ilf_run (and lane) marks the end of its kernels for every slot of the run; a ring PER STREAM (0: the compute
+  // stream, 1 + i: lane i) is enough because waiting on an event that was re-recorded on the same stream only waits longer
   static constexpr int RUN_RING = 64;
-  cudaEvent_t run_ring[RUN_RING] = {};
-  unsigned run_pos = 0;
+  cudaEvent_t run_ring[1 + MAX_LANES][RUN_RING] = {};
+  unsigned run_pos[1 + MAX_LANES] = {};
+  cudaEvent_t next_run_event(int ring) { return run_ring[ring][run_pos[ring]++ % RUN_RING]; }
   double kernel_ms[ILF_NUM_KERNELS] = {};
   double kernel_bytes[ILF_NUM_KERNELS] = {};
   long long kernel_launches[ILF_NUM_KERNELS] = {};
@@ -344,7 +354,13 @@ int create_impl(ilf_ctx** out, const ilf_config* cfg, const ilf_band* band) {
   CU(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   CU(ctx, cudaStreamCreateWithFlags(&ctx->s_up, cudaStreamNonBlocking));
   CU(ctx, cudaStreamCreateWithFlags(&ctx->s_down, cudaStreamNonBlocking));
-  for (cudaEvent_t& e : ctx->run_ring) CU(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  ctx->num_lanes = std::max(1, std::min((int)ilf_ctx::MAX_LANES, env_int("ILF_RUN_LANES", 2)));
+  ctx->lane_min_slots = std::max(2, env_int("ILF_RUN_LANE_MIN", 8));
+  ctx->lane_policy = env_int("ILF_RUN_LANE_POLICY", 1);
+  if (ctx->num_lanes > 1)
+    for (int i = 0; i < ctx->num_lanes; i++) CU(ctx, cudaStreamCreateWithFlags(&ctx->lane[i], cudaStreamNonBlocking));
+  for (auto& ring : ctx->run_ring)
+    for (cudaEvent_t& e : ring) CU(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   ctx->slots.resize(cfg->num_slots);
   CU(ctx, cudaMalloc(&ctx->slots_dev, sizeof(SlotDev) * cfg->num_slots));
   const size_t units = (size_t)g.units_pitch * g.units_h;  // device grids are pitched
@@ -374,7 +390,7 @@ int create_impl(ilf_ctx** out, const ilf_config* cfg, const ilf_band* band) {
     s.pinned_side_bytes = s.side_off[3];
     CU(ctx, cudaMallocHost(&s.pinned_side, s.pinned_side_bytes));
     CU(ctx, cudaEventCreateWithFlags(&s.ev_up, cudaEventDisableTiming));
-    s.ev_run = ctx->run_ring[0];  // never recorded yet: waiting on it is a no-op
+    s.ev_run = ctx->run_ring[0][0];  // never recorded yet: waiting on it is a no-op
     CU(ctx, cudaEventCreateWithFlags(&s.ev_down, cudaEventDisableTiming));
     for (int k = 0; k < 3; k++) CU(ctx, cudaEventCreateWithFlags(&s.ev_side[k], cudaEventDisableTiming));
     memset(&s.dev, 0, sizeof(s.dev));
@@ -436,7 +452,7 @@ int ilf_create_band(ilf_ctx** out, const ilf_config* cfg, const ilf_band* band) 
 int ilf_destroy(ilf_ctx* ctx) {
   if (!ctx) return ILF_OK;
   cudaSetDevice(ctx->cfg.device);
-  for (cudaStream_t st : {ctx->s_up, ctx->stream, ctx->s_down}) if (st) cudaStreamSynchronize(st);
+  for (cudaStream_t st : {ctx->s_up, ctx->stream, ctx->s_down, ctx->lane[0], ctx->lane[1], ctx->lane[2], ctx->lane[3]}) if (st) cudaStreamSynchronize(st);
   for (Slot& s : ctx->slots) {
     for (auto& nb : s.nb) if (nb.ipc_base) cudaIpcCloseMemHandle(nb.ipc_base);
     cudaFree(s.planes); cudaFree(s.info); cudaFree(s.info_c); cudaFree(s.mv); cudaFree(s.ctu_slice); cudaFree(s.db_params);
@@ -447,13 +463,14 @@ int ilf_destroy(ilf_ctx* ctx) {
     if (s.pinned_side) cudaFreeHost(s.pinned_side);
     for (cudaEvent_t e : {s.ev_up, s.ev_down, s.ev_side[0], s.ev_side[1], s.ev_side[2]}) if (e) cudaEventDestroy(e);
   }
-  for (cudaEvent_t e : ctx->run_ring) if (e) cudaEventDestroy(e);
+  for (auto& ring : ctx->run_ring)
+    for (cudaEvent_t e : ring) if (e) cudaEventDestroy(e);
   for (cudaEvent_t e : ctx->chunk_ev) if (e) cudaEventDestroy(e);
   cudaFree(ctx->slots_dev);
   cudaFree(ctx->hash_scratch);
   for (auto& t : ctx->timed) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
   for (cudaEvent_t e : ctx->free_events) cudaEventDestroy(e);
-  for (cudaStream_t st : {ctx->s_up, ctx->stream, ctx->s_down}) if (st) cudaStreamDestroy(st);
+  for (cudaStream_t st : {ctx->s_up, ctx->stream, ctx->s_down, ctx->lane[0], ctx->lane[1], ctx->lane[2], ctx->lane[3]}) if (st) cudaStreamDestroy(st);
   delete ctx;
   return ILF_OK;
 }
@@ -760,6 +777,12 @@ int ilf_band_exchange(ilf_ctx* ctx, int slot) {
 }
 
 // Decoded-picture hash of the slot's current picture, computed where the picture is (ilf_hash.cu).
+// Orders stream `st` after the kernels issued so far on the slot when they ran on another stream (a lane, or the compute stream).
+static int order_after_run(ilf_ctx* ctx, Slot& s, cudaStream_t st) {
+  if (s.run_stream && s.run_stream != st) CU(ctx, cudaStreamWaitEvent(st, s.ev_run, 0));
+  return ILF_OK;
+}
+
 int ilf_picture_hash(ilf_ctx* ctx, int slot, int kind, uint32_t out[3]) {
   if (int rc = check_slot(ctx, slot)) return rc;
   if (!out || (kind != ILF_HASH_CRC && kind != ILF_HASH_CHECKSUM)) return fail(ctx, ILF_ERR_ARG, "bad hash kind or null output");
@@ -769,6 +792,7 @@ int ilf_picture_hash(ilf_ctx* ctx, int slot, int kind, uint32_t out[3]) {
   CU(ctx, cudaSetDevice(ctx->cfg.device));
   if (!ctx->hash_scratch) CU(ctx, cudaMalloc(&ctx->hash_scratch, (6 * 16384 + 8) * sizeof(uint32_t)));
   if (s.h2d_pending) CU(ctx, cudaStreamWaitEvent(ctx->stream, s.ev_up, 0));   // a picture no stage has touched yet
+  if (int rc = order_after_run(ctx, s, ctx->stream)) return rc;
   const int16_t* planes[3];
   for (int p = 0; p < 3; p++) planes[p] = plane_ptr(ctx, s, s.result_buf[p], p);
   uint32_t crc[3], sum[3];
@@ -999,7 +1023,8 @@ static int timed_collect(ilf_ctx* ctx) {
 // One stage over a batch of slots.  Buffer rotation per plane: the stage reads the plane's current buffer and writes
 // the other work buffer (1 or 2), never buffer 0, so the uploaded input survives and ilf_run can be repeated.  Planes
 // for which the stage is off in the whole picture are skipped and keep their buffer.
-static int run_stage(ilf_ctx* ctx, int first, int n, int stage) {
+// lane_of / lane: when given, only the slots i of [first, first + n) with lane_of[i - first] == lane take part.
+static int run_stage(ilf_ctx* ctx, int first, int n, int stage, cudaStream_t stream, const uint8_t* lane_of = nullptr, int lane = 0) {
   const Geom& g = ctx->g;
   const double plane_bytes[3] = {2.0 * g.width * g.rows * 2, 2.0 * (g.width / 2) * (g.rows / 2) * 2, 2.0 * (g.width / 2) * (g.rows / 2) * 2};  // read + write
   for (int c0 = first; c0 < first + n; c0 += MAX_BATCH) {
@@ -1010,10 +1035,11 @@ static int run_stage(ilf_ctx* ctx, int first, int n, int stage) {
     for (int i = 0; i < cn; i++) {
       Slot& s = ctx->slots[c0 + i];
       unsigned v = 0;
+      const bool mine = !lane_of || lane_of[c0 + i - first] == lane;
       for (int p = 0; p < 3; p++) {
-        on[i][p] = stage == 0 ? true : (stage == 1 ? s.sao_on[p] : s.alf_on[p]);
+        on[i][p] = mine && (stage == 0 ? true : (stage == 1 ? s.sao_on[p] : s.alf_on[p]));
         v |= (unsigned)s.result_buf[p] << (2 * p);
-        if (!on[i][p]) { v |= 1u << (6 + p); continue; }
+        if (!on[i][p]) { v |= 1u << (6 + p); continue; }   // (a slot of another lane is not launched at all: compact() below)
         s.result_buf[p] = s.result_buf[p] == 1 ? 2 : 1;
       }
       if (stage == 2) v |= ((s.dev.alf_mode & 1) ? CTL_ALF_DOT_Y : 0) | (s.alf_is7 ? CTL_ALF_7X7 : 0) | ((s.dev.alf_mode & 4) ? CTL_ALF_HIC_Y : 0) |
@@ -1044,7 +1070,7 @@ static int run_stage(ilf_ctx* ctx, int first, int n, int stage) {
         const int m = compact(true, true, ctl, bytes, mode);
         if (!m) continue;
         if (int rc = timed_begin(ctx, stage, bytes)) return rc;
-        launch_deblock(g, ctx->slots_dev, c0, m, ctl, mode, ctx->stream);
+        launch_deblock(g, ctx->slots_dev, c0, m, ctl, mode, stream);
         if (int rc = timed_end(ctx)) return rc;
         ctx->launches++;
       }
@@ -1052,7 +1078,7 @@ static int run_stage(ilf_ctx* ctx, int first, int n, int stage) {
       const int m = compact(true, true, ctl, bytes);
       if (m) {
         if (int rc = timed_begin(ctx, stage, bytes)) return rc;
-        launch_sao(g, ctx->slots_dev, c0, m, ctl, ctx->stream);
+        launch_sao(g, ctx->slots_dev, c0, m, ctl, stream);
         if (int rc = timed_end(ctx)) return rc;
         ctx->launches++;
       }
@@ -1064,7 +1090,7 @@ static int run_stage(ilf_ctx* ctx, int first, int n, int stage) {
         const int m = compact(true, true, ctl, bytes);
         if (m) {
           if (int rc = timed_begin(ctx, ILF_KERNEL_ALF_LUMA, bytes)) return rc;
-          launch_alf(g, ctx->slots_dev, c0, m, ctl, 3, ctx->stream);
+          launch_alf(g, ctx->slots_dev, c0, m, ctl, 3, stream);
           if (int rc = timed_end(ctx)) return rc;
           ctx->launches++;
         }
@@ -1072,14 +1098,14 @@ static int run_stage(ilf_ctx* ctx, int first, int n, int stage) {
         int m = compact(true, false, ctl, bytes);
         if (m) {
           if (int rc = timed_begin(ctx, ILF_KERNEL_ALF_LUMA, bytes)) return rc;
-          launch_alf(g, ctx->slots_dev, c0, m, ctl, 1, ctx->stream);
+          launch_alf(g, ctx->slots_dev, c0, m, ctl, 1, stream);
           if (int rc = timed_end(ctx)) return rc;
           ctx->launches++;
         }
         m = compact(false, true, ctl, bytes);
         if (m) {
           if (int rc = timed_begin(ctx, ILF_KERNEL_ALF_CHROMA, bytes)) return rc;
-          launch_alf(g, ctx->slots_dev, c0, m, ctl, 2, ctx->stream);
+          launch_alf(g, ctx->slots_dev, c0, m, ctl, 2, stream);
           if (int rc = timed_end(ctx)) return rc;
           ctx->launches++;
         }
@@ -1108,18 +1134,62 @@ int ilf_run(ilf_ctx* ctx, int first_slot, int num_slots, unsigned stages) {
   // A full run always restarts from the uploaded input.
   if (stages & ILF_STAGE_DEBLOCK)
     for (int i = first_slot; i < first_slot + num_slots; i++) ctx->slots[i].result_buf[0] = ctx->slots[i].result_buf[1] = ctx->slots[i].result_buf[2] = 0;
-  for (int i = first_slot; i < first_slot + num_slots; i++) {
-    Slot& s = ctx->slots[i];
-    if (s.h2d_pending) { CU(ctx, cudaStreamWaitEvent(ctx->stream, s.ev_up, 0)); s.h2d_pending = false; }
-    if (s.d2h_pending) { CU(ctx, cudaStreamWaitEvent(ctx->stream, s.ev_down, 0)); s.d2h_pending = false; }  // a download may still read the buffer this run overwrites
+  // A chain over a large batch is dealt to the lanes (contiguous groups of slots, each group's stages on its own stream): the
+  // groups are independent, so one group's kernel fills the SMs that another group's draining kernel leaves idle.  Per-kernel
+  // timing keeps everything on the compute stream (serial kernels are what it measures).
+  const bool chain = (stages & (stages - 1)) != 0;
+  const int lanes = (ctx->num_lanes > 1 && chain && !ctx->timing && num_slots >= ctx->lane_min_slots) ? ctx->num_lanes : 1;
+  // slot -> lane.  Policy 0: contiguous groups of equal size.  Policy 1: slots dealt by estimated cost (planes x stages that run,
+  // ALF counted double), heaviest first to the least loaded lane, so that every lane carries a similar mix of kernels.
+  std::vector<uint8_t> lane_of(num_slots, 0);
+  if (lanes > 1) {
+    if (ctx->lane_policy == 0) {
+      for (int i = 0; i < num_slots; i++) lane_of[i] = (uint8_t)((long long)i * lanes / num_slots);
+    } else {
+      std::vector<std::pair<int, int>> cost(num_slots);
+      for (int i = 0; i < num_slots; i++) {
+        const Slot& s = ctx->slots[first_slot + i];
+        int c = 0;
+        for (int p = 0; p < 3; p++) {
+          const int w = p == 0 ? 4 : 1;
+          if (stages & ILF_STAGE_DEBLOCK) c += w;
+          if ((stages & ILF_STAGE_SAO) && s.sao_on[p]) c += w;
+          if ((stages & ILF_STAGE_ALF) && s.alf_on[p]) c += 2 * w;
+        }
+        cost[i] = {-c, i};
+      }
+      std::sort(cost.begin(), cost.end());
+      int load[ilf_ctx::MAX_LANES] = {};
+      for (auto& ci : cost) {
+        int best = 0;
+        for (int l = 1; l < lanes; l++) if (load[l] < load[best]) best = l;
+        lane_of[ci.second] = (uint8_t)best;
+        load[best] -= ci.first;
+      }
+    }
   }
   int rc = ILF_OK;
-  for (int st = 0; st < 3 && rc == ILF_OK; st++)
-    if (stages & (1u << st)) rc = run_stage(ctx, first_slot, num_slots, st);
-  // whatever was launched is fenced by the run event, also on an error path: later uploads / downloads of these slots wait for it
-  cudaEvent_t done = ctx->run_ring[ctx->run_pos++ % ilf_ctx::RUN_RING];
-  CU(ctx, cudaEventRecord(done, ctx->stream));
-  for (int i = first_slot; i < first_slot + num_slots; i++) ctx->slots[i].ev_run = done;
+  for (int gi = 0; gi < lanes; gi++) {
+    cudaStream_t st = lanes == 1 ? ctx->stream : ctx->lane[gi];
+    int members = 0;
+    for (int i = 0; i < num_slots; i++) {
+      if (lane_of[i] != gi) continue;
+      members++;
+      Slot& s = ctx->slots[first_slot + i];
+      if (s.h2d_pending) { CU(ctx, cudaStreamWaitEvent(st, s.ev_up, 0)); s.h2d_pending = false; }
+      if (s.d2h_pending) { CU(ctx, cudaStreamWaitEvent(st, s.ev_down, 0)); s.d2h_pending = false; }  // a download may still read the buffer this run overwrites
+      if (int rc2 = order_after_run(ctx, s, st)) return rc2;
+    }
+    if (!members) continue;
+    for (int k = 0; k < 3 && rc == ILF_OK; k++)
+      if (stages & (1u << k)) rc = run_stage(ctx, first_slot, num_slots, k, st, lanes == 1 ? nullptr : lane_of.data(), gi);
+    // whatever was launched is fenced by the run event, also on an error path: later uploads / downloads of these slots wait for it
+    cudaEvent_t done = ctx->next_run_event(lanes == 1 ? 0 : 1 + gi);
+    CU(ctx, cudaEventRecord(done, st));
+    for (int i = 0; i < num_slots; i++)
+      if (lane_of[i] == gi) { ctx->slots[first_slot + i].ev_run = done; ctx->slots[first_slot + i].run_stream = st; }
+    if (lanes > 1) CU(ctx, cudaStreamWaitEvent(ctx->stream, done, 0));   // the compute stream joins the lane (the lane does not wait for anything)
+  }
   return rc;
 }
 
@@ -1134,6 +1204,7 @@ int ilf_alf_classify(ilf_ctx* ctx, int slot, uint8_t* out) {
   if (!s.uploaded) return fail(ctx, ILF_ERR_STATE, "slot %d: classify before upload", slot);
   CU(ctx, cudaSetDevice(ctx->cfg.device));
   if (s.h2d_pending) { CU(ctx, cudaStreamWaitEvent(ctx->stream, s.ev_up, 0)); s.h2d_pending = false; }
+  if (int rc = order_after_run(ctx, s, ctx->stream)) return rc;
   BatchCtl ctl;
   ctl.v[0] = (uint16_t)s.result_buf[0];
   ctl.slot[0] = 0;
@@ -1186,6 +1257,7 @@ int ilf_sao_stats(ilf_ctx* ctx, int first_slot, int num_slots) {
     Slot& s = ctx->slots[i];
     if (!s.uploaded || !s.has_org) return fail(ctx, ILF_ERR_STATE, "slot %d: statistics need ilf_upload and ilf_set_original", i);
     if (s.h2d_pending) { CU(ctx, cudaStreamWaitEvent(ctx->stream, s.ev_up, 0)); s.h2d_pending = false; }
+    if (int rc = order_after_run(ctx, s, ctx->stream)) return rc;
   }
   for (int c0 = first_slot; c0 < first_slot + num_slots; c0 += MAX_BATCH) {
     const int cn = std::min(MAX_BATCH, first_slot + num_slots - c0);
@@ -1202,9 +1274,9 @@ int ilf_sao_stats(ilf_ctx* ctx, int first_slot, int num_slots) {
     ctx->launches++;
     CU(ctx, cudaGetLastError());
   }
-  cudaEvent_t done = ctx->run_ring[ctx->run_pos++ % ilf_ctx::RUN_RING];
+  cudaEvent_t done = ctx->next_run_event(0);
   CU(ctx, cudaEventRecord(done, ctx->stream));
-  for (int i = first_slot; i < first_slot + num_slots; i++) ctx->slots[i].ev_run = done;
+  for (int i = first_slot; i < first_slot + num_slots; i++) { ctx->slots[i].ev_run = done; ctx->slots[i].run_stream = ctx->stream; }
   return ILF_OK;
 }
 
@@ -1236,6 +1308,7 @@ int ilf_alf_stats(ilf_ctx* ctx, int first_slot, int num_slots) {
       if (int rc = push_desc(ctx, i)) return rc;
     }
     if (s.h2d_pending) { CU(ctx, cudaStreamWaitEvent(ctx->stream, s.ev_up, 0)); s.h2d_pending = false; }
+    if (int rc = order_after_run(ctx, s, ctx->stream)) return rc;
     CU(ctx, cudaMemsetAsync(s.alf_stats, 0, bytes, ctx->stream));
   }
   for (int c0 = first_slot; c0 < first_slot + num_slots; c0 += MAX_BATCH) {
@@ -1254,9 +1327,9 @@ int ilf_alf_stats(ilf_ctx* ctx, int first_slot, int num_slots) {
     ctx->launches += 4;
     CU(ctx, cudaGetLastError());
   }
-  cudaEvent_t done = ctx->run_ring[ctx->run_pos++ % ilf_ctx::RUN_RING];
+  cudaEvent_t done = ctx->next_run_event(0);
   CU(ctx, cudaEventRecord(done, ctx->stream));
-  for (int i = first_slot; i < first_slot + num_slots; i++) ctx->slots[i].ev_run = done;
+  for (int i = first_slot; i < first_slot + num_slots; i++) { ctx->slots[i].ev_run = done; ctx->slots[i].run_stream = ctx->stream; }
   return ILF_OK;
 }
 
@@ -1287,6 +1360,7 @@ int ilf_kernel_times(ilf_ctx* ctx, double ms_sum[ILF_NUM_KERNELS], long long lau
   return ILF_OK;
 }
 long long ilf_launch_count(const ilf_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int ilf_run_lanes(const ilf_ctx* ctx) { return ctx ? ctx->num_lanes : ILF_ERR_ARG; }
 int ilf_alf_path(ilf_ctx* ctx, int slot) {
   if (int rc = check_slot(ctx, slot)) return rc;
   if (!ctx->slots[slot].has_alf) return fail(ctx, ILF_ERR_STATE, "slot %d: ALF parameters not set", slot);

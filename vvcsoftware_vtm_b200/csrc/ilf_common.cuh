@@ -114,6 +114,10 @@ inline int pick_segments(int bands_total, int ntx, int resident, float startup_t
   return best;
 }
 
+// Experiment knob: extra dynamic shared memory per CTA (bytes, from the environment) -- caps how many CTAs of a kernel an SM holds,
+// which is how mixed residency of two kernels running on different streams is steered (tools/exp_lanes.py).
+inline int env_int(const char* name, int dflt = 0) { const char* v = getenv(name); return v ? atoi(v) : dflt; }
+
 // cudaFuncSetAttribute is per device: a process may hold contexts on several GPUs (and threads), so "already raised" is tracked
 // per device under a lock, and the caller raises the attributes while it holds it (set_attrs runs once per device).
 template <typename F>

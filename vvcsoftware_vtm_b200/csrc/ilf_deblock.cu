@@ -501,7 +501,8 @@ __global__ void __launch_bounds__(NTHREADS, ILF_DB_MIN_CTAS) deblock_kernel(Geom
 
 template <int MV>
 static void launch_deblock_mv(const Geom& g, const SlotDev* slots, int first_slot, int num_slots, const BatchCtl& ctl, cudaStream_t st) {
-  const int smem = DB_STAGES * stage_stride<MV>() + DB_STAGES * 16 + (int)sizeof(DbShared);
+  static const int pad = env_int("ILF_DB_SMEM_PAD");
+  const int smem = DB_STAGES * stage_stride<MV>() + DB_STAGES * 16 + (int)sizeof(DbShared) + pad;
   static bool attr_set[64] = {};
   once_per_device(attr_set, [&] { cudaFuncSetAttribute(deblock_kernel<MV>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); });
   const int bands = (g.rows + 4 + TH - 1) / TH, ntx = (g.width + TW - 1) / TW;

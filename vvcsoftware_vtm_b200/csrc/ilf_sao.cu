@@ -121,8 +121,22 @@ __device__ __forceinline__ void eo_rows(const EoCtx& e, const Row (&v)[R + 2], c
 
 // One tile of the walk: `cur` is the tile's stage (SR rows x TW samples), `prev` / `next` the neighbouring tiles' stages (or
 // nullptr at the picture border, where the availability flags already exclude the missing neighbour).
+// The strip's CTU parameters (two 16-byte words of ilf_sao_ctu): loaded one tile ahead by the walk, so that their latency is
+// not exposed at the start of every tile (everything below branches on the type).
+struct CtuPrm { uint4 a, b; };
+__device__ __forceinline__ CtuPrm load_ctu_prm(const Geom& g, const SlotDev& sd, int plane, int tx, int by0) {
+  const int k = threadIdx.x % KPR, rg = threadIdx.x / KPR;
+  const int sh = plane ? 1 : 0;
+  const int ctu_log2 = g.ctu_log2 - sh;
+  const int cx = min((tx * TW + 8 * k) >> ctu_log2, g.ctus_w - 1), cy = min((by0 + R * rg + (g.row0 >> sh)) >> ctu_log2, g.ctus_h - 1);
+  const uint4* __restrict__ prm = reinterpret_cast<const uint4*>(sd.sao + (size_t)cy * g.ctus_w + cx);
+  CtuPrm p;
+  p.a = __ldg(prm); p.b = __ldg(prm + 1);
+  return p;
+}
+
 __device__ __forceinline__ void sao_tile(const Geom& g, const SlotDev& sd, int plane, int16_t* __restrict__ dst, int tx, int by0, const int16_t* cur,
-                                         const int16_t* prev, const int16_t* next) {
+                                         const int16_t* prev, const int16_t* next, const CtuPrm& cp) {
   const int k = threadIdx.x % KPR, rg = threadIdx.x / KPR;
   const int sh = plane ? 1 : 0;
   const int pw = g.width >> sh, ph_local = g.rows >> sh, ph_global = g.height >> sh;
@@ -133,8 +147,7 @@ __device__ __forceinline__ void sao_tile(const Geom& g, const SlotDev& sd, int p
   const int gy0 = y0 + (g.row0 >> sh);  // picture row
   const int ctu_log2 = g.ctu_log2 - sh, ctu_sz = 1 << ctu_log2;
   const int cx = x0 >> ctu_log2, cy = gy0 >> ctu_log2;
-  const uint4* __restrict__ prm = reinterpret_cast<const uint4*>(sd.sao + (size_t)cy * g.ctus_w + cx);
-  const uint4 pa = __ldg(prm), pb = __ldg(prm + 1);
+  const uint4 pa = cp.a, pb = cp.b;
   // ilf_sao_ctu: offset[3][4] int16 (24 bytes), type[3] int8 at byte 24, band_pos[3] at 27, avail at 30
   const int type = (int)(int8_t)((plane == 0 ? pb.z : plane == 1 ? pb.z >> 8 : pb.z >> 16) & 0xFF);
   const int16_t* base = cur + (R * rg) * TW + 8 * k;  // staged row 0 of the strip = the row above it
@@ -245,13 +258,16 @@ __global__ void __launch_bounds__(NTHREADS, SAO_CTAS) sao_kernel(Geom g, const S
   Pos pp = {walk.stage(ta) - 1, 0u}, pc = {walk.stage(ta), 0u}, pn = {walk.stage(ta), 0u};   // ta - first is 0 or 1: all in the first lap
   pn.next();
   auto sptr = [&](const Pos& p) { return reinterpret_cast<int16_t*>(smem + p.st * STAGE_BYTES); };
+  CtuPrm cp = load_ctu_prm(g, sd, plane, ta, by0);
   for (int tx = ta; tx < tb; tx++) {
+    const CtuPrm cp_next = load_ctu_prm(g, sd, plane, min(tx + 1, tb - 1), by0);   // consumed by the next step
     if (tx == ta) {
       if (tx > walk.first) ring::mbar_wait(&full[pp.st], pp.par);
       ring::mbar_wait(&full[pc.st], pc.par);
     }
     if (tx + 1 <= walk.last) ring::mbar_wait(&full[pn.st], pn.par);
-    sao_tile(g, sd, plane, dst, tx, by0, sptr(pc), tx > 0 ? sptr(pp) : nullptr, tx + 1 < ntx ? sptr(pn) : nullptr);
+    sao_tile(g, sd, plane, dst, tx, by0, sptr(pc), tx > 0 ? sptr(pp) : nullptr, tx + 1 < ntx ? sptr(pn) : nullptr, cp);
+    cp = cp_next;
     __syncthreads();  // every thread is done with tile tx - 1: its stage can be refilled
     if (tid == 0 && tx - 1 >= walk.first && tx - 1 + STAGES <= walk.last) issue(tx - 1 + STAGES);
     pp = pc; pc = pn; pn.next();
@@ -262,7 +278,8 @@ __global__ void __launch_bounds__(NTHREADS, SAO_CTAS) sao_kernel(Geom g, const S
 
 void launch_sao(const Geom& g, const SlotDev* slots, int first_slot, int num_slots, const BatchCtl& ctl, cudaStream_t st) {
   static bool attr_set[64] = {};
-  once_per_device(attr_set, [&] { cudaFuncSetAttribute(sao_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES); });
+  static const int smem = SMEM_BYTES + env_int("ILF_SAO_SMEM_PAD");
+  once_per_device(attr_set, [&] { cudaFuncSetAttribute(sao_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); });
   const int bands_y = (g.rows + BR - 1) / BR, bands_c = (g.rows / 2 + BR - 1) / BR;
   // enough CTAs to fill the machine when the batch is small: split bands into horizontal segments
   const int ntx = (g.width + TW - 1) / TW;
@@ -270,7 +287,7 @@ void launch_sao(const Geom& g, const SlotDev* slots, int first_slot, int num_slo
   int nseg = (148 * SAO_CTAS + bands - 1) / bands;
   nseg = nseg < 1 ? 1 : (nseg > ntx ? ntx : nseg);
   dim3 grid(nseg, bands_y + 2 * bands_c, num_slots);
-  launch_pdl(sao_kernel, grid, dim3(NTHREADS), SMEM_BYTES, st, g, slots, first_slot, ctl, bands_y, bands_c, nseg);
+  launch_pdl(sao_kernel, grid, dim3(NTHREADS), smem, st, g, slots, first_slot, ctl, bands_y, bands_c, nseg);
 }
 
 }  // namespace ilf

@@ -93,6 +93,8 @@ def load_library():
     lib.ilf_download_extended.argtypes = [vp, i, vp, pd, vp, pd, vp, pd, i]
     lib.ilf_launch_count.argtypes = [vp]
     lib.ilf_launch_count.restype = C.c_longlong
+    lib.ilf_run_lanes.argtypes = [vp]
+    lib.ilf_run_lanes.restype = C.c_int
     lib.ilf_slot_input_planes.argtypes = [vp, i, C.POINTER(vp * 3), C.POINTER(C.c_int32 * 3)]
     lib.ilf_slot_output_planes.argtypes = [vp, i, C.POINTER(vp * 3), C.POINTER(C.c_int32 * 3)]
     lib.ilf_stream.argtypes = [vp]
@@ -325,6 +327,10 @@ class InLoopFilter:
         if r < 0:
             self._ck(r)
         return r
+
+    def run_lanes(self):
+        """Compute streams a chain over a large batch is dealt to (ilf_run_lanes; 1 = off)."""
+        return int(self._lib.ilf_run_lanes(self._h))
 
     def launch_count(self):
         return int(self._lib.ilf_launch_count(self._h))
