@@ -1,7 +1,7 @@
 """Drop-in gate, encoder side: the reference EncoderApp linked with the host shim, so that EncGOP::compressGOP's
 LoopFilter::loopFilterPic (EncGOP.cpp:2122), the statistics pass of EncSampleAdaptiveOffset::SAOProcess (:2135,
 EncSampleAdaptiveOffset.cpp:227) and the classification + covariance passes of EncAdaptiveLoopFilter::ALFProcess
-(EncAdaptiveLoopFilter.cpp:257-260) run on libilf_b200.so, must write the same bitstream and the same reconstruction, byte for byte, as the stock encoder: every
+(EncAdaptiveLoopFilter.cpp:257-260) and the filter application at the end of its search (:433-462) run on libilf_b200.so, must write the same bitstream and the same reconstruction, byte for byte, as the stock encoder: every
 decision the encoder takes after deblocking (SAO statistics, ALF covariances, reference pictures of later frames)
 depends on every deblocked sample."""
 import hashlib
@@ -38,6 +38,7 @@ def test_encoder_with_gpu_deblocking_writes_the_same_stream(cfg, frames, qp, ext
             assert r.stderr.count("deblock_us=") >= frames, r.stderr[-2000:]      # every picture's deblocking went through the CUDA library ...
             assert r.stderr.count("sao_stats_us=") >= frames, r.stderr[-2000:]    # ... and so did the statistics pass of its SAO search
             assert r.stderr.count("alf_stats_us=") >= frames, r.stderr[-2000:]    # ... and the classification + covariances of its ALF search
+            assert r.stderr.count("alf_apply_us=") >= 1, r.stderr[-2000:]         # ... and the ALF filters of the pictures whose search switched ALF on
         outs[tag] = (_md5(bit), _md5(rec))
     assert outs["gpu"] == outs["cpu"]
     # and the stock decoder accepts the GPU-encoded stream with every picture hash (OK)

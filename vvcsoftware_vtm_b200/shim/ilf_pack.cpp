@@ -430,7 +430,7 @@ void ilfReconstructAlfCoeff( AlfSliceParam& p, bool luma, short* coeffFinal, boo
       for( int j = 0; j < nCoef - 1; j++ ) c[f * rowLen + j] = c[f * rowLen + j] - c[( f - 1 ) * rowLen + j];
 }
 
-void ilfPackAlf( CodingStructure& cs, AlfSliceParam& p, IlfPackedAlf& out )
+void ilfPackAlf( CodingStructure& cs, AlfSliceParam& p, IlfPackedAlf& out, bool encoder )
 {
   std::memset( &out.params, 0, sizeof( out.params ) );
   out.enabled = p.enabledFlag[COMPONENT_Y] || p.enabledFlag[COMPONENT_Cb] || p.enabledFlag[COMPONENT_Cr];
@@ -439,8 +439,8 @@ void ilfPackAlf( CodingStructure& cs, AlfSliceParam& p, IlfPackedAlf& out )
   if( !out.enabled ) return;
   short coeffFinal[MAX_NUM_ALF_CLASSES * MAX_NUM_ALF_LUMA_COEFF];
   std::memset( coeffFinal, 0, sizeof( coeffFinal ) );
-  ilfReconstructAlfCoeff( p, true, coeffFinal, false );
-  ilfReconstructAlfCoeff( p, false, nullptr, false );
+  if( !encoder || p.enabledFlag[COMPONENT_Y] ) ilfReconstructAlfCoeff( p, true, coeffFinal, encoder );
+  if( !encoder || p.enabledFlag[COMPONENT_Cb] || p.enabledFlag[COMPONENT_Cr] ) ilfReconstructAlfCoeff( p, false, nullptr, false );
   for( int cls = 0; cls < 25; cls++ )
     for( int j = 0; j < 13; j++ ) out.params.luma_coeff[cls][j] = coeffFinal[cls * MAX_NUM_ALF_LUMA_COEFF + j];
   for( int j = 0; j < 7; j++ ) out.params.chroma_coeff[j] = p.chromaCoeff[j];

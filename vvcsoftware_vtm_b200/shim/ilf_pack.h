@@ -88,7 +88,10 @@ void ilfPackSao( CodingStructure& cs, SAOBlkParam* saoBlkParams, const uint32_t 
 
 // ALF: reconstructs the coefficients (mutating alfSliceParam like the reference) and flattens.
 void ilfReconstructAlfCoeff( AlfSliceParam& alfSliceParam, bool isLuma, short* coeffFinal /* [25*13], luma only */, bool redo );
-void ilfPackAlf( CodingStructure& cs, AlfSliceParam& alfSliceParam, IlfPackedAlf& out );
+// encoder = true: called after EncAdaptiveLoopFilter::alfEncoder, which has already run reconstructCoeff with bRedo on the enabled
+// channels (EncAdaptiveLoopFilter.cpp:431): the luma deltas are put back the same way and a disabled channel is left untouched,
+// so alfSliceParam reaches the bitstream writer exactly as the reference leaves it.
+void ilfPackAlf( CodingStructure& cs, AlfSliceParam& alfSliceParam, IlfPackedAlf& out, bool encoder = false );
 
 
 // Encoder SAO statistics of cs's picture through the shim's context (ilf_shim.cpp): `src` is the deblocked picture the
@@ -99,5 +102,8 @@ void ilfShimSaoStatistics( CodingStructure& cs, const ilfPlanes& org, const ilfP
 // Encoder ALF statistics and block classification of `rec` (the SAO'd picture) against `org`: out[numCtus][ILF_ALF_STATS_WORDS],
 // classMap[unitsH][unitsW] = classIdx | transposeIdx << 5.
 void ilfShimAlfStatistics( CodingStructure& cs, const ilfPlanes& org, const ilfPlanes& rec, int64_t* out, uint8_t* classMap );
+// Encoder ALF application: filters the picture ilfShimAlfStatistics left in the slot with the parameters alfEncoder chose and
+// writes the result into cs.getRecoBuf() (what the m_filter7x7Blk / m_filter5x5Blk loops of EncAdaptiveLoopFilter.cpp:433-462 do).
+void ilfShimAlfApply( CodingStructure& cs, AlfSliceParam& alfSliceParam );
 
 #endif

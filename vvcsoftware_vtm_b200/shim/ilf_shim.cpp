@@ -272,3 +272,22 @@ void ilfShimAlfStatistics( CodingStructure& cs, const ilfPlanes& org, const ilfP
   ck( s, ilf_get_alf_stats( s.ctx, 0, out ), "ilf_get_alf_stats" );
   if( s.timing ) fprintf( stderr, "[ILFTIME] poc=%d alf_stats_us=%lld impl=b200\n", cs.slice->getPOC(), usSince( t0 ) );
 }
+
+// Encoder ALF application (called by EncAdaptiveLoopFilter::ALFProcess in ilf_shim_enc.cpp after the filter search): the SAO'd
+// picture is still in the slot from the statistics pass, so nothing goes up but the parameters; the filtered picture comes down
+// into the reconstruction buffer.  A plane whose ALF is off keeps the uploaded samples, as in the reference (the reconstruction
+// buffer already holds them).
+void ilfShimAlfApply( CodingStructure& cs, AlfSliceParam& alfSliceParam )
+{
+  const auto t0 = clk::now();
+  ShimState& s  = contextFor( cs );
+  IlfPackedAlf pa;
+  ilfPackAlf( cs, alfSliceParam, pa, true );
+  if( !pa.enabled ) return;
+  ck( s, ilf_set_alf_params( s.ctx, 0, &pa.params, pa.ctuEnable.data() ), "ilf_set_alf_params" );
+  ck( s, ilf_alf( s.ctx, 0 ), "ilf_alf" );
+  PelUnitBuf reco = cs.getRecoBuf();
+  PelBuf     y = reco.get( COMPONENT_Y ), cb = reco.get( COMPONENT_Cb ), cr = reco.get( COMPONENT_Cr );
+  ck( s, ilf_download( s.ctx, 0, y.buf, y.stride, cb.buf, cb.stride, cr.buf, cr.stride ), "ilf_download" );
+  if( s.timing ) fprintf( stderr, "[ILFTIME] poc=%d alf_apply_us=%lld impl=b200\n", cs.slice->getPOC(), usSince( t0 ) );
+}

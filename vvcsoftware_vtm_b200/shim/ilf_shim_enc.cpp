@@ -3,7 +3,8 @@
 //   EncAdaptiveLoopFilter::ALFProcess       replaces source/Lib/EncoderLib/EncAdaptiveLoopFilter.cpp:220-268
 //     its deriveClassification (:257) and deriveStatsForFiltering (:260, :1317-1514) become ilf_upload / ilf_set_original /
 //     ilf_alf_stats / ilf_alf_classify / ilf_get_alf_stats on the SAO'd picture; the filter derivation (alfEncoder) stays the
-//     reference's own code and reads the class map and the covariances exactly as its own passes would have left them.
+//     reference's own code and reads the class map and the covariances exactly as its own passes would have left them; the
+//     per-CTU filter application at its end (:433-462) becomes ilf_set_alf_params / ilf_alf / ilf_download on the resident picture.
 //
 //   EncSampleAdaptiveOffset::SAOProcess     replaces source/Lib/EncoderLib/EncSampleAdaptiveOffset.cpp:213-253
 //     its call of getStatistics (:227, :278-331, getBlkStats :1122-1487) becomes ilf_set_original / ilf_sao_stats /
@@ -101,9 +102,9 @@ void EncAdaptiveLoopFilter::ALFProcess( CodingStructure& cs, const double* lambd
   m_lambda[COMPONENT_Cb] = lambdas[COMPONENT_Cb] * double( 1 << shiftChroma );
   m_lambda[COMPONENT_Cr] = lambdas[COMPONENT_Cr] * double( 1 << shiftChroma );
   PelUnitBuf orgYuv = cs.getOrgBuf();
-  m_tempBuf.copyFrom( cs.getRecoBuf() );
-  PelUnitBuf recYuv = m_tempBuf.getBuf( cs.area );
-  recYuv.extendBorderPel( MAX_ALF_FILTER_LENGTH >> 1 );
+  // the reference copies the picture into m_tempBuf and pads it (:250-252) as the source of its CPU filters; here the source is
+  // the copy in the slot (the device kernels pad on the fly), so the reconstruction buffer itself goes up
+  PelUnitBuf recYuv = cs.getRecoBuf();
 
   // ---- classification + statistics on the device ----
   const PreCalcValues& pcv = *cs.pcv;
@@ -164,7 +165,16 @@ void EncAdaptiveLoopFilter::ALFProcess( CodingStructure& cs, const double* lambd
       }
   }
 
-  // ---- filter derivation: the reference's own search (:262-268) ----
+  // ---- filter derivation: the reference's own search (:262-268).  alfEncoder ends with the reconstruction loops that call
+  //      m_filter7x7Blk / m_filter5x5Blk per CTU (:433-462); those two are function pointers of the base class, pointed at a
+  //      function that does nothing while the search runs -- the picture is filtered on the device afterwards ----
+  const auto filter5 = m_filter5x5Blk, filter7 = m_filter7x7Blk;
+  m_filter5x5Blk = m_filter7x7Blk = []( AlfClassifier**, const PelUnitBuf&, const CPelUnitBuf&, const Area&, const ComponentID, short*, const ClpRng& ) {};
   alfEncoder( cs, alfSliceParam, orgYuv, recYuv, cs.getRecoBuf(), CHANNEL_TYPE_LUMA );
   if( alfSliceParam.enabledFlag[COMPONENT_Y] ) alfEncoder( cs, alfSliceParam, orgYuv, recYuv, cs.getRecoBuf(), CHANNEL_TYPE_CHROMA );
+  m_filter5x5Blk = filter5;
+  m_filter7x7Blk = filter7;
+
+  // ---- filter application on the device: the SAO'd picture is in the slot since the statistics pass ----
+  ilfShimAlfApply( cs, alfSliceParam );
 }
