@@ -23,6 +23,7 @@
 #include <cstdlib>
 #include <thread>
 #include <utility>
+#include <mutex>
 #include <vector>
 
 #include "CommonLib/AdaptiveLoopFilter.h"
@@ -53,6 +54,14 @@ struct ShimState
     if( ctx ) ilf_destroy( ctx );
   }
 };
+
+// The shim keeps one context and one resident picture per process; its entry points are serialised, so that several decoder or
+// encoder objects in one process cannot interleave inside them (they take turns).
+std::recursive_mutex& shimMutex()
+{
+  static std::recursive_mutex m;
+  return m;
+}
 
 ShimState& state()
 {
@@ -154,6 +163,7 @@ void report( ShimState& s, const CodingStructure& cs )
 // ------------------------------------------------------------------------------------------------------------
 void LoopFilter::loopFilterPic( CodingStructure& cs )
 {
+  std::lock_guard<std::recursive_mutex> lock( shimMutex() );
   const auto t0 = clk::now();
   ShimState& s  = contextFor( cs );
   const auto tc = clk::now();
@@ -197,6 +207,7 @@ void LoopFilter::loopFilterPic( CodingStructure& cs )
 // ------------------------------------------------------------------------------------------------------------
 void SampleAdaptiveOffset::SAOProcess( CodingStructure& cs, SAOBlkParam* saoBlkParams )
 {
+  std::lock_guard<std::recursive_mutex> lock( shimMutex() );
   CHECK( !saoBlkParams, "No parameters present" );
   const auto t0 = clk::now();
   ShimState& s  = contextFor( cs );
@@ -219,6 +230,7 @@ void SampleAdaptiveOffset::SAOProcess( CodingStructure& cs, SAOBlkParam* saoBlkP
 // ------------------------------------------------------------------------------------------------------------
 void AdaptiveLoopFilter::ALFProcess( CodingStructure& cs, AlfSliceParam& alfSliceParam )
 {
+  std::lock_guard<std::recursive_mutex> lock( shimMutex() );
   const auto t0 = clk::now();
   ShimState& s  = contextFor( cs );
   if( alfSliceParam.enabledFlag[COMPONENT_Y] || alfSliceParam.enabledFlag[COMPONENT_Cb] || alfSliceParam.enabledFlag[COMPONENT_Cr] )
@@ -242,6 +254,7 @@ void AdaptiveLoopFilter::ALFProcess( CodingStructure& cs, AlfSliceParam& alfSlic
 // slot, so only the source picture crosses PCIe here.
 void ilfShimSaoStatistics( CodingStructure& cs, const ilfPlanes& org, const ilfPlanes& src, const uint8_t* ctuAvail, int64_t* out )
 {
+  std::lock_guard<std::recursive_mutex> lock( shimMutex() );
   const auto t0 = clk::now();
   ShimState& s  = contextFor( cs );
   if( !( s.mirrored == cs.picture && s.mirroredPoc == cs.slice->getPOC() ) )
@@ -260,6 +273,7 @@ void ilfShimSaoStatistics( CodingStructure& cs, const ilfPlanes& org, const ilfP
 // picture go up, 21 KB of integers per CTU and one byte per 4x4 block come back.
 void ilfShimAlfStatistics( CodingStructure& cs, const ilfPlanes& org, const ilfPlanes& rec, int64_t* out, uint8_t* classMap )
 {
+  std::lock_guard<std::recursive_mutex> lock( shimMutex() );
   const auto t0 = clk::now();
   ShimState& s  = contextFor( cs );
   ck( s, ilf_upload( s.ctx, 0, rec.p[0], rec.stride[0], rec.p[1], rec.stride[1], rec.p[2], rec.stride[2] ), "ilf_upload" );
@@ -279,6 +293,7 @@ void ilfShimAlfStatistics( CodingStructure& cs, const ilfPlanes& org, const ilfP
 // buffer already holds them).
 void ilfShimAlfApply( CodingStructure& cs, AlfSliceParam& alfSliceParam )
 {
+  std::lock_guard<std::recursive_mutex> lock( shimMutex() );
   const auto t0 = clk::now();
   ShimState& s  = contextFor( cs );
   IlfPackedAlf pa;
