@@ -167,6 +167,7 @@ struct ilf_ctx {
   int num_ctus = 0;
   CopyPool copy_pool;
   uint32_t* hash_scratch = nullptr;   // ilf_picture_hash
+  int* db_work = nullptr;             // tile queues of the deblocking kernel: two ints per stream (the compute stream, then the lanes)
   cudaEvent_t chunk_ev[COPY_CHUNKS_MAX] = {};   // download: chunk i has reached the staging buffer
 };
 
@@ -361,6 +362,8 @@ int create_impl(ilf_ctx** out, const ilf_config* cfg, const ilf_band* band) {
     for (int i = 0; i < ctx->num_lanes; i++) CU(ctx, cudaStreamCreateWithFlags(&ctx->lane[i], cudaStreamNonBlocking));
   for (auto& ring : ctx->run_ring)
     for (cudaEvent_t& e : ring) CU(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  CU(ctx, cudaMalloc(&ctx->db_work, sizeof(int) * 2 * (1 + ilf_ctx::MAX_LANES)));
+  CU(ctx, cudaMemset(ctx->db_work, 0, sizeof(int) * 2 * (1 + ilf_ctx::MAX_LANES)));
   ctx->slots.resize(cfg->num_slots);
   CU(ctx, cudaMalloc(&ctx->slots_dev, sizeof(SlotDev) * cfg->num_slots));
   const size_t units = (size_t)g.units_pitch * g.units_h;  // device grids are pitched
@@ -399,14 +402,14 @@ int create_impl(ilf_ctx** out, const ilf_config* cfg, const ilf_band* band) {
     s.dev.alf_class = s.alf_class;
     {
       const size_t grid_bytes = units * 4;
-      if (int rc = make_map3(ctx, &s.dev.tm_info, CU_TENSOR_MAP_DATA_TYPE_UINT32, s.info, g.units_w, g.units_h, 1, (size_t)g.units_pitch * 4, grid_bytes, 32, 8)) return rc;
-      if (int rc = make_map3(ctx, &s.dev.tm_info_c, CU_TENSOR_MAP_DATA_TYPE_UINT32, s.info_c, g.units_w, g.units_h, 1, (size_t)g.units_pitch * 4, grid_bytes, 32, 8)) return rc;
-      if (int rc = make_map3(ctx, &s.dev.tm_mv16, CU_TENSOR_MAP_DATA_TYPE_UINT32, s.mv, g.units_w * 2, g.units_h, 1, (size_t)g.units_pitch * 8, units * 8, 64, 8)) return rc;
-      if (int rc = make_map3(ctx, &s.dev.tm_mv32, CU_TENSOR_MAP_DATA_TYPE_UINT32, s.mv, g.units_w * 4, g.units_h, 1, (size_t)g.units_pitch * 16, units * 16, 128, 8)) return rc;
+      if (int rc = make_map3(ctx, &s.dev.tm_info, CU_TENSOR_MAP_DATA_TYPE_UINT32, s.info, g.units_w, g.units_h, 1, (size_t)g.units_pitch * 4, grid_bytes, DB_BOX_UNITS, 8)) return rc;
+      if (int rc = make_map3(ctx, &s.dev.tm_info_c, CU_TENSOR_MAP_DATA_TYPE_UINT32, s.info_c, g.units_w, g.units_h, 1, (size_t)g.units_pitch * 4, grid_bytes, DB_BOX_UNITS, 8)) return rc;
+      if (int rc = make_map3(ctx, &s.dev.tm_mv16, CU_TENSOR_MAP_DATA_TYPE_UINT32, s.mv, g.units_w * 2, g.units_h, 1, (size_t)g.units_pitch * 8, units * 8, DB_BOX_MV16_WORDS, 8)) return rc;
+      if (int rc = make_map3(ctx, &s.dev.tm_mv32, CU_TENSOR_MAP_DATA_TYPE_UINT32, s.mv, g.units_w * 4, g.units_h, 1, (size_t)g.units_pitch * 16, units * 16, DB_BOX_MV32_WORDS, 8)) return rc;
     }
     for (int p = 0; p < 3; p++) {
       const int pw = p ? cfg->width / 2 : cfg->width, ph = p ? g.rows / 2 : g.rows, pitch = p ? g.pitch_c : g.pitch_y;
-      if (int rc = make_map3(ctx, &s.dev.tm_db[p], CU_TENSOR_MAP_DATA_TYPE_UINT16, plane_ptr(ctx, s, 0, p), pw, ph, 3, (size_t)pitch * 2, ctx->buf_elems * 2, p ? RING_TILE_W / 2 : RING_TILE_W,
+      if (int rc = make_map3(ctx, &s.dev.tm_db[p], CU_TENSOR_MAP_DATA_TYPE_UINT16, plane_ptr(ctx, s, 0, p), pw, ph, 3, (size_t)pitch * 2, ctx->buf_elems * 2, p ? DB_BOX_CW : DB_BOX_W,
                              p ? DB_BAND_ROWS / 2 : DB_BAND_ROWS))
         return rc;
       if (int rc = make_map3(ctx, &s.dev.tm_sao[p], CU_TENSOR_MAP_DATA_TYPE_UINT16, plane_ptr(ctx, s, 0, p), pw, ph, 3, (size_t)pitch * 2, ctx->buf_elems * 2, SAO_TILE,
@@ -468,6 +471,7 @@ int ilf_destroy(ilf_ctx* ctx) {
   for (cudaEvent_t e : ctx->chunk_ev) if (e) cudaEventDestroy(e);
   cudaFree(ctx->slots_dev);
   cudaFree(ctx->hash_scratch);
+  cudaFree(ctx->db_work);
   for (auto& t : ctx->timed) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
   for (cudaEvent_t e : ctx->free_events) cudaEventDestroy(e);
   for (cudaStream_t st : {ctx->s_up, ctx->stream, ctx->s_down, ctx->lane[0], ctx->lane[1], ctx->lane[2], ctx->lane[3]}) if (st) cudaStreamDestroy(st);
@@ -1024,6 +1028,11 @@ static int timed_collect(ilf_ctx* ctx) {
 // the other work buffer (1 or 2), never buffer 0, so the uploaded input survives and ilf_run can be repeated.  Planes
 // for which the stage is off in the whole picture are skipped and keep their buffer.
 // lane_of / lane: when given, only the slots i of [first, first + n) with lane_of[i - first] == lane take part.
+static int stream_index(const ilf_ctx* ctx, cudaStream_t st) {
+  for (int i = 0; i < ilf_ctx::MAX_LANES; i++) if (ctx->lane[i] && ctx->lane[i] == st) return 1 + i;
+  return 0;
+}
+
 static int run_stage(ilf_ctx* ctx, int first, int n, int stage, cudaStream_t stream, const uint8_t* lane_of = nullptr, int lane = 0) {
   const Geom& g = ctx->g;
   const double plane_bytes[3] = {2.0 * g.width * g.rows * 2, 2.0 * (g.width / 2) * (g.rows / 2) * 2, 2.0 * (g.width / 2) * (g.rows / 2) * 2};  // read + write
@@ -1070,7 +1079,7 @@ static int run_stage(ilf_ctx* ctx, int first, int n, int stage, cudaStream_t str
         const int m = compact(true, true, ctl, bytes, mode);
         if (!m) continue;
         if (int rc = timed_begin(ctx, stage, bytes)) return rc;
-        launch_deblock(g, ctx->slots_dev, c0, m, ctl, mode, stream);
+        launch_deblock(g, ctx->slots_dev, c0, m, ctl, mode, ctx->db_work + 2 * stream_index(ctx, stream), stream);
         if (int rc = timed_end(ctx)) return rc;
         ctx->launches++;
       }

@@ -42,15 +42,21 @@ constexpr int ALF_TILE = ALF_TILE_W;
 #endif
 constexpr int SAO_TILE = SAO_TILE_W;   // tile width of the SAO walk (its TMA boxes are SAO_TILE x 34)
 constexpr int DB_BAND_ROWS = 32;   // luma rows a deblocking CTA owns (shifted up by 4 rows; chroma: 16 rows shifted by 2)
+// Deblocking works on independent tiles: a box carries the tile plus the reach of the vertical edges on its borders (4 luma / 2
+// chroma samples, 1 unit), widened to 8 samples / 4 units on each side because a TMA box must START on a 16-byte boundary
+// (a box that starts 8 bytes off faults with "illegal instruction"); motion boxes start 2 (int16: 8 bytes per unit) / 1 (int32)
+// units left of the tile and are counted in 32-bit words (2 / 4 per unit; rows are multiples of 16 bytes).
+constexpr int DB_BOX_W = RING_TILE_W + 16, DB_BOX_CW = RING_TILE_W / 2 + 16, DB_BOX_UNITS = RING_TILE_W / 4 + 8;
+constexpr int DB_BOX_MV16_WORDS = (RING_TILE_W / 4 + 4) * 2, DB_BOX_MV32_WORDS = (RING_TILE_W / 4 + 2) * 4;
 constexpr int SAO_BAND_ROWS = 32;  // rows a SAO CTA owns; the box adds one halo row above and below
 constexpr int ALF_BAND_ROWS = 32;  // rows an ALF CTA owns; the box adds 3 (luma, 7x7 + classification) or 2 (chroma, 5x5) halo rows on each side
 constexpr int ALF_HALO_Y = 3, ALF_HALO_C = 2;
 
 struct alignas(64) SlotDev {
   // TMA descriptors of the slot's planes, tensor (x, y, buffer): dims (plane width, held rows, 3)
-  CUtensorMap tm_db[3];     // box RING_TILE_W x DB_BAND_ROWS (luma), RING_TILE_W/2 x DB_BAND_ROWS/2 (chroma)
-  CUtensorMap tm_info, tm_info_c;  // unit grids, tensor (unit x, unit y, 1) of uint32: box 32 x 8
-  CUtensorMap tm_mv16, tm_mv32;    // motion vectors as uint32 words (2 / 4 per unit): box 64 x 8 / 128 x 8
+  CUtensorMap tm_db[3];     // box DB_BOX_W x DB_BAND_ROWS (luma), DB_BOX_CW x DB_BAND_ROWS/2 (chroma)
+  CUtensorMap tm_info, tm_info_c;  // unit grids, tensor (unit x, unit y, 1) of uint32: box DB_BOX_UNITS x 8
+  CUtensorMap tm_mv16, tm_mv32;    // motion vectors as uint32 words (2 / 4 per unit): box DB_BOX_MV16_WORDS x 8 / DB_BOX_MV32_WORDS x 8
   CUtensorMap tm_sao[3];    // box SAO_TILE x (SAO_BAND_ROWS + 2)
   CUtensorMap tm_alf[3];    // box (ALF_TILE + 16) x (ALF_BAND_ROWS + 2 * halo), loaded 8 samples left of the tile
   int16_t* buf[3][3];       // [buffer: 0 = input, 1, 2 = work][plane]
@@ -151,7 +157,7 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
 }
 
 // One launch covers `num_slots` <= MAX_BATCH grid layers; layer z works on slot first_slot + ctl.slot[z] under control word ctl.v[z].
-void launch_deblock(const Geom& g, const SlotDev* slots, int first_slot, int num_slots, const BatchCtl& ctl, int mv_mode, cudaStream_t st);
+void launch_deblock(const Geom& g, const SlotDev* slots, int first_slot, int num_slots, const BatchCtl& ctl, int mv_mode, int* work, cudaStream_t st);
 void launch_sao(const Geom& g, const SlotDev* slots, int first_slot, int num_slots, const BatchCtl& ctl, cudaStream_t st);
 void launch_alf(const Geom& g, const SlotDev* slots, int first_slot, int num_slots, const BatchCtl& ctl, int planes /* bit 0 luma, bit 1 chroma */, cudaStream_t st);
 void launch_sao_stats(const Geom& g, const SlotDev* slots, int first_slot, int num_slots, const BatchCtl& ctl, cudaStream_t st);

@@ -4,32 +4,37 @@
 // horizontal edges".  Filtered edges lie on the 8x8 luma grid (:313-324), each reads 4 and writes 3 samples
 // per side (:856-916), and the on/off + strong/weak decisions of a 4-line segment use lines 0 and 3 of that
 // segment only (:640-671).  Vertically, a band of 32 luma rows shifted up by 4 rows is therefore dependency-closed for
-// the horizontal edges in its middle once its vertical edges are done; horizontally the kernel WALKS the band: a
-// vertical edge on a tile boundary needs 4 samples of the tile to its left, and those are carried over.
+// the horizontal edges in its middle once its vertical edges are done.  Horizontally a TILE of 128 output columns
+// [x0, x0 + 128) is dependency-closed once it is given four more columns on each side: the vertical edges x0 + 8e, e = 0..16,
+// read [x0 - 4, x0 + 132) and leave [x0, x0 + 128) final (edge 16 is the next tile's edge 0: both tiles compute it, each keeps
+// its own side).
 //
-// Data movement: band walking over a TMA ring (ilf_ring.cuh).  A CTA owns the band rows [32 ty - 4, 32 ty + 28) (chroma
-// [16 ty - 2, 16 ty + 14), units [8 ty - 1, 8 ty + 7)) and walks it in tiles of 128 luma columns.  One stage of the ring
-// holds everything a tile needs, fetched by five or six aligned TMA boxes several tiles ahead of the arithmetic: luma
-// 128 x 32, Cb and Cr 64 x 16, the unit grid 32 x 8 (and its chroma-tree layer), motion vectors 32 x 8.  Per tile:
-//   1. vertical edges x0 + 8e, e = 0..15 (luma) / cx0 + 8k, k = 0..7 (chroma), in shared memory.  Edge 0 lies on the tile
-//      boundary: its P side is the last four columns of the PREVIOUS tile, whose stage stays in the ring for one more step.
-//   2. horizontal edges over columns whose vertical filtering is complete.  The tile's last four luma (one chroma) columns
-//      wait for the next tile's edge 0; the pass lags by 16 columns instead -- [x0 - 16, x0 + 112) luma, [cx0 - 16, cx0 + 48)
-//      chroma, the previous tile's last columns coming from its stage -- so that every stored warp row starts on a 32-byte
-//      sector.  A task (4 luma columns x 8 rows, or 2 chroma columns x 8 rows) loads its block, filters the edge in its middle
-//      when there is one, and stores the block straight to the destination plane: a warp's 32 tasks write 256 (128)
-//      contiguous bytes per row.  There is no separate write-back pass and only two CTA barriers per tile.
-// Every sample crosses HBM once in and once out (the reference makes two picture passes).  A walk that starts inside the
-// picture (small batches split bands into segments) first runs the vertical edges of the tile to its left without storing;
-// the last walk of a band ends with a flush step for the lagging columns.
+// Data movement: INDEPENDENT TILES in raster order.  A CTA takes DB_TILES_PER_CTA consecutive tiles of a band (rows
+// [32 ty - 4, 32 ty + 28), chroma [16 ty - 2, 16 ty + 14), units [8 ty - 1, 8 ty + 7)), issues the TMA boxes of ALL of them
+// at once -- per tile: luma 144 x 32 from x0 - 8, Cb and Cr 80 x 16 from cx0 - 8, the unit grid 40 x 8 from unit ux0 - 4 (and its
+// chroma-tree layer), motion vectors of units ux0 - 2 .. ux0 + 33 -- into one shared-memory stage each, and works through
+// them; the grid enumerates (segment, band, picture) with the segment fastest, so the hardware scheduler hands tiles out in
+// raster order and the CTAs resident at any moment cover a compact window of the picture.  That order is what the
+// memory system rewards (profiles/r02_ring_vs_copy.txt, tools/ubench/tma_ring.cu): the same boxes moved by persistent CTAs that
+// each walk a band -- the design of round 1 -- reach 4.7 TB/s, in raster order with short independent walks 5.7 TB/s, because a
+// band walk spreads the concurrent accesses over every row of every picture (one 256-byte piece per DRAM page at a time).
+// Per tile:
+//   1. vertical edges x0 + 8e, e = 0..16 (luma) / cx0 + 8k, k = 0..8 (chroma), in shared memory;
+//   2. one CTA barrier;
+//   3. horizontal edges: a task (4 luma columns x 8 rows, or 2 chroma columns x 8 rows) loads its block, filters the edge in its
+//      middle when there is one, and stores the block straight to the destination plane: a warp's 32 tasks write 256 (128)
+//      contiguous, sector-aligned bytes per row.  There is no separate write-back pass.
+// Every sample crosses HBM once in and once out (the reference makes two picture passes); the 16 halo columns of a box are
+// L2 hits (the neighbouring tiles are in flight at the same time).
 //
 // Per-edge derivation on the device (xGetBoundaryStrengthSingle :419-541, QP/tc/beta :626-634, chroma QP
 // :811-829) from the packed per-4x4 grid described in include/ilf_b200.h.
 //
 // Work split: the unit of deblocking work is a SEGMENT (4 lines of one edge).  The 128 threads of a CTA take one
-// segment each in four phases -- luma vertical (16 edge columns x 8), chroma vertical (2 planes x 8 x 8 units),
-// luma horizontal (4 edge rows x 32), chroma horizontal (2 x 2 x 32) -- so edge flag, bS, QP, tc and beta are
-// derived once per segment, segments without an edge cost a few instructions, and no lane idles by construction.
+// segment each in four phases -- luma vertical (17 edge columns x 8: eight threads take a second one), chroma vertical
+// (2 planes x 9 x 8 units), luma horizontal (4 edge rows x 32), chroma horizontal (2 x 2 x 32) -- so edge flag, bS, QP, tc and
+// beta are derived once per segment and segments without an edge cost a few instructions.
+#include <algorithm>
 #include <cstdlib>
 
 #include "ilf_common.cuh"
@@ -41,39 +46,23 @@ namespace {
 constexpr int TW = RING_TILE_W, TH = DB_BAND_ROWS;  // luma tile; the band is shifted up by 4 rows
 constexpr int CTW = TW / 2, CTH = TH / 2;           // chroma tile per plane; shifted up by 2 rows
 constexpr int UW = TW / 4, UH = TH / 4;             // units per tile: 32 x 8, rows shifted up by 1
-// ILF_DB_SPLIT=1: 256 threads, the first 128 run the luma phases and the second 128 the chroma phases of a tile side by side
-// (the per-tile critical path is what limits a CTA's throughput); 0: 128 threads run luma then chroma.
-#ifndef ILF_DB_SPLIT
-#define ILF_DB_SPLIT 0
-#endif
-// ILF_DB_WS=1: warp specialisation.  256 threads: the first 128 run the vertical pass of tile k + 1 while the second 128 run the
-// horizontal pass (and the stores) of tile k; an mbarrier per stage ("vertical pass done") orders the two groups, a named
-// barrier inside the horizontal group releases the stage of tile k - 1 to the ring.  No CTA-wide barrier in the loop.
-#ifndef ILF_DB_WS
-#define ILF_DB_WS 0
-#endif
+constexpr int BW = DB_BOX_W, BCW = DB_BOX_CW, BUW = DB_BOX_UNITS;   // box widths: the tile plus 8 samples (4 units) on each side
+constexpr int MV16_UNITS = DB_BOX_MV16_WORDS / 2, MV32_UNITS = DB_BOX_MV32_WORDS / 4;   // motion boxes start at unit ux0 - 2 / ux0 - 1
 // ILF_DB_STCS=1: results leave with st.global.cs (streaming, evict-first) stores.
 #ifndef ILF_DB_STCS
 #define ILF_DB_STCS 0
 #endif
-constexpr int NTHREADS = (ILF_DB_SPLIT || ILF_DB_WS) ? 256 : 128;  // 128 tasks in each of the four phases
+constexpr int NTHREADS = 160;   // 136 / 144 vertical-edge tasks in one round; the horizontal passes use 128 of them
+// Ring depth and residency (measured, 17 4K pictures): 3 stages x 3 CTAs per SM 0.237 ms, 2 x 4 0.206 ms, 2 x 5 0.194 ms -- the kernel
+// is bound by the latency of a tile's dependent phases, so more, smaller CTAs win over deeper prefetch; 67 registers at 5 CTAs.
 #ifndef ILF_DB_STAGES
-#define ILF_DB_STAGES 4
+#define ILF_DB_STAGES 2
 #endif
 #ifndef ILF_DB_MIN_CTAS
-#define ILF_DB_MIN_CTAS 3
+#define ILF_DB_MIN_CTAS 5
 #endif
-constexpr int DB_STAGES = ILF_DB_STAGES;             // ring depth: previous tile, current tile, DB_STAGES - 2 in flight
-// The horizontal pass of a step stores 128 luma / 64 chroma columns that END before the tile does: the tile's last columns
-// wait for the next tile's first vertical edge.  Lagging by 16 samples (4 luma units / 8 chroma unit halves) instead of the
-// minimum (4 luma / 2 chroma samples) makes every stored warp row start on a 32-byte sector: no partly written sectors.
-#ifndef ILF_DB_LAG_Y
-#define ILF_DB_LAG_Y 4
-#endif
-#ifndef ILF_DB_LAG_C
-#define ILF_DB_LAG_C 8
-#endif
-constexpr int LAG_Y = ILF_DB_LAG_Y, LAG_C = ILF_DB_LAG_C;  // in units of 4 luma / 2 chroma columns
+constexpr int DB_STAGES = ILF_DB_STAGES;            // ring depth: the tile being filtered + DB_STAGES - 1 in flight (>= 2)
+static_assert(DB_STAGES >= 2 && DB_STAGES <= 8, "a stage's next tile id is read one step after it was written only behind a barrier when there are two or more stages");
 
 __constant__ uint8_t c_tc[66] = {0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  1,  1,  1,  1,
                                  1,  1,  1,  1,  1,  2,  2,  2,  2,  3,  3,  3,  3,  4,  4,  4,  5,  5,  6,  6,  7,  8,
@@ -89,37 +78,37 @@ __constant__ uint8_t c_chroma_scale[70] = {0,  1,  2,  3,  4,  5,  6,  7,  8,  9
 template <int MV> struct MvT { uint32_t dummy; };
 template <> struct MvT<1> { uint2 v; };   // int16 x 4 per unit
 template <> struct MvT<2> { int4 v; };    // int32 x 4 per unit
+template <int MV> struct MvBox { static constexpr int UNITS = 1, OFF = 0; };
+template <> struct MvBox<1> { static constexpr int UNITS = MV16_UNITS, OFF = 2; };
+template <> struct MvBox<2> { static constexpr int UNITS = MV32_UNITS, OFF = 1; };
 
-// One stage of the ring = what the TMA unit delivers for a tile (dense boxes, each 128-byte aligned).
+// One stage = what the TMA unit delivers for a tile (dense boxes, each 128-byte aligned): sample column c of the tile is
+// box column c + 8, unit column c is box column c + 4 (motion: c + 2 / c + 1).
 template <int MV>
 struct Stage {
-  int16_t y[TH][TW];
-  int16_t c[2][CTH][CTW];
-  uint32_t info[UH][UW];
-  uint32_t info_c[UH][UW];
-  MvT<MV> mv[MV ? UH : 1][MV ? UW : 1];
+  int16_t y[TH][BW];
+  int16_t c[2][CTH][BCW];
+  uint32_t info[UH][BUW];
+  uint32_t info_c[UH][BUW];
+  MvT<MV> mv[MV ? UH : 1][MvBox<MV>::UNITS];
 };
+static_assert(sizeof(int16_t[TH][BW]) % 128 == 0 && sizeof(int16_t[CTH][BCW]) % 128 == 0 && sizeof(uint32_t[UH][BUW]) % 128 == 0, "TMA destinations are 128-byte aligned");
 template <int MV> __host__ __device__ constexpr int stage_stride() { return (int)((sizeof(Stage<MV>) + 127) & ~size_t(127)); }
 template <int MV> __host__ __device__ constexpr int stage_tx_bytes(bool ctree) {
-  return TH * TW * 2 + 2 * CTH * CTW * 2 + UH * UW * 4 + (ctree ? UH * UW * 4 : 0) + (MV == 1 ? UH * UW * 8 : (MV == 2 ? UH * UW * 16 : 0));
+  return TH * BW * 2 + 2 * CTH * BCW * 2 + UH * BUW * 4 + (ctree ? UH * BUW * 4 : 0) + (MV == 1 ? UH * MV16_UNITS * 8 : (MV == 2 ? UH * MV32_UNITS * 16 : 0));
 }
 
-// The tile's window: unit column -1 / sample columns -4 .. -1 (chroma -2, -1) are the last columns of the previous tile's
-// stage (nullptr at the start of a walk: no unit flags there, so nothing is filtered against it).
+// The tile's window: unit columns -1 .. 32, sample columns -4 .. 131 (chroma -2 .. 65) are in the stage; what lies outside
+// the picture arrives as zeros (no unit flags there, so nothing is filtered against it).
 template <int MV>
 struct Tile {
   Stage<MV>* st;
-  Stage<MV>* prev;
   bool ctree;
-  __device__ __forceinline__ uint32_t info(int r, int c) const { return c < 0 ? (prev ? prev->info[r][UW + c] : 0u) : st->info[r][c]; }
-  __device__ __forceinline__ uint32_t cinfo(int r, int c) const {
-    if (!ctree) return info(r, c);
-    return c < 0 ? (prev ? prev->info_c[r][UW + c] : 0u) : st->info_c[r][c];
-  }
-  __device__ __forceinline__ MvT<MV> mv(int r, int c) const { return c < 0 ? prev->mv[MV ? r : 0][MV ? UW + c : 0] : st->mv[MV ? r : 0][MV ? c : 0]; }
-  // sample pointers: column c of the tile; negative columns live at the end of the previous tile's rows (same pitch)
-  __device__ __forceinline__ int16_t* y(int r, int c) const { return c < 0 ? &prev->y[r][TW + c] : &st->y[r][c]; }
-  __device__ __forceinline__ int16_t* ch(int pl, int r, int c) const { return c < 0 ? &prev->c[pl][r][CTW + c] : &st->c[pl][r][c]; }
+  __device__ __forceinline__ uint32_t info(int r, int c) const { return st->info[r][c + 4]; }
+  __device__ __forceinline__ uint32_t cinfo(int r, int c) const { return ctree ? st->info_c[r][c + 4] : st->info[r][c + 4]; }
+  __device__ __forceinline__ MvT<MV> mv(int r, int c) const { return st->mv[MV ? r : 0][MV ? c + MvBox<MV>::OFF : 0]; }
+  __device__ __forceinline__ int16_t* y(int r, int c) const { return &st->y[r][c + 8]; }
+  __device__ __forceinline__ int16_t* ch(int pl, int r, int c) const { return &st->c[pl][r][c + 8]; }
 };
 
 template <int MV> __device__ __forceinline__ void mv_get(const MvT<MV>& v, int m[4]);
@@ -182,6 +171,12 @@ __device__ __forceinline__ void filter_luma_line(int v[8], int tc, bool sw, bool
 // Per-picture parameters and the tc / beta / chroma-QP tables, copied to shared memory once per CTA: the per-segment
 // derivations index them with per-thread values (constant memory would serialise) and must not wait on global loads.
 struct DbShared {
+  int tile[8];               // tile in (or on its way into) every stage of the ring: tx | ty << 8 | z << 20, -1 = the queue is empty
+  int cur_slot;              // grid layer whose parameters are in prm
+  int next;                  // tile drawn for the stage that is being emptied
+  int16_t* dst[3];           // destination planes, control word and chroma-tree flag of grid layer cur_slot
+  unsigned ctl;
+  int ctree;
   ilf_deblock_params prm;
   const uint8_t* ctu_slice;  // nullptr: every CTU in slice 0
   uint8_t tc[66 + 2], beta[64], chroma_scale[70 + 2];
@@ -256,267 +251,251 @@ __device__ __forceinline__ void unpack2(uint32_t w, int& a, int& b) { a = (int)(
 __device__ __forceinline__ uint32_t pack2(int a, int b) { return (uint32_t)(uint16_t)a | ((uint32_t)b << 16); }
 
 template <int MV>
-__global__ void __launch_bounds__(NTHREADS, ILF_DB_MIN_CTAS) deblock_kernel(Geom g, const SlotDev* __restrict__ slots, int first_slot, BatchCtl bc, int nseg) {
+__global__ void __launch_bounds__(NTHREADS, ILF_DB_MIN_CTAS) deblock_kernel(Geom g, const SlotDev* __restrict__ slots, int first_slot, BatchCtl bc, int num_slots, int* __restrict__ work) {
   extern __shared__ __align__(128) unsigned char smem[];
   constexpr int STRIDE = stage_stride<MV>();
-  constexpr int stages = DB_STAGES;
+  constexpr int S = DB_STAGES;
   pdl_launch_dependents();
-  const SlotDev& sd = slots[first_slot + bc.slot[blockIdx.z]];
-  const unsigned ctl = bc.v[blockIdx.z];
-  const int src_b = ctl_src(ctl, 0), dst_b = ctl_dst(ctl, 0);  // deblocking starts from the uploaded picture: all planes in one buffer
   const int tid = threadIdx.x;
-  const int lt = tid & 127;  // task index within a phase
-  const bool do_luma = !ILF_DB_SPLIT || tid < 128, do_chroma = !ILF_DB_SPLIT || tid >= 128;
-  const bool grp_v = !ILF_DB_WS || tid < 128, grp_h = !ILF_DB_WS || tid >= 128;  // vertical-pass / horizontal-pass group
-  const int ty = blockIdx.y;
-  const int y0 = ty * TH - 4, cy0 = ty * CTH - 2, uy0 = ty * UH - 1;  // band origin (local rows)
   const int rows = g.rows, crow = g.rows >> 1, cw = g.width >> 1;
-  const int ntx = (g.width + TW - 1) / TW;
-  const int ta = (int)blockIdx.x * ntx / nseg, tb = ((int)blockIdx.x + 1) * ntx / nseg;  // this walk stores the columns of tiles [ta, tb)
-  if (ta >= tb) return;
-  // tiles the walk loads: a walk that starts inside the picture runs tile ta - 1 first (no stores) so that tile ta finds its
-  // left neighbour vertically filtered; the last walk of the band ends with a flush step (tile index ntx, nothing loaded)
-  const int first = max(ta - 1, 0), last = tb - 1;
-  const int t_end = tb == ntx ? ntx : tb - 1;  // last step of the walk
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + stages * STRIDE);
-  uint64_t* vdone = full + stages;   // ILF_DB_WS: the vertical pass of the stage's tile is complete (128 arrivals)
-  DbShared& sh = *reinterpret_cast<DbShared*>(smem + stages * STRIDE + 16 * stages);
-  const bool has_ctree = sd.info_c != nullptr;
-  const bool no_meta = (g.debug & 3) == 3;  // measurement aid: copy-only without the unit grids
-  const uint32_t tx_bytes = no_meta ? (uint32_t)(TH * TW * 2 + 2 * CTH * CTW * 2) : (uint32_t)stage_tx_bytes<MV>(has_ctree);
-  // The boxes of a tile are issued by the first lanes of the CTA's warps, one part each (ILF_DB_ISSUE_WARPS = 4), so that
-  // their descriptor fetches overlap: part 0 arms the barrier and loads luma, 1 both chroma planes, 2 the unit grids, 3 motion.
-  auto issue_part = [&](int t, int si, int part) {  // tile t into stage si
+  const int ntx = (g.width + TW - 1) / TW, bands = (g.rows + 4 + TH - 1) / TH;
+  const int total = ntx * bands * num_slots;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + S * STRIDE);
+  DbShared& sh = *reinterpret_cast<DbShared*>(smem + S * STRIDE + 8 * S);
+  // tile id -> (grid layer, band, tile of the band): raster order inside a picture, pictures one after the other
+  auto pack_id = [&](int id) { if (id >= total) return -1; const int tx = id % ntx, r = id / ntx; return tx | (r % bands) << 8 | (r / bands) << 20; };
+  auto decode = [&](int id, int& z, int& ty, int& tx) { tx = id & 255; ty = (id >> 8) & 4095; z = id >> 20; };
+  // The boxes of a tile are issued by the first lanes of the CTA's warps, one part each, so that their descriptor fetches
+  // overlap: part 0 arms the barrier and loads luma, 1 both chroma planes, 2 the unit grids, 3 motion.
+  auto issue_part = [&](int id, int si, int part) {  // tile id into stage si
+    int z, ty, tx;
+    decode(id, z, ty, tx);
+    const SlotDev& sd = slots[first_slot + bc.slot[z]];
+    const int src_b = ctl_src(bc.v[z], 0);
+    const int y0 = ty * TH - 4, cy0 = ty * CTH - 2, uy0 = ty * UH - 1;  // band origin (local rows)
+    const bool has_ctree = (part == 0 || part == 2) ? (z == sh.cur_slot ? sh.ctree != 0 : sd.info_c != nullptr) : false;
     Stage<MV>* st = reinterpret_cast<Stage<MV>*>(smem + si * STRIDE);
     uint64_t* bar = &full[si];
     if (part == 0) {
-      ring::mbar_expect_tx(bar, tx_bytes);
-      ring::tma_load_3d(&st->y[0][0], &sd.tm_db[0], bar, t * TW, y0, src_b);
+      ring::mbar_expect_tx(bar, (uint32_t)stage_tx_bytes<MV>(has_ctree));
+      ring::tma_load_3d(&st->y[0][0], &sd.tm_db[0], bar, tx * TW - 8, y0, src_b);
     } else if (part == 1) {
-      ring::tma_load_3d(&st->c[0][0][0], &sd.tm_db[1], bar, t * CTW, cy0, src_b);
-      ring::tma_load_3d(&st->c[1][0][0], &sd.tm_db[2], bar, t * CTW, cy0, src_b);
-    } else if (no_meta) {
+      ring::tma_load_3d(&st->c[0][0][0], &sd.tm_db[1], bar, tx * CTW - 8, cy0, src_b);
+      ring::tma_load_3d(&st->c[1][0][0], &sd.tm_db[2], bar, tx * CTW - 8, cy0, src_b);
     } else if (part == 2) {
-      ring::tma_load_3d(&st->info[0][0], &sd.tm_info, bar, t * UW, uy0, 0);
-      if (has_ctree) ring::tma_load_3d(&st->info_c[0][0], &sd.tm_info_c, bar, t * UW, uy0, 0);
+      ring::tma_load_3d(&st->info[0][0], &sd.tm_info, bar, tx * UW - 4, uy0, 0);
+      if (has_ctree) ring::tma_load_3d(&st->info_c[0][0], &sd.tm_info_c, bar, tx * UW - 4, uy0, 0);
     } else {
-      if (MV == 1) ring::tma_load_3d(&st->mv[0][0], &sd.tm_mv16, bar, t * UW * 2, uy0, 0);
-      if (MV == 2) ring::tma_load_3d(&st->mv[0][0], &sd.tm_mv32, bar, t * UW * 4, uy0, 0);
+      if (MV == 1) ring::tma_load_3d(&st->mv[0][0], &sd.tm_mv16, bar, (tx * UW - MvBox<1>::OFF) * 2, uy0, 0);
+      if (MV == 2) ring::tma_load_3d(&st->mv[0][0], &sd.tm_mv32, bar, (tx * UW - MvBox<2>::OFF) * 4, uy0, 0);
     }
   };
-#ifndef ILF_DB_ISSUE_WARPS
-#define ILF_DB_ISSUE_WARPS 4
-#endif
-  // every thread calls issue(); the lanes that own a part do the work
-  auto issue = [&](int t, int si) {
-    if (ILF_DB_ISSUE_WARPS == 4) { if ((tid & 31) == 0 && tid < 128) issue_part(t, si, tid >> 5); }
-    else if (tid == 0) { for (int part = 0; part < 4; part++) issue_part(t, si, part); }
-  };
   if (tid == 0) {
-    for (int i = 0; i < stages; i++) { ring::mbar_init(&full[i], 1); ring::mbar_init(&vdone[i], 128); }
+    for (int i = 0; i < S; i++) ring::mbar_init(&full[i], 1);
     ring::mbar_init_fence();
+    sh.cur_slot = -1;
   }
-  __syncthreads();
-  pdl_wait();  // the previous chain's last stage has finished with the buffers this stage reads and writes
-  for (int t = first; t <= last && t < first + stages; t++) issue(t, t - first);
-  // picture parameters and tables -> shared memory (overlaps the first loads)
-  for (int i = tid; i < (int)(sizeof(ilf_deblock_params) / 4); i += NTHREADS) reinterpret_cast<uint32_t*>(&sh.prm)[i] = __ldg(reinterpret_cast<const uint32_t*>(sd.db_params) + i);
   if (tid < 66) sh.tc[tid] = c_tc[tid];
   if (tid < 64) sh.beta[tid] = c_beta[tid];
   if (tid < 70) sh.chroma_scale[tid] = c_chroma_scale[tid];
-  if (tid == 0) sh.ctu_slice = __ldg(&sd.db_params->num_slices) == 1 ? nullptr : sd.ctu_slice;  // one slice: no per-CTU lookup
+  pdl_wait();  // the previous chain's last stage has finished with the buffers this stage reads and writes -- and has reset the work counter
+  // Work queue: tiles are drawn from one counter in raster order, so the CTAs resident at any moment work on a compact window of
+  // the picture whatever their relative progress; a CTA keeps S - 1 tiles in flight ahead of the one it filters.
+  if (tid == 0)
+    for (int i = 0; i < S; i++) sh.tile[i] = pack_id(atomicAdd(&work[0], 1));
   __syncthreads();
+  if ((tid & 31) == 0)
+    for (int i = 0; i < S; i++) if (sh.tile[i] >= 0 && tid < 128) issue_part(sh.tile[i], i, tid >> 5);
 
   const int max_y = (1 << g.bd_luma) - 1, max_c = (1 << g.bd_chroma) - 1;
-  int16_t* __restrict__ dst_y = sd.buf[dst_b][0];
-  int16_t* __restrict__ dst_cb = sd.buf[dst_b][1];
-  int16_t* __restrict__ dst_cr = sd.buf[dst_b][2];
   const bool filt = !(g.debug & 1);
-
-  int si = 0;           // stage of the current tile
-  uint32_t phase = 0;   // barrier phase of that stage
-  Stage<MV>* prev = nullptr;
-  for (int tx = first; tx <= t_end; tx++) {
-    const bool flush = tx == ntx;     // nothing loaded: only the previous tile's lagging columns are finished and stored
+  int si = 0;
+  uint32_t phases = 0;   // bit s: parity of stage s's next completion
+  for (;;) {
+    const int id = sh.tile[si];
+    if (id < 0) break;
+    int z, ty, tx;
+    decode(id, z, ty, tx);
+    if (sh.cur_slot != z) {   // CTA-uniform: the picture's parameters -> shared memory (once per picture a CTA meets)
+      __syncthreads();
+      const SlotDev& sd = slots[first_slot + bc.slot[z]];
+      for (int i = tid; i < (int)(sizeof(ilf_deblock_params) / 4); i += NTHREADS) reinterpret_cast<uint32_t*>(&sh.prm)[i] = __ldg(reinterpret_cast<const uint32_t*>(sd.db_params) + i);
+      if (tid == 0) {
+        sh.ctu_slice = __ldg(&sd.db_params->num_slices) == 1 ? nullptr : sd.ctu_slice;  // one slice: no per-CTU lookup
+        const unsigned c = bc.v[z];
+        const int db = ctl_dst(c, 0);  // deblocking starts from the uploaded picture: all planes in one buffer
+        sh.ctl = c; sh.dst[0] = sd.buf[db][0]; sh.dst[1] = sd.buf[db][1]; sh.dst[2] = sd.buf[db][2];
+        sh.ctree = sd.info_c != nullptr;
+        sh.cur_slot = z;
+      }
+      __syncthreads();
+    }
+    const int y0 = ty * TH - 4, cy0 = ty * CTH - 2;
+    int16_t* __restrict__ dst_y = sh.dst[0];
+    int16_t* __restrict__ dst_cb = sh.dst[1];
+    int16_t* __restrict__ dst_cr = sh.dst[2];
     Tile<MV> t;
     t.st = reinterpret_cast<Stage<MV>*>(smem + si * STRIDE);
-    t.prev = prev;
-    t.ctree = has_ctree;
-    if (!flush && grp_v) ring::mbar_wait(&full[si], phase);
-    // tx < ta: the tile left of the walk.  Its last columns are stored by this walk's first step, so its vertical edges
-    // are filtered here like any other tile's (all but edge 0, which does not reach those columns); nothing is stored.
-    const bool pre = tx < ta;
+    t.ctree = sh.ctree != 0;
+    ring::mbar_wait(&full[si], (phases >> si) & 1u);
+    phases ^= 1u << si;
     const int x0 = tx * TW, cx0 = tx * CTW;
 
-    // ---- vertical edges, luma: task = 4 lines x 8 samples.  16 edge columns x 8 segment rows ----
-    if (grp_v && do_luma && filt && !flush && ((lt & 15) > 0 || prev)) {
-      const int e = lt & 15, sg = lt >> 4;
-      const EdgeParams ep = luma_edge_params<MV>(t, g, sh, sg, 2 * e, sg, 2 * e - 1, true, x0 + 8 * e, y0 + 4 * sg);
-      if (ep.bs) {
-        int16_t* pp = t.y(4 * sg, 8 * e - 4);
-        int16_t* pq = t.y(4 * sg, 8 * e);
-        int L[4][8];
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-          const uint2 a = *reinterpret_cast<const uint2*>(pp + i * TW), b = *reinterpret_cast<const uint2*>(pq + i * TW);
-          unpack2(a.x, L[i][0], L[i][1]); unpack2(a.y, L[i][2], L[i][3]); unpack2(b.x, L[i][4], L[i][5]); unpack2(b.y, L[i][6], L[i][7]);
-        }
-        if (filter_luma_segment(L, ep, max_y)) {
+    // ---- vertical edges, luma: task = 4 lines x 8 samples.  17 edge columns x 8 segment rows (tasks 128 .. 135: edge 16) ----
+    if (filt) {
+      if (tid < 17 * 8) {
+        const int task = tid;
+        const int e = task < 128 ? (task & 15) : 16, sg = task < 128 ? (task >> 4) : task - 128;
+        const EdgeParams ep = luma_edge_params<MV>(t, g, sh, sg, 2 * e, sg, 2 * e - 1, true, x0 + 8 * e, y0 + 4 * sg);
+        if (ep.bs) {
+          int16_t* pp = t.y(4 * sg, 8 * e - 4);
+          int16_t* pq = t.y(4 * sg, 8 * e);
+          int L[4][8];
 #pragma unroll
           for (int i = 0; i < 4; i++) {
-            *reinterpret_cast<uint2*>(pp + i * TW) = make_uint2(pack2(L[i][0], L[i][1]), pack2(L[i][2], L[i][3]));
-            *reinterpret_cast<uint2*>(pq + i * TW) = make_uint2(pack2(L[i][4], L[i][5]), pack2(L[i][6], L[i][7]));
+            const uint2 a = *reinterpret_cast<const uint2*>(pp + i * BW), b = *reinterpret_cast<const uint2*>(pq + i * BW);
+            unpack2(a.x, L[i][0], L[i][1]); unpack2(a.y, L[i][2], L[i][3]); unpack2(b.x, L[i][4], L[i][5]); unpack2(b.y, L[i][6], L[i][7]);
+          }
+          if (filter_luma_segment(L, ep, max_y)) {
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+              *reinterpret_cast<uint2*>(pp + i * BW) = make_uint2(pack2(L[i][0], L[i][1]), pack2(L[i][2], L[i][3]));
+              *reinterpret_cast<uint2*>(pq + i * BW) = make_uint2(pack2(L[i][4], L[i][5]), pack2(L[i][6], L[i][7]));
+            }
+          }
+        }
+      }
+      // ---- vertical edges, chroma: task = one unit = 2 lines x 4 samples.  2 planes x 9 edge columns x 8 unit rows (tasks 128 .. 143: edge 8) ----
+      if (tid < 2 * 9 * 8) {
+        const int task = tid;
+        const int pl = task < 128 ? (task >> 6) : ((task - 128) >> 3), k = task < 128 ? ((task >> 3) & 7) : 8, sg = task & 7;
+        bool no_p, no_q;
+        const int tc = chroma_tc(t.cinfo(sg, 4 * k), t.cinfo(sg, 4 * k - 1), g, sh, true, pl, 2 * (cx0 + 8 * k), 2 * (cy0 + 2 * sg), no_p, no_q);
+        if (tc >= 0) {
+          int16_t* pp = t.ch(pl, 2 * sg, 8 * k - 2);
+          int16_t* pq = t.ch(pl, 2 * sg, 8 * k);
+#pragma unroll
+          for (int i = 0; i < 2; i++) {
+            const int m2 = pp[i * BCW], m3 = pp[i * BCW + 1], m4 = pq[i * BCW], m5 = pq[i * BCW + 1];
+            const int delta = clip3i(-tc, tc, (((m4 - m3) << 2) + m2 - m5 + 4) >> 3);
+            if (!no_p) pp[i * BCW + 1] = (int16_t)clip3i(0, max_c, m3 + delta);
+            if (!no_q) pq[i * BCW] = (int16_t)clip3i(0, max_c, m4 - delta);
           }
         }
       }
     }
-    // ---- vertical edges, chroma: task = one unit = 2 lines x 4 samples.  2 planes x 8 edge columns x 8 unit rows ----
-    if (grp_v && do_chroma && filt && !flush && (((lt >> 3) & 7) > 0 || prev)) {
-      const int pl = lt >> 6, k = (lt >> 3) & 7, sg = lt & 7;
-      bool no_p, no_q;
-      const int tc = chroma_tc(t.cinfo(sg, 4 * k), t.cinfo(sg, 4 * k - 1), g, sh, true, pl, 2 * (cx0 + 8 * k), 2 * (cy0 + 2 * sg), no_p, no_q);
-      if (tc >= 0) {
-        int16_t* pp = t.ch(pl, 2 * sg, 8 * k - 2);
-        int16_t* pq = t.ch(pl, 2 * sg, 8 * k);
-#pragma unroll
-        for (int i = 0; i < 2; i++) {
-          const int m2 = pp[i * CTW], m3 = pp[i * CTW + 1], m4 = pq[i * CTW], m5 = pq[i * CTW + 1];
-          const int delta = clip3i(-tc, tc, (((m4 - m3) << 2) + m2 - m5 + 4) >> 3);
-          if (!no_p) pp[i * CTW + 1] = (int16_t)clip3i(0, max_c, m3 + delta);
-          if (!no_q) pq[i * CTW] = (int16_t)clip3i(0, max_c, m4 - delta);
-        }
-      }
-    }
-    if (ILF_DB_WS && grp_v && tid < 128 && !flush) ring::mbar_arrive(&vdone[si]);
-    if (pre) {
-      prev = t.st;
-      if (++si == stages) { si = 0; phase ^= 1u; }
-      continue;
-    }
-    if (ILF_DB_WS) {
-      if (tid >= 128 && !flush) ring::mbar_wait(&vdone[si], phase);
-    } else {
-      __syncthreads();
-      // every thread is past the previous step's horizontal pass: the stage before the previous one is free
-      {
-        const int tf = tx - 2;  // tile whose stage is refilled
-        if (tf >= first && tf + stages <= last) issue(tf + stages, (si + stages - 2) % stages);
-      }
-    }
+    __syncthreads();
+    if (tid == 0) sh.next = pack_id(atomicAdd(&work[0], 1));   // the tile that will take this stage (its latency hides behind the horizontal pass)
 
-    // ---- horizontal edges, luma: task = 4 columns x 8 rows, filtered and stored.  4 edge rows x unit columns -LAG_Y .. 31 - LAG_Y
+    // ---- horizontal edges, luma: task = 4 columns x 8 rows, filtered and stored.  4 edge rows x 32 unit columns
     //      (a warp = one edge row: 256 contiguous bytes per stored row) ----
-    {
-      const int u = (lt & 31) - LAG_Y, h = lt >> 5;
-      if (grp_h && do_luma && (u < 0 ? prev != nullptr : !flush)) {
-        const int16_t* sp = t.y(8 * h, 4 * u);
-        uint2 raw[8];
+    if (tid < 128) {
+      const int u = tid & 31, h = tid >> 5;
+      const int16_t* sp = t.y(8 * h, 4 * u);
+      uint2 raw[8];
 #pragma unroll
-        for (int i = 0; i < 8; i++) raw[i] = *reinterpret_cast<const uint2*>(sp + i * TW);
-        if (filt) {
-          const EdgeParams ep = luma_edge_params<MV>(t, g, sh, 2 * h + 1, u, 2 * h, u, false, x0 + 4 * u, y0 + 4 + 8 * h);
-          if (ep.bs) {
-            int L[4][8];
+      for (int i = 0; i < 8; i++) raw[i] = *reinterpret_cast<const uint2*>(sp + i * BW);
+      if (filt) {
+        const EdgeParams ep = luma_edge_params<MV>(t, g, sh, 2 * h + 1, u, 2 * h, u, false, x0 + 4 * u, y0 + 4 + 8 * h);
+        if (ep.bs) {
+          int L[4][8];
 #pragma unroll
-            for (int i = 0; i < 8; i++) { unpack2(raw[i].x, L[0][i], L[1][i]); unpack2(raw[i].y, L[2][i], L[3][i]); }
-            if (filter_luma_segment(L, ep, max_y)) {
+          for (int i = 0; i < 8; i++) { unpack2(raw[i].x, L[0][i], L[1][i]); unpack2(raw[i].y, L[2][i], L[3][i]); }
+          if (filter_luma_segment(L, ep, max_y)) {
 #pragma unroll
-              for (int i = 1; i < 7; i++) raw[i] = make_uint2(pack2(L[0][i], L[1][i]), pack2(L[2][i], L[3][i]));
-            }
+            for (int i = 1; i < 7; i++) raw[i] = make_uint2(pack2(L[0][i], L[1][i]), pack2(L[2][i], L[3][i]));
           }
         }
-        const int x = x0 + 4 * u;
-        if (x < g.width) {
-          int16_t* op = dst_y + (size_t)(y0 + 8 * h) * g.pitch_y + x;
+      }
+      const int x = x0 + 4 * u;
+      if (x < g.width) {
+        int16_t* op = dst_y + (size_t)(y0 + 8 * h) * g.pitch_y + x;
 #pragma unroll
-          for (int i = 0; i < 8; i++) {
-            const int y = y0 + 8 * h + i;
-            if (y >= 0 && y < rows) {
+        for (int i = 0; i < 8; i++) {
+          const int y = y0 + 8 * h + i;
+          if (y >= 0 && y < rows) {
 #if ILF_DB_STCS
-              __stcs(reinterpret_cast<uint2*>(op + (size_t)i * g.pitch_y), raw[i]);
+            __stcs(reinterpret_cast<uint2*>(op + (size_t)i * g.pitch_y), raw[i]);
 #else
-              *reinterpret_cast<uint2*>(op + (size_t)i * g.pitch_y) = raw[i];
+            *reinterpret_cast<uint2*>(op + (size_t)i * g.pitch_y) = raw[i];
 #endif
-            }
           }
         }
       }
     }
     // ---- horizontal edges, chroma: task = 2 columns x 8 rows (the edge lies between rows 1 and 2), filtered and stored.
-    //      2 planes x 2 row groups x unit columns -LAG_C .. 31 - LAG_C ----
-    {
-      const int pl = lt >> 6, h = (lt >> 5) & 1, u = (lt & 31) - LAG_C;
-      if (grp_h && do_chroma && (u < 0 ? prev != nullptr : !flush)) {
-        const int16_t* sp = t.ch(pl, 8 * h, 2 * u);
-        uint32_t raw[8];
+    //      2 planes x 2 row groups x 32 unit columns ----
+    if (tid < 128) {
+      const int pl = tid >> 6, h = (tid >> 5) & 1, u = tid & 31;
+      const int16_t* sp = t.ch(pl, 8 * h, 2 * u);
+      uint32_t raw[8];
 #pragma unroll
-        for (int i = 0; i < 8; i++) raw[i] = *reinterpret_cast<const uint32_t*>(sp + i * CTW);
-        if (filt) {
-          bool no_p, no_q;
-          const int tc = chroma_tc(t.cinfo(4 * h + 1, u), t.cinfo(4 * h, u), g, sh, false, pl, 2 * (cx0 + 2 * u), 2 * (cy0 + 2 + 8 * h), no_p, no_q);
-          if (tc >= 0) {
-            int a[4], b[4];
+      for (int i = 0; i < 8; i++) raw[i] = *reinterpret_cast<const uint32_t*>(sp + i * BCW);
+      if (filt) {
+        bool no_p, no_q;
+        const int tc = chroma_tc(t.cinfo(4 * h + 1, u), t.cinfo(4 * h, u), g, sh, false, pl, 2 * (cx0 + 2 * u), 2 * (cy0 + 2 + 8 * h), no_p, no_q);
+        if (tc >= 0) {
+          int a[4], b[4];
 #pragma unroll
-            for (int i = 0; i < 4; i++) unpack2(raw[i], a[i], b[i]);
-            const int da = clip3i(-tc, tc, (((a[2] - a[1]) << 2) + a[0] - a[3] + 4) >> 3);
-            const int db = clip3i(-tc, tc, (((b[2] - b[1]) << 2) + b[0] - b[3] + 4) >> 3);
-            if (!no_p) raw[1] = pack2(clip3i(0, max_c, a[1] + da), clip3i(0, max_c, b[1] + db));
-            if (!no_q) raw[2] = pack2(clip3i(0, max_c, a[2] - da), clip3i(0, max_c, b[2] - db));
-          }
+          for (int i = 0; i < 4; i++) unpack2(raw[i], a[i], b[i]);
+          const int da = clip3i(-tc, tc, (((a[2] - a[1]) << 2) + a[0] - a[3] + 4) >> 3);
+          const int db = clip3i(-tc, tc, (((b[2] - b[1]) << 2) + b[0] - b[3] + 4) >> 3);
+          if (!no_p) raw[1] = pack2(clip3i(0, max_c, a[1] + da), clip3i(0, max_c, b[1] + db));
+          if (!no_q) raw[2] = pack2(clip3i(0, max_c, a[2] - da), clip3i(0, max_c, b[2] - db));
         }
-        const int x = cx0 + 2 * u;
-        if (x < cw) {
-          int16_t* op = (pl ? dst_cr : dst_cb) + (size_t)(cy0 + 8 * h) * g.pitch_c + x;
+      }
+      const int x = cx0 + 2 * u;
+      if (x < cw) {
+        int16_t* op = (pl ? dst_cr : dst_cb) + (size_t)(cy0 + 8 * h) * g.pitch_c + x;
 #pragma unroll
-          for (int i = 0; i < 8; i++) {
-            const int y = cy0 + 8 * h + i;
-            if (y >= 0 && y < crow) {
+        for (int i = 0; i < 8; i++) {
+          const int y = cy0 + 8 * h + i;
+          if (y >= 0 && y < crow) {
 #if ILF_DB_STCS
-              __stcs(reinterpret_cast<uint32_t*>(op + (size_t)i * g.pitch_c), raw[i]);
+            __stcs(reinterpret_cast<uint32_t*>(op + (size_t)i * g.pitch_c), raw[i]);
 #else
-              *reinterpret_cast<uint32_t*>(op + (size_t)i * g.pitch_c) = raw[i];
+            *reinterpret_cast<uint32_t*>(op + (size_t)i * g.pitch_c) = raw[i];
 #endif
-            }
           }
         }
       }
     }
-    if (ILF_DB_WS && tid >= 128) {
-      // the horizontal group is done with the previous tile's stage: it goes back to the ring (the vertical group is at
-      // least one tile ahead and touches this tile's and the next tile's stages only)
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (tid == 128) {
-        const int tf = tx - 1;
-        if (tf >= first && tf + stages <= last) for (int part = 0; part < 4; part++) issue_part(tf + stages, (si + stages - 1) % stages, part);
-      }
+    // every thread is done with the stage: it is refilled with the next tile of the queue
+    __syncthreads();
+    {
+      const int nid = sh.next;
+      if ((tid & 31) == 0 && tid < 128 && nid >= 0) issue_part(nid, si, tid >> 5);
+      if (tid == 0) sh.tile[si] = nid;   // read S steps from now, behind more barriers
     }
-    // no barrier here: the next step's vertical pass touches the next stage and the last four columns of this one, the
-    // horizontal pass above reads neither
-    prev = t.st;
-    if (++si == stages) { si = 0; phase ^= 1u; }
+    if (++si == S) si = 0;
+  }
+  // the last CTA to leave resets the queue for the next launch on this stream (every CTA has drawn its last id by now)
+  if (tid == 0) {
+    __threadfence();
+    if (atomicAdd(&work[1], 1) == (int)gridDim.x - 1) { work[0] = 0; work[1] = 0; __threadfence(); }
   }
 }
 
 }  // namespace
 
 template <int MV>
-static void launch_deblock_mv(const Geom& g, const SlotDev* slots, int first_slot, int num_slots, const BatchCtl& ctl, cudaStream_t st) {
+static void launch_deblock_mv(const Geom& g, const SlotDev* slots, int first_slot, int num_slots, const BatchCtl& ctl, int* work, cudaStream_t st) {
   static const int pad = env_int("ILF_DB_SMEM_PAD");
-  const int smem = DB_STAGES * stage_stride<MV>() + DB_STAGES * 16 + (int)sizeof(DbShared) + pad;
+  const int smem = DB_STAGES * stage_stride<MV>() + DB_STAGES * 8 + (int)sizeof(DbShared) + pad;
   static bool attr_set[64] = {};
   once_per_device(attr_set, [&] { cudaFuncSetAttribute(deblock_kernel<MV>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); });
   const int bands = (g.rows + 4 + TH - 1) / TH, ntx = (g.width + TW - 1) / TW;
-  int nseg = pick_segments(bands * num_slots, ntx, 148 * ILF_DB_MIN_CTAS, 1.5f);  // a segment that starts inside the picture runs one extra tile
-  static const int force = getenv("ILF_DB_NSEG") ? atoi(getenv("ILF_DB_NSEG")) : 0;  // experiment knob
-  if (force > 0) nseg = force < ntx ? force : ntx;
-  dim3 grid(nseg, bands, num_slots);
-  launch_pdl(deblock_kernel<MV>, grid, dim3(NTHREADS), smem, st, g, slots, first_slot, ctl, nseg);
+  const long long total = (long long)ntx * bands * num_slots;
+  static const int ctas = env_int("ILF_DB_CTAS", 2 * 148 * ILF_DB_MIN_CTAS);   // CTAs drawing tiles from the queue: two per resident slot, so that a lane sharing the GPU finds slots
+  dim3 grid((unsigned)std::min<long long>(total, ctas));
+  launch_pdl(deblock_kernel<MV>, grid, dim3(NTHREADS), smem, st, g, slots, first_slot, ctl, num_slots, work);
 }
 
-void launch_deblock(const Geom& g, const SlotDev* slots, int first_slot, int num_slots, const BatchCtl& ctl, int mv_mode, cudaStream_t st) {
-  if (mv_mode == 0) launch_deblock_mv<0>(g, slots, first_slot, num_slots, ctl, st);
-  else if (mv_mode == 1) launch_deblock_mv<1>(g, slots, first_slot, num_slots, ctl, st);
-  else launch_deblock_mv<2>(g, slots, first_slot, num_slots, ctl, st);
+// work: two ints in device memory, zero before the first launch and owned by the launching stream (the kernel leaves them zero).
+void launch_deblock(const Geom& g, const SlotDev* slots, int first_slot, int num_slots, const BatchCtl& ctl, int mv_mode, int* work, cudaStream_t st) {
+  if (mv_mode == 0) launch_deblock_mv<0>(g, slots, first_slot, num_slots, ctl, work, st);
+  else if (mv_mode == 1) launch_deblock_mv<1>(g, slots, first_slot, num_slots, ctl, work, st);
+  else launch_deblock_mv<2>(g, slots, first_slot, num_slots, ctl, work, st);
 }
 
 }  // namespace ilf

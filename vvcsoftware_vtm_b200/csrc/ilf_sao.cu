@@ -286,6 +286,8 @@ void launch_sao(const Geom& g, const SlotDev* slots, int first_slot, int num_slo
   const int bands = (bands_y + 2 * bands_c) * num_slots;
   int nseg = (148 * SAO_CTAS + bands - 1) / bands;
   nseg = nseg < 1 ? 1 : (nseg > ntx ? ntx : nseg);
+  static const int force = env_int("ILF_SAO_NSEG");   // experiment knob
+  if (force > 0) nseg = force < ntx ? force : ntx;
   dim3 grid(nseg, bands_y + 2 * bands_c, num_slots);
   launch_pdl(sao_kernel, grid, dim3(NTHREADS), smem, st, g, slots, first_slot, ctl, bands_y, bands_c, nseg);
 }
