@@ -367,7 +367,7 @@ def ncu_traffic(kernel, batch):
     for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json")), reverse=True):
         try:
             k = json.load(open(path))["kernels"].get(kernel)
-            if k and k["grid"].strip("()").split(",")[-1].strip() == str(batch):
+            if k and (k.get("batch") == batch or k["grid"].strip("()").split(",")[-1].strip() == str(batch)):
                 return {"bytes_per_launch": round(k["dram_read_bytes"] + k["dram_write_bytes"]), "read": round(k["dram_read_bytes"]), "write": round(k["dram_write_bytes"]),
                         "source": os.path.relpath(path, ROOT)}
         except Exception:

@@ -52,7 +52,13 @@ constexpr int MV16_UNITS = DB_BOX_MV16_WORDS / 2, MV32_UNITS = DB_BOX_MV32_WORDS
 #ifndef ILF_DB_STCS
 #define ILF_DB_STCS 0
 #endif
-constexpr int NTHREADS = 160;   // 136 / 144 vertical-edge tasks in one round; the horizontal passes use 128 of them
+// ILF_DB_WIDE=1: 288 threads -- the luma and the chroma tasks of a phase run side by side (136 + 144 vertical, 128 + 128 horizontal)
+// instead of one after the other.
+#ifndef ILF_DB_WIDE
+#define ILF_DB_WIDE 0
+#endif
+constexpr int NTHREADS = ILF_DB_WIDE ? 288 : 160;   // 136 / 144 vertical-edge tasks in one round; the horizontal passes use 128 of them
+constexpr int VC0 = ILF_DB_WIDE ? 136 : 0, HC0 = ILF_DB_WIDE ? 128 : 0;   // first thread of the chroma tasks of the vertical / horizontal phase
 // Ring depth and residency (measured, 17 4K pictures): 3 stages x 3 CTAs per SM 0.237 ms, 2 x 4 0.206 ms, 2 x 5 0.194 ms -- the kernel
 // is bound by the latency of a tile's dependent phases, so more, smaller CTAs win over deeper prefetch; 67 registers at 5 CTAs.
 #ifndef ILF_DB_STAGES
@@ -366,8 +372,8 @@ __global__ void __launch_bounds__(NTHREADS, ILF_DB_MIN_CTAS) deblock_kernel(Geom
         }
       }
       // ---- vertical edges, chroma: task = one unit = 2 lines x 4 samples.  2 planes x 9 edge columns x 8 unit rows (tasks 128 .. 143: edge 8) ----
-      if (tid < 2 * 9 * 8) {
-        const int task = tid;
+      if (tid >= VC0 && tid < VC0 + 2 * 9 * 8) {
+        const int task = tid - VC0;
         const int pl = task < 128 ? (task >> 6) : ((task - 128) >> 3), k = task < 128 ? ((task >> 3) & 7) : 8, sg = task & 7;
         bool no_p, no_q;
         const int tc = chroma_tc(t.cinfo(sg, 4 * k), t.cinfo(sg, 4 * k - 1), g, sh, true, pl, 2 * (cx0 + 8 * k), 2 * (cy0 + 2 * sg), no_p, no_q);
@@ -425,8 +431,9 @@ __global__ void __launch_bounds__(NTHREADS, ILF_DB_MIN_CTAS) deblock_kernel(Geom
     }
     // ---- horizontal edges, chroma: task = 2 columns x 8 rows (the edge lies between rows 1 and 2), filtered and stored.
     //      2 planes x 2 row groups x 32 unit columns ----
-    if (tid < 128) {
-      const int pl = tid >> 6, h = (tid >> 5) & 1, u = tid & 31;
+    if (tid >= HC0 && tid < HC0 + 128) {
+      const int ht = tid - HC0;
+      const int pl = ht >> 6, h = (ht >> 5) & 1, u = ht & 31;
       const int16_t* sp = t.ch(pl, 8 * h, 2 * u);
       uint32_t raw[8];
 #pragma unroll
