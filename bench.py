@@ -388,14 +388,23 @@ def host_ceiling(world, h2d_bytes_per_picture, mpx):
         return None
 
 
-def kernel_table(kt, peak):
+def kernel_table(kt, peak, steps=None):
+    """Per kernel: average launch duration, algorithmic GB/s and fraction of the HBM peak; with `steps` also the kernel's time per
+    step (a stage can take several launches per step: deblocking launches the pictures with a chroma tree apart from the others)."""
     tab = {}
     for k, (ms, n, nbytes) in kt.items():
         if n:
             # algorithmic bytes as counted by the library: 2 B x (read + write) x samples of the planes the launches processed
             tab[k] = {"avg_ms": round(ms / n, 4), "launches": n, "algo_mb_per_launch": round(nbytes / n / 1e6, 1), "algo_gbs": round(nbytes / (ms * 1e-3) / 1e9, 1),
                       "frac": round(nbytes / (ms * 1e-3) / 1e9 / peak, 4)}
+            if steps:
+                tab[k]["ms_per_step"] = round(ms / steps, 4)
+                tab[k]["launches_per_step"] = round(n / steps, 2)
     return tab
+
+
+def dominant(tab):
+    return max(tab, key=lambda k: tab[k].get("ms_per_step", tab[k]["avg_ms"]))
 
 
 def chain_table(kt, ms_region, steps, pixels_per_step, peak):
@@ -587,8 +596,8 @@ def bands_record(args, wl, rank, world, local, dist, torch, v):
                "bands": bands.band_partition((h + 127) // 128, world), "halo_rows_per_side": 16, "halo_bytes_per_picture_rank0": halo_rows * w * 3,
                "exchange": "one copy kernel per step reads the neighbours' input planes over NVLink P2P (CUDA IPC mapping between the per-GPU processes), no collective",
                "bands_parity": "ok", "parity_how": "CRC-32 per plane of every rank's own rows (all CTUs on) == the same rows of the whole picture filtered by one context on rank 0",
-               "per_kernel": kernel_table(ktimes, peak), "chain": chain_table(ktimes, ms_total, steps, B * own_px, peak),
-               "all_on": {"value": round(value_on, 1), "ms_per_step": round(ms_on / steps, 4), "per_kernel": kernel_table(kt_on, peak), "chain": chain_table(kt_on, ms_on, steps, B * own_px, peak)},
+               "per_kernel": kernel_table(ktimes, peak, steps), "chain": chain_table(ktimes, ms_total, steps, B * own_px, peak),
+               "all_on": {"value": round(value_on, 1), "ms_per_step": round(ms_on / steps, 4), "per_kernel": kernel_table(kt_on, peak, steps), "chain": chain_table(kt_on, ms_on, steps, B * own_px, peak)},
                "n1_whole_picture_same_run": whole,
                "strong_scaling_efficiency": {"stream_decisions": round(value / (world * whole["value"]), 3), "all_on": round(value_on / (world * whole["all_on_value"]), 3),
                                              "formula": "value / (n_gpus x whole-picture value of rank 0 in this run)"},
@@ -680,7 +689,7 @@ def run_bands(args, wl):
     if rank == 0:
         peak, peak_src = hbm_peak()
         pk = rec["per_kernel"]
-        dom = max(pk, key=lambda k: pk[k]["avg_ms"])
+        dom = dominant(pk)
         line = {"metric": "deblock+SAO+ALF Mpixel/s", "value": rec["value"], "unit": "Mpixel/s", "n_gpus": world, "steps": rec["steps"], "warmup": max(args.warmup, 3),
                 "ms_per_step": rec["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int16", "data": "synthetic",
                 "config": {"workload": wl["desc"], "pictures_per_step": rec["pictures_per_step"], "bands": rec["bands"]},
@@ -891,11 +900,11 @@ def run_b200(args, wl):
         sub["streams_64"] = streams_record(args, rank, world, local, dist, torch, v)
     if rank == 0:
         peak, peak_src = hbm_peak()
-        per_kernel = kernel_table(ktimes, peak)
-        dom = max(per_kernel, key=lambda k: per_kernel[k]["avg_ms"])
+        per_kernel = kernel_table(ktimes, peak, args.steps)
+        dom = dominant(per_kernel)
         ach = per_kernel[dom]["algo_gbs"]
-        pk_on = kernel_table(kt_on, peak)
-        dom_on = max(pk_on, key=lambda k: pk_on[k]["avg_ms"])
+        pk_on = kernel_table(kt_on, peak, args.steps)
+        dom_on = dominant(pk_on)
         cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count()
         cpu = cpu_baseline(wl, cores, side, planes) if (world == 1 and not args.no_cpu_baseline and not args.quick) else None
         dropin = dropin_leg() if (world == 1 and not args.quick) else None
