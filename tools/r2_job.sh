@@ -1,11 +1,11 @@
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_synthetic.py tests/test_gpu_fullsize.py -m gpu -x -q 2>&1 | tail -2
-for i in 1 2; do
-timeout 150 python bench.py --quick --steps 20 --warmup 5 --e2e-steps 2 > gpurun_out/b_q.json 2>gpurun_out/b_q.err || tail -5 gpurun_out/b_q.err
-python - <<'PY'
-import json
-d=json.load(open('gpurun_out/b_q.json'))
+run() { n=$1; shift; env "$@" timeout 150 python bench.py --quick --steps 20 --warmup 5 --e2e-steps 2 > gpurun_out/b_$n.json 2>gpurun_out/b_$n.err || tail -5 gpurun_out/b_$n.err
+  python - "$n" <<'PY'
+import json,sys
+d=json.load(open('gpurun_out/b_%s.json'%sys.argv[1]))
 r=d['roofline']; a=r['all_on']
-print('ms', d['ms_per_step'], 'chain', r['chain']['frac'], '| ALL_ON ms', a['ms_per_step'], 'chain', a['chain']['frac'], '| db', r['per_kernel']['deblock'], 'dom', r['kernel'], r['frac'])
+print(sys.argv[1],'ms', d['ms_per_step'], 'chain', r['chain']['frac'], '| ALL_ON ms', a['ms_per_step'], 'chain', a['chain']['frac'])
 PY
-done
+}
+run l2p2 ILF_RUN_LANES=2 ILF_RUN_LANE_POLICY=2
+run l3p2 ILF_RUN_LANES=3 ILF_RUN_LANE_POLICY=2
