@@ -283,7 +283,11 @@ void launch_sao(const Geom& g, const SlotDev* slots, int first_slot, int num_slo
   const int bands_y = (g.rows + BR - 1) / BR, bands_c = (g.rows / 2 + BR - 1) / BR;
   // enough CTAs to fill the machine when the batch is small: split bands into horizontal segments
   const int ntx = (g.width + TW - 1) / TW;
-  const int bands = (bands_y + 2 * bands_c) * num_slots;
+  // bands that really run: a plane whose SAO is off in the whole picture is skipped (its CTAs leave at once)
+  int bands = 0;
+  for (int z = 0; z < num_slots; z++)
+    bands += (ctl_skip(ctl.v[z], 0) ? 0 : bands_y) + (ctl_skip(ctl.v[z], 1) ? 0 : bands_c) + (ctl_skip(ctl.v[z], 2) ? 0 : bands_c);
+  if (bands < 1) bands = 1;
   int nseg = (148 * SAO_CTAS + bands - 1) / bands;
   nseg = nseg < 1 ? 1 : (nseg > ntx ? ntx : nseg);
   static const int force = env_int("ILF_SAO_NSEG");   // experiment knob
