@@ -495,7 +495,10 @@ static void launch_deblock_mv(const Geom& g, const SlotDev* slots, int first_slo
   once_per_device(attr_set, [&] { cudaFuncSetAttribute(deblock_kernel<MV>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); });
   const int bands = (g.rows + 4 + TH - 1) / TH, ntx = (g.width + TW - 1) / TW;
   const long long total = (long long)ntx * bands * num_slots;
-  static const int ctas = env_int("ILF_DB_CTAS", 2 * 148 * ILF_DB_MIN_CTAS);   // CTAs drawing tiles from the queue: two per resident slot, so that a lane sharing the GPU finds slots
+  // CTAs drawing tiles from the queue: the resident ones plus a fifth.  Exactly the resident number starves the kernel when
+  // another lane's CTAs hold slots (stream chain 0.290 ms); every CTA beyond those that ever get a slot while the queue is
+  // non-empty only runs its prologue at the end of the launch (twice the resident number: 0.275 ms; 800 - 1000 CTAs: 0.271 ms).
+  static const int ctas = env_int("ILF_DB_CTAS", 148 * (ILF_DB_MIN_CTAS + 1));
   dim3 grid((unsigned)std::min<long long>(total, ctas));
   launch_pdl(deblock_kernel<MV>, grid, dim3(NTHREADS), smem, st, g, slots, first_slot, ctl, num_slots, work);
 }
