@@ -9,31 +9,34 @@
 // read [x0 - 4, x0 + 132) and leave [x0, x0 + 128) final (edge 16 is the next tile's edge 0: both tiles compute it, each keeps
 // its own side).
 //
-// Data movement: INDEPENDENT TILES in raster order.  A CTA takes DB_TILES_PER_CTA consecutive tiles of a band (rows
-// [32 ty - 4, 32 ty + 28), chroma [16 ty - 2, 16 ty + 14), units [8 ty - 1, 8 ty + 7)), issues the TMA boxes of ALL of them
-// at once -- per tile: luma 144 x 32 from x0 - 8, Cb and Cr 80 x 16 from cx0 - 8, the unit grid 40 x 8 from unit ux0 - 4 (and its
-// chroma-tree layer), motion vectors of units ux0 - 2 .. ux0 + 33 -- into one shared-memory stage each, and works through
-// them; the grid enumerates (segment, band, picture) with the segment fastest, so the hardware scheduler hands tiles out in
-// raster order and the CTAs resident at any moment cover a compact window of the picture.  That order is what the
-// memory system rewards (profiles/r02_ring_vs_copy.txt, tools/ubench/tma_ring.cu): the same boxes moved by persistent CTAs that
-// each walk a band -- the design of round 1 -- reach 4.7 TB/s, in raster order with short independent walks 5.7 TB/s, because a
-// band walk spreads the concurrent accesses over every row of every picture (one 256-byte piece per DRAM page at a time).
+// Data movement: INDEPENDENT TILES drawn from a raster-order work queue.  The tiles of a launch are numbered in raster order
+// inside a picture (tile of a band, band: rows [32 ty - 4, 32 ty + 28), chroma [16 ty - 2, 16 ty + 14), units [8 ty - 1, 8 ty + 7)),
+// picture after picture; 148 x 6 CTAs draw tile numbers from one device counter (atomicAdd; the last CTA to leave resets it for
+// the next launch on the stream) and each keeps a ring of DB_STAGES shared-memory stages: the TMA boxes of a tile -- luma 144 x 32
+// from x0 - 8, Cb and Cr 80 x 16 from cx0 - 8, the unit grid 40 x 8 from unit ux0 - 4 (and its chroma-tree layer), motion vectors of
+// units ux0 - 2 .. ux0 + 33 -- land in one stage while the tile of the other stage is filtered.  Because the queue hands tiles out in
+// raster order whatever the CTAs' relative progress, the CTAs resident at any moment cover a compact window of the picture.
+// That order is what the memory system rewards (profiles/r02_ring_vs_copy.txt, tools/ubench/tma_ring.cu): the same boxes moved by
+// persistent CTAs that each walk a band -- the design of round 1 -- copy at 4.7 TB/s, handed out in raster order 5.7 TB/s, because
+// a band walk spreads the concurrent accesses over every row of every picture (one 256-byte piece per DRAM page at a time).
 // Per tile:
 //   1. vertical edges x0 + 8e, e = 0..16 (luma) / cx0 + 8k, k = 0..8 (chroma), in shared memory;
-//   2. one CTA barrier;
+//   2. a CTA barrier;
 //   3. horizontal edges: a task (4 luma columns x 8 rows, or 2 chroma columns x 8 rows) loads its block, filters the edge in its
 //      middle when there is one, and stores the block straight to the destination plane: a warp's 32 tasks write 256 (128)
-//      contiguous, sector-aligned bytes per row.  There is no separate write-back pass.
+//      contiguous, sector-aligned bytes per row.  There is no separate write-back pass;
+//   4. a CTA barrier, after which the stage is refilled with the tile drawn during step 3.
 // Every sample crosses HBM once in and once out (the reference makes two picture passes); the 16 halo columns of a box are
 // L2 hits (the neighbouring tiles are in flight at the same time).
 //
 // Per-edge derivation on the device (xGetBoundaryStrengthSingle :419-541, QP/tc/beta :626-634, chroma QP
 // :811-829) from the packed per-4x4 grid described in include/ilf_b200.h.
 //
-// Work split: the unit of deblocking work is a SEGMENT (4 lines of one edge).  The 128 threads of a CTA take one
-// segment each in four phases -- luma vertical (17 edge columns x 8: eight threads take a second one), chroma vertical
-// (2 planes x 9 x 8 units), luma horizontal (4 edge rows x 32), chroma horizontal (2 x 2 x 32) -- so edge flag, bS, QP, tc and
-// beta are derived once per segment and segments without an edge cost a few instructions.
+// Work split: the unit of deblocking work is a SEGMENT (4 lines of one edge).  The 160 threads of a CTA take one
+// segment each in four phases -- luma vertical (17 edge columns x 8 = 136 tasks), chroma vertical (2 planes x 9 x 8 = 144),
+// luma horizontal (4 edge rows x 32 = 128), chroma horizontal (2 x 2 x 32 = 128) -- so edge flag, bS, QP, tc and beta are
+// derived once per segment and segments without an edge cost a few instructions.  The fifth warp has vertical tasks only: its
+// first thread draws the next tile from the queue while the other four run the horizontal pass.
 #include <algorithm>
 #include <cstdlib>
 
